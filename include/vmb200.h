@@ -1,0 +1,201 @@
+/*
+ * vmb200.h -- C ABI of libvmb200.so: the B200 (sm_100a) implementation of the VideoMamba
+ * per-block Mamba-mixer hot path.
+ *
+ * The reference (tannerhoalst/VideoMamba) is pure Python and has no FFI of its own; the seam
+ * this library replaces is the set of third-party operator calls the reference makes
+ * (SURVEY.md section 8b).  Each entry point below names the reference call site it stands in
+ * for (paths relative to the reference root).  Signatures use plain pointers and sizes only:
+ * every pointer is a DEVICE pointer unless stated otherwise, every call only ENQUEUES work on
+ * `stream` (a cudaStream_t / CUstream passed as void*), never synchronises, never allocates
+ * and never frees.  Return value: 0 on success, negative on error (VMB_ERR_*); the message of
+ * the last error on the calling thread is available from vmb_last_error().
+ *
+ * Layout convention: activations are TOKEN-MAJOR, i.e. (batch, token, channel) with channel
+ * stride 1 and explicit batch / token strides counted in ELEMENTS.  (The reference works
+ * channel-major (B, D, L) because the upstream kernels do; a (B, L, D) buffer viewed as
+ * (B, D, L) is the same memory.)  State tensors keep the reference layouts:
+ * conv_state (B, d_inner, d_conv), ssm_state (B, d_inner, d_state), both contiguous.
+ */
+#ifndef VMB200_H_
+#define VMB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMB_ABI_VERSION 1
+
+/* element types */
+#define VMB_F32 0
+#define VMB_BF16 1
+
+/* status codes */
+#define VMB_OK 0
+#define VMB_ERR_INVALID (-1)     /* bad argument (null pointer, bad size, bad dtype) */
+#define VMB_ERR_UNSUPPORTED (-2) /* shape / option outside what the kernels cover */
+#define VMB_ERR_CUDA (-3)        /* a CUDA call failed; see vmb_last_error() */
+
+typedef void* vmb_stream_t;
+
+#if defined(VMB_BUILDING) && defined(__GNUC__)
+#define VMB_API __attribute__((visibility("default")))
+#else
+#define VMB_API
+#endif
+
+VMB_API int vmb_abi_version(void);
+VMB_API const char* vmb_last_error(void);
+/* Host-side query: SM count and compute capability of the current device. */
+VMB_API int vmb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused residual-add + RMSNorm / LayerNorm.
+ * Replaces mamba_ssm.ops.triton.layer_norm.{rms_norm_fn, layer_norm_fn} as called at
+ * models/videomamba/videomamba.py:151-166 (prenorm=True) and :902-918 (prenorm=False).
+ *   acc = float(x) (+ float(residual));  residual_out = acc (optional);
+ *   y   = x_dtype( norm(acc) * weight (+ bias) ),  norm = RMS (is_rms) or LayerNorm.
+ * x: (rows, dim) with row stride ldx; residual / y / residual_out: (rows, dim) contiguous.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_add_norm_fwd(const void* x, int x_dtype, int64_t ldx,
+                     const void* residual, int residual_dtype,     /* nullable */
+                     const void* weight, const void* bias, int w_dtype, /* bias nullable */
+                     void* y,                                      /* x_dtype */
+                     void* residual_out, int residual_out_dtype,   /* nullable */
+                     int64_t rows, int dim, float eps, int is_rms, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projection  C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]),  fp32 accumulate.
+ * Replaces the cuBLAS calls behind in_proj / x_proj / dt_proj / out_proj:
+ * models/videomamba/mamba_simple.py:333-339, :409, :413, :445-446 (and :464, :476-479, :496).
+ * dtype VMB_BF16 with TMA-compatible shapes runs on tcgen05 tensor cores (TMEM accumulators);
+ * VMB_F32 and odd shapes run a CUDA-core kernel in true fp32.
+ * lda / ldw / ldc are row strides in elements.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_linear_fwd(const void* A, int64_t lda, const void* W, int64_t ldw,
+                   const void* bias,                              /* nullable, same dtype */
+                   void* C, int64_t ldc, int64_t M, int N, int K, int dtype,
+                   vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d (+ optional SiLU), token-major, with streaming history.
+ * Replaces causal_conv1d.causal_conv1d_fn at models/videomamba/mamba_simple.py:383-399 together
+ * with the torch.cat / F.pad state handling around it (:381-404):
+ *   hist = [conv_state_in (B,Di,W) or zeros ; x];  y[l] = act(bias + sum_k w[k]*hist[W+l+k-(W-1)])
+ *   conv_state_out = last W columns of hist (pre-conv inputs).
+ * reverse != 0: the logical sequence is the physical one read back to front (token i of the
+ * logical sequence is row L-1-i); history and state columns are in logical order.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_causal_conv1d_fwd(const void* x, int64_t x_bstride, int64_t x_tstride,
+                          const void* weight /* (Di, W) */, const void* bias /* nullable */,
+                          const void* conv_state_in, int cs_in_dtype,  /* nullable */
+                          void* y, int64_t y_bstride, int64_t y_tstride,
+                          void* conv_state_out, int cs_out_dtype,      /* nullable */
+                          int B, int L, int Di, int W, int silu, int reverse, int dtype,
+                          vmb_stream_t stream);
+
+/* Single-token conv step: rolls conv_state (B,Di,W) in place, returns act(conv).
+ * Replaces causal_conv1d.causal_conv1d_update at models/videomamba/mamba_simple.py:468-474. */
+VMB_API int vmb_causal_conv1d_update(const void* x /* (B,Di) */, int64_t x_bstride,
+                             void* conv_state, int cs_dtype,
+                             const void* weight, const void* bias,
+                             void* y /* (B,Di) */, int64_t y_bstride,
+                             int B, int Di, int W, int silu, int dtype, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Selective scan (S6 recurrence), token-major.
+ * Replaces mamba_ssm.ops.selective_scan_interface.selective_scan_fn as reached through
+ * _selective_scan_with_state (models/videomamba/mamba_simple.py:109-172, call :423-435) with the
+ * semantics of _selective_scan_ref (:30-106):
+ *   delta = softplus(delta_raw + dt_bias);  h = exp(delta*A)*h + delta*B_t*u_t;
+ *   y_t = <C_t,h> + D*u_t;  y_t *= silu(z_t);  h_last = h after the final token (fp32).
+ * u, delta_raw, z, y: (B, L, Di) views.  B_t / C_t are read from one token-major buffer `bc`
+ * of row stride bc_tstride: B at columns [b_off, b_off+N), C at [c_off, c_off+N).
+ * A2 = A * log2(e) with A = -exp(A_log) (fp32, (Di,N)).  reverse != 0 walks tokens L-1..0.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vmb_scan_args {
+  const void* u;      int64_t u_bstride, u_tstride;
+  const void* delta;  int64_t d_bstride, d_tstride;
+  const void* z;      int64_t z_bstride, z_tstride;      /* nullable */
+  const void* bc;     int64_t bc_bstride, bc_tstride;    int32_t b_off, c_off;
+  const float* A2;        /* (Di, N) fp32, A*log2(e) */
+  const float* D;         /* (Di) fp32, nullable */
+  const float* dt_bias;   /* (Di) fp32, nullable */
+  const void* h0;     int32_t h0_dtype;                  /* (B,Di,N), nullable */
+  void* y;            int64_t y_bstride, y_tstride;
+  float* h_last;                                         /* (B,Di,N) fp32, nullable */
+  int32_t B, L, Di, N;
+  int32_t dtype;          /* element type of u / delta / z / bc / y */
+  int32_t softplus;       /* apply softplus to delta_raw + dt_bias */
+  int32_t reverse;
+} vmb_scan_args;
+VMB_API int vmb_selective_scan_fwd(const vmb_scan_args* args, vmb_stream_t stream);
+
+/* Single recurrent step, state (B,Di,N) updated in place.  Replaces
+ * mamba_ssm.ops.triton.selective_state_update at models/videomamba/mamba_simple.py:483-494
+ * (and the per-token fallback loop :158-171).  x, dt, z, y: (B,Di); Bm, Cm: (B,N). */
+VMB_API int vmb_selective_state_update(void* state, int state_dtype,
+                               const void* x, int64_t x_bstride,
+                               const void* dt, int64_t dt_bstride,
+                               const float* A2, const void* Bm, int64_t b_bstride,
+                               const void* Cm, int64_t c_bstride,
+                               const float* D, const void* z, int64_t z_bstride,
+                               const float* dt_bias, int softplus,
+                               void* y, int64_t y_bstride,
+                               int B, int Di, int N, int dtype, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole mixer block: in_proj -> conv(+SiLU) -> x_proj -> dt_proj -> scan(+gate) -> out_proj.
+ * Replaces the body of Mamba.forward, models/videomamba/mamba_simple.py:332-446, for the
+ * stateless, (conv_state, ssm_state)-streaming and ssm-only cases, and stands where
+ * mamba_ssm's mamba_inner_fn (:352-366) stands on the reference's fast path.
+ * All weights are in `dtype`; A2 / D / dt_bias are fp32 (prepared once per weight load).
+ * `workspace` must hold vmb_mixer_workspace_bytes(...) bytes (device memory, 256-B aligned).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vmb_mixer_args {
+  const void* hidden;  int64_t h_bstride, h_tstride;     /* (B, L, D) */
+  void* out;           int64_t o_bstride, o_tstride;     /* (B, L, D) */
+  const void* w_in;    /* (2Di, D)  */
+  const void* b_in;    /* (2Di) nullable */
+  const void* w_conv;  /* (Di, W)   */
+  const void* b_conv;  /* (Di) nullable */
+  const void* w_x;     /* (R+2N, Di) */
+  const void* w_dt;    /* (Di, R)   */
+  const void* w_out;   /* (D, Di)   */
+  const void* b_out;   /* (D) nullable */
+  const float* A2;     /* (Di, N) fp32 */
+  const float* Dskip;  /* (Di) fp32 */
+  const float* dt_bias;/* (Di) fp32 */
+  /* fast-path operands prepared at weight-load time (nullable => generic path):
+   * w_x_pad (Xp, Di) zero-padded rows, w_dt_pad (Di, Rp) zero-padded columns */
+  const void* w_x_pad; const void* w_dt_pad; int32_t Xp, Rp;
+  const void* conv_state_in;  int32_t cs_in_dtype;       /* nullable */
+  void* conv_state_out;       int32_t cs_out_dtype;      /* nullable */
+  const void* ssm_state_in;   int32_t ss_in_dtype;       /* nullable */
+  float* ssm_state_out;                                  /* nullable, fp32 */
+  void* workspace;     int64_t workspace_bytes;
+  int32_t B, L, D, Di, N, R, W;
+  int32_t dtype;
+  int32_t reverse;     /* walk tokens L-1..0 (conv and scan) */
+  int32_t path;        /* 0 = auto, 1 = force generic kernels, 2 = force fast kernels */
+} vmb_mixer_args;
+VMB_API int64_t vmb_mixer_workspace_bytes(int B, int L, int D, int Di, int N, int R, int dtype);
+VMB_API int vmb_mixer_fwd(const vmb_mixer_args* args, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Streaming state I/O: move per-stream state rows between a resident pool and a batch.
+ * Serves the (conv_state, ssm_state) carry of the streaming contract
+ * (models/videomamba/streaming.py:77-92, models/videomamba/videomamba.py:526-549): row i of
+ * `batch` <-> row index[i] of `pool`; rows are `row_elems` elements of `dtype`.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_state_gather(const void* pool, const int32_t* index, void* batch,
+                     int n_rows, int64_t row_elems, int dtype, vmb_stream_t stream);
+VMB_API int vmb_state_scatter(void* pool, const int32_t* index, const void* batch,
+                      int n_rows, int64_t row_elems, int dtype, vmb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMB200_H_ */

@@ -1,0 +1,57 @@
+"""Test helper: run the package's HOST logic on CPU by standing the oracle in for the kernels.
+
+Only tests use this (``-m "not gpu"`` suite): it monkeypatches the marshalling layer
+(``videomamba_b200.ops``) with oracle-backed functions so the module / model / streaming code
+paths can be exercised without a GPU.  The product itself has no such path.
+"""
+import torch
+
+from oracle import videomamba_oracle as orc
+
+
+def _params(w):
+    return {k: v.detach() for k, v in w.raw.items() if v is not None}
+
+
+def mixer_fwd(w, hidden, conv_state=None, ssm_state=None, want_conv_state=False,
+              want_ssm_state=False, reverse=False, path=0):
+    p = _params(w)
+    x = torch.flip(hidden, dims=[1]) if reverse else hidden
+    out, (new_conv, last) = orc.mixer_ref(p, x, conv_state, ssm_state, want_state=True)
+    if reverse:
+        out = torch.flip(out, dims=[1])
+    if want_conv_state and conv_state is not None:
+        new_conv = new_conv.to(torch.promote_types(conv_state.dtype, hidden.dtype))
+    return out, (new_conv if want_conv_state else None), (last if want_ssm_state else None)
+
+
+def add_norm(x, weight, bias, residual, eps, is_rms, prenorm, residual_in_fp32):
+    return orc.add_norm_ref(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms)
+
+
+def linear(x, weight, bias=None):
+    return orc._linear(x, weight.to(x.dtype), bias)
+
+
+def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None):
+    return orc.causal_conv1d_update_ref(x, conv_state, weight.reshape(x.shape[1], -1), bias,
+                                        activation)
+
+
+def state_update(ssm_state, x, dt, w, B, C, z):
+    p = _params(w)
+    A = -torch.exp(p["A_log"].float())
+    return orc.selective_state_update_ref(ssm_state, x, dt, A, B, C, p["D"], z=z,
+                                          dt_bias=p["dt_proj.bias"], dt_softplus=True)
+
+
+def install(monkeypatch):
+    import videomamba_b200.mixer as mixer_mod
+    import videomamba_b200.ops as ops
+
+    monkeypatch.setattr(ops, "mixer_fwd", mixer_fwd)
+    monkeypatch.setattr(ops, "add_norm", add_norm)
+    monkeypatch.setattr(ops, "linear", linear)
+    monkeypatch.setattr(ops, "causal_conv1d_update", causal_conv1d_update)
+    monkeypatch.setattr(mixer_mod, "_state_update", state_update)
+    monkeypatch.setattr(mixer_mod.Mamba, "_require_cuda", staticmethod(lambda t: None))

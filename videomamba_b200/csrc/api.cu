@@ -1,0 +1,250 @@
+// C ABI of libvmb200 (see include/vmb200.h): argument checking, kernel selection, and the
+// whole-mixer orchestration that stands where the body of the reference's Mamba.forward
+// (models/videomamba/mamba_simple.py:332-446) issues its operator calls.
+#include <cstdarg>
+#include <cstdio>
+
+#include "internal.h"
+
+namespace vmb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return VMB_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline int xdbl_pitch(int R, int N) { return (int)align_up(R + 2 * N, 16); }
+
+struct MixerWorkspace {
+  int64_t xz, xc, xdbl, delta, y, total;  // byte offsets
+};
+
+MixerWorkspace plan_workspace(int B, int L, int Di, int N, int R, int dtype) {
+  const int64_t es = dtype_size(dtype);
+  const int64_t M = (int64_t)B * L;
+  MixerWorkspace w;
+  int64_t off = 0;
+  w.xz = off;    off = align_up(off + M * 2 * Di * es, 256);
+  w.xc = off;    off = align_up(off + M * Di * es, 256);
+  w.xdbl = off;  off = align_up(off + M * xdbl_pitch(R, N) * es, 256);
+  w.delta = off; off = align_up(off + M * Di * es, 256);
+  w.y = off;     off = align_up(off + M * Di * es, 256);
+  w.total = off;
+  return w;
+}
+
+template <typename V>
+__global__ void state_rows_kernel(const V* __restrict__ src, V* __restrict__ dst,
+                                  const int32_t* __restrict__ index, int64_t row_vecs,
+                                  bool gather) {
+  const int r = blockIdx.y;
+  const int64_t p = index[r];
+  const V* s = gather ? src + p * row_vecs : src + (int64_t)r * row_vecs;
+  V* d = gather ? dst + (int64_t)r * row_vecs : dst + p * row_vecs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < row_vecs;
+       i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = s[i];
+}
+
+int state_rows(const void* src, void* dst, const int32_t* index, int n_rows, int64_t row_elems,
+               int dtype, bool gather, cudaStream_t st) {
+  VMB_CHECK_ARG(src && dst && index, "state_gather/scatter: null pointer");
+  VMB_CHECK_ARG(dtype_ok(dtype), "state_gather/scatter: bad dtype");
+  VMB_CHECK_ARG(n_rows >= 0 && n_rows <= 65535 && row_elems >= 0, "state_gather/scatter: bad sizes");
+  if (n_rows == 0 || row_elems == 0) return VMB_OK;
+  const int64_t bytes = row_elems * dtype_size(dtype);
+  const bool v16 = bytes % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(dst) % 16 == 0;
+  if (v16) {
+    const int64_t nv = bytes / 16;
+    dim3 grid((unsigned)std::min<int64_t>((nv + 255) / 256, 64), n_rows);
+    state_rows_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)src, (uint4*)dst, index, nv,
+                                                   gather);
+  } else if (dtype == VMB_BF16) {
+    dim3 grid((unsigned)std::min<int64_t>((row_elems + 255) / 256, 64), n_rows);
+    state_rows_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, index,
+                                                      row_elems, gather);
+  } else {
+    dim3 grid((unsigned)std::min<int64_t>((row_elems + 255) / 256, 64), n_rows);
+    state_rows_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, index,
+                                                      row_elems, gather);
+  }
+  VMB_LAUNCH_CHECK("state_rows_kernel");
+  return VMB_OK;
+}
+
+}  // namespace
+}  // namespace vmb
+
+using namespace vmb;
+
+extern "C" int vmb_abi_version(void) { return VMB_ABI_VERSION; }
+extern "C" const char* vmb_last_error(void) { return g_err; }
+
+extern "C" int vmb_device_info(int* sms, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  VMB_CUDA(cudaGetDevice(&dev));
+  int n = 0, ma = 0, mi = 0;
+  VMB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  VMB_CUDA(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev));
+  VMB_CUDA(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sms) *sms = n;
+  if (cc_major) *cc_major = ma;
+  if (cc_minor) *cc_minor = mi;
+  return VMB_OK;
+}
+
+extern "C" int vmb_linear_fwd(const void* A, int64_t lda, const void* W, int64_t ldw,
+                              const void* bias, void* C, int64_t ldc, int64_t M, int N, int K,
+                              int dtype, vmb_stream_t stream) {
+  VMB_CHECK_ARG(A && W && C, "linear: null A / W / C");
+  VMB_CHECK_ARG(dtype_ok(dtype), "linear: bad dtype %d", dtype);
+  VMB_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear: bad sizes M=%lld N=%d K=%d", (long long)M, N, K);
+  VMB_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "linear: row stride smaller than row");
+  if (M == 0) return VMB_OK;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == VMB_BF16 && gemm_tc_supported(A, lda, W, ldw, C, ldc, M, N, K))
+    return gemm_tc(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  return linear_simt(A, lda, W, ldw, bias, C, ldc, M, N, K, dtype, st);
+}
+
+extern "C" int vmb_selective_scan_fwd(const vmb_scan_args* a, vmb_stream_t stream) {
+  VMB_CHECK_ARG(a != nullptr, "selective_scan: null args");
+  VMB_CHECK_ARG(a->u && a->delta && a->bc && a->A2 && a->y, "selective_scan: null tensor");
+  VMB_CHECK_ARG(dtype_ok(a->dtype), "selective_scan: bad dtype %d", a->dtype);
+  VMB_CHECK_ARG(a->B >= 0 && a->L >= 0 && a->Di > 0 && a->N > 0, "selective_scan: bad sizes");
+  VMB_CHECK_ARG(a->B <= 65535, "selective_scan: batch %d > 65535", a->B);
+  VMB_CHECK_ARG(!a->h0 || dtype_ok(a->h0_dtype), "selective_scan: bad h0 dtype");
+  if (a->B == 0) return VMB_OK;
+  return scan_generic(*a, as_stream(stream));
+}
+
+extern "C" int64_t vmb_mixer_workspace_bytes(int B, int L, int D, int Di, int N, int R,
+                                             int dtype) {
+  (void)D;
+  if (B < 0 || L < 0 || Di <= 0 || N <= 0 || R <= 0 || !dtype_ok(dtype)) return -1;
+  return plan_workspace(B, L, Di, N, R, dtype).total + 256;
+}
+
+extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
+  VMB_CHECK_ARG(p != nullptr, "mixer: null args");
+  VMB_CHECK_ARG(p->hidden && p->out && p->w_in && p->w_conv && p->w_x && p->w_dt && p->w_out &&
+                    p->A2 && p->Dskip && p->dt_bias,
+                "mixer: null tensor");
+  VMB_CHECK_ARG(dtype_ok(p->dtype), "mixer: bad dtype %d", p->dtype);
+  VMB_CHECK_ARG(p->B >= 0 && p->L >= 0 && p->D > 0 && p->Di > 0 && p->N > 0 && p->R > 0 &&
+                    p->W > 0,
+                "mixer: bad sizes");
+  if (p->B == 0 || p->L == 0) {
+    if (p->L == 0 && p->B > 0 && (p->conv_state_out || p->ssm_state_out))
+      VMB_UNSUPPORTED("mixer: empty sequence with state output");
+    return VMB_OK;
+  }
+  const int B = p->B, L = p->L, D = p->D, Di = p->Di, N = p->N, R = p->R;
+  const int X = R + 2 * N, Xw = xdbl_pitch(R, N);
+  const int64_t M = (int64_t)B * L;
+  const MixerWorkspace ws = plan_workspace(B, L, Di, N, R, p->dtype);
+  VMB_CHECK_ARG(p->workspace != nullptr, "mixer: null workspace");
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(p->workspace), 256));
+  VMB_CHECK_ARG(p->workspace_bytes >= ws.total + (base - (char*)p->workspace),
+                "mixer: workspace too small (%lld < %lld)", (long long)p->workspace_bytes,
+                (long long)ws.total);
+  VMB_CHECK_ARG(p->h_bstride == (int64_t)L * p->h_tstride && p->o_bstride == (int64_t)L * p->o_tstride,
+                "mixer: hidden / out must be uniformly strided over (batch, token)");
+  void* xz = base + ws.xz;
+  void* xc = base + ws.xc;
+  void* xdbl = base + ws.xdbl;
+  void* delta = base + ws.delta;
+  void* y = base + ws.y;
+  const int64_t es = dtype_size(p->dtype);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+
+  // in_proj (mamba_simple.py:333-339): xz (M, 2Di), x = [:, :Di], z = [:, Di:]
+  rc = vmb_linear_fwd(p->hidden, p->h_tstride, p->w_in, D, p->b_in, xz, 2 * Di, M, 2 * Di, D,
+                      p->dtype, stream);
+  if (rc) return rc;
+  // causal conv + SiLU with optional history (mamba_simple.py:381-404)
+  rc = vmb_causal_conv1d_fwd(xz, (int64_t)L * 2 * Di, 2 * Di, p->w_conv, p->b_conv,
+                             p->conv_state_in, p->cs_in_dtype, xc, (int64_t)L * Di, Di,
+                             p->conv_state_out, p->cs_out_dtype, B, L, Di, p->W, 1, p->reverse,
+                             p->dtype, stream);
+  if (rc) return rc;
+
+  FastScanArgs f;
+  f.u = xc; f.u_bs = (int64_t)L * Di; f.u_ts = Di;
+  f.z = (char*)xz + (int64_t)Di * es; f.z_bs = (int64_t)L * 2 * Di; f.z_ts = 2 * Di;
+  f.xdbl = xdbl; f.x_bs = (int64_t)L * Xw; f.x_ts = Xw;
+  f.w_dt_pad = p->w_dt_pad; f.A2 = p->A2; f.D = p->Dskip; f.dt_bias = p->dt_bias;
+  f.h0 = p->ssm_state_in; f.h0_dtype = p->ss_in_dtype;
+  f.y = y; f.y_bs = (int64_t)L * Di; f.y_ts = Di; f.h_last = p->ssm_state_out;
+  f.B = B; f.L = L; f.Di = Di; f.N = N; f.R = R; f.Rp = p->Rp; f.Xp = p->Xp; f.reverse = p->reverse;
+  const bool fast_ok = p->dtype == VMB_BF16 && p->w_x_pad && p->w_dt_pad && p->Xp == Xw &&
+                       scan_fast_supported(f);
+  if (p->path == 2 && !fast_ok) VMB_UNSUPPORTED("mixer: fast path requested but not available");
+  const bool fast = fast_ok && p->path != 1;
+
+  if (fast) {
+    // x_proj with zero-padded weight rows: x_dbl (M, Xp) = [dt_low | B | C | 0]
+    rc = vmb_linear_fwd(xc, Di, p->w_x_pad, Di, nullptr, xdbl, Xw, M, Xw, Di, p->dtype, stream);
+    if (rc) return rc;
+    rc = scan_fast(f, st);
+    if (rc) return rc;
+  } else {
+    // x_proj (mamba_simple.py:409) and dt_proj (:413-414): delta_raw rounded to the model dtype
+    rc = vmb_linear_fwd(xc, Di, p->w_x, Di, nullptr, xdbl, Xw, M, X, Di, p->dtype, stream);
+    if (rc) return rc;
+    rc = vmb_linear_fwd(xdbl, Xw, p->w_dt, R, nullptr, delta, Di, M, Di, R, p->dtype, stream);
+    if (rc) return rc;
+    vmb_scan_args s;
+    s.u = xc; s.u_bstride = (int64_t)L * Di; s.u_tstride = Di;
+    s.delta = delta; s.d_bstride = (int64_t)L * Di; s.d_tstride = Di;
+    s.z = f.z; s.z_bstride = f.z_bs; s.z_tstride = f.z_ts;
+    s.bc = xdbl; s.bc_bstride = (int64_t)L * Xw; s.bc_tstride = Xw; s.b_off = R; s.c_off = R + N;
+    s.A2 = p->A2; s.D = p->Dskip; s.dt_bias = p->dt_bias;
+    s.h0 = p->ssm_state_in; s.h0_dtype = p->ss_in_dtype;
+    s.y = y; s.y_bstride = (int64_t)L * Di; s.y_tstride = Di; s.h_last = p->ssm_state_out;
+    s.B = B; s.L = L; s.Di = Di; s.N = N; s.dtype = p->dtype; s.softplus = 1;
+    s.reverse = p->reverse;
+    rc = vmb_selective_scan_fwd(&s, stream);
+    if (rc) return rc;
+  }
+  // out_proj (mamba_simple.py:445-446)
+  return vmb_linear_fwd(y, Di, p->w_out, Di, p->b_out, p->out, p->o_tstride, M, D, Di, p->dtype,
+                        stream);
+}
+
+extern "C" int vmb_state_gather(const void* pool, const int32_t* index, void* batch, int n_rows,
+                                int64_t row_elems, int dtype, vmb_stream_t stream) {
+  return state_rows(pool, batch, index, n_rows, row_elems, dtype, true, as_stream(stream));
+}
+
+extern "C" int vmb_state_scatter(void* pool, const int32_t* index, const void* batch, int n_rows,
+                                 int64_t row_elems, int dtype, vmb_stream_t stream) {
+  return state_rows(batch, pool, index, n_rows, row_elems, dtype, false, as_stream(stream));
+}

@@ -1,0 +1,264 @@
+// Depthwise causal conv1d (+SiLU), token-major, with streaming history (HBM-bound).
+//
+// Stands in for causal_conv1d_fn and the torch.cat / F.pad state handling around it
+// (reference models/videomamba/mamba_simple.py:381-404) and for causal_conv1d_update (:468-474).
+// A thread owns VEC consecutive channels (one 128-bit load per token) and slides a W-tap
+// window down a chunk of tokens, so x is read once (+ W-1 halo rows per chunk) and y written once.
+// Algorithmic bytes per token: 2 * Di * sizeof(T).
+#include "common.cuh"
+
+namespace vmb {
+namespace {
+
+constexpr int kChunk = 64;  // tokens per CTA along the sequence
+
+template <typename T, int VEC> struct VecIO;
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float* f) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct VecIO<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      f[2 * i] = __low2float(h);
+      f[2 * i + 1] = __high2float(h);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <typename T> struct VecIO<T, 1> {
+  static __device__ __forceinline__ void load(const T* p, float* f) { f[0] = to_f32<T>(*p); }
+  static __device__ __forceinline__ void store(T* p, const float* f) { *p = from_f32<T>(f[0]); }
+};
+
+template <typename T, int VEC, int W, bool kAccurate>
+__global__ void __launch_bounds__(128)
+conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* __restrict__ weight,
+                  const T* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
+                  T* __restrict__ y, int64_t y_bs, int64_t y_ts, void* __restrict__ cs_out,
+                  int cs_out_dtype, int L, int Di, int silu, int reverse) {
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (c0 >= Di) return;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * kChunk;
+  const int t1 = min(t0 + kChunk, L);
+
+  float w[VEC][W], bv[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) w[v][k] = to_f32<T>(weight[(int64_t)(c0 + v) * W + k]);
+    bv[v] = bias ? to_f32<T>(bias[c0 + v]) : 0.f;
+  }
+  const T* xb = x + (int64_t)b * x_bs + c0;
+  T* yb = y + (int64_t)b * y_bs + c0;
+  auto row = [&](int i) -> int64_t { return reverse ? (int64_t)(L - 1 - i) : (int64_t)i; };
+  // logical history element i (may be negative => carried state or zero)
+  auto load_hist = [&](int i, float* f) {
+    if (i >= 0) {
+      VecIO<T, VEC>::load(xb + row(i) * x_ts, f);
+    } else if (cs_in != nullptr) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        f[v] = load_as_f32(cs_in, ((int64_t)b * Di + c0 + v) * W + (W + i), cs_in_dtype);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) f[v] = 0.f;
+    }
+  };
+
+  float win[W][VEC];  // win[k] = hist[t + k - (W-1)]
+#pragma unroll
+  for (int k = 0; k < W - 1; ++k) load_hist(t0 + k - (W - 1), win[k + 1]);
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) {
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) win[k][v] = win[k + 1][v];
+    VecIO<T, VEC>::load(xb + row(t) * x_ts, win[W - 1]);
+    float o[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float acc = bv[v];
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc = fmaf(w[v][k], win[k][v], acc);
+      o[v] = silu ? silu_f<kAccurate>(acc) : acc;
+    }
+    VecIO<T, VEC>::store(yb + row(t) * y_ts, o);
+  }
+
+  // The CTA that owns the final chunk also emits the next conv state: hist[L-W .. L-1].
+  if (cs_out != nullptr && t1 == L) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      float f[VEC];
+      load_hist(L - W + k, f);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        store_from_f32(cs_out, ((int64_t)b * Di + c0 + v) * W + k, cs_out_dtype, f[v]);
+    }
+  }
+}
+
+template <typename T, int W>
+__global__ void conv1d_update_kernel(const T* __restrict__ x, int64_t x_bs, void* __restrict__ cs,
+                                     int cs_dtype, const T* __restrict__ weight,
+                                     const T* __restrict__ bias, T* __restrict__ y, int64_t y_bs,
+                                     int B, int Di, int silu) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (d >= Di) return;
+  const int64_t base = ((int64_t)b * Di + d) * W;
+  float win[W];
+#pragma unroll
+  for (int k = 0; k < W - 1; ++k) win[k] = load_as_f32(cs, base + k + 1, cs_dtype);
+  win[W - 1] = to_f32<T>(x[(int64_t)b * x_bs + d]);
+  // the state is stored in its own dtype first; the conv then reads the ROUNDED values, as
+  // the reference does (it convolves conv_state after writing x into it)
+  float acc = bias ? to_f32<T>(bias[d]) : 0.f;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    store_from_f32(cs, base + k, cs_dtype, win[k]);
+    const float r = load_as_f32(cs, base + k, cs_dtype);
+    acc = fmaf(to_f32<T>(weight[(int64_t)d * W + k]), r, acc);
+  }
+  y[(int64_t)b * y_bs + d] = from_f32<T>(silu ? silu_accurate(acc) : acc);
+}
+
+template <typename T, int VEC, int W>
+int launch_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, const void* bias,
+               const void* cs_in, int cs_in_dtype, void* y, int64_t y_bs, int64_t y_ts,
+               void* cs_out, int cs_out_dtype, int B, int L, int Di, int silu, int reverse,
+               cudaStream_t st) {
+  const int cthreads = (Di + VEC - 1) / VEC;
+  const int block = cthreads >= 128 ? 128 : ((cthreads + 31) / 32) * 32;
+  dim3 grid((cthreads + block - 1) / block, (L + kChunk - 1) / kChunk, B);
+  constexpr bool kAccurate = sizeof(T) == 4;
+  conv1d_fwd_kernel<T, VEC, W, kAccurate><<<grid, block, 0, st>>>(
+      (const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
+      y_ts, cs_out, cs_out_dtype, L, Di, silu, reverse);
+  VMB_LAUNCH_CHECK("conv1d_fwd_kernel");
+  return VMB_OK;
+}
+
+template <typename T, int VEC>
+int dispatch_w(int W, const void* x, int64_t x_bs, int64_t x_ts, const void* weight,
+               const void* bias, const void* cs_in, int cs_in_dtype, void* y, int64_t y_bs,
+               int64_t y_ts, void* cs_out, int cs_out_dtype, int B, int L, int Di, int silu,
+               int reverse, cudaStream_t st) {
+#define VMB_CW(WW)                                                                             \
+  case WW:                                                                                     \
+    return launch_fwd<T, VEC, WW>(x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs,    \
+                                  y_ts, cs_out, cs_out_dtype, B, L, Di, silu, reverse, st)
+  switch (W) {
+    VMB_CW(1); VMB_CW(2); VMB_CW(3); VMB_CW(4);
+    default: VMB_UNSUPPORTED("causal_conv1d: d_conv=%d not supported (1..4)", W);
+  }
+#undef VMB_CW
+}
+
+}  // namespace
+}  // namespace vmb
+
+extern "C" int vmb_causal_conv1d_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight,
+                                     const void* bias, const void* cs_in, int cs_in_dtype, void* y,
+                                     int64_t y_bs, int64_t y_ts, void* cs_out, int cs_out_dtype,
+                                     int B, int L, int Di, int W, int silu, int reverse, int dtype,
+                                     vmb_stream_t stream) {
+  using namespace vmb;
+  VMB_CHECK_ARG(x && weight && y, "causal_conv1d: null x / weight / y");
+  VMB_CHECK_ARG(dtype_ok(dtype), "causal_conv1d: bad dtype %d", dtype);
+  VMB_CHECK_ARG(B >= 0 && L >= 0 && Di > 0, "causal_conv1d: bad sizes");
+  if (!cs_in) cs_in_dtype = VMB_F32;
+  if (!cs_out) cs_out_dtype = VMB_F32;
+  VMB_CHECK_ARG(dtype_ok(cs_in_dtype) && dtype_ok(cs_out_dtype), "causal_conv1d: bad state dtype");
+  VMB_CHECK_ARG(B <= 65535, "causal_conv1d: batch %d > 65535", B);
+  if (B == 0) return VMB_OK;
+  if (L == 0) {
+    // nothing to convolve; the state just carries over (or stays zero)
+    if (cs_out) {
+      const size_t n = (size_t)B * Di * W;
+      if (cs_in && cs_in_dtype == cs_out_dtype)
+        VMB_CUDA(cudaMemcpyAsync(cs_out, cs_in, n * dtype_size(cs_out_dtype),
+                                 cudaMemcpyDeviceToDevice, as_stream(stream)));
+      else if (!cs_in)
+        VMB_CUDA(cudaMemsetAsync(cs_out, 0, n * dtype_size(cs_out_dtype), as_stream(stream)));
+      else
+        VMB_UNSUPPORTED("causal_conv1d: L=0 with a state dtype change");
+    }
+    return VMB_OK;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int vec = dtype == VMB_BF16 ? 8 : 4;
+  const bool aligned = Di % vec == 0 && x_bs % vec == 0 && x_ts % vec == 0 && y_bs % vec == 0 &&
+                       y_ts % vec == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+                       reinterpret_cast<uintptr_t>(y) % 16 == 0;
+  if (dtype == VMB_BF16) {
+    if (aligned)
+      return dispatch_w<__nv_bfloat16, 8>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y,
+                                          y_bs, y_ts, cs_out, cs_out_dtype, B, L, Di, silu,
+                                          reverse, st);
+    return dispatch_w<__nv_bfloat16, 1>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs,
+                                        y_ts, cs_out, cs_out_dtype, B, L, Di, silu, reverse, st);
+  }
+  if (aligned)
+    return dispatch_w<float, 4>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs, y_ts,
+                                cs_out, cs_out_dtype, B, L, Di, silu, reverse, st);
+  return dispatch_w<float, 1>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs, y_ts,
+                              cs_out, cs_out_dtype, B, L, Di, silu, reverse, st);
+}
+
+extern "C" int vmb_causal_conv1d_update(const void* x, int64_t x_bs, void* conv_state, int cs_dtype,
+                                        const void* weight, const void* bias, void* y,
+                                        int64_t y_bs, int B, int Di, int W, int silu, int dtype,
+                                        vmb_stream_t stream) {
+  using namespace vmb;
+  VMB_CHECK_ARG(x && conv_state && weight && y, "conv1d_update: null pointer");
+  VMB_CHECK_ARG(dtype_ok(dtype) && dtype_ok(cs_dtype), "conv1d_update: bad dtype");
+  VMB_CHECK_ARG(B <= 65535, "conv1d_update: batch %d > 65535", B);
+  if (B <= 0) return VMB_OK;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((Di + 127) / 128, B);
+#define VMB_CU(T, WW)                                                                          \
+  conv1d_update_kernel<T, WW><<<grid, 128, 0, st>>>((const T*)x, x_bs, conv_state, cs_dtype,   \
+                                                    (const T*)weight, (const T*)bias, (T*)y,   \
+                                                    y_bs, B, Di, silu)
+  if (dtype == VMB_BF16) {
+    switch (W) {
+      case 1: VMB_CU(__nv_bfloat16, 1); break;
+      case 2: VMB_CU(__nv_bfloat16, 2); break;
+      case 3: VMB_CU(__nv_bfloat16, 3); break;
+      case 4: VMB_CU(__nv_bfloat16, 4); break;
+      default: VMB_UNSUPPORTED("conv1d_update: d_conv=%d not supported", W);
+    }
+  } else {
+    switch (W) {
+      case 1: VMB_CU(float, 1); break;
+      case 2: VMB_CU(float, 2); break;
+      case 3: VMB_CU(float, 3); break;
+      case 4: VMB_CU(float, 4); break;
+      default: VMB_UNSUPPORTED("conv1d_update: d_conv=%d not supported", W);
+    }
+  }
+#undef VMB_CU
+  VMB_LAUNCH_CHECK("conv1d_update_kernel");
+  return VMB_OK;
+}

@@ -1,0 +1,37 @@
+// Internal (non-ABI) entry points shared between the translation units of libvmb200.
+#pragma once
+#include "common.cuh"
+
+namespace vmb {
+
+// linear_simt.cu -- CUDA-core projection (true fp32 / any shape)
+int linear_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+                int64_t ldc, int64_t M, int N, int K, int dtype, cudaStream_t st);
+
+// gemm_tc.cu -- tcgen05 / TMEM / TMA bf16 projection.  Returns VMB_ERR_UNSUPPORTED (without
+// setting an error the caller must report) when the shape does not fit the tensor-core kernel.
+bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, const void* C,
+                       int64_t ldc, int64_t M, int N, int K);
+int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+            int64_t ldc, int64_t M, int N, int K, cudaStream_t st);
+
+// scan_generic.cu
+int scan_generic(const vmb_scan_args& a, cudaStream_t st);
+
+// scan_fast.cu -- production bf16 scan with the dt projection fused in.
+struct FastScanArgs {
+  const void* u;  int64_t u_bs, u_ts;       // conv output (B, L, Di)
+  const void* z;  int64_t z_bs, z_ts;       // gate (B, L, Di)
+  const void* xdbl; int64_t x_bs, x_ts;     // (B, L, Xp): [0,R) dt_low | [R,R+N) B | [R+N,R+2N) C
+  const void* w_dt_pad;                     // (Di, Rp) bf16, zero padded
+  const float* A2; const float* D; const float* dt_bias;
+  const void* h0; int h0_dtype;
+  void* y; int64_t y_bs, y_ts;
+  float* h_last;
+  int B, L, Di, N, R, Rp, Xp;
+  int reverse;
+};
+bool scan_fast_supported(const FastScanArgs& a);
+int scan_fast(const FastScanArgs& a, cudaStream_t st);
+
+}  // namespace vmb

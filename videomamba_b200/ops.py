@@ -1,0 +1,501 @@
+"""Tensor-level operators of the B200 mixer path (thin marshalling over the C ABI).
+
+Two groups:
+
+* token-major primitives used by the modules of this package (``add_norm``, ``linear``,
+  ``mixer_fwd`` ...): activations are (batch, token, channel);
+* drop-in replacements for the third-party operators the reference imports, with THEIR
+  signatures and channel-major layouts (``causal_conv1d_fn``, ``selective_scan_fn``,
+  ``rms_norm_fn`` ...; reference call sites listed in SURVEY.md section 8b).
+
+Everything enqueues on the current CUDA stream of the tensors' device and returns immediately.
+PyTorch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import VMB_BF16, VMB_F32, MixerArgs, ScanArgs
+
+LOG2E = 1.4426950408889634
+
+_CUDA_ONLY_MSG = ("VideoMamba requires CUDA tensors in this package because "
+                  "the mixer kernels are CUDA-only (sm_100a).")
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return VMB_F32
+    if t.dtype == torch.bfloat16:
+        return VMB_BF16
+    raise TypeError(f"videomamba_b200 kernels support float32 and bfloat16, got {t.dtype}")
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(t: Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(_CUDA_ONLY_MSG)
+
+
+class _on_device:
+    """Make the tensor's device current for the duration of a launch (no-op when it already is)."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t: Tensor):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def xdbl_pitch(dt_rank: int, d_state: int) -> int:
+    """Row pitch (elements) of the x_dbl buffer: [dt_low | B | C] padded to a multiple of 16."""
+    return (dt_rank + 2 * d_state + 15) // 16 * 16
+
+
+# ----------------------------------------------------------------------------------------------
+# token-major primitives
+# ----------------------------------------------------------------------------------------------
+def add_norm(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
+             eps: float, is_rms: bool, prenorm: bool, residual_in_fp32: bool):
+    """Fused residual add + norm over the last dim.  Returns ``y`` or ``(y, residual_out)``."""
+    _require_cuda(x)
+    lib = _lib.load()
+    dim = x.shape[-1]
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    x2 = x.reshape(-1, dim)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < dim):
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    res2 = None
+    if residual is not None:
+        if residual.shape != x.shape:
+            raise ValueError("residual must have the same shape as x")
+        res2 = residual.reshape(-1, dim).contiguous()
+        res_dtype = residual.dtype
+    else:
+        res_dtype = torch.float32 if residual_in_fp32 else x.dtype
+    y = torch.empty((rows, dim), dtype=x.dtype, device=x.device)
+    need_res_out = prenorm and (residual is not None or res_dtype != x.dtype)
+    res_out = torch.empty((rows, dim), dtype=res_dtype, device=x.device) if need_res_out else None
+    weight = weight.contiguous()
+    if bias is not None:
+        bias = bias.to(weight.dtype).contiguous()
+    with _on_device(x):
+        rc = lib.vmb_add_norm_fwd(
+            _p(x2), _dt(x2), x2.stride(0) if rows > 1 else dim,
+            _p(res2), _dt(res2) if res2 is not None else VMB_F32,
+            _p(weight), _p(bias), _dt(weight), _p(y),
+            _p(res_out), _dt(res_out) if res_out is not None else VMB_F32,
+            rows, dim, float(eps), 1 if is_rms else 0, _stream(x))
+    _lib.check(rc, "vmb_add_norm_fwd")
+    y = y.reshape(x.shape)
+    if not prenorm:
+        return y
+    if res_out is None:       # no incoming residual and same dtype: the sum IS x
+        return y, x
+    return y, res_out.reshape(x.shape)
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """``x @ weight.T (+ bias)`` over the last dim (fp32 accumulate, one rounding)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise ValueError("linear: weight / input size mismatch")
+    if weight.dtype != x.dtype:
+        weight = weight.to(x.dtype)
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < K):
+        x2 = x2.contiguous()
+    weight = weight if weight.stride(-1) == 1 else weight.contiguous()
+    M = x2.shape[0]
+    out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    with _on_device(x):
+        rc = lib.vmb_linear_fwd(_p(x2), x2.stride(0) if M > 1 else K, _p(weight), weight.stride(0),
+                                _p(bias), _p(out), N, M, N, K, _dt(x2), _stream(x))
+    _lib.check(rc, "vmb_linear_fwd")
+    return out.reshape(*x.shape[:-1], N)
+
+
+def _token_major(t: Tensor) -> Tensor:
+    """(B, L, C) tensor with channel stride 1 (copy only when needed)."""
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def causal_conv1d_tokens(x: Tensor, weight: Tensor, bias: Optional[Tensor],
+                         conv_state: Optional[Tensor] = None, want_state: bool = False,
+                         silu: bool = True, reverse: bool = False):
+    """Depthwise causal conv on token-major ``x (B, L, Di)``; ``weight (Di, W)``.
+    Returns ``y`` or ``(y, new_conv_state (B, Di, W))``."""
+    _require_cuda(x)
+    lib = _lib.load()
+    x = _token_major(x)
+    B, L, Di = x.shape
+    W = weight.shape[-1]
+    weight = weight.reshape(Di, W).to(x.dtype).contiguous()
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    y = torch.empty((B, L, Di), dtype=x.dtype, device=x.device)
+    cs_in = None
+    if conv_state is not None:
+        if tuple(conv_state.shape) != (B, Di, W):
+            raise ValueError(f"conv_state must have shape {(B, Di, W)}, got {tuple(conv_state.shape)}")
+        cs_in = conv_state.contiguous()
+    cs_out = None
+    if want_state:
+        cs_dtype = x.dtype if conv_state is None else torch.promote_types(conv_state.dtype, x.dtype)
+        cs_out = torch.empty((B, Di, W), dtype=cs_dtype, device=x.device)
+    with _on_device(x):
+        rc = lib.vmb_causal_conv1d_fwd(
+            _p(x), x.stride(0), x.stride(1), _p(weight), _p(bias),
+            _p(cs_in), _dt(cs_in) if cs_in is not None else VMB_F32,
+            _p(y), y.stride(0), y.stride(1),
+            _p(cs_out), _dt(cs_out) if cs_out is not None else VMB_F32,
+            B, L, Di, W, 1 if silu else 0, 1 if reverse else 0, _dt(x), _stream(x))
+    _lib.check(rc, "vmb_causal_conv1d_fwd")
+    return (y, cs_out) if want_state else y
+
+
+def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_off: int, c_off: int,
+                          d_state: int, D: Optional[Tensor] = None, z: Optional[Tensor] = None,
+                          dt_bias: Optional[Tensor] = None, softplus: bool = True,
+                          h0: Optional[Tensor] = None, want_last: bool = False,
+                          reverse: bool = False):
+    """Token-major selective scan.  ``u, delta, z: (B, L, Di)``; ``bc: (B, L, >=c_off+N)`` holds
+    B_t at ``[b_off, b_off+N)`` and C_t at ``[c_off, c_off+N)``; ``A2 = A*log2(e)`` fp32 (Di, N)."""
+    _require_cuda(u)
+    lib = _lib.load()
+    u, delta, bc = _token_major(u), _token_major(delta), _token_major(bc)
+    if z is not None:
+        z = _token_major(z)
+    B, L, Di = u.shape
+    y = torch.empty((B, L, Di), dtype=u.dtype, device=u.device)
+    h_last = torch.empty((B, Di, d_state), dtype=torch.float32, device=u.device) if want_last else None
+    if h0 is not None:
+        h0 = h0.contiguous()
+    a = ScanArgs()
+    a.u, a.u_bstride, a.u_tstride = u.data_ptr(), u.stride(0), u.stride(1)
+    a.delta, a.d_bstride, a.d_tstride = delta.data_ptr(), delta.stride(0), delta.stride(1)
+    if z is not None:
+        a.z, a.z_bstride, a.z_tstride = z.data_ptr(), z.stride(0), z.stride(1)
+    a.bc, a.bc_bstride, a.bc_tstride = bc.data_ptr(), bc.stride(0), bc.stride(1)
+    a.b_off, a.c_off = b_off, c_off
+    a.A2 = A2.data_ptr()
+    a.D = None if D is None else D.data_ptr()
+    a.dt_bias = None if dt_bias is None else dt_bias.data_ptr()
+    if h0 is not None:
+        a.h0, a.h0_dtype = h0.data_ptr(), _dt(h0)
+    a.y, a.y_bstride, a.y_tstride = y.data_ptr(), y.stride(0), y.stride(1)
+    a.h_last = None if h_last is None else h_last.data_ptr()
+    a.B, a.L, a.Di, a.N = B, L, Di, d_state
+    a.dtype, a.softplus, a.reverse = _dt(u), 1 if softplus else 0, 1 if reverse else 0
+    with _on_device(u):
+        rc = lib.vmb_selective_scan_fwd(C.byref(a), _stream(u))
+    _lib.check(rc, "vmb_selective_scan_fwd")
+    return (y, h_last) if want_last else y
+
+
+class MixerWeights:
+    """Kernel-ready view of one mixer's parameters (built once per weight version)."""
+
+    __slots__ = ("w_in", "b_in", "w_conv", "b_conv", "w_x", "w_dt", "w_out", "b_out", "A2", "Dskip",
+                 "dt_bias", "w_x_pad", "w_dt_pad", "Xp", "Rp", "D", "Di", "N", "R", "W", "dtype",
+                 "a_geometric", "raw")
+
+    def __init__(self, in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dp, out_w, out_b):
+        self.dtype = in_w.dtype
+        _dt(in_w)
+        # the parameters this view was built from, under their state_dict names
+        self.raw = {"in_proj.weight": in_w, "in_proj.bias": in_b, "conv1d.weight": conv_w,
+                    "conv1d.bias": conv_b, "x_proj.weight": x_w, "dt_proj.weight": dt_w,
+                    "dt_proj.bias": dt_b, "A_log": A_log, "D": Dp, "out_proj.weight": out_w,
+                    "out_proj.bias": out_b}
+        dev = in_w.device
+        self.Di, self.W = conv_w.shape[0], conv_w.shape[-1]
+        self.D = in_w.shape[1]
+        self.N = A_log.shape[1]
+        self.R = dt_w.shape[1]
+        cast = lambda t: None if t is None else t.detach().to(self.dtype).contiguous()
+        self.w_in, self.b_in = cast(in_w), cast(in_b)
+        self.w_conv, self.b_conv = cast(conv_w.reshape(self.Di, self.W)), cast(conv_b)
+        self.w_x, self.w_dt = cast(x_w), cast(dt_w)
+        self.w_out, self.b_out = cast(out_w), cast(out_b)
+        A = -torch.exp(A_log.detach().float())                      # mamba_simple.py:341
+        self.A2 = (A * LOG2E).contiguous()
+        self.Dskip = Dp.detach().float().contiguous()               # mamba_simple.py:429
+        self.dt_bias = (dt_b.detach().float().contiguous() if dt_b is not None
+                        else torch.zeros(self.Di, device=dev))      # mamba_simple.py:431
+        # A[d, n] == (n+1) * A[d, 0] (exact S4D-real structure, mamba_simple.py:265-272)?
+        ratio = A / A[:, :1]
+        target = torch.arange(1, self.N + 1, device=dev, dtype=torch.float32)
+        self.a_geometric = bool(torch.all((ratio - target).abs() <= 1e-6 * target))
+        self.Xp = xdbl_pitch(self.R, self.N)
+        self.Rp = (self.R + 15) // 16 * 16
+        self.w_x_pad = self.w_dt_pad = None
+        if self.dtype == torch.bfloat16:
+            X = self.R + 2 * self.N
+            self.w_x_pad = torch.zeros(self.Xp, self.Di, dtype=self.dtype, device=dev)
+            self.w_x_pad[:X] = self.w_x
+            self.w_dt_pad = torch.zeros(self.Di, self.Rp, dtype=self.dtype, device=dev)
+            self.w_dt_pad[:, :self.R] = self.w_dt
+
+
+def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = None,
+              ssm_state: Optional[Tensor] = None, want_conv_state: bool = False,
+              want_ssm_state: bool = False, reverse: bool = False, path: int = 0):
+    """Whole Mamba mixer on token-major ``hidden (B, L, D)``.
+    Returns ``(out, new_conv_state | None, last_ssm_state | None)``."""
+    _require_cuda(hidden)
+    lib = _lib.load()
+    if hidden.dtype != w.dtype:
+        raise TypeError(f"hidden dtype {hidden.dtype} does not match the mixer weights ({w.dtype})")
+    B, L, D = hidden.shape
+    if D != w.D:
+        raise ValueError(f"hidden size {D} does not match d_model {w.D}")
+    if hidden.stride(-1) != 1 or (B > 1 and hidden.stride(0) != L * hidden.stride(1)) \
+            or hidden.stride(1) < D:
+        hidden = hidden.contiguous()
+    dev = hidden.device
+    out = torch.empty((B, L, D), dtype=w.dtype, device=dev)
+    cs_in = None
+    if conv_state is not None:
+        if tuple(conv_state.shape) != (B, w.Di, w.W):
+            raise ValueError(f"conv_state must have shape {(B, w.Di, w.W)}, "
+                             f"got {tuple(conv_state.shape)}")
+        cs_in = conv_state.contiguous()
+    ss_in = None
+    if ssm_state is not None:
+        if tuple(ssm_state.shape) != (B, w.Di, w.N):
+            raise ValueError(f"ssm_state must have shape {(B, w.Di, w.N)}, "
+                             f"got {tuple(ssm_state.shape)}")
+        ss_in = ssm_state.contiguous()
+    cs_out = ss_out = None
+    if want_conv_state:
+        cs_dtype = w.dtype if cs_in is None else torch.promote_types(cs_in.dtype, w.dtype)
+        cs_out = torch.empty((B, w.Di, w.W), dtype=cs_dtype, device=dev)
+    if want_ssm_state:
+        ss_out = torch.empty((B, w.Di, w.N), dtype=torch.float32, device=dev)
+    if B == 0 or L == 0:
+        if L == 0 and B > 0:
+            if cs_out is not None:
+                cs_out.copy_(cs_in) if cs_in is not None else cs_out.zero_()
+            if ss_out is not None:
+                ss_out.copy_(ss_in) if ss_in is not None else ss_out.zero_()
+        return out, cs_out, ss_out
+    dt = _dt(hidden)
+    nbytes = lib.vmb_mixer_workspace_bytes(B, L, D, w.Di, w.N, w.R, dt)
+    if nbytes < 0:
+        raise RuntimeError("vmb_mixer_workspace_bytes rejected the shape")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    a = MixerArgs()
+    a.hidden, a.h_bstride, a.h_tstride = hidden.data_ptr(), L * hidden.stride(1), hidden.stride(1)
+    a.out, a.o_bstride, a.o_tstride = out.data_ptr(), out.stride(0), out.stride(1)
+    a.w_in, a.b_in = w.w_in.data_ptr(), None if w.b_in is None else w.b_in.data_ptr()
+    a.w_conv, a.b_conv = w.w_conv.data_ptr(), None if w.b_conv is None else w.b_conv.data_ptr()
+    a.w_x, a.w_dt = w.w_x.data_ptr(), w.w_dt.data_ptr()
+    a.w_out, a.b_out = w.w_out.data_ptr(), None if w.b_out is None else w.b_out.data_ptr()
+    a.A2, a.Dskip, a.dt_bias = w.A2.data_ptr(), w.Dskip.data_ptr(), w.dt_bias.data_ptr()
+    if w.w_x_pad is not None:
+        a.w_x_pad, a.w_dt_pad = w.w_x_pad.data_ptr(), w.w_dt_pad.data_ptr()
+    a.Xp, a.Rp = w.Xp, w.Rp
+    if cs_in is not None:
+        a.conv_state_in, a.cs_in_dtype = cs_in.data_ptr(), _dt(cs_in)
+    if cs_out is not None:
+        a.conv_state_out, a.cs_out_dtype = cs_out.data_ptr(), _dt(cs_out)
+    if ss_in is not None:
+        a.ssm_state_in, a.ss_in_dtype = ss_in.data_ptr(), _dt(ss_in)
+    if ss_out is not None:
+        a.ssm_state_out = ss_out.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    a.B, a.L, a.D, a.Di, a.N, a.R, a.W = B, L, D, w.Di, w.N, w.R, w.W
+    a.dtype, a.reverse, a.path = dt, 1 if reverse else 0, path
+    with _on_device(hidden):
+        rc = lib.vmb_mixer_fwd(C.byref(a), _stream(hidden))
+    _lib.check(rc, "vmb_mixer_fwd")
+    return out, cs_out, ss_out
+
+
+def state_gather(pool: Tensor, index: Tensor) -> Tensor:
+    """rows ``pool[index]`` of a resident per-stream state pool (leading dim = stream slot)."""
+    _require_cuda(pool)
+    lib = _lib.load()
+    pool = pool.contiguous()
+    index = index.to(device=pool.device, dtype=torch.int32).contiguous()
+    n = index.numel()
+    row = pool[0].numel() if pool.shape[0] > 0 else 0
+    out = torch.empty((n, *pool.shape[1:]), dtype=pool.dtype, device=pool.device)
+    with _on_device(pool):
+        rc = lib.vmb_state_gather(_p(pool), _p(index), _p(out), n, row, _dt(pool), _stream(pool))
+    _lib.check(rc, "vmb_state_gather")
+    return out
+
+
+def state_scatter(pool: Tensor, index: Tensor, batch: Tensor) -> None:
+    """``pool[index] = batch`` in place (index entries must be distinct)."""
+    _require_cuda(pool)
+    lib = _lib.load()
+    if not pool.is_contiguous():
+        raise ValueError("state pool must be contiguous")
+    batch = batch.to(pool.dtype).contiguous()
+    index = index.to(device=pool.device, dtype=torch.int32).contiguous()
+    n = index.numel()
+    row = pool[0].numel() if pool.shape[0] > 0 else 0
+    with _on_device(pool):
+        rc = lib.vmb_state_scatter(_p(pool), _p(index), _p(batch), n, row, _dt(pool), _stream(pool))
+    _lib.check(rc, "vmb_state_scatter")
+
+
+# ----------------------------------------------------------------------------------------------
+# drop-in operator signatures (channel-major, as the reference calls them)
+# ----------------------------------------------------------------------------------------------
+def causal_conv1d_fn(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, seq_idx=None,
+                     initial_states=None, return_final_states: bool = False, final_states_out=None,
+                     activation: Optional[str] = None):
+    """``causal_conv1d.causal_conv1d_fn`` (reference mamba_simple.py:383-399): x (B, D, L)."""
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu, or swish")
+    if seq_idx is not None or initial_states is not None or return_final_states:
+        raise NotImplementedError("seq_idx / initial_states are not used by VideoMamba")
+    y = causal_conv1d_tokens(x.transpose(1, 2), weight, bias, None, False,
+                             silu=activation is not None)
+    return y.transpose(1, 2)
+
+
+def causal_conv1d_update(x: Tensor, conv_state: Tensor, weight: Tensor,
+                         bias: Optional[Tensor] = None, activation: Optional[str] = None) -> Tensor:
+    """``causal_conv1d.causal_conv1d_update`` (mamba_simple.py:468-474): x (B, D), state in place."""
+    _require_cuda(x)
+    lib = _lib.load()
+    if not conv_state.is_contiguous():
+        raise ValueError("conv_state must be contiguous (it is updated in place)")
+    B, Di = x.shape
+    W = weight.shape[-1]
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    weight = weight.reshape(Di, W).to(x.dtype).contiguous()
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    y = torch.empty((B, Di), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        rc = lib.vmb_causal_conv1d_update(_p(x), x.stride(0), _p(conv_state), _dt(conv_state),
+                                          _p(weight), _p(bias), _p(y), y.stride(0), B, Di, W,
+                                          1 if activation in ("silu", "swish") else 0, _dt(x),
+                                          _stream(x))
+    _lib.check(rc, "vmb_causal_conv1d_update")
+    return y
+
+
+def selective_scan_fn(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, C_: Tensor,
+                      D: Optional[Tensor] = None, z: Optional[Tensor] = None,
+                      delta_bias: Optional[Tensor] = None, delta_softplus: bool = False,
+                      return_last_state: bool = False, initial_state: Optional[Tensor] = None):
+    """``mamba_ssm...selective_scan_fn`` with ``initial_state`` support (mamba_simple.py:125-152).
+    u, delta, z: (B, D, L); A: (D, N) real; B, C: (B, N, L)."""
+    if A.is_complex() or B.dim() != 3 or C_.dim() != 3:
+        raise NotImplementedError("only real A and (B, N, L) input-dependent B / C are supported")
+    N = A.shape[1]
+    bc = torch.cat([B.transpose(1, 2), C_.transpose(1, 2)], dim=-1).to(u.dtype).contiguous()
+    A2 = (A.float() * LOG2E).contiguous()
+    out = selective_scan_tokens(
+        u.transpose(1, 2), delta.to(u.dtype).transpose(1, 2), A2, bc, 0, N, N,
+        None if D is None else D.float().contiguous(),
+        None if z is None else z.to(u.dtype).transpose(1, 2),
+        None if delta_bias is None else delta_bias.float().contiguous(),
+        delta_softplus, initial_state, return_last_state)
+    if return_last_state:
+        return out[0].transpose(1, 2), out[1]
+    return out.transpose(1, 2)
+
+
+def selective_state_update(state: Tensor, x: Tensor, dt: Tensor, A: Tensor, B: Tensor, C_: Tensor,
+                           D: Optional[Tensor] = None, z: Optional[Tensor] = None,
+                           dt_bias: Optional[Tensor] = None, dt_softplus: bool = False) -> Tensor:
+    """``mamba_ssm...selective_state_update`` (mamba_simple.py:483-494): state (B, D, N) in place."""
+    _require_cuda(x)
+    lib = _lib.load()
+    if not state.is_contiguous():
+        raise ValueError("state must be contiguous (it is updated in place)")
+    Bsz, Di = x.shape
+    N = A.shape[1]
+    rowmajor = lambda t: t if t.stride(-1) == 1 else t.contiguous()
+    x, dt = rowmajor(x), rowmajor(dt.to(x.dtype))
+    B, C_ = rowmajor(B.to(x.dtype)), rowmajor(C_.to(x.dtype))
+    if z is not None:
+        z = rowmajor(z.to(x.dtype))
+    A2 = (A.float() * LOG2E).contiguous()
+    Df = None if D is None else D.float().contiguous()
+    bias = None if dt_bias is None else dt_bias.float().contiguous()
+    y = torch.empty((Bsz, Di), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        rc = lib.vmb_selective_state_update(
+            _p(state), _dt(state), _p(x), x.stride(0), _p(dt), dt.stride(0), _p(A2),
+            _p(B), B.stride(0), _p(C_), C_.stride(0), _p(Df), _p(z),
+            0 if z is None else z.stride(0), _p(bias), 1 if dt_softplus else 0,
+            _p(y), y.stride(0), Bsz, Di, N, _dt(x), _stream(x))
+    _lib.check(rc, "vmb_selective_state_update")
+    return y
+
+
+def _norm_fn(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms):
+    return add_norm(x, weight, bias, residual, eps, is_rms, prenorm, residual_in_fp32)
+
+
+def rms_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False,
+                **_unused):
+    """``mamba_ssm.ops.triton.layer_norm.rms_norm_fn`` (videomamba.py:157-165, :909-917)."""
+    return _norm_fn(x, weight, bias, residual, eps, prenorm, residual_in_fp32, True)
+
+
+def layer_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False,
+                  **_unused):
+    """``mamba_ssm.ops.triton.layer_norm.layer_norm_fn``."""
+    return _norm_fn(x, weight, bias, residual, eps, prenorm, residual_in_fp32, False)
+
+
+def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                   out_proj_weight, out_proj_bias, A, B=None, C_=None, D=None, delta_bias=None,
+                   delta_softplus=True):
+    """``mamba_ssm...mamba_inner_fn`` (mamba_simple.py:352-366): xz (B, 2Di, L) -> (B, L, D).
+    conv -> x_proj -> dt_proj -> scan -> out_proj on an already in-projected ``xz``."""
+    if B is not None or C_ is not None or not delta_softplus:
+        raise NotImplementedError("only input-dependent B / C with softplus are supported")
+    Di = xz.shape[1] // 2
+    N, R = A.shape[1], delta_proj_weight.shape[1]
+    xz_t = xz.transpose(1, 2)
+    xc = causal_conv1d_tokens(xz_t[..., :Di], conv1d_weight, conv1d_bias)
+    x_dbl = linear(xc, x_proj_weight)
+    delta = linear(x_dbl[..., :R], delta_proj_weight)
+    y = selective_scan_tokens(xc, delta, (A.float() * LOG2E).contiguous(), x_dbl, R, R + N, N,
+                              None if D is None else D.float().contiguous(), xz_t[..., Di:],
+                              None if delta_bias is None else delta_bias.float().contiguous(), True)
+    return linear(y, out_proj_weight, out_proj_bias)
