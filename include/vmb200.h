@@ -195,6 +195,28 @@ VMB_API int vmb_state_gather(const void* pool, const int32_t* index, void* batch
 VMB_API int vmb_state_scatter(void* pool, const int32_t* index, const void* batch,
                       int n_rows, int64_t row_elems, int dtype, vmb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-stage device timing (measurement aid, off by default; nothing like it exists in the
+ * reference).  While enabled, every entry point above brackets the kernels it enqueues with
+ * cudaEvents on `stream`, tagged with the stage they belong to.  vmb_prof_read synchronises
+ * the recorded events, adds their elapsed milliseconds and launch counts per stage into the
+ * caller's arrays (VMB_PROF_KINDS entries each, HOST pointers) and optionally clears the log.
+ * Must be disabled while a stream is being captured into a CUDA graph.
+ * ---------------------------------------------------------------------------------------- */
+#define VMB_PROF_ADD_NORM 0
+#define VMB_PROF_IN_PROJ 1
+#define VMB_PROF_CONV 2
+#define VMB_PROF_X_PROJ 3
+#define VMB_PROF_DT_PROJ 4
+#define VMB_PROF_SCAN 5
+#define VMB_PROF_OUT_PROJ 6
+#define VMB_PROF_OTHER 7
+#define VMB_PROF_KINDS 8
+VMB_API int vmb_prof_enable(int on);
+VMB_API int vmb_prof_read(double* ms_sum, int64_t* launches, int reset);
+/* Number of kernels this library has enqueued so far in this process (all threads). */
+VMB_API int64_t vmb_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,239 @@
+"""GPU: operator-level parity of the libvmb200 kernels (called through the C ABI via
+videomamba_b200.ops) against the CPU oracle on the same seeded inputs.
+
+Bars (north star): fp32 1e-5, bf16 2e-2, relative = max|a-b| / max|b|."""
+import pytest
+import torch
+
+from oracle import videomamba_oracle as orc
+from oracle.videomamba_oracle import rel_err
+from videomamba_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _tol(dt):
+    return 2e-2 if dt == torch.bfloat16 else 1e-5
+
+
+def _rand(gen, *shape, dtype=torch.float32, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rms", [True, False])
+@pytest.mark.parametrize("dim", [16, 192, 384, 576, 1152])
+def test_add_norm(dtype, rms, dim):
+    gen = torch.Generator().manual_seed(dim + rms)
+    x = _rand(gen, 3, 37, dim, dtype=dtype)
+    res = _rand(gen, 3, 37, dim)
+    w = (1 + 0.1 * torch.randn(dim, generator=gen)).to(dtype)
+    b = None if rms else (0.1 * torch.randn(dim, generator=gen)).to(dtype)
+    for residual in (None, res):
+        for prenorm in (True, False):
+            want = orc.add_norm_ref(x, w, b, residual, 1e-5, prenorm, True, rms)
+            got = ops.add_norm(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV),
+                               None if residual is None else residual.to(DEV), 1e-5, rms, prenorm,
+                               True)
+            if prenorm:
+                assert got[1].dtype == torch.float32
+                assert rel_err(got[0], want[0]) <= _tol(dtype)
+                assert rel_err(got[1], want[1]) <= 1e-6
+            else:
+                assert got.dtype == dtype and rel_err(got, want) <= _tol(dtype)
+
+
+def test_add_norm_empty_and_dtype_rules():
+    x = torch.randn(0, 16, device=DEV)
+    assert ops.add_norm(x, torch.ones(16, device=DEV), None, None, 1e-5, True, False, True).shape == (0, 16)
+    xb = torch.randn(2, 5, 16, device=DEV, dtype=torch.bfloat16)
+    y, r = ops.add_norm(xb, torch.ones(16, device=DEV, dtype=torch.bfloat16), None, None, 1e-5, True,
+                        True, False)
+    assert r.dtype == torch.bfloat16 and torch.equal(r, xb)   # no residual, same dtype: sum is x
+    y, r = ops.add_norm(xb, torch.ones(16, device=DEV, dtype=torch.bfloat16), None,
+                        torch.zeros(2, 5, 16, device=DEV, dtype=torch.bfloat16), 1e-5, True, True, True)
+    assert r.dtype == torch.bfloat16                          # keeps the incoming residual dtype
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mnk", [(5, 3, 1), (37, 44, 192), (300, 1536, 384), (4500, 56, 768),
+                                 (260, 384, 24), (129, 768, 12), (64, 16, 16)])
+def test_linear(dtype, mnk):
+    M, N, K = mnk
+    gen = torch.Generator().manual_seed(M * N + K)
+    a = _rand(gen, M, K, dtype=dtype)
+    w = _rand(gen, N, K, dtype=dtype, scale=K ** -0.5)
+    bias = _rand(gen, N, dtype=dtype)
+    got = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV))
+    want = orc._linear(a, w, bias)
+    assert got.dtype == dtype and rel_err(got, want) <= _tol(dtype)
+    # strided input view (dt_low slice of x_dbl) and no bias
+    wide = _rand(gen, M, K + 9, dtype=dtype)
+    got = ops.linear(wide.to(DEV)[:, :K], w.to(DEV))
+    assert rel_err(got, orc._linear(wide[:, :K], w)) <= _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", [(2, 70, 768, 4), (3, 5, 16, 2), (1, 2, 24, 4), (2, 130, 384, 3),
+                                  (1, 1, 8, 4)])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_causal_conv1d(dtype, geom, reverse):
+    B, L, Di, W = geom
+    gen = torch.Generator().manual_seed(L * Di + W)
+    x = _rand(gen, B, L, Di, dtype=dtype)
+    w = _rand(gen, Di, W, dtype=dtype, scale=0.5)
+    b = _rand(gen, Di, dtype=dtype, scale=0.5)
+    cs = _rand(gen, B, Di, W, dtype=dtype)
+    for state in (None, cs):
+        xl = torch.flip(x, dims=[1]) if reverse else x          # logical order
+        xcm = xl.transpose(1, 2)
+        if state is not None:
+            cat = torch.cat([state, xcm], dim=-1)
+            want = orc.causal_conv1d_ref(cat, w, b, "silu")[..., -L:]
+            want_state = cat[..., -W:]
+        else:
+            want = orc.causal_conv1d_ref(xcm, w, b, "silu")
+            want_state = torch.nn.functional.pad(xcm, (W - L, 0))
+        want = want.transpose(1, 2)
+        if reverse:
+            want = torch.flip(want, dims=[1])
+        got, got_state = ops.causal_conv1d_tokens(
+            x.to(DEV), w.to(DEV), b.to(DEV), None if state is None else state.to(DEV),
+            want_state=True, reverse=reverse)
+        assert rel_err(got, want) <= _tol(dtype)
+        assert got_state.shape == (B, Di, W)
+        assert torch.equal(got_state.cpu(), want_state.contiguous())   # pre-conv inputs: bit exact
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_causal_conv1d_strided_views_and_dropin_signature(dtype):
+    gen = torch.Generator().manual_seed(3)
+    xz = _rand(gen, 2, 33, 2 * 64, dtype=dtype)
+    w = _rand(gen, 64, 4, dtype=dtype, scale=0.5)
+    got = ops.causal_conv1d_tokens(xz.to(DEV)[..., :64], w.to(DEV), None)
+    want = orc.causal_conv1d_ref(xz[..., :64].transpose(1, 2), w, None, "silu").transpose(1, 2)
+    assert rel_err(got, want) <= _tol(dtype)
+    xcm = _rand(gen, 2, 24, 19, dtype=dtype)        # (B, D, L) as the reference passes it
+    w2 = _rand(gen, 24, 4, dtype=dtype, scale=0.5)
+    got = ops.causal_conv1d_fn(xcm.to(DEV), w2.to(DEV), None, activation=None)
+    assert got.shape == xcm.shape
+    assert rel_err(got, orc.causal_conv1d_ref(xcm, w2, None, None)) <= _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", [(2, 24, 37, 16), (1, 768, 200, 16), (3, 16, 5, 4), (2, 40, 64, 8),
+                                  (1, 130, 33, 1)])
+def test_selective_scan_fn_dropin(dtype, geom):
+    B, D, L, N = geom
+    gen = torch.Generator().manual_seed(D + L)
+    u = _rand(gen, B, D, L, dtype=dtype)
+    delta = _rand(gen, B, D, L, dtype=dtype)
+    A = -torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(D, 1)
+                   + 0.1 * torch.randn(D, N, generator=gen))
+    Bm = _rand(gen, B, N, L, dtype=dtype)
+    Cm = _rand(gen, B, N, L, dtype=dtype)
+    Dp = torch.randn(D, generator=gen)
+    z = _rand(gen, B, D, L, dtype=dtype)
+    bias = torch.randn(D, generator=gen) - 2.0
+    h0 = torch.randn(B, D, N, generator=gen)
+    for init in (None, h0):
+        want, want_last = orc.selective_scan_ref(u, delta, A, Bm, Cm, Dp, z, bias, True, init, True)
+        got, last = ops.selective_scan_fn(
+            u.to(DEV), delta.to(DEV), A.to(DEV), Bm.to(DEV), Cm.to(DEV), Dp.to(DEV), z=z.to(DEV),
+            delta_bias=bias.to(DEV), delta_softplus=True, return_last_state=True,
+            initial_state=None if init is None else init.to(DEV))
+        assert got.shape == (B, D, L) and last.dtype == torch.float32
+        assert rel_err(got, want) <= _tol(dtype)
+        assert rel_err(last, want_last) <= _tol(dtype)
+    # no z / no D / no softplus / no bias
+    want = orc.selective_scan_ref(u, delta, A, Bm, Cm)
+    got = ops.selective_scan_fn(u.to(DEV), delta.to(DEV), A.to(DEV), Bm.to(DEV), Cm.to(DEV))
+    assert rel_err(got, want) <= _tol(dtype)
+
+
+def test_selective_scan_golden_fixture(golden):
+    g = golden("scan_fp32.pt")
+    c = lambda k: g[k].to(DEV)
+    got, last = ops.selective_scan_fn(c("u"), c("delta"), c("A"), c("B"), c("C"), c("D"), z=c("z"),
+                                      delta_bias=c("delta_bias"), delta_softplus=True,
+                                      return_last_state=True, initial_state=c("h0"))
+    assert rel_err(got, g["out"]) <= 1e-5 and rel_err(last, g["last"]) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_scan_state_carry_property_at_long_length(dtype):
+    """Size-independent property at the long-clip length (cfg-5: 25 089 tokens): scanning in
+    two pieces with the state carried equals one scan, and reverse == flip(forward(flip))."""
+    B, D, L, N = 1, 256, 25089, 16
+    gen = torch.Generator().manual_seed(9)
+    mk = lambda *s: _rand(gen, *s, dtype=dtype).to(DEV)
+    u, delta, z = mk(B, L, D), mk(B, L, D), mk(B, L, D)
+    bc = mk(B, L, 2 * N)
+    A2 = (-torch.arange(1, N + 1).float().repeat(D, 1) * ops.LOG2E).to(DEV)
+    Dp = torch.ones(D, device=DEV)
+    bias = torch.full((D,), -3.0, device=DEV)
+    full, last = ops.selective_scan_tokens(u, delta, A2, bc, 0, N, N, Dp, z, bias, True, None, True)
+    k = 12545
+    a, ha = ops.selective_scan_tokens(u[:, :k], delta[:, :k], A2, bc[:, :k], 0, N, N, Dp, z[:, :k],
+                                      bias, True, None, True)
+    b, hb = ops.selective_scan_tokens(u[:, k:], delta[:, k:], A2, bc[:, k:], 0, N, N, Dp, z[:, k:],
+                                      bias, True, ha, True)
+    assert torch.equal(torch.cat([a, b], 1), full) and torch.equal(hb, last)
+    fl = lambda t: torch.flip(t, dims=[1]).contiguous()
+    rev = ops.selective_scan_tokens(fl(u), fl(delta), A2, fl(bc), 0, N, N, Dp, fl(z), bias, True,
+                                    None, False, reverse=True)
+    assert torch.equal(fl(rev), full)
+    assert torch.isfinite(full.float()).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_single_step_ops(dtype):
+    gen = torch.Generator().manual_seed(21)
+    B, Di, W, N = 3, 48, 4, 16
+    x = _rand(gen, B, Di, dtype=dtype)
+    cs = _rand(gen, B, Di, W, dtype=dtype)
+    w = _rand(gen, Di, W, dtype=dtype, scale=0.5)
+    b = _rand(gen, Di, dtype=dtype)
+    cs_ref = cs.clone()
+    want = orc.causal_conv1d_update_ref(x, cs_ref, w, b, "silu")
+    cs_dev = cs.to(DEV)
+    got = ops.causal_conv1d_update(x.to(DEV), cs_dev, w.to(DEV), b.to(DEV), "silu")
+    assert rel_err(got, want) <= _tol(dtype) and torch.equal(cs_dev.cpu(), cs_ref)
+    st = torch.randn(B, Di, N, generator=gen)
+    dt = _rand(gen, B, Di, dtype=dtype)
+    A = -torch.rand(Di, N, generator=gen) * 4
+    Bm, Cm, z = _rand(gen, B, N, dtype=dtype), _rand(gen, B, N, dtype=dtype), _rand(gen, B, Di, dtype=dtype)
+    Dp, bias = torch.randn(Di, generator=gen), torch.randn(Di, generator=gen)
+    st_ref = st.clone()
+    want = orc.selective_state_update_ref(st_ref, x, dt, A, Bm, Cm, Dp, z, bias, True)
+    st_dev = st.to(DEV)
+    got = ops.selective_state_update(st_dev, x.to(DEV), dt.to(DEV), A.to(DEV), Bm.to(DEV),
+                                     Cm.to(DEV), Dp.to(DEV), z.to(DEV), bias.to(DEV), True)
+    assert rel_err(got, want) <= _tol(dtype) and rel_err(st_dev, st_ref) <= 1e-5
+
+
+def test_state_gather_scatter_roundtrip():
+    pool = torch.randn(9, 24, 16, device=DEV)
+    idx = torch.tensor([7, 0, 3], device=DEV)
+    rows = ops.state_gather(pool, idx)
+    assert torch.equal(rows, pool[idx])
+    new = torch.randn_like(rows)
+    want = pool.clone()
+    want[idx] = new
+    ops.state_scatter(pool, idx, new)
+    assert torch.equal(pool, want)
+    poolb = torch.randn(5, 7, 3, device=DEV).to(torch.bfloat16)    # odd row size: scalar path
+    assert torch.equal(ops.state_gather(poolb, torch.tensor([4, 4, 1], device=DEV)), poolb[[4, 4, 1]])
+    assert ops.state_gather(pool, torch.zeros(0, dtype=torch.long, device=DEV)).shape == (0, 24, 16)
+
+
+def test_unsupported_inputs_raise_python_errors():
+    x = torch.randn(2, 5, 16, device=DEV, dtype=torch.float16)
+    with pytest.raises(TypeError, match="float32 and bfloat16"):
+        ops.linear(x, torch.randn(4, 16, device=DEV, dtype=torch.float16))
+    with pytest.raises(RuntimeError, match="requires CUDA tensors"):
+        ops.linear(torch.randn(2, 4), torch.randn(3, 4))
+    with pytest.raises(RuntimeError, match="d_conv"):
+        ops.causal_conv1d_tokens(torch.randn(1, 4, 8, device=DEV), torch.randn(8, 7, device=DEV), None)

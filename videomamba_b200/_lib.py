@@ -80,7 +80,11 @@ SIGNATURES = {
     "vmb_mixer_fwd": (c_int, [C.POINTER(MixerArgs), c_void_p]),
     "vmb_state_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "vmb_state_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "vmb_launch_count": (c_int64, []),
+    "vmb_prof_enable": (c_int, [c_int]),
+    "vmb_prof_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),
 }
+PROF_KINDS = ("add_norm", "in_proj", "conv", "x_proj", "dt_proj", "scan", "out_proj", "other")
 
 _lib = None
 _lock = threading.Lock()

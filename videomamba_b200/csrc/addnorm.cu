@@ -169,6 +169,7 @@ extern "C" int vmb_add_norm_fwd(const void* x, int x_dtype, int64_t ldx, const v
   if (!residual_out) residual_out_dtype = VMB_F32;
   VMB_CHECK_ARG(dtype_ok(residual_dtype) && dtype_ok(residual_out_dtype), "add_norm: bad dtype");
   cudaStream_t st = as_stream(stream);
+  ProfScope ps(VMB_PROF_ADD_NORM, st);
   const bool rms = is_rms != 0;
   const int key = (x_dtype << 3) | (residual_dtype << 2) | (residual_out_dtype << 1) | w_dtype;
 #define VMB_AN_CASE(K, TX, TR, TO, TW)                                                          \

@@ -3,6 +3,8 @@
 // (models/videomamba/mamba_simple.py:332-446) issues its operator calls.
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "internal.h"
 
@@ -33,6 +35,35 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// ---- per-stage timing ------------------------------------------------------------------------
+bool g_prof_on = false;
+unsigned long long g_launches = 0;
+namespace {
+struct ProfRec { int kind; cudaEvent_t a, b; bool closed; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_log;
+std::vector<cudaEvent_t> g_prof_free;
+cudaEvent_t prof_event() {
+  if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+void prof_begin(int kind, cudaStream_t st, int* slot) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{kind, prof_event(), prof_event(), false};
+  if (!r.a || !r.b || cudaEventRecord(r.a, st) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  g_prof_log.push_back(r);
+  *slot = (int)g_prof_log.size() - 1;
+}
+void prof_end(int slot, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < 0 || slot >= (int)g_prof_log.size()) return;
+  if (cudaEventRecord(g_prof_log[slot].b, st) == cudaSuccess) g_prof_log[slot].closed = true;
+  else (void)cudaGetLastError();
 }
 
 namespace {
@@ -186,14 +217,20 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   int rc;
 
   // in_proj (mamba_simple.py:333-339): xz (M, 2Di), x = [:, :Di], z = [:, Di:]
-  rc = vmb_linear_fwd(p->hidden, p->h_tstride, p->w_in, D, p->b_in, xz, 2 * Di, M, 2 * Di, D,
-                      p->dtype, stream);
+  {
+    ProfScope ps(VMB_PROF_IN_PROJ, st);
+    rc = vmb_linear_fwd(p->hidden, p->h_tstride, p->w_in, D, p->b_in, xz, 2 * Di, M, 2 * Di, D,
+                        p->dtype, stream);
+  }
   if (rc) return rc;
   // causal conv + SiLU with optional history (mamba_simple.py:381-404)
-  rc = vmb_causal_conv1d_fwd(xz, (int64_t)L * 2 * Di, 2 * Di, p->w_conv, p->b_conv,
-                             p->conv_state_in, p->cs_in_dtype, xc, (int64_t)L * Di, Di,
-                             p->conv_state_out, p->cs_out_dtype, B, L, Di, p->W, 1, p->reverse,
-                             p->dtype, stream);
+  {
+    ProfScope ps(VMB_PROF_CONV, st);
+    rc = vmb_causal_conv1d_fwd(xz, (int64_t)L * 2 * Di, 2 * Di, p->w_conv, p->b_conv,
+                               p->conv_state_in, p->cs_in_dtype, xc, (int64_t)L * Di, Di,
+                               p->conv_state_out, p->cs_out_dtype, B, L, Di, p->W, 1, p->reverse,
+                               p->dtype, stream);
+  }
   if (rc) return rc;
 
   FastScanArgs f;
@@ -211,15 +248,27 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
 
   if (fast) {
     // x_proj with zero-padded weight rows: x_dbl (M, Xp) = [dt_low | B | C | 0]
-    rc = vmb_linear_fwd(xc, Di, p->w_x_pad, Di, nullptr, xdbl, Xw, M, Xw, Di, p->dtype, stream);
+    {
+      ProfScope ps(VMB_PROF_X_PROJ, st);
+      rc = vmb_linear_fwd(xc, Di, p->w_x_pad, Di, nullptr, xdbl, Xw, M, Xw, Di, p->dtype, stream);
+    }
     if (rc) return rc;
-    rc = scan_fast(f, st);
+    {
+      ProfScope ps(VMB_PROF_SCAN, st);
+      rc = scan_fast(f, st);
+    }
     if (rc) return rc;
   } else {
     // x_proj (mamba_simple.py:409) and dt_proj (:413-414): delta_raw rounded to the model dtype
-    rc = vmb_linear_fwd(xc, Di, p->w_x, Di, nullptr, xdbl, Xw, M, X, Di, p->dtype, stream);
+    {
+      ProfScope ps(VMB_PROF_X_PROJ, st);
+      rc = vmb_linear_fwd(xc, Di, p->w_x, Di, nullptr, xdbl, Xw, M, X, Di, p->dtype, stream);
+    }
     if (rc) return rc;
-    rc = vmb_linear_fwd(xdbl, Xw, p->w_dt, R, nullptr, delta, Di, M, Di, R, p->dtype, stream);
+    {
+      ProfScope ps(VMB_PROF_DT_PROJ, st);
+      rc = vmb_linear_fwd(xdbl, Xw, p->w_dt, R, nullptr, delta, Di, M, Di, R, p->dtype, stream);
+    }
     if (rc) return rc;
     vmb_scan_args s;
     s.u = xc; s.u_bstride = (int64_t)L * Di; s.u_tstride = Di;
@@ -231,9 +280,13 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
     s.y = y; s.y_bstride = (int64_t)L * Di; s.y_tstride = Di; s.h_last = p->ssm_state_out;
     s.B = B; s.L = L; s.Di = Di; s.N = N; s.dtype = p->dtype; s.softplus = 1;
     s.reverse = p->reverse;
-    rc = vmb_selective_scan_fwd(&s, stream);
+    {
+      ProfScope ps(VMB_PROF_SCAN, st);
+      rc = vmb_selective_scan_fwd(&s, stream);
+    }
     if (rc) return rc;
   }
+  ProfScope ps_out(VMB_PROF_OUT_PROJ, st);
   // out_proj (mamba_simple.py:445-446)
   return vmb_linear_fwd(y, Di, p->w_out, Di, p->b_out, p->out, p->o_tstride, M, D, Di, p->dtype,
                         stream);
@@ -248,3 +301,28 @@ extern "C" int vmb_state_scatter(void* pool, const int32_t* index, const void* b
                                  int64_t row_elems, int dtype, vmb_stream_t stream) {
   return state_rows(batch, pool, index, n_rows, row_elems, dtype, false, as_stream(stream));
 }
+
+extern "C" int vmb_prof_enable(int on) {
+  g_prof_on = on != 0;
+  return VMB_OK;
+}
+
+extern "C" int vmb_prof_read(double* ms_sum, int64_t* launches, int reset) {
+  VMB_CHECK_ARG(ms_sum && launches, "prof_read: null output");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (const ProfRec& r : g_prof_log) {
+    if (!r.closed || r.kind < 0 || r.kind >= VMB_PROF_KINDS) continue;
+    VMB_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    VMB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_sum[r.kind] += ms;
+    launches[r.kind] += 1;
+  }
+  if (reset) {
+    for (const ProfRec& r : g_prof_log) { g_prof_free.push_back(r.a); g_prof_free.push_back(r.b); }
+    g_prof_log.clear();
+  }
+  return VMB_OK;
+}
+
+extern "C" int64_t vmb_launch_count(void) { return (int64_t)g_launches; }

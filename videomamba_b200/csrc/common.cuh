@@ -32,8 +32,11 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::vmb::cuda_fail(e__, #call); \
   } while (0)
 
+extern unsigned long long g_launches;  // kernels enqueued by this library (vmb_launch_count)
+
 #define VMB_LAUNCH_CHECK(name)                                   \
   do {                                                           \
+    ++::vmb::g_launches;                                         \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return ::vmb::cuda_fail(e__, name);  \
   } while (0)
@@ -42,6 +45,17 @@ inline cudaStream_t as_stream(vmb_stream_t s) { return reinterpret_cast<cudaStre
 inline int dtype_size(int dt) { return dt == VMB_BF16 ? 2 : 4; }
 inline bool dtype_ok(int dt) { return dt == VMB_F32 || dt == VMB_BF16; }
 int sm_count();
+
+// ---- per-stage timing (vmb_prof_*): a scope brackets the launches of one stage with events --
+extern bool g_prof_on;
+void prof_begin(int kind, cudaStream_t st, int* slot);
+void prof_end(int slot, cudaStream_t st);
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t st;
+  ProfScope(int kind, cudaStream_t s) : st(s) { if (g_prof_on) prof_begin(kind, s, &slot); }
+  ~ProfScope() { if (slot >= 0) prof_end(slot, st); }
+};
 
 // ---- element conversion -------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
