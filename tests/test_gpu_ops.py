@@ -147,9 +147,11 @@ def test_selective_scan_fn_dropin(dtype, geom):
         assert got.shape == (B, D, L) and last.dtype == torch.float32
         assert rel_err(got, want) <= _tol(dtype)
         assert rel_err(last, want_last) <= _tol(dtype)
-    # no z / no D / no softplus / no bias
-    want = orc.selective_scan_ref(u, delta, A, Bm, Cm)
-    got = ops.selective_scan_fn(u.to(DEV), delta.to(DEV), A.to(DEV), Bm.to(DEV), Cm.to(DEV))
+    # no z / no D / no softplus / no bias (delta is then a step size: keep it positive, a
+    # negative one turns the decay into exponential growth and overflows in both)
+    dpos = (delta.float().abs() * 0.1).to(dtype)
+    want = orc.selective_scan_ref(u, dpos, A, Bm, Cm)
+    got = ops.selective_scan_fn(u.to(DEV), dpos.to(DEV), A.to(DEV), Bm.to(DEV), Cm.to(DEV))
     assert rel_err(got, want) <= _tol(dtype)
 
 

@@ -160,10 +160,10 @@ extern "C" int vmb_add_norm_fwd(const void* x, int x_dtype, int64_t ldx, const v
                                 vmb_stream_t stream) {
   using namespace vmb;
   using bf16 = __nv_bfloat16;
-  VMB_CHECK_ARG(x && weight && y, "add_norm: null x / weight / y");
   VMB_CHECK_ARG(dtype_ok(x_dtype) && dtype_ok(w_dtype), "add_norm: bad dtype");
   VMB_CHECK_ARG(rows >= 0 && dim > 0, "add_norm: bad sizes rows=%lld dim=%d", (long long)rows, dim);
-  if (rows == 0) return VMB_OK;
+  if (rows == 0) return VMB_OK;  // empty batch: pointers may legitimately be null
+  VMB_CHECK_ARG(x && weight && y, "add_norm: null x / weight / y");
   if (dim % 4 != 0 || ldx % 4 != 0) VMB_UNSUPPORTED("add_norm: dim and ldx must be multiples of 4");
   if (!residual) residual_dtype = VMB_F32;
   if (!residual_out) residual_out_dtype = VMB_F32;

@@ -104,10 +104,10 @@ __global__ void state_rows_kernel(const V* __restrict__ src, V* __restrict__ dst
 
 int state_rows(const void* src, void* dst, const int32_t* index, int n_rows, int64_t row_elems,
                int dtype, bool gather, cudaStream_t st) {
-  VMB_CHECK_ARG(src && dst && index, "state_gather/scatter: null pointer");
   VMB_CHECK_ARG(dtype_ok(dtype), "state_gather/scatter: bad dtype");
   VMB_CHECK_ARG(n_rows >= 0 && n_rows <= 65535 && row_elems >= 0, "state_gather/scatter: bad sizes");
   if (n_rows == 0 || row_elems == 0) return VMB_OK;
+  VMB_CHECK_ARG(src && dst && index, "state_gather/scatter: null pointer");
   const int64_t bytes = row_elems * dtype_size(dtype);
   const bool v16 = bytes % 16 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 &&
                    reinterpret_cast<uintptr_t>(dst) % 16 == 0;
@@ -153,9 +153,9 @@ extern "C" int vmb_device_info(int* sms, int* cc_major, int* cc_minor) {
 extern "C" int vmb_linear_fwd(const void* A, int64_t lda, const void* W, int64_t ldw,
                               const void* bias, void* C, int64_t ldc, int64_t M, int N, int K,
                               int dtype, vmb_stream_t stream) {
-  VMB_CHECK_ARG(A && W && C, "linear: null A / W / C");
   VMB_CHECK_ARG(dtype_ok(dtype), "linear: bad dtype %d", dtype);
   VMB_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear: bad sizes M=%lld N=%d K=%d", (long long)M, N, K);
+  VMB_CHECK_ARG(M == 0 || (A && W && C), "linear: null A / W / C");
   VMB_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "linear: row stride smaller than row");
   if (M == 0) return VMB_OK;
   cudaStream_t st = as_stream(stream);

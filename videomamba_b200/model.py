@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from . import ops
 from .block import Block, DropPath, RMSNorm, apply_norm, create_block
 from .streaming import (STREAMING_CONTRACT_VERSION, ForwardReturnSemantics, StateShape,
                         forward_return_semantics as _return_semantics)
@@ -103,8 +104,25 @@ class PatchEmbed(nn.Module):
         k = (kernel_size, self.patch_size[0], self.patch_size[1])
         self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=k, stride=k)
 
+    def tokens(self, x: Tensor) -> Tensor:
+        """(B, C, T, H, W) -> patch tokens (B, T', h, w, D), frame-major.  Kernel == stride, so the
+        Conv3d of the reference (videomamba.py:359-368) is one dense projection over
+        non-overlapping patches: an im2col permute followed by the library's linear kernel (true
+        fp32 in fp32 mode -- cuDNN would use TF32 -- and tensor cores in bf16)."""
+        k = self.tubelet_size
+        ph, pw = self.patch_size
+        B, C, T, H, W = x.shape
+        t, h, w = T // k, H // ph, W // pw
+        x = x[:, :, :t * k, :h * ph, :w * pw]
+        cols = x.reshape(B, C, t, k, h, ph, w, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+        cols = cols.reshape(B * t * h * w, C * k * ph * pw)
+        weight = self.proj.weight.reshape(self.proj.weight.shape[0], -1)
+        out = ops.linear(cols.to(weight.dtype), weight, self.proj.bias)
+        return out.reshape(B, t, h, w, -1)
+
     def forward(self, x: Tensor) -> Tensor:
-        return self.proj(x)
+        """(B, D, T', h, w), the layout the reference's Conv3d returns (a view of ``tokens``)."""
+        return self.tokens(x).permute(0, 4, 1, 2, 3)
 
 
 class PretrainVideoMamba(nn.Module):
