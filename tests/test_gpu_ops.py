@@ -75,6 +75,50 @@ def test_linear(dtype, mnk):
     assert rel_err(got, orc._linear(wide[:, :K], w)) <= _tol(dtype)
 
 
+@pytest.mark.parametrize("mnk", [(12837, 1536, 384), (8197, 64, 768), (5000, 384, 768),
+                                 (4096, 192, 384), (3000, 576, 1152), (2000, 80, 1152),
+                                 (999, 2304, 576), (128, 768, 192), (70, 48, 384), (4100, 768, 24)])
+def test_tensor_core_projection_exact_integers(mnk):
+    """bf16 tcgen05 projection at the production widths (Tiny / Small / Middle in_proj, x_proj,
+    out_proj, patch embed, dt_proj): operands are small integers, so every fp32 partial sum is
+    exact and the result must EQUAL the fp32 product rounded once to bf16 -- any mis-indexed tile,
+    swizzle or k-block shows up as a mismatch, not as noise."""
+    M, N, K = mnk
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = torch.randint(-2, 3, (M, K), generator=gen).to(torch.bfloat16).to(DEV)
+    w = torch.randint(-2, 3, (N, K), generator=gen).to(torch.bfloat16).to(DEV)
+    bias = torch.randint(-4, 5, (N,), generator=gen).to(torch.bfloat16).to(DEV)
+    for b in (None, bias):
+        got = ops.linear(a, w, b)
+        acc = a.double() @ w.double().t()            # exact (products and sums of small integers)
+        if b is not None:
+            acc = acc + b.double()
+        want = acc.to(torch.float32).to(torch.bfloat16)
+        assert torch.equal(got, want), (mnk, (got.float() - want.float()).abs().max().item())
+    # output written into a wider buffer (x_dbl pitch) must not touch the padding columns
+    from videomamba_b200 import _lib
+    lib = _lib.load()
+    out = torch.full((M, N + 16), 7.0, dtype=torch.bfloat16, device=DEV)
+    rc = lib.vmb_linear_fwd(ops._p(a), K, ops._p(w), K, None, ops._p(out), N + 16, M, N, K,
+                            _lib.VMB_BF16, ops._stream(a))
+    _lib.check(rc, "vmb_linear_fwd")
+    want = (a.double() @ w.double().t()).to(torch.float32).to(torch.bfloat16)
+    assert torch.equal(out[:, :N], want) and bool((out[:, N:] == 7.0).all())
+
+
+def test_tensor_core_projection_random_values():
+    """Random bf16 operands against a float64 product of the same bf16 values: the only error left
+    is the fp32 accumulation order and the final rounding (<= 1 bf16 ulp of the result)."""
+    gen = torch.Generator().manual_seed(5)
+    for M, N, K in [(6000, 1536, 384), (6000, 384, 768), (6000, 64, 768)]:
+        a = torch.randn(M, K, generator=gen).to(torch.bfloat16).to(DEV)
+        w = (torch.randn(N, K, generator=gen) * K ** -0.5).to(torch.bfloat16).to(DEV)
+        got = ops.linear(a, w).double()
+        want = a.double() @ w.double().t()
+        err = (got - want).abs()
+        assert float((err / (want.abs() + 1e-2)).max()) <= 2.0 ** -8, (M, N, K)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("geom", [(2, 70, 768, 4), (3, 5, 16, 2), (1, 2, 24, 4), (2, 130, 384, 3),
                                   (1, 1, 8, 4)])

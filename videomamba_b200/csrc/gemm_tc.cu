@@ -1,8 +1,450 @@
-// placeholder until the tcgen05 kernel lands
+// bf16 dense projection on the 5th-generation tensor cores:  C[M,N] = A[M,K] * W[N,K]^T (+ bias).
+//
+// Stands in for the cuBLAS calls behind nn.Linear / F.linear on the reference's mixer path
+// (models/videomamba/mamba_simple.py:333-339 in_proj, :409 x_proj, :445-446 out_proj) and behind
+// the Conv3d patch embedding (models/videomamba/videomamba.py:359-368, kernel == stride).
+//
+// Design (B200 / sm_100a, one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   TMA producer: A tile (128 x 64) and W tile (BN x 64) per k-block into a kStages-deep
+//            ring of 128B-swizzled shared-memory buffers (cp.async.bulk.tensor + mbarrier tx).
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 ->
+//            fp32) with both operands read from shared memory through UMMA descriptors;
+//            accumulators live in TMEM (2 x BN columns: double buffered across tiles).
+//   warp 2   TMEM allocation / release.
+//   warps 4-7 epilogue: tcgen05.ld the accumulator (thread = output row), add bias, round once to
+//            bf16, stage 128 x 64 sub-tiles in swizzled shared memory and write them with TMA
+//            stores (coalesced, rows beyond M / columns beyond N are clipped by the hardware).
+// Tiles are walked n-fastest so the CTAs running at the same time share the A rows in L2.
+// Both operands are K-contiguous, exactly how nn.Linear stores its weight, so no transposes.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "internal.h"
+
 namespace vmb {
-bool gemm_tc_supported(const void*, int64_t, const void*, int64_t, const void*, int64_t, int64_t, int, int) { return false; }
-int gemm_tc(const void*, int64_t, const void*, int64_t, const void*, void*, int64_t, int64_t, int, int, cudaStream_t) {
-  VMB_UNSUPPORTED("gemm_tc: not built");
+namespace {
+
+constexpr int BM = 128;       // rows of C per tile (UMMA M)
+constexpr int BK = 64;        // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;  // first epilogue warp
+constexpr int kSubN = 64;     // columns per epilogue sub-tile (128 bytes of bf16)
+
+__host__ __device__ constexpr int stages_for(int bn) { return bn <= 128 ? 6 : 4; }
+__host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 64 ? 128 : (bn <= 128 ? 256 : 512); }
+__host__ __device__ constexpr size_t smem_bytes_for(int bn) {
+  return 1024 /* alignment slack */ + (size_t)stages_for(bn) * (BM * BK * 2 + bn * BK * 2) +
+         2 * (BM * kSubN * 2) + 256 /* barriers + tmem pointer */;
 }
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread l of the warp receives row (lane base + l).
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 128 epilogue threads
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor of a K-major, 128B-swizzled operand tile whose rows are 128 bytes
+// (64 bf16) and whose 8-row groups are 1024 bytes apart (dense):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major:
+//   1), [32,46) stride byte offset >> 4 (= 1024 >> 4), [46,48) version = 1, [61,64) layout = 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: fp32 accumulate (bits 4-5 = 1), A and B bf16 (bits 7-9 and
+// 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ bias,
+               int M, int N, int K) {
+  constexpr int kStages = stages_for(BN);
+  constexpr int kTmemCols = tmem_cols_for(BN);
+  constexpr uint32_t kABytes = BM * BK * 2;
+  constexpr uint32_t kWBytes = BN * BK * 2;
+  constexpr uint32_t kSubBytes = BM * kSubN * 2;
+  constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_w = smem_a + kStages * kABytes;
+  const uint32_t smem_c = smem_w + kStages * kWBytes;
+  const uint32_t bars = smem_c + 2 * kSubBytes;
+  // barrier layout (8 bytes each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2]
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic view of smem_base
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int k_blocks = (K + BK - 1) / BK;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_c);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), kABytes + kWBytes);
+          tma_load_2d(smem_a + stage * kABytes, &map_a, full_bar(stage), kb * BK, m0);
+          tma_load_2d(smem_w + stage * kWBytes, &map_w, full_bar(stage), kb * BK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem_a + stage * kABytes);
+          const uint64_t b_desc = umma_desc_sw128(smem_w + stage * kWBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in (addr >> 4)
+            tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb | k) != 0);
+          }
+          tc_commit(empty_bar(stage));               // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue =====
+    const int ew = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32 ew, 32 ew + 32)
+    const int row = ew * 32 + lane;                  // row of the tile this thread owns
+    const bool issuer = threadIdx.x == kEpiWarp0 * 32;
+    int local = 0;
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int sub = 0; sub < BN / kSubN; ++sub) {
+        if (n0 + sub * kSubN >= N) break;            // whole sub-tile beyond N (uniform)
+        uint32_t v0[32], v1[32];
+        tc_ld_32x32(t_row + sub * kSubN, v0);
+        tc_ld_32x32(t_row + sub * kSubN + 32, v1);
+        tc_wait_ld();
+        if (sub == BN / kSubN - 1 || n0 + (sub + 1) * kSubN >= N) {
+          // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        if (bias != nullptr) {
+          const int nb = n0 + sub * kSubN;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float b0 = nb + j < N ? __bfloat162float(bias[nb + j]) : 0.f;
+            const float b1 = nb + 32 + j < N ? __bfloat162float(bias[nb + 32 + j]) : 0.f;
+            v0[j] = __float_as_uint(__uint_as_float(v0[j]) + b0);
+            v1[j] = __float_as_uint(__uint_as_float(v1[j]) + b1);
+          }
+        }
+        // the store that last read this staging buffer (two sub-tiles ago) must be done reading
+        if (issuer) tma_store_wait_read<1>();
+        epi_bar_sync();
+        uint8_t* dst = smem_gen + (smem_c - smem_base) + buf * kSubBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                // 8 chunks of 16 bytes = 8 bf16 each
+          uint32_t p[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = c * 8 + q * 2;
+            const float lo = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+            const float hi = __uint_as_float(j + 1 < 32 ? v0[j + 1] : v1[j + 1 - 32]);
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            p[q] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (issuer) {
+          tma_store_2d(&map_c, smem_c + buf * kSubBytes, n0 + sub * kSubN, m0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side: tensor maps ----------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                              CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int64_t rows, cols, ld; int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](int64_t v) { h ^= std::hash<int64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_rows);
+    return h;
+  }
+};
+
+// 2-D bf16 row-major tensor (rows x cols, row stride ld elements), box = box_rows x 64, 128B swizzle.
+int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return VMB_OK; }
+  }
+  EncodeFn fn = encode_fn();
+  if (!fn) { set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available"); return VMB_ERR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return VMB_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return VMB_OK;
+}
+
+template <int BN>
+int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+           int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+  CUtensorMap ma, mw, mc;
+  int rc;
+  if ((rc = make_map(&ma, A, M, K, lda, BM))) return rc;
+  if ((rc = make_map(&mw, W, N, K, ldw, BN))) return rc;
+  if ((rc = make_map(&mc, C, M, N, ldc, BM))) return rc;
+  static bool attr_set[64] = {false};
+  constexpr size_t smem = smem_bytes_for(BN);
+  int dev = 0;
+  VMB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    VMB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = (int)std::min<int64_t>(tiles, sm_count());
+  gemm_tc_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias, (int)M, N, K);
+  VMB_LAUNCH_CHECK("gemm_tc_kernel");
+  return VMB_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, const void* C,
+                       int64_t ldc, int64_t M, int N, int K) {
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  // TMA: 16-byte aligned bases and row pitches; keep tiny problems on the CUDA-core kernel
+  return al16(A) && al16(W) && al16(C) && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 &&
+         K % 8 == 0 && N % 8 == 0 && K >= 16 && N >= 16 && M >= 1 && M < (1ll << 31) - BM &&
+         M * (int64_t)N >= 64 * 64;
+}
+
+int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+            int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+  if (N <= 64) return launch<64>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N <= 128) return launch<128>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N % 256 == 0) return launch<256>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N % 192 == 0 || N < 256) return launch<192>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  return launch<256>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+}
+
+}  // namespace vmb
