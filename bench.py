@@ -323,7 +323,7 @@ def run_ours(args):
     tokens = B * L
     es = 2
     w = mixer._kernel_weights()
-    fused = bool(getattr(w, "fused_scan", False))
+    fused = "dt_proj" not in stages      # the fused scan expands dt inside the kernel
     if fused:
         # fused conv+dt_proj+scan+gate kernel: reads x, z, x_dbl row; writes y
         bytes_per_token = 3 * Di * es + w.Xp * es

@@ -133,6 +133,32 @@ typedef struct vmb_scan_args {
 } vmb_scan_args;
 VMB_API int vmb_selective_scan_fwd(const vmb_scan_args* args, vmb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused dt_proj + selective scan (bf16, d_state = 16): the production form of the two reference
+ * steps models/videomamba/mamba_simple.py:413-414 (dt_proj) and :423-435 (selective_scan_fn),
+ * so that delta (B, L, Di) is never materialised:
+ *   delta = softplus(w_dt[d, :R] . xdbl[t, :R] + dt_bias[d]);  then the recurrence above with
+ *   B_t = xdbl[t, R:R+N], C_t = xdbl[t, R+N:R+2N].
+ * u, z, y: (B, L, Di) token-major views; xdbl: (B, L, Xp) rows [dt_low | B | C | pad];
+ * w_dt: (Di, Rp) bf16 with Rp >= R (row pitch).  Returns VMB_ERR_UNSUPPORTED for shapes the
+ * fused kernel does not cover (the caller then uses vmb_linear_fwd + vmb_selective_scan_fwd).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vmb_fused_scan_args {
+  const void* u;      int64_t u_bstride, u_tstride;
+  const void* z;      int64_t z_bstride, z_tstride;
+  const void* xdbl;   int64_t x_bstride, x_tstride;
+  const void* w_dt;       /* (Di, Rp) bf16 */
+  const float* A2;        /* (Di, N) fp32, A*log2(e) */
+  const float* D;         /* (Di) fp32, nullable */
+  const float* dt_bias;   /* (Di) fp32, nullable */
+  const void* h0;     int32_t h0_dtype;                  /* (B,Di,N), nullable */
+  void* y;            int64_t y_bstride, y_tstride;
+  float* h_last;                                         /* (B,Di,N) fp32, nullable */
+  int32_t B, L, Di, N, R, Rp, Xp;
+  int32_t reverse;
+} vmb_fused_scan_args;
+VMB_API int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* args, vmb_stream_t stream);
+
 /* Single recurrent step, state (B,Di,N) updated in place.  Replaces
  * mamba_ssm.ops.triton.selective_state_update at models/videomamba/mamba_simple.py:483-494
  * (and the per-token fallback loop :158-171).  x, dt, z, y: (B,Di); Bm, Cm: (B,N). */

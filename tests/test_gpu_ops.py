@@ -199,6 +199,83 @@ def test_selective_scan_fn_dropin(dtype, geom):
     assert rel_err(got, want) <= _tol(dtype)
 
 
+def _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, h0, reverse, R, N):
+    """float64 evaluation of the fused op on the SAME bf16 inputs (mamba_simple.py:413-414 without
+    the intermediate rounding of delta, then :30-106)."""
+    if reverse:
+        u, z, xdbl = u.flip(1), z.flip(1), xdbl.flip(1)
+    u, z, xd = u.double(), z.double(), xdbl.double()
+    dt = torch.nn.functional.softplus(xd[..., :R] @ w_dt[:, :R].double().t() + bias.double())
+    Bm, Cm = xd[..., R:R + N], xd[..., R + N:R + 2 * N]
+    Bsz, L, Di = u.shape
+    h = torch.zeros(Bsz, Di, N, dtype=torch.float64, device=u.device) if h0 is None else h0.double().clone()
+    ys = torch.empty(Bsz, L, Di, dtype=torch.float64, device=u.device)
+    Ad = A.double()
+    for t in range(L):
+        h = torch.exp(dt[:, t, :, None] * Ad) * h + (dt[:, t] * u[:, t])[:, :, None] * Bm[:, t, None, :]
+        ys[:, t] = (h * Cm[:, t, None, :]).sum(-1)
+    y = (ys + u * Dp.double()) * (z * torch.sigmoid(z))
+    return (y.flip(1) if reverse else y), h
+
+
+@pytest.mark.parametrize("geom", [(2, 777, 768, 24, 64), (1, 100, 384, 12, 48), (3, 33, 1152, 36, 80),
+                                  (2, 1, 768, 24, 64), (1, 31, 768, 24, 56)])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_fused_scan_against_float64(geom, reverse):
+    """The fused dt_proj + scan kernel (bf16) against float64 on identical inputs, with and without an
+    initial state, ragged lengths (tile tails), all three production dt ranks."""
+    Bsz, L, Di, R, Xp = geom
+    N = 16
+    gen = torch.Generator().manual_seed(L + Di)
+    bf = torch.bfloat16
+    u = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
+    z = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
+    xdbl = _rand(gen, Bsz, L, Xp, dtype=bf).to(DEV)
+    w_dt = _rand(gen, Di, R, dtype=bf, scale=R ** -0.5).to(DEV)
+    A = -torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Di, 1)
+                   + 0.1 * torch.randn(Di, N, generator=gen)).to(DEV)
+    Dp = torch.randn(Di, generator=gen).to(DEV)
+    bias = (torch.randn(Di, generator=gen) - 3.0).to(DEV)
+    h0 = torch.randn(Bsz, Di, N, generator=gen).to(DEV)
+    A2 = (A * ops.LOG2E).contiguous()
+    for init in (None, h0):
+        want, want_h = _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, init, reverse, R, N)
+        got, got_h = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, init,
+                                                     want_last=True, reverse=reverse)
+        assert got.dtype == bf and got_h.dtype == torch.float32
+        assert rel_err(got, want) <= 6e-3, rel_err(got, want)
+        assert rel_err(got_h, want_h) <= 2e-3, rel_err(got_h, want_h)
+    # strided views: z living in the second half of an xz buffer, u / y with a wider pitch
+    xz = _rand(gen, Bsz, L, 2 * Di, dtype=bf).to(DEV)
+    want, _ = _fused_scan_ref64(xz[..., :Di], xz[..., Di:], xdbl, w_dt, A, Dp, bias, None, reverse, R, N)
+    got = ops.selective_scan_fused_tokens(xz[..., :Di], xz[..., Di:], xdbl, w_dt, A2, R, N, Dp, bias,
+                                          reverse=reverse)
+    assert rel_err(got, want) <= 6e-3
+
+
+def test_fused_scan_chunk_carry_at_full_length():
+    """Size-independent property at the long-clip size (25 089 tokens): scanning in three chunks
+    with the state carried equals one pass, bit for bit (the kernel is sequential in t)."""
+    gen = torch.Generator().manual_seed(9)
+    bf = torch.bfloat16
+    Bsz, L, Di, R, Xp, N = 1, 25089, 768, 24, 64, 16
+    u = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
+    z = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
+    xdbl = _rand(gen, Bsz, L, Xp, dtype=bf).to(DEV)
+    w_dt = _rand(gen, Di, R, dtype=bf, scale=R ** -0.5).to(DEV)
+    A2 = (-torch.arange(1, N + 1).float().repeat(Di, 1) * ops.LOG2E).to(DEV)
+    Dp = torch.ones(Di, device=DEV)
+    bias = torch.full((Di,), -3.0, device=DEV)
+    full, h_full = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, want_last=True)
+    h, parts = None, []
+    for lo, hi in ((0, 7000), (7000, 7001), (7001, L)):
+        y, h = ops.selective_scan_fused_tokens(u[:, lo:hi], z[:, lo:hi], xdbl[:, lo:hi], w_dt, A2, R,
+                                               N, Dp, bias, h, want_last=True)
+        parts.append(y)
+    assert torch.equal(torch.cat(parts, 1), full) and torch.equal(h, h_full)
+    assert torch.isfinite(full.float()).all()
+
+
 def test_selective_scan_golden_fixture(golden):
     g = golden("scan_fp32.pt")
     c = lambda k: g[k].to(DEV)

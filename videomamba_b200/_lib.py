@@ -35,6 +35,21 @@ class ScanArgs(C.Structure):
     ]
 
 
+class FusedScanArgs(C.Structure):
+    """struct vmb_fused_scan_args"""
+    _fields_ = [
+        ("u", c_void_p), ("u_bstride", c_int64), ("u_tstride", c_int64),
+        ("z", c_void_p), ("z_bstride", c_int64), ("z_tstride", c_int64),
+        ("xdbl", c_void_p), ("x_bstride", c_int64), ("x_tstride", c_int64),
+        ("w_dt", c_void_p), ("A2", c_void_p), ("D", c_void_p), ("dt_bias", c_void_p),
+        ("h0", c_void_p), ("h0_dtype", c_int32),
+        ("y", c_void_p), ("y_bstride", c_int64), ("y_tstride", c_int64),
+        ("h_last", c_void_p),
+        ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32), ("R", c_int32),
+        ("Rp", c_int32), ("Xp", c_int32), ("reverse", c_int32),
+    ]
+
+
 class MixerArgs(C.Structure):
     """struct vmb_mixer_args"""
     _fields_ = [
@@ -72,6 +87,7 @@ SIGNATURES = {
                                          c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p]),
     "vmb_selective_scan_fwd": (c_int, [C.POINTER(ScanArgs), c_void_p]),
+    "vmb_selective_scan_fused_fwd": (c_int, [C.POINTER(FusedScanArgs), c_void_p]),
     "vmb_selective_state_update": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64,
                                            c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                            c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64,

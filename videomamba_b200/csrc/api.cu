@@ -175,6 +175,29 @@ extern "C" int vmb_selective_scan_fwd(const vmb_scan_args* a, vmb_stream_t strea
   return scan_generic(*a, as_stream(stream));
 }
 
+extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_stream_t stream) {
+  VMB_CHECK_ARG(a != nullptr, "fused_scan: null args");
+  VMB_CHECK_ARG(a->B >= 0 && a->L >= 0 && a->Di > 0 && a->N > 0 && a->R > 0, "fused_scan: bad sizes");
+  if (a->B == 0 || a->L == 0) {
+    if (a->L == 0 && a->B > 0 && a->h_last) VMB_UNSUPPORTED("fused_scan: empty sequence with state output");
+    return VMB_OK;
+  }
+  VMB_CHECK_ARG(a->u && a->z && a->xdbl && a->w_dt && a->A2 && a->y, "fused_scan: null tensor");
+  VMB_CHECK_ARG(!a->h0 || dtype_ok(a->h0_dtype), "fused_scan: bad h0 dtype");
+  FastScanArgs f;
+  f.u = a->u; f.u_bs = a->u_bstride; f.u_ts = a->u_tstride;
+  f.z = a->z; f.z_bs = a->z_bstride; f.z_ts = a->z_tstride;
+  f.xdbl = a->xdbl; f.x_bs = a->x_bstride; f.x_ts = a->x_tstride;
+  f.w_dt_pad = a->w_dt; f.A2 = a->A2; f.D = a->D; f.dt_bias = a->dt_bias;
+  f.h0 = a->h0; f.h0_dtype = a->h0_dtype;
+  f.y = a->y; f.y_bs = a->y_bstride; f.y_ts = a->y_tstride; f.h_last = a->h_last;
+  f.B = a->B; f.L = a->L; f.Di = a->Di; f.N = a->N; f.R = a->R; f.Rp = a->Rp; f.Xp = a->Xp;
+  f.reverse = a->reverse;
+  if (!scan_fast_supported(f)) VMB_UNSUPPORTED("fused_scan: shape / alignment not covered by the fused kernel");
+  ProfScope ps(VMB_PROF_SCAN, as_stream(stream));
+  return scan_fast(f, as_stream(stream));
+}
+
 extern "C" int64_t vmb_mixer_workspace_bytes(int B, int L, int D, int Di, int N, int R,
                                              int dtype) {
   (void)D;

@@ -21,7 +21,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import VMB_BF16, VMB_F32, MixerArgs, ScanArgs
+from ._lib import VMB_BF16, VMB_F32, FusedScanArgs, MixerArgs, ScanArgs
 
 LOG2E = 1.4426950408889634
 
@@ -222,6 +222,44 @@ def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_of
     with _on_device(u):
         rc = lib.vmb_selective_scan_fwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_fwd")
+    return (y, h_last) if want_last else y
+
+
+def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor, A2: Tensor,
+                                dt_rank: int, d_state: int, D: Optional[Tensor] = None,
+                                dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
+                                want_last: bool = False, reverse: bool = False):
+    """Fused dt_proj + softplus + scan + D skip + SiLU(z) gate (bf16, d_state 16).
+    ``u, z: (B, L, Di)``; ``xdbl: (B, L, Xp)`` rows ``[dt_low (R) | B (N) | C (N) | pad]``;
+    ``w_dt: (Di, >=R)`` bf16; ``A2 = A*log2(e)`` fp32.  Raises when the shape is not covered."""
+    _require_cuda(u)
+    lib = _lib.load()
+    u, z, xdbl = _token_major(u), _token_major(z), _token_major(xdbl)
+    w_dt = w_dt if w_dt.stride(-1) == 1 else w_dt.contiguous()
+    B, L, Di = u.shape
+    y = torch.empty((B, L, Di), dtype=u.dtype, device=u.device)
+    h_last = torch.empty((B, Di, d_state), dtype=torch.float32, device=u.device) if want_last else None
+    if h0 is not None:
+        h0 = h0.contiguous()
+    a = FusedScanArgs()
+    a.u, a.u_bstride, a.u_tstride = u.data_ptr(), u.stride(0), u.stride(1)
+    a.z, a.z_bstride, a.z_tstride = z.data_ptr(), z.stride(0), z.stride(1)
+    a.xdbl, a.x_bstride, a.x_tstride = xdbl.data_ptr(), xdbl.stride(0), xdbl.stride(1)
+    a.w_dt, a.A2 = w_dt.data_ptr(), A2.data_ptr()
+    a.D = None if D is None else D.data_ptr()
+    a.dt_bias = None if dt_bias is None else dt_bias.data_ptr()
+    if h0 is not None:
+        a.h0, a.h0_dtype = h0.data_ptr(), _dt(h0)
+    a.y, a.y_bstride, a.y_tstride = y.data_ptr(), y.stride(0), y.stride(1)
+    a.h_last = None if h_last is None else h_last.data_ptr()
+    a.B, a.L, a.Di, a.N, a.R = B, L, Di, d_state, dt_rank
+    a.Rp, a.Xp, a.reverse = w_dt.stride(0), xdbl.shape[-1], 1 if reverse else 0
+    if u.dtype != torch.bfloat16 or z.dtype != u.dtype or xdbl.dtype != u.dtype \
+            or w_dt.dtype != u.dtype:
+        raise TypeError("the fused scan is a bf16 kernel")
+    with _on_device(u):
+        rc = lib.vmb_selective_scan_fused_fwd(C.byref(a), _stream(u))
+    _lib.check(rc, "vmb_selective_scan_fused_fwd")
     return (y, h_last) if want_last else y
 
 
