@@ -140,7 +140,8 @@ VMB_API int vmb_selective_scan_fwd(const vmb_scan_args* args, vmb_stream_t strea
  *   delta = softplus(w_dt[d, :R] . xdbl[t, :R] + dt_bias[d]);  then the recurrence above with
  *   B_t = xdbl[t, R:R+N], C_t = xdbl[t, R+N:R+2N].
  * u, z, y: (B, L, Di) token-major views; xdbl: (B, L, Xp) rows [dt_low | B | C | pad];
- * w_dt: (Di, Rp) bf16 with Rp >= R (row pitch).  Returns VMB_ERR_UNSUPPORTED for shapes the
+ * w_dt: (Di, Rp) bf16, Rp >= R rounded up to a multiple of 16, columns >= R zero (the projection
+ * runs in 16-wide k-steps on the tensor pipe).  Returns VMB_ERR_UNSUPPORTED for shapes the
  * fused kernel does not cover (the caller then uses vmb_linear_fwd + vmb_selective_scan_fwd).
  * ---------------------------------------------------------------------------------------- */
 typedef struct vmb_fused_scan_args {

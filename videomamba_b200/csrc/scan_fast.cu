@@ -8,17 +8,21 @@
 // :109-172; semantics of _selective_scan_ref :30-106).  Difference in rounding points: the
 // reference rounds delta_raw to bf16 between the two ops, here it stays fp32 (closer to exact).
 //
-// Work decomposition (the kernel is bound by MUFU ex2 and issue slots, not by HBM):
-//   * CTA = (batch b, 32 channels), 128 threads; walks the sequence in tiles of 32 tokens.
-//   * a channel's 16 states are split over 4 adjacent lanes (4 states each): 4x the threads of a
-//     thread-per-channel scan, no redundant exponentials;
-//   * per group of 4 tokens each of the 4 lanes "owns" one token: it does the token's dt_proj dot
-//     product (weights in registers), softplus, SiLU(z) and D*u once, and the group exchanges
-//     delta / delta*u with width-4 shuffles; the per-token partial outputs of the 4 lanes are
-//     combined with a 3-shuffle transpose-reduce that leaves each owner with its token's y.
-//   * tiles of u, z and x_dbl are staged in shared memory with 16-byte cp.async copies, double
-//     buffered; x_dbl is expanded to fp32 once per tile so B_t / C_t / dt_low are read back as
-//     conflict-free 128-bit broadcasts; y leaves through shared memory as 16-byte stores.
+// The kernel is bound by MUFU ex2 throughput, instruction issue and shared-memory bandwidth, not
+// by HBM (DESIGN.md "scan"), so the layout minimises instructions and smem bytes per (token,
+// channel):
+//   * CTA = (batch b, 32 channels), 64 threads (2 warps x 16 channels); the sequence is walked in
+//     tiles of 32 tokens staged with 16-byte cp.async copies, double buffered.
+//   * phase A (per tile, per warp): the dt projection of the tile, delta_raw[32 tokens x 16
+//     channels] = dt_low[32 x R] * w_dt^T, runs on the tensor pipe (mma.sync m16n8k16, the A
+//     fragments come straight from the staged bf16 x_dbl rows via ldmatrix, w_dt fragments stay in
+//     registers); softplus and delta*u are applied to the accumulator fragments, which are
+//     written to shared memory as {delta0, delta1, du0, du1} per channel pair.
+//   * phase B: a thread owns a 2-channel x 4-state block of the recurrence (4 adjacent lanes
+//     cover the 16 states), so one 128-bit broadcast load each of B_t, C_t and the pair's
+//     {delta, du} feeds 8 state updates; the 4 lanes' partial outputs are combined with two
+//     shuffles, and every lane finalises one (token, channel) of a 2-token step: + D*u, * SiLU(z).
+//   * B_t / C_t are expanded to fp32 once per tile; y leaves through shared memory as 16-byte stores.
 //   * reverse = 1 walks the sequence back to front (tile rows are gathered in logical order), which
 //     is what the flipped branch of BiMambaRefinerBlock needs without any torch.flip copy.
 #include <cstdlib>
@@ -29,32 +33,30 @@ namespace vmb {
 namespace {
 
 constexpr int kCh = 32;                 // channels per CTA
-constexpr int kThreads = 128;           // 32 channels x 4 lanes
+constexpr int kThreads = 64;            // 2 warps x (8 channel pairs x 4 state quads)
 constexpr int kTT = 32;                 // tokens per tile
-constexpr int kUZRowBytes = 80;         // 64 B of channels + 16 B pad (bank spread for 4-row reads)
+constexpr int kRowBytes = 80;           // u / z / y tile rows: 64 B of channels + 16 B pad
 constexpr int kN = 16;
-constexpr int kYRowBytes = 80;          // 64 B of channels + 16 B pad
 
-__host__ __device__ constexpr int dt_stride(int R) {  // floats per sDT row: odd number of 16-B groups
-  return ((R / 4) % 2 == 1) ? R : R + 4;
-}
+// x_dbl tile row pitch in bytes: an odd number of 16-byte chunks keeps ldmatrix conflict free
+__host__ __device__ constexpr int x_row_bytes(int Xp) { return ((Xp / 8) % 2 == 1) ? Xp * 2 : Xp * 2 + 16; }
 
 struct Smem {   // byte offsets; u / z / x are double buffered: stage s lives at base + s * stride
-  int u0, z0, x0, xstride, bc, dt, y, total;
-  __host__ __device__ int u(int s) const { return u0 + s * (kTT * kUZRowBytes); }
-  __host__ __device__ int z(int s) const { return z0 + s * (kTT * kUZRowBytes); }
+  int u0, z0, x0, xstride, bc, dd, y, total;
+  __host__ __device__ int u(int s) const { return u0 + s * (kTT * kRowBytes); }
+  __host__ __device__ int z(int s) const { return z0 + s * (kTT * kRowBytes); }
   __host__ __device__ int x(int s) const { return x0 + s * xstride; }
 };
-__host__ __device__ inline Smem smem_plan(int R, int Xp) {
+__host__ __device__ inline Smem smem_plan(int Xp) {
   Smem s;
   int off = 0;
-  s.u0 = off; off += 2 * kTT * kUZRowBytes;
-  s.z0 = off; off += 2 * kTT * kUZRowBytes;
-  s.xstride = kTT * Xp * 2;
+  s.u0 = off; off += 2 * kTT * kRowBytes;
+  s.z0 = off; off += 2 * kTT * kRowBytes;
+  s.xstride = kTT * x_row_bytes(Xp);
   s.x0 = off; off += 2 * s.xstride;
-  s.bc = off; off += kTT * 2 * kN * 4;
-  s.dt = off; off += kTT * dt_stride(R) * 4;
-  s.y = off; off += kTT * kYRowBytes;
+  s.bc = off; off += kTT * 2 * kN * 4;          // [token][B0..15 | C0..15] fp32
+  s.dd = off; off += kTT * (kCh / 2) * 16;      // [token][channel pair]{delta0, delta1, du0, du1}
+  s.y = off; off += kTT * kRowBytes;
   s.total = off;
   return s;
 }
@@ -83,45 +85,96 @@ __device__ __forceinline__ float softplus_mufu(float x) {
 __device__ __forceinline__ float silu_tanh(float z) {
   return z * fmaf(tanh_approx(0.5f * z), 0.5f, 0.5f);
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-template <int R, bool kPacked>
+// One channel's 4 states of this lane for one token: h <- exp2(delta*A2)*h + du*B ; returns <C, h>.
+__device__ __forceinline__ float step4(float (&h)[4], const float (&A2)[4], float delta, float du,
+                                       const float4& Bv, const float4& Cv) {
+  const float2 d2 = make_float2(delta, delta), du2 = make_float2(du, du);
+  const float2 x01 = __fmul2_rn(d2, make_float2(A2[0], A2[1]));
+  const float2 x23 = __fmul2_rn(d2, make_float2(A2[2], A2[3]));
+  const float2 e01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
+  const float2 e23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
+  const float2 b01 = __fmul2_rn(du2, make_float2(Bv.x, Bv.y));
+  const float2 b23 = __fmul2_rn(du2, make_float2(Bv.z, Bv.w));
+  const float2 h01 = __ffma2_rn(e01, make_float2(h[0], h[1]), b01);
+  const float2 h23 = __ffma2_rn(e23, make_float2(h[2], h[3]), b23);
+  h[0] = h01.x; h[1] = h01.y; h[2] = h23.x; h[3] = h23.y;
+  float2 q = __fmul2_rn(h01, make_float2(Cv.x, Cv.y));
+  q = __ffma2_rn(h23, make_float2(Cv.z, Cv.w), q);
+  return q.x + q.y;
+}
+
+template <int R>
 __global__ void __launch_bounds__(kThreads, 6)
 scan_fast_kernel(const FastScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int X = R + 2 * kN;
-  constexpr int kDts = dt_stride(R);
-  const Smem sp = smem_plan(R, a.Xp);
+  constexpr int KST = (R + 15) / 16;           // k-steps of the dt projection
+  const Smem sp = smem_plan(a.Xp);
+  const int xrow = x_row_bytes(a.Xp);
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
 
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int j = tid & 3;                       // state quad [4j, 4j+4) and token slot in a group
-  const int cl = tid >> 2;                     // channel within the CTA
+  const int warp = tid >> 5, lane = tid & 31;
+  const int j = lane & 3;                      // state quad [4j, 4j+4) (phase B) / column pair (phase A)
+  const int pr = lane >> 2;                    // channel pair within the warp (phase B) / row (phase A)
   const int c0 = blockIdx.x * kCh;
-  const int c = c0 + cl;
+  const int cw = c0 + 16 * warp;               // first channel of this warp
   const int b = blockIdx.y;
   const int L = a.L;
   using bf16 = __nv_bfloat16;
 
   // ---- per-thread constants ---------------------------------------------------------------
-  float A2[4], h[4], w[R];
+  // phase B: channels ca = cw + 2 pr and ca + 1, states 4j .. 4j+3
+  const int ca = cw + 2 * pr;
+  float A2a[4], A2b[4], ha[4], hb[4];
   {
-    const float4 av = *reinterpret_cast<const float4*>(a.A2 + (int64_t)c * kN + 4 * j);
-    A2[0] = av.x; A2[1] = av.y; A2[2] = av.z; A2[3] = av.w;
-    const int64_t hoff = ((int64_t)b * a.Di + c) * kN + 4 * j;
-    if (a.h0 != nullptr) {
+    const float4 va = *reinterpret_cast<const float4*>(a.A2 + (int64_t)ca * kN + 4 * j);
+    const float4 vb = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(ca + 1) * kN + 4 * j);
+    A2a[0] = va.x; A2a[1] = va.y; A2a[2] = va.z; A2a[3] = va.w;
+    A2b[0] = vb.x; A2b[1] = vb.y; A2b[2] = vb.z; A2b[3] = vb.w;
+    const int64_t hoff = ((int64_t)b * a.Di + ca) * kN + 4 * j;
 #pragma unroll
-      for (int n = 0; n < 4; ++n) h[n] = load_as_f32(a.h0, hoff + n, a.h0_dtype);
-    } else {
-#pragma unroll
-      for (int n = 0; n < 4; ++n) h[n] = 0.f;
+    for (int n = 0; n < 4; ++n) {
+      ha[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
+      hb[n] = a.h0 ? load_as_f32(a.h0, hoff + kN + n, a.h0_dtype) : 0.f;
     }
-    const bf16* wr = reinterpret_cast<const bf16*>(a.w_dt_pad) + (int64_t)c * a.Rp;
-#pragma unroll
-    for (int r = 0; r < R; ++r) w[r] = __bfloat162float(wr[r]);
   }
-  const float Dv = a.D ? a.D[c] : 0.f;
-  const float bias = a.dt_bias ? a.dt_bias[c] : 0.f;
+  // finalising lane: channel ca + (j & 1)
+  const int cf = 16 * warp + 2 * pr + (j & 1);  // channel within the CTA
+  const float Dv = a.D ? a.D[c0 + cf] : 0.f;
+  // phase A: B fragments of w_dt^T for the two 8-channel n-tiles, and the dt bias of this lane's
+  // 4 accumulator columns: channels cw + 8 n + 2 j + {0, 1}
+  uint32_t bfrag[2][KST][2];
+  float bias[2][2];
+  {
+    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const bf16* wr = wd + (int64_t)(cw + 8 * n + pr) * a.Rp;   // B operand column = channel row
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * j);
+        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * j);
+      }
+      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j] : 0.f;
+      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j + 1] : 0.f;
+    }
+  }
 
   const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + c0;
   const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + c0;
@@ -132,20 +185,22 @@ scan_fast_kernel(const FastScanArgs a) {
 
   auto issue_tile = [&](int tile, int st) {
     const int t0 = tile * kTT;
-    {
-      const int row = tid >> 2, ch = tid & 3;  // 32 rows x 4 chunks of 8 channels
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {              // u / z: 32 rows x 4 chunks of 8 channels
+      const int e = tid + i * kThreads;
+      const int row = e >> 2, ch = e & 3;
       const int t = t0 + row;
       const bool ok = t < L;
-      const int64_t pr = ok ? phys(t) : 0;
-      cp_async16(sbase + sp.u(st) + row * kUZRowBytes + ch * 16, ug + pr * a.u_ts + ch * 8, ok);
-      cp_async16(sbase + sp.z(st) + row * kUZRowBytes + ch * 16, zg + pr * a.z_ts + ch * 8, ok);
+      const int64_t prow = ok ? phys(t) : 0;
+      cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + prow * a.u_ts + ch * 8, ok);
+      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + prow * a.z_ts + ch * 8, ok);
     }
     for (int e = tid; e < kTT * xchunks; e += kThreads) {
       const int row = e / xchunks, ch = e - row * xchunks;
       const int t = t0 + row;
       const bool ok = t < L;
-      const int64_t pr = ok ? phys(t) : 0;
-      cp_async16(sbase + sp.x(st) + (row * xchunks + ch) * 16, xg + pr * a.x_ts + ch * 8, ok);
+      const int64_t prow = ok ? phys(t) : 0;
+      cp_async16(sbase + sp.x(st) + row * xrow + ch * 16, xg + prow * a.x_ts + ch * 8, ok);
     }
   };
 
@@ -153,110 +208,101 @@ scan_fast_kernel(const FastScanArgs a) {
   issue_tile(0, 0);
   cp_async_commit();
 
+  float* const sbc = reinterpret_cast<float*>(smem + sp.bc);
+  float4* const sdd = reinterpret_cast<float4*>(smem + sp.dd);   // [token][16 pairs]
+  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
+
   for (int tile = 0; tile < ntiles; ++tile) {
     const int st = tile & 1;
     const int t0 = tile * kTT;
     if (tile + 1 < ntiles) issue_tile(tile + 1, st ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
-    __syncthreads();
+    __syncthreads();                           // tile landed; previous tile's sBC / sDD / sY readers done
 
-    // ---- expand this tile's x_dbl rows to fp32: dt_low -> sDT, [B | C] -> sBC ----------------
+    const bf16* su = reinterpret_cast<const bf16*>(smem + sp.u(st));
+    const bf16* sz = reinterpret_cast<const bf16*>(smem + sp.z(st));
+
+    // ---- expand B_t / C_t of the tile to fp32 ---------------------------------------------------
     {
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(smem + sp.x(st));
-      float* sdt = reinterpret_cast<float*>(smem + sp.dt);
-      float* sbc = reinterpret_cast<float*>(smem + sp.bc);
-      const int xw = a.Xp / 2;                 // 32-bit words per row
-      for (int e = tid; e < kTT * (X / 2); e += kThreads) {
-        const int row = e / (X / 2), p = e - row * (X / 2);
-        const uint32_t v = xr[row * xw + p];
-        const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
-        float* dst = (2 * p < R) ? sdt + row * kDts + 2 * p : sbc + row * (2 * kN) + (2 * p - R);
-        *reinterpret_cast<float2*>(dst) = make_float2(lo, hi);
+      const uint8_t* xr = smem + sp.x(st);
+#pragma unroll
+      for (int i = 0; i < (kTT * kN) / kThreads; ++i) {          // 32 tokens x 16 bf16 pairs
+        const int e = tid + i * kThreads;
+        const int row = e >> 4, p = e & 15;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(xr + row * xrow + (R + 2 * p) * 2);
+        *reinterpret_cast<float2*>(sbc + row * (2 * kN) + 2 * p) = make_float2(bf16lo(v), bf16hi(v));
       }
     }
-    __syncthreads();
 
-    // ---- the scan over the tile, 4 tokens per step -----------------------------------------------
+    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
     {
-      const bf16* su = reinterpret_cast<const bf16*>(smem + sp.u(st));
-      const bf16* sz = reinterpret_cast<const bf16*>(smem + sp.z(st));
-      const float* sdt = reinterpret_cast<const float*>(smem + sp.dt);
-      const float* sbc = reinterpret_cast<const float*>(smem + sp.bc);
-      bf16* sy = reinterpret_cast<bf16*>(smem + sp.y);
-      const int src0 = lane & ~3;
-#pragma unroll 2
-      for (int g = 0; g < kTT / 4; ++g) {
-        const int row = 4 * g + j;
-        // owner part: this lane's token of the group
-        const float uval = __bfloat162float(su[row * (kUZRowBytes / 2) + cl]);
-        const float zval = __bfloat162float(sz[row * (kUZRowBytes / 2) + cl]);
-        float acc0 = bias, acc1 = 0.f;
-        const float4* dtr = reinterpret_cast<const float4*>(sdt + row * kDts);
+      const uint32_t xs = sbase + sp.x(st);
 #pragma unroll
-        for (int r4 = 0; r4 < R / 4; ++r4) {
-          const float4 v = dtr[r4];
-          acc0 = fmaf(v.x, w[4 * r4 + 0], acc0);
-          acc1 = fmaf(v.y, w[4 * r4 + 1], acc1);
-          acc0 = fmaf(v.z, w[4 * r4 + 2], acc0);
-          acc1 = fmaf(v.w, w[4 * r4 + 3], acc1);
+      for (int m = 0; m < 2; ++m) {
+        float acc[2][4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KST; ++ks) {
+          uint32_t af[4];
+          const int row = 16 * m + (lane & 7) + 8 * ((lane >> 3) & 1);
+          ldmatrix_x4(xs + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
+          mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+          mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
         }
-        float delta = softplus_mufu(acc0 + acc1);
-        if (t0 + row >= L) delta = 0.f;        // padding token: decay 1, drive 0 -> state untouched
-        const float du = delta * uval;
-        const float gate = silu_tanh(zval);
-        const float skip = Dv * uval;
-
-        float p[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float dk = __shfl_sync(0xffffffffu, delta, src0 | k);
-          const float duk = __shfl_sync(0xffffffffu, du, src0 | k);
-          const float4 Bv = *reinterpret_cast<const float4*>(sbc + (4 * g + k) * (2 * kN) + 4 * j);
-          const float4 Cv = *reinterpret_cast<const float4*>(sbc + (4 * g + k) * (2 * kN) + kN + 4 * j);
-          if constexpr (kPacked) {
-            const float2 d2 = make_float2(dk, dk), du2 = make_float2(duk, duk);
-            const float2 x01 = __fmul2_rn(d2, make_float2(A2[0], A2[1]));
-            const float2 x23 = __fmul2_rn(d2, make_float2(A2[2], A2[3]));
-            const float2 e01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
-            const float2 e23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
-            const float2 b01 = __fmul2_rn(du2, make_float2(Bv.x, Bv.y));
-            const float2 b23 = __fmul2_rn(du2, make_float2(Bv.z, Bv.w));
-            const float2 h01 = __ffma2_rn(e01, make_float2(h[0], h[1]), b01);
-            const float2 h23 = __ffma2_rn(e23, make_float2(h[2], h[3]), b23);
-            h[0] = h01.x; h[1] = h01.y; h[2] = h23.x; h[3] = h23.y;
-            float2 q = __fmul2_rn(h01, make_float2(Cv.x, Cv.y));
-            q = __ffma2_rn(h23, make_float2(Cv.z, Cv.w), q);
-            p[k] = q.x + q.y;
-          } else {
-            const float e0 = ex2_approx(dk * A2[0]), e1 = ex2_approx(dk * A2[1]);
-            const float e2 = ex2_approx(dk * A2[2]), e3 = ex2_approx(dk * A2[3]);
-            h[0] = fmaf(e0, h[0], duk * Bv.x);
-            h[1] = fmaf(e1, h[1], duk * Bv.y);
-            h[2] = fmaf(e2, h[2], duk * Bv.z);
-            h[3] = fmaf(e3, h[3], duk * Bv.w);
-            p[k] = fmaf(h[0], Cv.x, h[1] * Cv.y) + fmaf(h[2], Cv.z, h[3] * Cv.w);
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int tl = 16 * m + pr + 8 * half;               // token row within the tile
+            float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
+            float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
+            if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }            // padding: decay 1, drive 0
+            const uint32_t uv = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const uint8_t*>(su) + tl * kRowBytes + (16 * warp + 8 * n + 2 * j) * 2);
+            sdd[tl * (kCh / 2) + 8 * warp + 4 * n + j] =
+                make_float4(d0, d1, d0 * bf16lo(uv), d1 * bf16hi(uv));
           }
-        }
-        // transpose-reduce: lane j ends up with sum over the 4 lanes of p[j]
-        const bool odd = j & 1, hi2 = j & 2;
-        const float keep0 = odd ? p[1] : p[0], send0 = odd ? p[0] : p[1];
-        const float keep1 = odd ? p[3] : p[2], send1 = odd ? p[2] : p[3];
-        const float q0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);
-        const float q1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
-        const float keep = hi2 ? q1 : q0, send = hi2 ? q0 : q1;
-        const float ysum = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        sy[row * (kYRowBytes / 2) + cl] = __float2bfloat16_rn((ysum + skip) * gate);
       }
+    }
+    __syncthreads();                           // sBC (both warps) and sDD visible
+
+    // ---- phase B: the recurrence, 2 tokens per step ----------------------------------------------
+#pragma unroll 2
+    for (int tt = 0; tt < kTT; tt += 2) {
+      float ys[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int t = tt + s;
+        const float4 dd = sdd[t * (kCh / 2) + 8 * warp + pr];
+        const float4 Bv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + 4 * j);
+        const float4 Cv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + kN + 4 * j);
+        const float pa = step4(ha, A2a, dd.x, dd.z, Bv, Cv);
+        const float pb = step4(hb, A2b, dd.y, dd.w, Bv, Cv);
+        const bool odd = j & 1;
+        float q = (odd ? pb : pa) + __shfl_xor_sync(0xffffffffu, odd ? pa : pb, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        ys[s] = q;                             // y of channel ca + (j & 1) at token t, in all 4 lanes
+      }
+      const int tf = tt + (j >> 1);            // this lane finalises (token tf, channel cf)
+      const float yv = (j >> 1) ? ys[1] : ys[0];
+      const float uval = __bfloat162float(su[tf * (kRowBytes / 2) + cf]);
+      const float zval = __bfloat162float(sz[tf * (kRowBytes / 2) + cf]);
+      sy[tf * (kRowBytes / 2) + cf] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_tanh(zval));
     }
     __syncthreads();
 
     // ---- y tile out: 32 rows x 64 bytes as 16-byte stores ------------------------------------------
-    {
-      const int row = tid >> 2, ch = tid & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * kThreads;
+      const int row = e >> 2, ch = e & 3;
       const int t = t0 + row;
       if (t < L) {
-        const uint4 v = *reinterpret_cast<const uint4*>(smem + sp.y + row * kYRowBytes + ch * 16);
+        const uint4 v = *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
         *reinterpret_cast<uint4*>(yg + phys(t) * a.y_ts + ch * 8) = v;
       }
     }
@@ -264,8 +310,9 @@ scan_fast_kernel(const FastScanArgs a) {
   }
 
   if (a.h_last != nullptr) {
-    *reinterpret_cast<float4*>(a.h_last + ((int64_t)b * a.Di + c) * kN + 4 * j) =
-        make_float4(h[0], h[1], h[2], h[3]);
+    float* hl = a.h_last + ((int64_t)b * a.Di + ca) * kN + 4 * j;
+    *reinterpret_cast<float4*>(hl) = make_float4(ha[0], ha[1], ha[2], ha[3]);
+    *reinterpret_cast<float4*>(hl + kN) = make_float4(hb[0], hb[1], hb[2], hb[3]);
   }
 }
 
@@ -279,13 +326,12 @@ int variant() {
 
 template <int R>
 int launch(const FastScanArgs& a, cudaStream_t st) {
-  const Smem sp = smem_plan(R, a.Xp);
+  const Smem sp = smem_plan(a.Xp);
   dim3 grid(a.Di / kCh, a.B);
-  const bool packed = (variant() & 1) == 0;
-  auto kern = packed ? scan_fast_kernel<R, true> : scan_fast_kernel<R, false>;
   if (sp.total > 48 * 1024)
-    VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-  kern<<<grid, kThreads, sp.total, st>>>(a);
+    VMB_CUDA(cudaFuncSetAttribute(scan_fast_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sp.total));
+  scan_fast_kernel<R><<<grid, kThreads, sp.total, st>>>(a);
   VMB_LAUNCH_CHECK("scan_fast_kernel");
   return VMB_OK;
 }
@@ -295,8 +341,10 @@ int launch(const FastScanArgs& a, cudaStream_t st) {
 bool scan_fast_supported(const FastScanArgs& a) {
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   const bool r_ok = a.R == 12 || a.R == 24 || a.R == 36;
+  const int kst16 = (a.R + 15) / 16 * 16;      // dt projection reads x_dbl / w_dt columns [0, kst16)
   return a.N == kN && r_ok && a.Di % kCh == 0 && a.Xp % 8 == 0 && a.Xp >= a.R + 2 * kN &&
-         a.Rp >= a.R && a.B >= 1 && a.B <= 65535 && a.L >= 1 && a.w_dt_pad != nullptr &&
+         a.Xp >= kst16 && a.Rp >= kst16 && a.Rp % 2 == 0 && a.B >= 1 && a.B <= 65535 && a.L >= 1 &&
+         a.w_dt_pad != nullptr && reinterpret_cast<uintptr_t>(a.w_dt_pad) % 4 == 0 &&
          al16(a.u) && al16(a.z) && al16(a.xdbl) && al16(a.y) && al16(a.A2) &&
          (a.h_last == nullptr || al16(a.h_last)) &&
          a.u_bs % 8 == 0 && a.u_ts % 8 == 0 && a.z_bs % 8 == 0 && a.z_ts % 8 == 0 &&

@@ -235,7 +235,11 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
     _require_cuda(u)
     lib = _lib.load()
     u, z, xdbl = _token_major(u), _token_major(z), _token_major(xdbl)
-    w_dt = w_dt if w_dt.stride(-1) == 1 else w_dt.contiguous()
+    rp = (dt_rank + 15) // 16 * 16      # the kernel reads whole 16-wide k-steps: zero-pad the rank
+    if w_dt.shape[1] < rp or w_dt.stride(-1) != 1 or bool((w_dt[:, dt_rank:] != 0).any()):
+        padded = torch.zeros((w_dt.shape[0], rp), dtype=w_dt.dtype, device=w_dt.device)
+        padded[:, :dt_rank] = w_dt[:, :dt_rank]
+        w_dt = padded
     B, L, Di = u.shape
     y = torch.empty((B, L, Di), dtype=u.dtype, device=u.device)
     h_last = torch.empty((B, Di, d_state), dtype=torch.float32, device=u.device) if want_last else None
