@@ -10,12 +10,14 @@
 namespace vmb {
 namespace {
 
-constexpr int kChunk = 64;  // tokens per CTA along the sequence
+constexpr int kChunk = 16;  // tokens per thread along the sequence
 
 template <typename T, int VEC> struct VecIO;
 template <> struct VecIO<float, 4> {
-  static __device__ __forceinline__ void load(const float* p, float* f) {
-    const float4 v = *reinterpret_cast<const float4*>(p);
+  using raw = float4;
+  static __device__ __forceinline__ raw ldg(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ void unpack(const raw& v, float* f) {
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
   }
   static __device__ __forceinline__ void store(float* p, const float* f) {
@@ -23,14 +25,15 @@ template <> struct VecIO<float, 4> {
   }
 };
 template <> struct VecIO<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
+  using raw = uint4;
+  static __device__ __forceinline__ raw ldg(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const raw& v, float* f) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-      f[2 * i] = __low2float(h);
-      f[2 * i + 1] = __high2float(h);
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* f) {
@@ -44,22 +47,38 @@ template <> struct VecIO<__nv_bfloat16, 8> {
   }
 };
 template <typename T> struct VecIO<T, 1> {
-  static __device__ __forceinline__ void load(const T* p, float* f) { f[0] = to_f32<T>(*p); }
+  using raw = T;
+  static __device__ __forceinline__ raw ldg(const T* p) { return *p; }
+  static __device__ __forceinline__ raw zero() { return from_f32<T>(0.f); }
+  static __device__ __forceinline__ void unpack(const raw& v, float* f) { f[0] = to_f32<T>(v); }
   static __device__ __forceinline__ void store(T* p, const float* f) { *p = from_f32<T>(f[0]); }
 };
 
+// A thread owns VEC consecutive channels and kChunk consecutive tokens.  All kChunk + W - 1 input
+// rows of the chunk are requested before any arithmetic (independent 128-bit loads in flight),
+// then the W-tap window slides down the rows held in registers.
 template <typename T, int VEC, int W, bool kAccurate>
 __global__ void __launch_bounds__(128)
 conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* __restrict__ weight,
                   const T* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
                   T* __restrict__ y, int64_t y_bs, int64_t y_ts, void* __restrict__ cs_out,
                   int cs_out_dtype, int L, int Di, int silu, int reverse) {
+  using IO = VecIO<T, VEC>;
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c0 >= Di) return;
   const int b = blockIdx.z;
   const int t0 = blockIdx.y * kChunk;
-  const int t1 = min(t0 + kChunk, L);
+  const T* xb = x + (int64_t)b * x_bs + c0;
+  T* yb = y + (int64_t)b * y_bs + c0;
+  auto row = [&](int i) -> int64_t { return reverse ? (int64_t)(L - 1 - i) : (int64_t)i; };
 
+  // rows t0 - (W-1) .. t0 + kChunk - 1 of the logical sequence (negative: carried state / zeros)
+  typename IO::raw raw[kChunk + W - 1];
+#pragma unroll
+  for (int i = 0; i < kChunk + W - 1; ++i) {
+    const int t = t0 + i - (W - 1);
+    raw[i] = (t >= 0 && t < L) ? IO::ldg(xb + row(t) * x_ts) : IO::zero();
+  }
   float w[VEC][W], bv[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -67,33 +86,28 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* 
     for (int k = 0; k < W; ++k) w[v][k] = to_f32<T>(weight[(int64_t)(c0 + v) * W + k]);
     bv[v] = bias ? to_f32<T>(bias[c0 + v]) : 0.f;
   }
-  const T* xb = x + (int64_t)b * x_bs + c0;
-  T* yb = y + (int64_t)b * y_bs + c0;
-  auto row = [&](int i) -> int64_t { return reverse ? (int64_t)(L - 1 - i) : (int64_t)i; };
-  // logical history element i (may be negative => carried state or zero)
-  auto load_hist = [&](int i, float* f) {
-    if (i >= 0) {
-      VecIO<T, VEC>::load(xb + row(i) * x_ts, f);
-    } else if (cs_in != nullptr) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v)
-        f[v] = load_as_f32(cs_in, ((int64_t)b * Di + c0 + v) * W + (W + i), cs_in_dtype);
-    } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) f[v] = 0.f;
-    }
-  };
 
   float win[W][VEC];  // win[k] = hist[t + k - (W-1)]
 #pragma unroll
-  for (int k = 0; k < W - 1; ++k) load_hist(t0 + k - (W - 1), win[k + 1]);
-#pragma unroll 4
-  for (int t = t0; t < t1; ++t) {
+  for (int k = 0; k < W - 1; ++k) {
+    const int t = t0 + k - (W - 1);
+    if (t < 0 && cs_in != nullptr) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        win[k + 1][v] = load_as_f32(cs_in, ((int64_t)b * Di + c0 + v) * W + (W + t), cs_in_dtype);
+    } else {
+      IO::unpack(raw[k], win[k + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kChunk; ++i) {
+    const int t = t0 + i;
+    if (t >= L) break;
 #pragma unroll
     for (int k = 0; k < W - 1; ++k)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) win[k][v] = win[k + 1][v];
-    VecIO<T, VEC>::load(xb + row(t) * x_ts, win[W - 1]);
+    IO::unpack(raw[i + W - 1], win[W - 1]);
     float o[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -102,15 +116,25 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* 
       for (int k = 0; k < W; ++k) acc = fmaf(w[v][k], win[k][v], acc);
       o[v] = silu ? silu_f<kAccurate>(acc) : acc;
     }
-    VecIO<T, VEC>::store(yb + row(t) * y_ts, o);
+    IO::store(yb + row(t) * y_ts, o);
   }
 
   // The CTA that owns the final chunk also emits the next conv state: hist[L-W .. L-1].
-  if (cs_out != nullptr && t1 == L) {
+  if (cs_out != nullptr && t0 < L && t0 + kChunk >= L) {
 #pragma unroll
     for (int k = 0; k < W; ++k) {
+      const int t = L - W + k;
       float f[VEC];
-      load_hist(L - W + k, f);
+      if (t >= 0) {
+        IO::unpack(IO::ldg(xb + row(t) * x_ts), f);
+      } else if (cs_in != nullptr) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          f[v] = load_as_f32(cs_in, ((int64_t)b * Di + c0 + v) * W + (W + t), cs_in_dtype);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) f[v] = 0.f;
+      }
 #pragma unroll
       for (int v = 0; v < VEC; ++v)
         store_from_f32(cs_out, ((int64_t)b * Di + c0 + v) * W + k, cs_out_dtype, f[v]);
