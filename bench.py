@@ -211,7 +211,6 @@ def run_ours(args):
     import torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun the way the driver does
@@ -222,12 +221,11 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
 
     from videomamba_b200 import _lib
+    from videomamba_b200.replica import init_replica_group
+    grp = init_replica_group(device=dev)      # NCCL: barrier + max-over-ranks of the timing only
+    rank = grp.rank
     lib = _lib.load()
 
     dtype = torch.bfloat16
@@ -239,16 +237,10 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+        grp.barrier(dev)
 
     def max_over_ranks(v: float) -> float:
-        if dist is None:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return grp.max_over_ranks(v, dev)
 
     def fwd(x):
         with torch.no_grad():
@@ -285,29 +277,55 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the public API with host buffers ("e2e") ----------------------------
+    # A double-buffered serving loop: step i+1's clips are copied host->device on a copy stream
+    # while step i computes, and step i's features go device->host on a second copy stream.  Every
+    # step's input copy and result copy are inside the timed region.
     vis0, pool0 = out
     vis_host = torch.empty(vis0.shape, dtype=vis0.dtype).pin_memory()
     pool_host = torch.empty(pool0.shape, dtype=pool0.dtype).pin_memory()
-    x_in = torch.empty_like(x_dev)
+    x_in = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    comp = torch.cuda.current_stream()
+    h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def e2e_step():
-        x_in.copy_(x_host, non_blocking=True)
-        vis, pool = fwd(x_in)
-        vis_host.copy_(vis, non_blocking=True)
-        pool_host.copy_(pool, non_blocking=True)
+    def e2e_loop(n):
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [None, None]
+        with torch.cuda.stream(h2d):
+            x_in[0].copy_(x_host, non_blocking=True)
+            ready[0].record(h2d)
+        last_out = None
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                with torch.cuda.stream(h2d):
+                    if done[b ^ 1] is not None:
+                        h2d.wait_event(done[b ^ 1])       # the forward that read this buffer is finished
+                    x_in[b ^ 1].copy_(x_host, non_blocking=True)
+                    ready[b ^ 1].record(h2d)
+            comp.wait_event(ready[b])
+            vis, pool = fwd(x_in[b])
+            done[b] = torch.cuda.Event()
+            done[b].record(comp)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done[b])
+                vis.record_stream(d2h)
+                pool.record_stream(d2h)
+                vis_host.copy_(vis, non_blocking=True)
+                pool_host.copy_(pool, non_blocking=True)
+                last_out = torch.cuda.Event()
+                last_out.record(d2h)
+        comp.wait_event(last_out)
 
-    for _ in range(2):
-        e2e_step()
+    e2e_loop(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    h2d = x_host.numel() * x_host.element_size()
-    d2h = vis_host.numel() * vis_host.element_size() + pool_host.numel() * pool_host.element_size()
+    h2d_bytes = x_host.numel() * x_host.element_size()
+    d2h_bytes = vis_host.numel() * vis_host.element_size() + pool_host.numel() * pool_host.element_size()
 
     # ---- roofline of the dominant HBM kernel (the selective scan) --------------------------------
     peaks = {}
@@ -332,15 +350,25 @@ def run_ours(args):
         # op-level selective_scan_fn: reads u, delta, z, B, C; writes y
         bytes_per_token = 4 * Di * es + 2 * N * es
         kernel = "scan_generic_kernel (softplus + scan + D skip + SiLU gate)"
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        wl = tr["workload"]
+        if fused and (wl["B"], wl["L"], wl["Di"]) == (B, L, Di):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]     # per launch, from ncu
+    except Exception:
+        pass
     roofline = None
     if "scan" in stages and stages["scan"]["launches_per_step"]:
         per_launch_ms = stages["scan"]["ms_per_step"] / stages["scan"]["launches_per_step"]
         achieved = tokens * bytes_per_token / (per_launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": tokens * bytes_per_token,
                     "ms_per_launch": per_launch_ms, "peak_source": peak_src,
-                    "share_of_step": stages["scan"]["ms_per_step"] / ms_per_step}
+                    "share_of_step": stages["scan"]["ms_per_step"] / ms_per_step,
+                    "note": "kernel is bound by instruction issue / MUFU ex2 (16 per token-channel), "
+                            "not by HBM: see DESIGN.md 3.2 and profiles/r01_mufu_issue_microbench.txt"}
     # projections against the tensor roofline (reported beside, not the dominant-kernel object)
     tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     D = mixer.d_model
@@ -354,8 +382,7 @@ def run_ours(args):
             tensor[k] = {"tflops": tf, "frac_of_sustained_peak": tf / tc_peak}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        grp.close()
         return 0
 
     cpu = None
@@ -373,8 +400,9 @@ def run_ours(args):
                    "parallelism": f"batch-sharded replicas x{world}, no collective",
                    "l2": "per-step working set (>= 150 MB of activations per layer) exceeds the 126 MB L2"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps,
+                "pipeline": "double-buffered H2D / compute / D2H on three streams"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -382,8 +410,7 @@ def run_ours(args):
         "tensor": tensor,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    grp.close()
     return 0
 
 
