@@ -11,9 +11,11 @@
 // The kernel is bound by MUFU ex2 throughput, instruction issue and shared-memory bandwidth, not
 // by HBM (DESIGN.md "scan"), so the layout minimises instructions and smem bytes per (token,
 // channel):
-//   * CTA = (batch b, 32 channels), 64 threads (2 warps x 16 channels); the sequence is walked in
-//     tiles of 32 tokens staged with 16-byte cp.async copies, double buffered.
-//   * phase A (per tile, per warp): the dt projection of the tile, delta_raw[32 tokens x 16
+//   * CTA = ONE warp = (batch b, 16 channels); the sequence is walked in tiles of 16 tokens staged
+//     with 16-byte cp.async copies (u / z double buffered).  One-warp CTAs need no block barriers,
+//     drift out of phase with each other (so some warp always has MUFU work ready), and 1536 of
+//     them spread over 148 SMs within 6 % of even (768 two-warp CTAs: 14 % idle tail).
+//   * phase A (per tile, per warp): the dt projection of the tile, delta_raw[16 tokens x 16
 //     channels] = dt_low[32 x R] * w_dt^T, runs on the tensor pipe (mma.sync m16n8k16, the A
 //     fragments come straight from the staged bf16 x_dbl rows via ldmatrix, w_dt fragments stay in
 //     registers); softplus and delta*u are applied to the accumulator fragments, which are
@@ -32,28 +34,27 @@
 namespace vmb {
 namespace {
 
-constexpr int kCh = 32;                 // channels per CTA
-constexpr int kThreads = 64;            // 2 warps x (8 channel pairs x 4 state quads)
-constexpr int kTT = 32;                 // tokens per tile
-constexpr int kRowBytes = 80;           // u / z / y tile rows: 64 B of channels + 16 B pad
+constexpr int kCh = 16;                 // channels per CTA (one warp: 8 channel pairs x 4 state quads)
+constexpr int kThreads = 32;
+constexpr int kTT = 16;                 // tokens per tile
+constexpr int kRowBytes = 48;           // u / z / y tile rows: 32 B of channels + 16 B pad
 constexpr int kN = 16;
 
 // x_dbl tile row pitch in bytes: an odd number of 16-byte chunks keeps ldmatrix conflict free
 __host__ __device__ constexpr int x_row_bytes(int Xp) { return ((Xp / 8) % 2 == 1) ? Xp * 2 : Xp * 2 + 16; }
 
-struct Smem {   // byte offsets; u / z / x are double buffered: stage s lives at base + s * stride
-  int u0, z0, x0, xstride, bc, dd, y, total;
+struct Smem {   // byte offsets; u / z are double buffered (stage s at base + s * stride); the raw
+                // x_dbl rows are consumed at the start of a tile, so one buffer is refilled right after
+  int u0, z0, x0, bc, dd, y, total;
   __host__ __device__ int u(int s) const { return u0 + s * (kTT * kRowBytes); }
   __host__ __device__ int z(int s) const { return z0 + s * (kTT * kRowBytes); }
-  __host__ __device__ int x(int s) const { return x0 + s * xstride; }
 };
 __host__ __device__ inline Smem smem_plan(int Xp) {
   Smem s;
   int off = 0;
   s.u0 = off; off += 2 * kTT * kRowBytes;
   s.z0 = off; off += 2 * kTT * kRowBytes;
-  s.xstride = kTT * x_row_bytes(Xp);
-  s.x0 = off; off += 2 * s.xstride;
+  s.x0 = off; off += kTT * x_row_bytes(Xp);
   s.bc = off; off += kTT * 2 * kN * 4;          // [token][B0..15 | C0..15] fp32
   s.dd = off; off += kTT * (kCh / 2) * 16;      // [token][channel pair]{delta0, delta1, du0, du1}
   s.y = off; off += kTT * kRowBytes;
@@ -74,12 +75,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// softplus with the reference's semantics (identity above 20 falls out of the formula in fp32)
+// softplus(x) = max(x, 0) + log1p(exp(-|x|)).  log1p through lg2(1 + e): its absolute error is
+// <= 1 ulp of 1.0 (6e-8), which is what matters for a step size that enters exp(delta*A) and
+// delta*u linearly; identity above 20 (the reference's threshold) falls out in fp32.
 __device__ __forceinline__ float softplus_mufu(float x) {
-  const float e = ex2_approx(-fabsf(x) * kLog2e);                       // exp(-|x|) in (0, 1]
-  const float big = lg2_approx(1.f + e) * kLn2;                         // log1p(e), e not tiny
-  const float small = e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.f);    // e - e^2/2 + e^3/3
-  return fmaxf(x, 0.f) + (e < 0.015625f ? small : big);
+  const float e = ex2_approx(-fabsf(x) * kLog2e);
+  return fmaf(lg2_approx(1.f + e), kLn2, fmaxf(x, 0.f));
 }
 // z * sigmoid(z) with sigmoid(z) = 0.5 * tanh(z / 2) + 0.5 (one MUFU)
 __device__ __forceinline__ float silu_tanh(float z) {
@@ -120,7 +121,7 @@ __device__ __forceinline__ float step4(float (&h)[4], const float (&A2)[4], floa
 }
 
 template <int R>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, 16)
 scan_fast_kernel(const FastScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int KST = (R + 15) / 16;           // k-steps of the dt projection
@@ -128,12 +129,10 @@ scan_fast_kernel(const FastScanArgs a) {
   const int xrow = x_row_bytes(a.Xp);
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int lane = threadIdx.x;
   const int j = lane & 3;                      // state quad [4j, 4j+4) (phase B) / column pair (phase A)
-  const int pr = lane >> 2;                    // channel pair within the warp (phase B) / row (phase A)
-  const int c0 = blockIdx.x * kCh;
-  const int cw = c0 + 16 * warp;               // first channel of this warp
+  const int pr = lane >> 2;                    // channel pair (phase B) / accumulator row (phase A)
+  const int cw = blockIdx.x * kCh;             // first channel of this warp
   const int b = blockIdx.y;
   const int L = a.L;
   using bf16 = __nv_bfloat16;
@@ -155,8 +154,8 @@ scan_fast_kernel(const FastScanArgs a) {
     }
   }
   // finalising lane: channel ca + (j & 1)
-  const int cf = 16 * warp + 2 * pr + (j & 1);  // channel within the CTA
-  const float Dv = a.D ? a.D[c0 + cf] : 0.f;
+  const int cf = 2 * pr + (j & 1);             // channel within the CTA
+  const float Dv = a.D ? a.D[cw + cf] : 0.f;
   // phase A: B fragments of w_dt^T for the two 8-channel n-tiles, and the dt bias of this lane's
   // 4 accumulator columns: channels cw + 8 n + 2 j + {0, 1}
   uint32_t bfrag[2][KST][2];
@@ -176,59 +175,56 @@ scan_fast_kernel(const FastScanArgs a) {
     }
   }
 
-  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + c0;
-  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + c0;
+  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
+  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
   const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
-  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + c0;
+  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
   const int xchunks = a.Xp / 8;                // 16-byte chunks per x_dbl row
   auto phys = [&](int t) -> int64_t { return a.reverse ? (int64_t)(L - 1 - t) : (int64_t)t; };
 
-  auto issue_tile = [&](int tile, int st) {
-    const int t0 = tile * kTT;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {              // u / z: 32 rows x 4 chunks of 8 channels
-      const int e = tid + i * kThreads;
-      const int row = e >> 2, ch = e & 3;
-      const int t = t0 + row;
-      const bool ok = t < L;
-      const int64_t prow = ok ? phys(t) : 0;
-      cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + prow * a.u_ts + ch * 8, ok);
-      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + prow * a.z_ts + ch * 8, ok);
-    }
-    for (int e = tid; e < kTT * xchunks; e += kThreads) {
-      const int row = e / xchunks, ch = e - row * xchunks;
-      const int t = t0 + row;
-      const bool ok = t < L;
-      const int64_t prow = ok ? phys(t) : 0;
-      cp_async16(sbase + sp.x(st) + row * xrow + ch * 16, xg + prow * a.x_ts + ch * 8, ok);
-    }
+  // a lane copies one 16-byte chunk of u and of z (16 rows x 2 chunks) ...
+  auto issue_uz = [&](int tile, int st) {
+    const int row = lane >> 1, ch = lane & 1;
+    const int t = tile * kTT + row;
+    const bool ok = t < L;
+    const int64_t prow = ok ? phys(t) : 0;
+    cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + prow * a.u_ts + ch * 8, ok);
+    cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + prow * a.z_ts + ch * 8, ok);
+  };
+  // ... and every other chunk of one x_dbl row (16 rows x 2 lanes)
+  auto issue_x = [&](int tile) {
+    const int row = lane >> 1;
+    const int t = tile * kTT + row;
+    const bool ok = t < L;
+    const bf16* src = xg + (ok ? phys(t) : 0) * a.x_ts;
+    for (int ch = lane & 1; ch < xchunks; ch += 2)
+      cp_async16(sbase + sp.x0 + row * xrow + ch * 16, src + ch * 8, ok);
   };
 
   const int ntiles = (L + kTT - 1) / kTT;
-  issue_tile(0, 0);
+  issue_uz(0, 0);
+  issue_x(0);
   cp_async_commit();
 
   float* const sbc = reinterpret_cast<float*>(smem + sp.bc);
-  float4* const sdd = reinterpret_cast<float4*>(smem + sp.dd);   // [token][16 pairs]
+  float4* const sdd = reinterpret_cast<float4*>(smem + sp.dd);   // [token][8 pairs]
   bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int st = tile & 1;
     const int t0 = tile * kTT;
-    if (tile + 1 < ntiles) issue_tile(tile + 1, st ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();                           // tile landed; previous tile's sBC / sDD / sY readers done
+    cp_async_wait<0>();
+    __syncwarp();                              // tile landed; last tile's smem readers are done
 
     const bf16* su = reinterpret_cast<const bf16*>(smem + sp.u(st));
     const bf16* sz = reinterpret_cast<const bf16*>(smem + sp.z(st));
 
     // ---- expand B_t / C_t of the tile to fp32 ---------------------------------------------------
     {
-      const uint8_t* xr = smem + sp.x(st);
+      const uint8_t* xr = smem + sp.x0;
 #pragma unroll
-      for (int i = 0; i < (kTT * kN) / kThreads; ++i) {          // 32 tokens x 16 bf16 pairs
-        const int e = tid + i * kThreads;
+      for (int i = 0; i < (kTT * kN) / kThreads; ++i) {          // 16 tokens x 16 bf16 pairs
+        const int e = lane + i * kThreads;
         const int row = e >> 4, p = e & 15;
         const uint32_t v = *reinterpret_cast<const uint32_t*>(xr + row * xrow + (R + 2 * p) * 2);
         *reinterpret_cast<float2*>(sbc + row * (2 * kN) + 2 * p) = make_float2(bf16lo(v), bf16hi(v));
@@ -237,38 +233,38 @@ scan_fast_kernel(const FastScanArgs a) {
 
     // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
     {
-      const uint32_t xs = sbase + sp.x(st);
+      float acc[2][4];
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        float acc[2][4];
+      for (int n = 0; n < 2; ++n)
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
+        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KST; ++ks) {
-          uint32_t af[4];
-          const int row = 16 * m + (lane & 7) + 8 * ((lane >> 3) & 1);
-          ldmatrix_x4(xs + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
-          mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-          mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-        }
-#pragma unroll
-        for (int n = 0; n < 2; ++n)
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int tl = 16 * m + pr + 8 * half;               // token row within the tile
-            float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
-            float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
-            if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }            // padding: decay 1, drive 0
-            const uint32_t uv = *reinterpret_cast<const uint32_t*>(
-                reinterpret_cast<const uint8_t*>(su) + tl * kRowBytes + (16 * warp + 8 * n + 2 * j) * 2);
-            sdd[tl * (kCh / 2) + 8 * warp + 4 * n + j] =
-                make_float4(d0, d1, d0 * bf16lo(uv), d1 * bf16hi(uv));
-          }
+      for (int ks = 0; ks < KST; ++ks) {
+        uint32_t af[4];
+        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
+        ldmatrix_x4(sbase + sp.x0 + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
+        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
       }
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int tl = pr + 8 * half;                          // token row within the tile
+          float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
+          float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
+          if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }              // padding: decay 1, drive 0
+          const uint32_t uv = *reinterpret_cast<const uint32_t*>(
+              reinterpret_cast<const uint8_t*>(su) + tl * kRowBytes + (8 * n + 2 * j) * 2);
+          sdd[tl * (kCh / 2) + 4 * n + j] = make_float4(d0, d1, d0 * bf16lo(uv), d1 * bf16hi(uv));
+        }
     }
-    __syncthreads();                           // sBC (both warps) and sDD visible
+    __syncwarp();                              // sBC / sDD visible; raw x_dbl rows no longer needed
+    if (tile + 1 < ntiles) {                   // prefetch the next tile behind the recurrence
+      issue_uz(tile + 1, st ^ 1);
+      issue_x(tile + 1);
+    }
+    cp_async_commit();
 
     // ---- phase B: the recurrence, 2 tokens per step ----------------------------------------------
 #pragma unroll 2
@@ -277,7 +273,7 @@ scan_fast_kernel(const FastScanArgs a) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const int t = tt + s;
-        const float4 dd = sdd[t * (kCh / 2) + 8 * warp + pr];
+        const float4 dd = sdd[t * (kCh / 2) + pr];
         const float4 Bv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + 4 * j);
         const float4 Cv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + kN + 4 * j);
         const float pa = step4(ha, A2a, dd.x, dd.z, Bv, Cv);
@@ -293,20 +289,18 @@ scan_fast_kernel(const FastScanArgs a) {
       const float zval = __bfloat162float(sz[tf * (kRowBytes / 2) + cf]);
       sy[tf * (kRowBytes / 2) + cf] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_tanh(zval));
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- y tile out: 32 rows x 64 bytes as 16-byte stores ------------------------------------------
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int e = tid + i * kThreads;
-      const int row = e >> 2, ch = e & 3;
+    // ---- y tile out: 16 rows x 32 bytes as 16-byte stores ------------------------------------------
+    {
+      const int row = lane >> 1, ch = lane & 1;
       const int t = t0 + row;
       if (t < L) {
         const uint4 v = *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
         *reinterpret_cast<uint4*>(yg + phys(t) * a.y_ts + ch * 8) = v;
       }
     }
-    // the next iteration's first __syncthreads orders these reads of sY before its next writes
+    // the __syncwarp at the top of the next iteration orders these reads before the next writes
   }
 
   if (a.h_last != nullptr) {
