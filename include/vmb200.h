@@ -157,7 +157,12 @@ typedef struct vmb_fused_scan_args {
   float* h_last;                                         /* (B,Di,N) fp32, nullable */
   int32_t B, L, Di, N, R, Rp, Xp;
   int32_t reverse;
+  /* optional scratch of vmb_fused_scan_workspace_bytes(...) bytes (device, 16-byte aligned): lets
+   * small batches split the sequence into concurrently processed segments (exact two-pass carry);
+   * without it the call still works, one warp per 16 channels of a sequence. */
+  void* workspace;    int64_t workspace_bytes;
 } vmb_fused_scan_args;
+VMB_API int64_t vmb_fused_scan_workspace_bytes(int B, int L, int Di, int N);
 VMB_API int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* args, vmb_stream_t stream);
 
 /* Single recurrent step, state (B,Di,N) updated in place.  Replaces

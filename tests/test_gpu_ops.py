@@ -253,27 +253,71 @@ def test_fused_scan_against_float64(geom, reverse):
     assert rel_err(got, want) <= 6e-3
 
 
-def test_fused_scan_chunk_carry_at_full_length():
-    """Size-independent property at the long-clip size (25 089 tokens): scanning in three chunks
-    with the state carried equals one pass, bit for bit (the kernel is sequential in t)."""
-    gen = torch.Generator().manual_seed(9)
+def _scan_inputs(Bsz, L, Di=768, R=24, Xp=64, N=16, seed=9):
+    gen = torch.Generator().manual_seed(seed)
     bf = torch.bfloat16
-    Bsz, L, Di, R, Xp, N = 1, 25089, 768, 24, 64, 16
     u = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
     z = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
     xdbl = _rand(gen, Bsz, L, Xp, dtype=bf).to(DEV)
     w_dt = _rand(gen, Di, R, dtype=bf, scale=R ** -0.5).to(DEV)
-    A2 = (-torch.arange(1, N + 1).float().repeat(Di, 1) * ops.LOG2E).to(DEV)
+    A2 = (-torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Di, 1)
+                     + 0.1 * torch.randn(Di, N, generator=gen)) * ops.LOG2E).to(DEV)
     Dp = torch.ones(Di, device=DEV)
     bias = torch.full((Di,), -3.0, device=DEV)
+    return u, z, xdbl, w_dt, A2, Dp, bias
+
+
+def test_fused_scan_chunk_carry_is_bitwise():
+    """Size-independent property: scanning in three chunks with the state carried equals one pass,
+    bit for bit (batch large enough that the kernel walks each sequence with one warp)."""
+    Bsz, L, R, N = 26, 1500, 24, 16
+    u, z, xdbl, w_dt, A2, Dp, bias = _scan_inputs(Bsz, L)
     full, h_full = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, want_last=True)
     h, parts = None, []
-    for lo, hi in ((0, 7000), (7000, 7001), (7001, L)):
+    for lo, hi in ((0, 700), (700, 701), (701, L)):
         y, h = ops.selective_scan_fused_tokens(u[:, lo:hi], z[:, lo:hi], xdbl[:, lo:hi], w_dt, A2, R,
                                                N, Dp, bias, h, want_last=True)
         parts.append(y)
     assert torch.equal(torch.cat(parts, 1), full) and torch.equal(h, h_full)
-    assert torch.isfinite(full.float()).all()
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_fused_scan_sequence_split_at_long_clip_size(reverse):
+    """Long-clip size (25 089 tokens, batch 1): the batch cannot fill the GPU, so the kernel splits
+    the sequence into segments with an exact two-pass carry.  The split result must agree with the
+    one-warp-per-sequence walk and with a chunked walk, outputs and final state."""
+    Bsz, L, R, N = 1, 25089, 24, 16
+    u, z, xdbl, w_dt, A2, Dp, bias = _scan_inputs(Bsz, L, seed=11)
+    h0 = torch.randn(Bsz, 768, N, generator=torch.Generator().manual_seed(3)).to(DEV)
+    from videomamba_b200 import _lib
+    assert _lib.load().vmb_fused_scan_workspace_bytes(Bsz, L, 768, N) > 0        # split is planned
+    split, h_split = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, h0,
+                                                     want_last=True, reverse=reverse)
+    plain, h_plain = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, h0,
+                                                     want_last=True, reverse=reverse, allow_split=False)
+    assert torch.isfinite(split.float()).all()
+    assert rel_err(split, plain) <= 4e-3 and rel_err(h_split, h_plain) <= 1e-4
+    # three chunks with carried state (each chunk is itself split or not, depending on its length)
+    order = [(0, 9000), (9000, 9001), (9001, L)]
+    if reverse:
+        order = [(L - hi, L - lo) for lo, hi in order]
+    h, parts = h0, []
+    for lo, hi in order:
+        y, h = ops.selective_scan_fused_tokens(u[:, lo:hi], z[:, lo:hi], xdbl[:, lo:hi], w_dt, A2, R,
+                                               N, Dp, bias, h, want_last=True, reverse=reverse)
+        parts.append(y)
+    if reverse:
+        parts = parts[::-1]
+    assert rel_err(torch.cat(parts, 1), plain) <= 4e-3 and rel_err(h, h_plain) <= 1e-4
+
+
+def test_fused_scan_split_against_float64():
+    Bsz, L, R, N = 2, 4100, 24, 16
+    u, z, xdbl, w_dt, A2, Dp, bias = _scan_inputs(Bsz, L, seed=5)
+    h0 = torch.randn(Bsz, 768, N, generator=torch.Generator().manual_seed(4)).to(DEV)
+    want, want_h = _fused_scan_ref64(u, z, xdbl, w_dt, A2 / ops.LOG2E, Dp, bias, h0, False, R, N)
+    got, got_h = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, h0, want_last=True)
+    assert rel_err(got, want) <= 6e-3 and rel_err(got_h, want_h) <= 2e-3
 
 
 def test_selective_scan_golden_fixture(golden):

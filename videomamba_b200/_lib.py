@@ -47,6 +47,7 @@ class FusedScanArgs(C.Structure):
         ("h_last", c_void_p),
         ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32), ("R", c_int32),
         ("Rp", c_int32), ("Xp", c_int32), ("reverse", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
     ]
 
 
@@ -87,6 +88,7 @@ SIGNATURES = {
                                          c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p]),
     "vmb_selective_scan_fwd": (c_int, [C.POINTER(ScanArgs), c_void_p]),
+    "vmb_fused_scan_workspace_bytes": (c_int64, [c_int] * 4),
     "vmb_selective_scan_fused_fwd": (c_int, [C.POINTER(FusedScanArgs), c_void_p]),
     "vmb_selective_state_update": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64,
                                            c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

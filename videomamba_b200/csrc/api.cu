@@ -72,7 +72,7 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 inline int xdbl_pitch(int R, int N) { return (int)align_up(R + 2 * N, 16); }
 
 struct MixerWorkspace {
-  int64_t xz, xc, xdbl, delta, y, total;  // byte offsets
+  int64_t xz, xc, xdbl, delta, y, seg, seg_bytes, total;  // byte offsets
 };
 
 MixerWorkspace plan_workspace(int B, int L, int Di, int N, int R, int dtype) {
@@ -85,6 +85,8 @@ MixerWorkspace plan_workspace(int B, int L, int Di, int N, int R, int dtype) {
   w.xdbl = off;  off = align_up(off + M * xdbl_pitch(R, N) * es, 256);
   w.delta = off; off = align_up(off + M * Di * es, 256);
   w.y = off;     off = align_up(off + M * Di * es, 256);
+  w.seg_bytes = dtype == VMB_BF16 ? scan_fast_workspace_bytes(B, L, Di, N) : 0;
+  w.seg = off;   off = align_up(off + w.seg_bytes, 256);
   w.total = off;
   return w;
 }
@@ -175,6 +177,11 @@ extern "C" int vmb_selective_scan_fwd(const vmb_scan_args* a, vmb_stream_t strea
   return scan_generic(*a, as_stream(stream));
 }
 
+extern "C" int64_t vmb_fused_scan_workspace_bytes(int B, int L, int Di, int N) {
+  if (B <= 0 || L <= 0 || Di <= 0 || N <= 0) return 0;
+  return scan_fast_workspace_bytes(B, L, Di, N);
+}
+
 extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_stream_t stream) {
   VMB_CHECK_ARG(a != nullptr, "fused_scan: null args");
   VMB_CHECK_ARG(a->B >= 0 && a->L >= 0 && a->Di > 0 && a->N > 0 && a->R > 0, "fused_scan: bad sizes");
@@ -193,6 +200,9 @@ extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_st
   f.y = a->y; f.y_bs = a->y_bstride; f.y_ts = a->y_tstride; f.h_last = a->h_last;
   f.B = a->B; f.L = a->L; f.Di = a->Di; f.N = a->N; f.R = a->R; f.Rp = a->Rp; f.Xp = a->Xp;
   f.reverse = a->reverse;
+  f.seg_ws = reinterpret_cast<float*>(a->workspace);
+  f.seg_ws_bytes = a->workspace ? a->workspace_bytes : 0;
+  VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->workspace) % 16 == 0, "fused_scan: workspace not 16-byte aligned");
   if (!scan_fast_supported(f)) VMB_UNSUPPORTED("fused_scan: shape / alignment not covered by the fused kernel");
   ProfScope ps(VMB_PROF_SCAN, as_stream(stream));
   return scan_fast(f, as_stream(stream));
@@ -264,6 +274,8 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   f.h0 = p->ssm_state_in; f.h0_dtype = p->ss_in_dtype;
   f.y = y; f.y_bs = (int64_t)L * Di; f.y_ts = Di; f.h_last = p->ssm_state_out;
   f.B = B; f.L = L; f.Di = Di; f.N = N; f.R = R; f.Rp = p->Rp; f.Xp = p->Xp; f.reverse = p->reverse;
+  f.seg_ws = ws.seg_bytes ? reinterpret_cast<float*>(base + ws.seg) : nullptr;
+  f.seg_ws_bytes = ws.seg_bytes;
   const bool fast_ok = p->dtype == VMB_BF16 && p->w_x_pad && p->w_dt_pad && p->Xp == Xw &&
                        scan_fast_supported(f);
   if (p->path == 2 && !fast_ok) VMB_UNSUPPORTED("mixer: fast path requested but not available");

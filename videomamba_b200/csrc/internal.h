@@ -30,7 +30,13 @@ struct FastScanArgs {
   float* h_last;
   int B, L, Di, N, R, Rp, Xp;
   int reverse;
+  // sequence split for small batches (filled by scan_fast itself): nseg segments of seg_len tokens,
+  // carried through seg_ws = [H (nseg,B,Di,N) | S (nseg,B,Di) | Hin (nseg,B,Di,N)] fp32
+  float* seg_ws = nullptr;
+  int64_t seg_ws_bytes = 0;
+  int nseg = 1, seg_len = 0;
 };
+int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N);
 bool scan_fast_supported(const FastScanArgs& a);
 int scan_fast(const FastScanArgs& a, cudaStream_t st);
 

@@ -25,8 +25,14 @@
 //     {delta, du} feeds 8 state updates; the 4 lanes' partial outputs are combined with two
 //     shuffles, and every lane finalises one (token, channel) of a 2-token step: + D*u, * SiLU(z).
 //   * B_t / C_t are expanded to fp32 once per tile; y leaves through shared memory as 16-byte stores.
+//   * small batches (fewer warps than the GPU needs) split the sequence into segments: a first
+//     pass computes every segment's end state from a zero start (recurrence only, no outputs) and
+//     its total decay exp(A * sum(delta)); a tiny kernel chains the carries; the second pass runs
+//     all segments concurrently from their true initial states.  Exact, 1.6x the work, up to 24x
+//     the parallelism (long-clip configuration, 25 089 tokens at batch 1).
 //   * reverse = 1 walks the sequence back to front (tile rows are gathered in logical order), which
 //     is what the flipped branch of BiMambaRefinerBlock needs without any torch.flip copy.
+#include <algorithm>
 #include <cstdlib>
 
 #include "internal.h"
@@ -120,7 +126,9 @@ __device__ __forceinline__ float step4(float (&h)[4], const float (&A2)[4], floa
   return q.x + q.y;
 }
 
-template <int R>
+// kStateOnly: first pass of the sequence split -- run the recurrence of one segment from a zero
+// state, emit its end state and sum(delta), skip everything that only the outputs need.
+template <int R, bool kStateOnly>
 __global__ void __launch_bounds__(kThreads, 16)
 scan_fast_kernel(const FastScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -134,8 +142,14 @@ scan_fast_kernel(const FastScanArgs a) {
   const int pr = lane >> 2;                    // channel pair (phase B) / accumulator row (phase A)
   const int cw = blockIdx.x * kCh;             // first channel of this warp
   const int b = blockIdx.y;
-  const int L = a.L;
+  const int seg = blockIdx.z;                  // sequence segment [tbeg, L) of the logical sequence
+  const int tbeg = seg * a.seg_len;
+  const int L = min(a.L, tbeg + a.seg_len);    // end of this segment (tokens beyond it are padding)
   using bf16 = __nv_bfloat16;
+  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;           // floats per segment of H / Hin
+  float* const wsH = a.seg_ws;
+  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
+  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
 
   // ---- per-thread constants ---------------------------------------------------------------
   // phase B: channels ca = cw + 2 pr and ca + 1, states 4j .. 4j+3
@@ -149,8 +163,15 @@ scan_fast_kernel(const FastScanArgs a) {
     const int64_t hoff = ((int64_t)b * a.Di + ca) * kN + 4 * j;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      ha[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
-      hb[n] = a.h0 ? load_as_f32(a.h0, hoff + kN + n, a.h0_dtype) : 0.f;
+      if (kStateOnly) {
+        ha[n] = 0.f; hb[n] = 0.f;
+      } else if (seg > 0) {                    // carried in from the previous segments
+        ha[n] = wsHin[seg * seg_stride + hoff + n];
+        hb[n] = wsHin[seg * seg_stride + hoff + kN + n];
+      } else {
+        ha[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
+        hb[n] = a.h0 ? load_as_f32(a.h0, hoff + kN + n, a.h0_dtype) : 0.f;
+      }
     }
   }
   // finalising lane: channel ca + (j & 1)
@@ -180,7 +201,7 @@ scan_fast_kernel(const FastScanArgs a) {
   const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
   bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
   const int xchunks = a.Xp / 8;                // 16-byte chunks per x_dbl row
-  auto phys = [&](int t) -> int64_t { return a.reverse ? (int64_t)(L - 1 - t) : (int64_t)t; };
+  auto phys = [&](int t) -> int64_t { return a.reverse ? (int64_t)(a.L - 1 - t) : (int64_t)t; };
 
   // a lane copies one 16-byte chunk of u and of z (16 rows x 2 chunks) ...
   auto issue_uz = [&](int tile, int st) {
@@ -189,7 +210,8 @@ scan_fast_kernel(const FastScanArgs a) {
     const bool ok = t < L;
     const int64_t prow = ok ? phys(t) : 0;
     cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + prow * a.u_ts + ch * 8, ok);
-    cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + prow * a.z_ts + ch * 8, ok);
+    if (!kStateOnly)
+      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + prow * a.z_ts + ch * 8, ok);
   };
   // ... and every other chunk of one x_dbl row (16 rows x 2 lanes)
   auto issue_x = [&](int tile) {
@@ -201,17 +223,19 @@ scan_fast_kernel(const FastScanArgs a) {
       cp_async16(sbase + sp.x0 + row * xrow + ch * 16, src + ch * 8, ok);
   };
 
+  const int tile_lo = tbeg / kTT;              // seg_len is a multiple of the tile
   const int ntiles = (L + kTT - 1) / kTT;
-  issue_uz(0, 0);
-  issue_x(0);
+  issue_uz(tile_lo, 0);
+  issue_x(tile_lo);
   cp_async_commit();
+  float sum_a = 0.f, sum_b = 0.f;              // sum of delta over the segment (state-only pass)
 
   float* const sbc = reinterpret_cast<float*>(smem + sp.bc);
   float4* const sdd = reinterpret_cast<float4*>(smem + sp.dd);   // [token][8 pairs]
   bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
 
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int st = tile & 1;
+  for (int tile = tile_lo; tile < ntiles; ++tile) {
+    const int st = (tile - tile_lo) & 1;
     const int t0 = tile * kTT;
     cp_async_wait<0>();
     __syncwarp();                              // tile landed; last tile's smem readers are done
@@ -267,32 +291,44 @@ scan_fast_kernel(const FastScanArgs a) {
     cp_async_commit();
 
     // ---- phase B: the recurrence, 2 tokens per step ----------------------------------------------
-#pragma unroll 2
-    for (int tt = 0; tt < kTT; tt += 2) {
-      float ys[2];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int t = tt + s;
+    if constexpr (kStateOnly) {
+#pragma unroll 4
+      for (int t = 0; t < kTT; ++t) {
         const float4 dd = sdd[t * (kCh / 2) + pr];
         const float4 Bv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + 4 * j);
-        const float4 Cv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + kN + 4 * j);
-        const float pa = step4(ha, A2a, dd.x, dd.z, Bv, Cv);
-        const float pb = step4(hb, A2b, dd.y, dd.w, Bv, Cv);
-        const bool odd = j & 1;
-        float q = (odd ? pb : pa) + __shfl_xor_sync(0xffffffffu, odd ? pa : pb, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        ys[s] = q;                             // y of channel ca + (j & 1) at token t, in all 4 lanes
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        (void)step4(ha, A2a, dd.x, dd.z, Bv, zero);
+        (void)step4(hb, A2b, dd.y, dd.w, Bv, zero);
+        sum_a += dd.x;
+        sum_b += dd.y;
       }
-      const int tf = tt + (j >> 1);            // this lane finalises (token tf, channel cf)
-      const float yv = (j >> 1) ? ys[1] : ys[0];
-      const float uval = __bfloat162float(su[tf * (kRowBytes / 2) + cf]);
-      const float zval = __bfloat162float(sz[tf * (kRowBytes / 2) + cf]);
-      sy[tf * (kRowBytes / 2) + cf] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_tanh(zval));
-    }
-    __syncwarp();
+      __syncwarp();
+    } else {
+#pragma unroll 2
+      for (int tt = 0; tt < kTT; tt += 2) {
+        float ys[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int t = tt + s;
+          const float4 dd = sdd[t * (kCh / 2) + pr];
+          const float4 Bv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + 4 * j);
+          const float4 Cv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + kN + 4 * j);
+          const float pa = step4(ha, A2a, dd.x, dd.z, Bv, Cv);
+          const float pb = step4(hb, A2b, dd.y, dd.w, Bv, Cv);
+          const bool odd = j & 1;
+          float q = (odd ? pb : pa) + __shfl_xor_sync(0xffffffffu, odd ? pa : pb, 1);
+          q += __shfl_xor_sync(0xffffffffu, q, 2);
+          ys[s] = q;                           // y of channel ca + (j & 1) at token t, in all 4 lanes
+        }
+        const int tf = tt + (j >> 1);          // this lane finalises (token tf, channel cf)
+        const float yv = (j >> 1) ? ys[1] : ys[0];
+        const float uval = __bfloat162float(su[tf * (kRowBytes / 2) + cf]);
+        const float zval = __bfloat162float(sz[tf * (kRowBytes / 2) + cf]);
+        sy[tf * (kRowBytes / 2) + cf] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_tanh(zval));
+      }
+      __syncwarp();
 
-    // ---- y tile out: 16 rows x 32 bytes as 16-byte stores ------------------------------------------
-    {
+      // ---- y tile out: 16 rows x 32 bytes as 16-byte stores ----------------------------------------
       const int row = lane >> 1, ch = lane & 1;
       const int t = t0 + row;
       if (t < L) {
@@ -303,6 +339,18 @@ scan_fast_kernel(const FastScanArgs a) {
     // the __syncwarp at the top of the next iteration orders these reads before the next writes
   }
 
+  if constexpr (kStateOnly) {
+    float* hs = wsH + seg * seg_stride + ((int64_t)b * a.Di + ca) * kN + 4 * j;
+    *reinterpret_cast<float4*>(hs) = make_float4(ha[0], ha[1], ha[2], ha[3]);
+    *reinterpret_cast<float4*>(hs + kN) = make_float4(hb[0], hb[1], hb[2], hb[3]);
+    if (j == 0) {
+      float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + ca;
+      ss[0] = sum_a;
+      ss[1] = sum_b;
+    }
+    return;
+  }
+  if (seg != a.nseg - 1) return;               // only the last segment holds the final state
   if (a.h_last != nullptr) {
     float* hl = a.h_last + ((int64_t)b * a.Di + ca) * kN + 4 * j;
     *reinterpret_cast<float4*>(hl) = make_float4(ha[0], ha[1], ha[2], ha[3]);
@@ -318,14 +366,61 @@ int variant() {
   return v;
 }
 
+// Chains the segment carries: Hin[0] = h0, Hin[s+1] = exp2(A2 * S[s]) * Hin[s] + H[s].
+__global__ void scan_carry_kernel(const FastScanArgs a) {
+  const int64_t per_seg = (int64_t)a.B * a.Di * kN;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, c, n)
+  if (i >= per_seg) return;
+  const int64_t bc = i / kN;
+  const int c = (int)(bc % a.Di);
+  const float A2 = a.A2[(int64_t)c * kN + (i % kN)];
+  const float* H = a.seg_ws;
+  const float* S = a.seg_ws + (int64_t)a.nseg * per_seg;
+  float* Hin = a.seg_ws + (int64_t)a.nseg * per_seg + (int64_t)a.nseg * a.B * a.Di;
+  float h = a.h0 ? load_as_f32(a.h0, i, a.h0_dtype) : 0.f;
+  for (int s = 0; s + 1 < a.nseg; ++s) {
+    h = fmaf(exp2f(A2 * S[(int64_t)s * a.B * a.Di + bc]), h, H[s * per_seg + i]);
+    Hin[(s + 1) * per_seg + i] = h;
+  }
+}
+
+// Segments only when the batch alone cannot fill the GPU (one warp per 16 channels of a sequence).
+void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
+  const int64_t warps = (int64_t)a.B * (a.Di / kCh);
+  const int64_t want = 8ll * sm_count();       // ~2 warps per scheduler
+  *nseg = 1;
+  *seg_len = (a.L + kTT - 1) / kTT * kTT;
+  if (warps >= want || a.L < 2048) return;
+  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 512);
+  if (n < 2) return;
+  const int len = ((a.L + n - 1) / n + kTT - 1) / kTT * kTT;
+  *nseg = (a.L + len - 1) / len;
+  *seg_len = len;
+}
+
 template <int R>
-int launch(const FastScanArgs& a, cudaStream_t st) {
+int launch(const FastScanArgs& a0, cudaStream_t st) {
+  FastScanArgs a = a0;
+  plan_segments(a, &a.nseg, &a.seg_len);
   const Smem sp = smem_plan(a.Xp);
-  dim3 grid(a.Di / kCh, a.B);
-  if (sp.total > 48 * 1024)
-    VMB_CUDA(cudaFuncSetAttribute(scan_fast_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  sp.total));
-  scan_fast_kernel<R><<<grid, kThreads, sp.total, st>>>(a);
+  if (sp.total > 48 * 1024) VMB_UNSUPPORTED("scan_fast: x_dbl rows too wide for the staging buffers");
+  if (a.nseg > 1) {
+    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
+    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
+      a.nseg = 1;                              // no workspace given: run unsplit (still correct)
+      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
+    }
+  }
+  if (a.nseg > 1) {
+    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
+    scan_fast_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
+    VMB_LAUNCH_CHECK("scan_fast_kernel<state>");
+    const int64_t n = (int64_t)a.B * a.Di * kN;
+    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    VMB_LAUNCH_CHECK("scan_carry_kernel");
+  }
+  dim3 grid(a.Di / kCh, a.B, a.nseg);
+  scan_fast_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
   VMB_LAUNCH_CHECK("scan_fast_kernel");
   return VMB_OK;
 }
@@ -344,6 +439,15 @@ bool scan_fast_supported(const FastScanArgs& a) {
          a.u_bs % 8 == 0 && a.u_ts % 8 == 0 && a.z_bs % 8 == 0 && a.z_ts % 8 == 0 &&
          a.x_bs % 8 == 0 && a.x_ts % 8 == 0 && a.y_bs % 8 == 0 && a.y_ts % 8 == 0 &&
          (variant() & 2) == 0;
+}
+
+int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
+  FastScanArgs a;
+  a.B = B; a.L = L; a.Di = Di; a.N = N;
+  int nseg, seg_len;
+  plan_segments(a, &nseg, &seg_len);
+  if (nseg <= 1) return 0;
+  return ((int64_t)nseg * B * Di * N * 2 + (int64_t)nseg * B * Di) * 4;
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {

@@ -228,7 +228,8 @@ def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_of
 def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor, A2: Tensor,
                                 dt_rank: int, d_state: int, D: Optional[Tensor] = None,
                                 dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
-                                want_last: bool = False, reverse: bool = False):
+                                want_last: bool = False, reverse: bool = False,
+                                allow_split: bool = True):
     """Fused dt_proj + softplus + scan + D skip + SiLU(z) gate (bf16, d_state 16).
     ``u, z: (B, L, Di)``; ``xdbl: (B, L, Xp)`` rows ``[dt_low (R) | B (N) | C (N) | pad]``;
     ``w_dt: (Di, >=R)`` bf16; ``A2 = A*log2(e)`` fp32.  Raises when the shape is not covered."""
@@ -261,6 +262,10 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
     if u.dtype != torch.bfloat16 or z.dtype != u.dtype or xdbl.dtype != u.dtype \
             or w_dt.dtype != u.dtype:
         raise TypeError("the fused scan is a bf16 kernel")
+    ws_bytes = lib.vmb_fused_scan_workspace_bytes(B, L, Di, d_state) if allow_split else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=u.device) if ws_bytes > 0 else None
+    if ws is not None:
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
     with _on_device(u):
         rc = lib.vmb_selective_scan_fused_fwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_fused_fwd")
