@@ -4,20 +4,21 @@
 // (models/videomamba/mamba_simple.py:333-339 in_proj, :409 x_proj, :445-446 out_proj) and behind
 // the Conv3d patch embedding (models/videomamba/videomamba.py:359-368, kernel == stride).
 //
-// Design (B200 / sm_100a, one persistent CTA per SM, 256 threads, warp-specialised):
+// Design (B200 / sm_100a, one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0   TMA producer: A tile (128 x 64) and W tile (BN x 64) per k-block into a kStages-deep
 //            ring of 128B-swizzled shared-memory buffers (cp.async.bulk.tensor + mbarrier tx).
 //   warp 1   MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 ->
 //            fp32) with both operands read from shared memory through UMMA descriptors;
 //            accumulators live in TMEM (2 x BN columns: double buffered across tiles).
-//   warp 2   TMEM allocation / release.
-//   warps 4-7 epilogue: tcgen05.ld the accumulator (thread = output row), add bias, round once to
+//            It also owns the TMEM allocation.
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (thread = output row), add bias, round once to
 //            bf16, stage 128 x 64 sub-tiles in swizzled shared memory and write them with TMA
 //            stores (coalesced, rows beyond M / columns beyond N are clipped by the hardware).
 // Tiles are walked n-fastest so the CTAs running at the same time share the A rows in L2.
 // Both operands are K-contiguous, exactly how nn.Linear stores its weight, so no transposes.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -29,14 +30,14 @@ namespace {
 constexpr int BM = 128;       // rows of C per tile (UMMA M)
 constexpr int BK = 64;        // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;  // first epilogue warp
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;  // first epilogue warp (a warp reads the TMEM lane quadrant warp % 4)
 constexpr int kSubN = 64;     // columns per epilogue sub-tile (128 bytes of bf16)
 
 __host__ __device__ constexpr int stages_for(int bn) { return bn <= 128 ? 6 : 4; }
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 64 ? 128 : (bn <= 128 ? 256 : 512); }
-__host__ __device__ constexpr size_t smem_bytes_for(int bn) {
-  return 1024 /* alignment slack */ + (size_t)stages_for(bn) * (BM * BK * 2 + bn * BK * 2) +
+__host__ __device__ constexpr size_t smem_bytes_for(int bn, int stages) {
+  return 1024 /* alignment slack */ + (size_t)stages * (BM * BK * 2 + bn * BK * 2) +
          2 * (BM * kSubN * 2) + 256 /* barriers + tmem pointer */;
 }
 
@@ -160,12 +161,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// kStages == stages_for(BN): the stand-alone configuration (fills the SM's shared memory).
+// kStages == 2: the small-footprint configuration (< 100 KB of shared memory, <= 104 registers) that
+// can be co-resident with the scan CTAs of another step running on a second stream.
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kThreads, kStages == 2 ? 3 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ bias,
                int M, int N, int K) {
-  constexpr int kStages = stages_for(BN);
   constexpr int kTmemCols = tmem_cols_for(BN);
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kWBytes = BN * BK * 2;
@@ -211,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "r"((uint32_t)kTmemCols)
                  : "memory");
@@ -269,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue =====
-    const int ew = warp - kEpiWarp0;                 // == warp % 4: TMEM lanes [32 ew, 32 ew + 32)
+    const int ew = warp & 3;                         // TMEM lanes [32 ew, 32 ew + 32)
     const int row = ew * 32 + lane;                  // row of the tile this thread owns
     const bool issuer = threadIdx.x == kEpiWarp0 * 32;
     int local = 0;
@@ -336,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)kTmemCols)
@@ -403,7 +406,7 @@ int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int6
   return VMB_OK;
 }
 
-template <int BN>
+template <int BN, int kStages>
 int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
            int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
   CUtensorMap ma, mw, mc;
@@ -412,19 +415,29 @@ int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* b
   if ((rc = make_map(&mw, W, N, K, ldw, BN))) return rc;
   if ((rc = make_map(&mc, C, M, N, ldc, BM))) return rc;
   static bool attr_set[64] = {false};
-  constexpr size_t smem = smem_bytes_for(BN);
+  constexpr size_t smem = smem_bytes_for(BN, kStages);
   int dev = 0;
   VMB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    VMB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    VMB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, kStages>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = (int)std::min<int64_t>(tiles, sm_count());
-  gemm_tc_kernel<BN><<<grid, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias, (int)M, N, K);
+  gemm_tc_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias,
+                                                            (int)M, N, K);
   VMB_LAUNCH_CHECK("gemm_tc_kernel");
   return VMB_OK;
+}
+
+// 0: stand-alone tiles (default).  1: small-footprint tiles (co-residency with the scan).
+int footprint() {
+  static int v = [] {
+    const char* e = std::getenv("VMB_GEMM_FOOTPRINT");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
 }
 
 }  // namespace
@@ -440,11 +453,16 @@ bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, c
 
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
             int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
-  if (N <= 64) return launch<64>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  if (N <= 128) return launch<128>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  if (N % 256 == 0) return launch<256>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  if (N % 192 == 0 || N < 256) return launch<192>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  return launch<256>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (footprint() == 1) {
+    if (N <= 64) return launch<64, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    return launch<128, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  }
+  if (N <= 64) return launch<64, stages_for(64)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N <= 128) return launch<128, stages_for(128)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N % 256 == 0) return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N % 192 == 0 || N < 256)
+    return launch<192, stages_for(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
 }
 
 }  // namespace vmb

@@ -45,6 +45,10 @@ constexpr int kThreads = 32;
 constexpr int kTT = 16;                 // tokens per tile
 constexpr int kRowBytes = 48;           // u / z / y tile rows: 32 B of channels + 16 B pad
 constexpr int kN = 16;
+#ifndef VMB_SCAN_MIN_CTAS
+#define VMB_SCAN_MIN_CTAS 20
+#endif
+constexpr int kMinCtas = VMB_SCAN_MIN_CTAS;   // register cap = 65536 / (32 * kMinCtas)
 
 // x_dbl tile row pitch in bytes: an odd number of 16-byte chunks keeps ldmatrix conflict free
 __host__ __device__ constexpr int x_row_bytes(int Xp) { return ((Xp / 8) % 2 == 1) ? Xp * 2 : Xp * 2 + 16; }
@@ -129,7 +133,7 @@ __device__ __forceinline__ float step4(float (&h)[4], const float (&A2)[4], floa
 // kStateOnly: first pass of the sequence split -- run the recurrence of one segment from a zero
 // state, emit its end state and sum(delta), skip everything that only the outputs need.
 template <int R, bool kStateOnly>
-__global__ void __launch_bounds__(kThreads, 16)
+__global__ void __launch_bounds__(kThreads, kMinCtas)
 scan_fast_kernel(const FastScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int KST = (R + 15) / 16;           // k-steps of the dt projection
