@@ -113,8 +113,14 @@ __device__ __forceinline__ float softplus_fast(float x) {
   return e < 0.00390625f ? e * (1.f - 0.5f * e + 0.33333334f * e * e)
                          : lg2_approx(1.f + e) * kLn2;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x) with sigmoid(x) = 0.5 * tanh(x / 2) + 0.5: one MUFU instead of ex2 + rcp
 __device__ __forceinline__ float silu_fast(float x) {
-  return x * rcp_approx(1.f + ex2_approx(-x * kLog2e));
+  return x * fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f);
 }
 
 template <bool kAccurate> __device__ __forceinline__ float softplus_f(float x) {
