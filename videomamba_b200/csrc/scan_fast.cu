@@ -761,7 +761,7 @@ int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {
-  if (variant() == 6) {        // VMB_SCAN_VARIANT=6: faster alone, but fills the SM (see profiles/)
+  if (variant() == 4) {        // VMB_SCAN_VARIANT=4 (v6 layout): faster alone, but fills the SM (see profiles/)
     switch (a.R) {
       case 12: return launch6<12>(a, st);
       case 24: return launch6<24>(a, st);
