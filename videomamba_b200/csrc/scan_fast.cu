@@ -642,6 +642,230 @@ scan6_kernel(const FastScanArgs a) {
 
 }  // namespace v6
 
+// =================================================================================================
+// v7: v4's small footprint (one-warp CTAs, <= 96 registers, 10 KB of shared memory, so two launches
+// can share an SM) with v6's lane layout: a lane owns ONE channel x 8 states (2 lanes per channel),
+// one shuffle per token PAIR, 32-bit address arithmetic.  Phase A is not overlapped with the
+// recurrence inside a warp; the other resident warps cover it.
+// =================================================================================================
+namespace v7 {
+
+constexpr int kDdRow = kCh * 8;                   // {delta, delta*u} per channel: 128 B per token
+
+template <int R, bool kStateOnly>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
+scan7_kernel(const FastScanArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int KST = (R + 15) / 16;
+  const Smem sp = smem_plan(a.Xp);
+  const int xrow = x_row_bytes(a.Xp);
+  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  using bf16 = __nv_bfloat16;
+
+  const int lane = threadIdx.x;
+  const int j4 = lane & 3, pr = lane >> 2;        // phase A: accumulator column pair / row
+  const int c = lane >> 1, jh = lane & 1;         // phase B: channel within the CTA / state half
+  const int cw = blockIdx.x * kCh;
+  const int b = blockIdx.y;
+  const int seg = blockIdx.z;
+  const int tbeg = seg * a.seg_len;
+  const int L = min(a.L, tbeg + a.seg_len);
+  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
+  float* const wsH = a.seg_ws;
+  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
+  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
+
+  float2 Ap[4], hp[4];
+  const int64_t hoff = ((int64_t)b * a.Di + cw + c) * kN + 8 * jh;
+  {
+    const float4 v0 = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(cw + c) * kN + 8 * jh);
+    const float4 v1 = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(cw + c) * kN + 8 * jh + 4);
+    Ap[0] = make_float2(v0.x, v0.y); Ap[1] = make_float2(v0.z, v0.w);
+    Ap[2] = make_float2(v1.x, v1.y); Ap[3] = make_float2(v1.z, v1.w);
+    float h[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (kStateOnly) h[n] = 0.f;
+      else if (seg > 0) h[n] = wsHin[seg * seg_stride + hoff + n];
+      else h[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hp[k] = make_float2(h[2 * k], h[2 * k + 1]);
+  }
+  const float Dv = a.D ? a.D[cw + c] : 0.f;       // finalising lane: channel c, token of the pair = jh
+  uint32_t bfrag[2][KST][2];
+  float bias[2][2];
+  {
+    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const bf16* wr = wd + (int64_t)(cw + 8 * n + pr) * a.Rp;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * j4);
+        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * j4);
+      }
+      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j4] : 0.f;
+      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j4 + 1] : 0.f;
+    }
+  }
+
+  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
+  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
+  const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
+  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
+  const int xchunks = a.Xp / 8;
+  // token t of the logical sequence lives at row p0 + dir * t; offsets inside one batch entry fit 32 bits
+  const int dir = a.reverse ? -1 : 1;
+  const int p0 = a.reverse ? a.L - 1 : 0;
+  const int u_ts = (int)a.u_ts, z_ts = (int)a.z_ts, x_ts = (int)a.x_ts, y_ts = (int)a.y_ts;
+
+  auto issue_tile = [&](int tile, int st) {
+    const int row = lane >> 1, ch = lane & 1;
+    const int t = tile * kTT + row;
+    const bool ok = t < L;
+    const int prow = ok ? p0 + dir * t : 0;
+    cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + (prow * u_ts + ch * 8), ok);
+    if (!kStateOnly)
+      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + (prow * z_ts + ch * 8), ok);
+    const bf16* src = xg + prow * x_ts;
+    for (int k = ch; k < xchunks; k += 2) cp_async16(sbase + sp.x0 + row * xrow + k * 16, src + k * 8, ok);
+  };
+
+  const int tile_lo = tbeg / kTT;
+  const int ntiles = (L + kTT - 1) / kTT;
+  issue_tile(tile_lo, 0);
+  cp_async_commit();
+  float sum_d = 0.f;
+
+  float* const sbc = reinterpret_cast<float*>(smem + sp.bc);
+  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
+
+  for (int tile = tile_lo; tile < ntiles; ++tile) {
+    const int st = (tile - tile_lo) & 1;
+    const int t0 = tile * kTT;
+    cp_async_wait<0>();
+    __syncwarp();                                  // tile landed; last tile's smem readers are done
+
+    const uint8_t* su = smem + sp.u(st);
+    const uint8_t* sz = smem + sp.z(st);
+
+    // ---- expand B_t / C_t of the tile to fp32 ---------------------------------------------------
+    {
+      const uint8_t* xr = smem + sp.x0;
+#pragma unroll
+      for (int i = 0; i < (kTT * kN) / kThreads; ++i) {          // 16 tokens x 16 bf16 pairs
+        const int e = lane + i * kThreads;
+        const int row = e >> 4, p = e & 15;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(xr + row * xrow + (R + 2 * p) * 2);
+        *reinterpret_cast<float2*>(sbc + row * (2 * kN) + 2 * p) = make_float2(bf16lo(v), bf16hi(v));
+      }
+    }
+    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
+    {
+      float acc[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        uint32_t af[4];
+        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
+        ldmatrix_x4(sbase + sp.x0 + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
+        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int tl = pr + 8 * half;
+          float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
+          float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
+          if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }              // padding: decay 1, drive 0
+          const uint32_t uv = *reinterpret_cast<const uint32_t*>(su + tl * kRowBytes + (8 * n + 2 * j4) * 2);
+          // 16-byte chunk (4 n + j4) of the row, swizzled by the row parity: the 8 lanes of a quarter
+          // warp (rows pr = 2k, 2k + 1) cover all 32 banks
+          *reinterpret_cast<float4*>(smem + sp.dd + tl * kDdRow + (((4 * n + j4) ^ ((tl & 1) << 2)) << 4)) =
+              make_float4(d0, d0 * bf16lo(uv), d1, d1 * bf16hi(uv));
+        }
+    }
+    __syncwarp();                                  // sBC / sDD visible; raw x_dbl rows no longer needed
+    if (tile + 1 < ntiles) issue_tile(tile + 1, st ^ 1);
+    cp_async_commit();
+
+    // ---- phase B: the recurrence ---------------------------------------------------------------------
+    const uint8_t* sdd0 = smem + sp.dd + (((c >> 1)) << 4) + (c & 1) * 8;          // even tokens
+    const uint8_t* sdd1 = smem + sp.dd + (((c >> 1) ^ 4) << 4) + (c & 1) * 8;      // odd tokens
+    const uint8_t* sb = smem + sp.bc + jh * 32;
+    float qs0 = 0.f;
+#pragma unroll
+    for (int t = 0; t < kTT; ++t) {
+      const float2 dd = *reinterpret_cast<const float2*>(((t & 1) ? sdd1 : sdd0) + t * kDdRow);
+      const float4 B0 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4));
+      const float4 B1 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4) + 16);
+      const float2 d2 = make_float2(dd.x, dd.x), du2 = make_float2(dd.y, dd.y);
+      float2 e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = __fmul2_rn(d2, Ap[k]);
+        e[k] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+      }
+      hp[0] = __ffma2_rn(e[0], hp[0], __fmul2_rn(du2, make_float2(B0.x, B0.y)));
+      hp[1] = __ffma2_rn(e[1], hp[1], __fmul2_rn(du2, make_float2(B0.z, B0.w)));
+      hp[2] = __ffma2_rn(e[2], hp[2], __fmul2_rn(du2, make_float2(B1.x, B1.y)));
+      hp[3] = __ffma2_rn(e[3], hp[3], __fmul2_rn(du2, make_float2(B1.z, B1.w)));
+      if constexpr (kStateOnly) {
+        sum_d += dd.x;
+      } else {
+        const float4 C0 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4) + 64);
+        const float4 C1 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4) + 80);
+        float2 q = __fmul2_rn(hp[0], make_float2(C0.x, C0.y));
+        q = __ffma2_rn(hp[1], make_float2(C0.z, C0.w), q);
+        q = __ffma2_rn(hp[2], make_float2(C1.x, C1.y), q);
+        q = __ffma2_rn(hp[3], make_float2(C1.z, C1.w), q);
+        const float s = q.x + q.y;
+        if (t & 1) {                               // lane jh finalises (token t - 1 + jh, channel c)
+          const float mine = jh ? s : qs0, send = jh ? qs0 : s;
+          const float yv = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+          const int tf = t - 1 + jh;
+          const float uval = __bfloat162float(*reinterpret_cast<const bf16*>(su + tf * kRowBytes + c * 2));
+          const float zval = __bfloat162float(*reinterpret_cast<const bf16*>(sz + tf * kRowBytes + c * 2));
+          sy[tf * (kRowBytes / 2) + c] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_fast(zval));
+        } else {
+          qs0 = s;
+        }
+      }
+    }
+    if constexpr (!kStateOnly) {
+      __syncwarp();
+      const int row = lane >> 1, ch = lane & 1;
+      const int t = t0 + row;
+      if (t < L)
+        *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
+            *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
+    }
+    // the __syncwarp at the top of the next iteration orders these reads before the next writes
+  }
+
+  if constexpr (kStateOnly) {
+    float* hs = wsH + seg * seg_stride + hoff;
+    *reinterpret_cast<float4*>(hs) = make_float4(hp[0].x, hp[0].y, hp[1].x, hp[1].y);
+    *reinterpret_cast<float4*>(hs + 4) = make_float4(hp[2].x, hp[2].y, hp[3].x, hp[3].y);
+    if (jh == 0) wsS[((int64_t)seg * a.B + b) * a.Di + cw + c] = sum_d;
+    return;
+  }
+  if (seg != a.nseg - 1) return;
+  if (a.h_last != nullptr) {
+    float* hl = a.h_last + hoff;
+    *reinterpret_cast<float4*>(hl) = make_float4(hp[0].x, hp[0].y, hp[1].x, hp[1].y);
+    *reinterpret_cast<float4*>(hl + 4) = make_float4(hp[2].x, hp[2].y, hp[3].x, hp[3].y);
+  }
+}
+
+}  // namespace v7
+
 int variant() {
   static int v = [] {
     const char* e = std::getenv("VMB_SCAN_VARIANT");
@@ -682,7 +906,7 @@ void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   *seg_len = len;
 }
 
-template <int R>
+template <int R, bool kV7>
 int launch(const FastScanArgs& a0, cudaStream_t st) {
   FastScanArgs a = a0;
   plan_segments(a, &a.nseg, &a.seg_len);
@@ -697,14 +921,16 @@ int launch(const FastScanArgs& a0, cudaStream_t st) {
   }
   if (a.nseg > 1) {
     dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
-    scan_fast_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
+    if (kV7) v7::scan7_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
+    else scan_fast_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
     VMB_LAUNCH_CHECK("scan_fast_kernel<state>");
     const int64_t n = (int64_t)a.B * a.Di * kN;
     scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
     VMB_LAUNCH_CHECK("scan_carry_kernel");
   }
   dim3 grid(a.Di / kCh, a.B, a.nseg);
-  scan_fast_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
+  if (kV7) v7::scan7_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
+  else scan_fast_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
   VMB_LAUNCH_CHECK("scan_fast_kernel");
   return VMB_OK;
 }
@@ -769,10 +995,18 @@ int scan_fast(const FastScanArgs& a, cudaStream_t st) {
       default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
     }
   }
+  if (variant() != 1) {        // default: v7; VMB_SCAN_VARIANT=1: v4 (2 channels x 4 states per lane)
+    switch (a.R) {
+      case 12: return launch<12, true>(a, st);
+      case 24: return launch<24, true>(a, st);
+      case 36: return launch<36, true>(a, st);
+      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
+    }
+  }
   switch (a.R) {
-    case 12: return launch<12>(a, st);
-    case 24: return launch<24>(a, st);
-    case 36: return launch<36>(a, st);
+    case 12: return launch<12, false>(a, st);
+    case 24: return launch<24, false>(a, st);
+    case 36: return launch<36, false>(a, st);
     default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
   }
 }
