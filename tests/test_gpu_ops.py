@@ -120,7 +120,7 @@ def test_tensor_core_projection_random_values():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("geom", [(2, 70, 768, 4), (3, 5, 16, 2), (1, 2, 24, 4), (2, 130, 384, 3),
+@pytest.mark.parametrize("geom", [(2, 70, 768, 4), (1, 200, 1152, 4), (3, 5, 16, 2), (1, 2, 24, 4), (2, 130, 384, 3),
                                   (1, 1, 8, 4)])
 @pytest.mark.parametrize("reverse", [False, True])
 def test_causal_conv1d(dtype, geom, reverse):
