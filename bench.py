@@ -389,9 +389,9 @@ def run_ours(args):
     w = mixer._kernel_weights()
     fused = "dt_proj" not in stages      # the fused scan expands dt inside the kernel
     if fused:
-        # fused conv+dt_proj+scan+gate kernel: reads x, z, x_dbl row; writes y
+        # fused dt_proj+softplus+scan+gate kernel: reads u (conv output), z, the x_dbl row; writes y
         bytes_per_token = 3 * Di * es + w.Xp * es
-        kernel = "scan_fused_kernel (conv + dt_proj + softplus + scan + D skip + SiLU gate)"
+        kernel = "scan7_kernel (dt_proj + softplus + S6 scan + D skip + SiLU gate, fused)"
     else:
         # op-level selective_scan_fn: reads u, delta, z, B, C; writes y
         bytes_per_token = 4 * Di * es + 2 * N * es
@@ -416,6 +416,15 @@ def run_ours(args):
                     "share_of_step": stages["scan"]["ms_per_step"] / serial_ms,
                     "note": "kernel is bound by instruction issue / MUFU ex2 (16 per token-channel), "
                             "not by HBM: see DESIGN.md 3.2 and profiles/r01_mufu_issue_microbench.txt"}
+    # the other HBM-bound kernels of the path against the same peak (algorithmic bytes per token:
+    # conv reads x and writes xc; add+norm reads hidden (bf16) + residual (fp32), writes both)
+    hbm_kernels = {}
+    Dm = mixer.d_model
+    for k, bpt in (("conv", 2 * Di * es), ("add_norm", Dm * es + 4 * Dm + 4 * Dm + Dm * es)):
+        if k in stages and stages[k]["launches_per_step"]:
+            per = stages[k]["ms_per_step"] / stages[k]["launches_per_step"]
+            gbs = tokens * bpt / (per * 1e-3) / 1e9
+            hbm_kernels[k] = {"achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak, "ms_per_launch": per}
     # projections against the tensor roofline (reported beside, not the dominant-kernel object)
     tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     D = mixer.d_model
@@ -456,6 +465,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "stages": stages,
+        "hbm_kernels": hbm_kernels,
         "tensor": tensor,
     }
     print(json.dumps(line), flush=True)
