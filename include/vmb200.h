@@ -228,6 +228,23 @@ VMB_API int vmb_state_scatter(void* pool, const int32_t* index, const void* batc
                       int n_rows, int64_t row_elems, int dtype, vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Front glue of the token path.
+ * vmb_patchify: clip x (B, C, T, H, W), contiguous -> patch rows cols (B*t*h*w, C*k*ph*pw) with
+ * t = T/k, h = H/ph, w = W/pw (trailing remainders are cropped), row order (b, t, y, x), column
+ * order (c, dt, dy, dx).  It is the im2col of the reference's Conv3d whose kernel equals its stride
+ * (PatchEmbed, models/videomamba/videomamba.py:359-368); the projection itself is vmb_linear_fwd.
+ * vmb_embed_tokens: out (B, has_cls + t*hw, D) = patches (B, t, hw, D) + spatial (hw, D) +
+ * temporal (t, D), each add rounded to `dtype` like the reference's two adds, and row 0 =
+ * cls_row (D) when cls_row is not NULL (models/videomamba/videomamba.py:806-823: position
+ * embeddings, CLS placement; continuation chunks pass NULL).
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_patchify(const void* x, void* cols, int64_t B, int C, int T, int H, int W, int k,
+                 int ph, int pw, int dtype, vmb_stream_t stream);
+VMB_API int vmb_embed_tokens(const void* patches, const void* spatial, const void* temporal,
+                     const void* cls_row,                          /* nullable */
+                     void* out, int64_t B, int t, int hw, int D, int dtype, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Per-stage device timing (measurement aid, off by default; nothing like it exists in the
  * reference).  While enabled, every entry point above brackets the kernels it enqueues with
  * cudaEvents on `stream`, tagged with the stage they belong to.  vmb_prof_read synchronises

@@ -45,6 +45,26 @@ def state_update(ssm_state, x, dt, w, B, C, z):
                                           dt_bias=p["dt_proj.bias"], dt_softplus=True)
 
 
+def patchify(x, tubelet, ph, pw):
+    # im2col of a Conv3d whose kernel equals its stride (reference videomamba.py:359-368)
+    B, C, T, H, W = x.shape
+    t, h, w = T // tubelet, H // ph, W // pw
+    x = x[:, :, :t * tubelet, :h * ph, :w * pw]
+    cols = x.reshape(B, C, t, tubelet, h, ph, w, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+    return cols.reshape(B * t * h * w, C * tubelet * ph * pw)
+
+
+def embed_tokens(patches, spatial, temporal, cls_row=None):
+    # reference videomamba.py:806-823: two adds in the model dtype, then CLS in front
+    B, t, hw, D = patches.shape
+    tokens = patches + spatial.to(patches.dtype).reshape(1, 1, hw, D)
+    tokens = tokens + temporal.to(patches.dtype).reshape(1, t, 1, D)
+    tokens = tokens.reshape(B, t * hw, D)
+    if cls_row is not None:
+        tokens = torch.cat((cls_row.to(patches.dtype).reshape(1, 1, D).expand(B, -1, -1), tokens), dim=1)
+    return tokens
+
+
 def install(monkeypatch):
     import videomamba_b200.mixer as mixer_mod
     import videomamba_b200.ops as ops
@@ -52,6 +72,8 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "mixer_fwd", mixer_fwd)
     monkeypatch.setattr(ops, "add_norm", add_norm)
     monkeypatch.setattr(ops, "linear", linear)
+    monkeypatch.setattr(ops, "patchify", patchify)
+    monkeypatch.setattr(ops, "embed_tokens", embed_tokens)
     monkeypatch.setattr(ops, "causal_conv1d_update", causal_conv1d_update)
     monkeypatch.setattr(mixer_mod, "_state_update", state_update)
     monkeypatch.setattr(mixer_mod.Mamba, "_require_cuda", staticmethod(lambda t: None))

@@ -120,6 +120,49 @@ def test_tensor_core_projection_random_values():
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", [(2, 3, 4, 32, 32, 1, 16, 16), (1, 3, 5, 30, 50, 2, 14, 12),
+                                  (2, 1, 2, 8, 9, 1, 4, 3), (0, 3, 2, 16, 16, 1, 16, 16)])
+def test_patchify_is_the_conv3d_im2col(dtype, geom):
+    """Pure data movement: bit exact against the reshape/permute of the strided Conv3d
+    (reference PatchEmbed, videomamba.py:359-368), including cropped remainders."""
+    B, C, T, H, W, k, ph, pw = geom
+    gen = torch.Generator().manual_seed(sum(geom))
+    x = _rand(gen, B, C, T, H, W, dtype=dtype)
+    t, h, w = T // k, H // ph, W // pw
+    want = x[:, :, :t * k, :h * ph, :w * pw].reshape(B, C, t, k, h, ph, w, pw) \
+        .permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * t * h * w, C * k * ph * pw)
+    got = ops.patchify(x.to(DEV), k, ph, pw)
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+    if B:       # and the projection over it equals the Conv3d
+        wgt = _rand(gen, 8, C, k, ph, pw, dtype=dtype, scale=0.1)
+        conv = torch.nn.functional.conv3d(x.float(), wgt.float(), stride=(k, ph, pw))
+        proj = (got.float().cpu() @ wgt.float().reshape(8, -1).T).reshape(B, t, h, w, 8).permute(0, 4, 1, 2, 3)
+        assert rel_err(proj, conv) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("geom", [(2, 3, 5, 16), (1, 1, 196, 384), (3, 2, 4, 6), (2, 0, 4, 8)])
+@pytest.mark.parametrize("with_cls", [True, False])
+def test_embed_tokens_matches_two_adds_and_cat(dtype, geom, with_cls):
+    """Position embeddings + CLS placement (reference videomamba.py:806-823): same rounding points as
+    the two adds in the model dtype, bit exact; CLS only when given (continuation chunks omit it)."""
+    B, t, hw, D = geom
+    gen = torch.Generator().manual_seed(sum(geom) + with_cls)
+    patches = _rand(gen, B, t, hw, D, dtype=dtype)
+    spatial, temporal = _rand(gen, hw, D, dtype=dtype), _rand(gen, t, D, dtype=dtype)
+    cls_row = _rand(gen, D, dtype=dtype) if with_cls else None
+    want = (patches + spatial.reshape(1, 1, hw, D)) + temporal.reshape(1, t, 1, D)
+    want = want.reshape(B, t * hw, D)
+    if with_cls:
+        want = torch.cat((cls_row.reshape(1, 1, D).expand(B, -1, -1), want), dim=1)
+    got = ops.embed_tokens(patches.to(DEV), spatial.to(DEV), temporal.to(DEV),
+                           None if cls_row is None else cls_row.to(DEV))
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("geom", [(2, 70, 768, 4), (1, 200, 1152, 4), (3, 5, 16, 2), (1, 2, 24, 4), (2, 130, 384, 3),
                                   (1, 1, 8, 4)])
 @pytest.mark.parametrize("reverse", [False, True])

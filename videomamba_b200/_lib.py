@@ -96,6 +96,10 @@ SIGNATURES = {
                                            c_int, c_int, c_int, c_int, c_void_p]),
     "vmb_mixer_workspace_bytes": (c_int64, [c_int] * 7),
     "vmb_mixer_fwd": (c_int, [C.POINTER(MixerArgs), c_void_p]),
+    "vmb_patchify": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_void_p]),
+    "vmb_embed_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
     "vmb_state_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "vmb_state_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "vmb_launch_count": (c_int64, []),

@@ -113,11 +113,9 @@ class PatchEmbed(nn.Module):
         ph, pw = self.patch_size
         B, C, T, H, W = x.shape
         t, h, w = T // k, H // ph, W // pw
-        x = x[:, :, :t * k, :h * ph, :w * pw]
-        cols = x.reshape(B, C, t, k, h, ph, w, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
-        cols = cols.reshape(B * t * h * w, C * k * ph * pw)
         weight = self.proj.weight.reshape(self.proj.weight.shape[0], -1)
-        out = ops.linear(cols.to(weight.dtype), weight, self.proj.bias)
+        cols = ops.patchify(x.to(weight.dtype), k, ph, pw)      # one gather kernel (csrc/embed.cu)
+        out = ops.linear(cols, weight, self.proj.bias)
         return out.reshape(B, t, h, w, -1)
 
     def forward(self, x: Tensor) -> Tensor:
@@ -380,19 +378,20 @@ class PretrainVideoMamba(nn.Module):
         if x.ndim != 5:
             raise ValueError("x must have shape [B, C, T, H, W].")
         self._validate_temporal_length(x.shape[2])
-        x = self.patch_embed(x)
-        B, C, T, H, W = x.shape
-        tokens = x.permute(0, 2, 3, 4, 1).reshape(B, T, H * W, C)
-        tokens = tokens + self._get_spatial_pos_embedding(H, W, x.dtype, x.device).unsqueeze(1)
-        tokens = tokens + self._get_temporal_pos_embedding(
-            T, offset=temporal_pos_offset, dtype=x.dtype, device=x.device).unsqueeze(2)
-        tokens = tokens.reshape(B, T * H * W, C)
-
+        patches = self.patch_embed.tokens(x)                    # (B, T', h, w, C), token-major
+        B, T, H, W, C = patches.shape
         has_cls = self._has_cls_token_for_forward(ssm_state, temporal_pos_offset)
+        cls_row = None
         if has_cls:
-            cls = self.cls_token.expand(B, -1, -1) + \
-                self.pos_embed[:, :1].to(device=x.device, dtype=x.dtype)
-            tokens = torch.cat((cls, tokens), dim=1)
+            cls_row = (self.cls_token + self.pos_embed[:, :1].to(
+                device=patches.device, dtype=patches.dtype)).reshape(C)
+        # position embeddings + CLS placement in one pass over the tokens (csrc/embed.cu)
+        tokens = ops.embed_tokens(
+            patches.reshape(B, T, H * W, C),
+            self._get_spatial_pos_embedding(H, W, patches.dtype, patches.device).reshape(H * W, C),
+            self._get_temporal_pos_embedding(T, offset=temporal_pos_offset, dtype=patches.dtype,
+                                             device=patches.device).reshape(T, C),
+            cls_row)
 
         _, visible = self._visible_token_positions(mask, B, tokens.shape[1], tokens.device,
                                                    require_cls_visible=has_cls)

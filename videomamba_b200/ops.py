@@ -145,6 +145,43 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     return out.reshape(*x.shape[:-1], N)
 
 
+def patchify(x: Tensor, tubelet: int, ph: int, pw: int) -> Tensor:
+    """Clip ``(B, C, T, H, W)`` -> patch rows ``(B*t*h*w, C*tubelet*ph*pw)`` (im2col of a Conv3d whose
+    kernel equals its stride; rows ordered (b, t, y, x), columns (c, dt, dy, dx))."""
+    _require_cuda(x)
+    lib = _lib.load()
+    x = x.contiguous()
+    B, C, T, H, W = x.shape
+    t, h, w = T // tubelet, H // ph, W // pw
+    cols = torch.empty((B * t * h * w, C * tubelet * ph * pw), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        rc = lib.vmb_patchify(_p(x), _p(cols), B, C, T, H, W, tubelet, ph, pw, _dt(x), _stream(x))
+    _lib.check(rc, "vmb_patchify")
+    return cols
+
+
+def embed_tokens(patches: Tensor, spatial: Tensor, temporal: Tensor,
+                 cls_row: Optional[Tensor] = None) -> Tensor:
+    """``(B, t, hw, D)`` patch tokens + spatial ``(hw, D)`` + temporal ``(t, D)`` position embeddings
+    (each add rounded to the token dtype), CLS row ``(D,)`` written at position 0 when given:
+    ``(B, has_cls + t*hw, D)``."""
+    _require_cuda(patches)
+    lib = _lib.load()
+    B, t, hw, D = patches.shape
+    dt = patches.dtype
+    patches = patches.contiguous()
+    spatial = spatial.to(dt).reshape(hw, D).contiguous()
+    temporal = temporal.to(dt).reshape(t, D).contiguous()
+    if cls_row is not None:
+        cls_row = cls_row.to(dt).reshape(D).contiguous()
+    out = torch.empty((B, (cls_row is not None) + t * hw, D), dtype=dt, device=patches.device)
+    with _on_device(patches):
+        rc = lib.vmb_embed_tokens(_p(patches), _p(spatial), _p(temporal), _p(cls_row), _p(out), B, t, hw,
+                                  D, _dt(patches), _stream(patches))
+    _lib.check(rc, "vmb_embed_tokens")
+    return out
+
+
 def _token_major(t: Tensor) -> Tensor:
     """(B, L, C) tensor with channel stride 1 (copy only when needed)."""
     if t.stride(-1) != 1:
