@@ -898,8 +898,8 @@ void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   const int64_t want = 8ll * sm_count();       // ~2 warps per scheduler
   *nseg = 1;
   *seg_len = (a.L + kTT - 1) / kTT * kTT;
-  if (warps >= want || a.L < 2048) return;
-  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 512);
+  if (warps >= want || a.L < 768) return;       // a lone warp needs ~230 clk per token, 3 per scheduler ~120 each
+  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 256);
   if (n < 2) return;
   const int len = ((a.L + n - 1) / n + kTT - 1) / kTT * kTT;
   *nseg = (a.L + len - 1) / len;
