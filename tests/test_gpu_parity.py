@@ -201,6 +201,30 @@ def test_oracle_parity_production_widths(dtype, width, perturbed):
         assert rel_err(stitched, got_vis) <= (2e-2 if dtype == torch.bfloat16 else 1e-5)
 
 
+@pytest.mark.parametrize("case", ["configs0_tiny_8f_fp32_b2", "configs1_small_16f_bf16_b1"])
+def test_oracle_parity_at_baseline_sizes(case):
+    """BASELINE.json configs[0] exactly (VideoMamba-Tiny, depth 24, 8 frames @224, fp32, batch 2; bar
+    1e-5) and configs[1] at full model / clip size (VideoMamba-Small, depth 24, 16 frames @224, bf16,
+    3 137 tokens, batch 1; bar 2e-2), general-A weights, against the CPU oracle on x_vis and x_pool."""
+    if case.startswith("configs0"):
+        dim, frames, batch, dtype = 192, 8, 2, torch.float32
+    else:
+        dim, frames, batch, dtype = 384, 16, 1, torch.bfloat16
+    cfg = dict(img_size=224, patch_size=16, depth=24, embed_dim=dim, kernel_size=1, num_frames=frames,
+               norm_epsilon=1e-5, rms_norm=True, fused_add_norm=True, residual_in_fp32=True,
+               pool_type="cls+avg", add_pool_norm=True)
+    sd = _synthetic(cfg, dtype, True, seed=7)
+    x = torch.rand(batch, 3, frames, 224, 224, generator=torch.Generator().manual_seed(2)).to(dtype)
+    oracle = orc.OracleVideoMamba(cfg, sd)          # the reference's rounding points in `dtype`
+    m = _model_from(cfg, sd, dtype)
+    with torch.no_grad():
+        want_vis, want_pool = oracle.forward(x)
+        got_vis, got_pool = m(x.to(DEV))
+    assert got_vis.shape == (batch, frames * 196, dim)
+    _close(got_vis, want_vis, _tol(dtype))
+    _close(got_pool, want_pool, _tol(dtype))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_mixer_forced_generic_equals_auto_path(dtype):
     """Both kernel selections of vmb_mixer_fwd must agree with the oracle (and so each other)."""
