@@ -895,12 +895,12 @@ __global__ void scan_carry_kernel(const FastScanArgs a) {
 // Segments only when the batch alone cannot fill the GPU (one warp per 16 channels of a sequence).
 void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   const int64_t warps = (int64_t)a.B * (a.Di / kCh);
-  const int64_t want = 8ll * sm_count();       // ~2 warps per scheduler
+  const int64_t want = 12ll * sm_count();      // 3 warps per scheduler
   *nseg = 1;
   *seg_len = (a.L + kTT - 1) / kTT * kTT;
   if (warps >= want || a.L < 768) return;       // a lone warp needs ~230 clk per token, 3 per scheduler ~120 each
   int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 256);
-  if (n < 2) return;
+  if (n < 3) return;                           // two segments cost 1.26x the work for less than that in occupancy
   const int len = ((a.L + n - 1) / n + kTT - 1) / kTT * kTT;
   *nseg = (a.L + len - 1) / len;
   *seg_len = len;
