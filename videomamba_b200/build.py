@@ -25,6 +25,10 @@ NVCC_FLAGS = [
 ]
 
 
+# experiments: extra nvcc flags (e.g. -DVMB_SCAN_MIN_CTAS=16) without editing this file
+NVCC_FLAGS += [f for f in os.environ.get("VMB_NVCC_EXTRA", "").split() if f]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isfile(cand) or cand == "nvcc"):
