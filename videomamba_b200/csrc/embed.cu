@@ -19,26 +19,26 @@ namespace {
 template <typename V, int VEC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const V* __restrict__ x, V* __restrict__ cols, int C, int T, int H, int W, int k,
-                int ph, int pw, int t, int h, int w, int64_t total_vecs) {
+                int ph, int pw, int t, int h, int w, int64_t rows) {
+  // a warp walks one used image row (b, c, tt, y); lanes take consecutive VEC-pixel vectors
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
   const int wv = (w * pw) / VEC;                   // vectors per used image row
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vecs;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    // i enumerates (b, c, tt, y, xv) over the used region, x fastest
-    int64_t r = i;
-    const int xv = (int)(r % wv); r /= wv;
-    const int y = (int)(r % (h * ph)); r /= (h * ph);
-    const int tt = (int)(r % (t * k)); r /= (t * k);
-    const int c = (int)(r % C);
-    const int64_t b = r / C;
+  int64_t q = r;
+  const int y = (int)(q % (h * ph)); q /= (h * ph);
+  const int tt = (int)(q % (t * k)); q /= (t * k);
+  const int c = (int)(q % C);
+  const int64_t b = q / C;
+  const int py = y / ph, dy = y % ph;
+  const int tp = tt / k, dt = tt % k;
+  const int64_t K = (int64_t)C * k * ph * pw;
+  const int64_t src_row = (((b * C + c) * T + tt) * H + y) * (int64_t)W;
+  const int64_t dst_row0 = ((b * t + tp) * h + py) * (int64_t)w;            // patch row of px = 0
+  const int64_t col0 = (((int64_t)c * k + dt) * ph + dy) * pw;
+  for (int xv = threadIdx.x & 31; xv < wv; xv += 32) {
     const int xpix = xv * VEC;
     const int px = xpix / pw, dx = xpix % pw;
-    const int py = y / ph, dy = y % ph;
-    const int tp = tt / k, dt = tt % k;
-    const int64_t src = ((((b * C + c) * T + tt) * H + y) * (int64_t)W + xpix) / VEC;
-    const int64_t row = ((b * t + tp) * h + py) * (int64_t)w + px;
-    const int64_t col = (((int64_t)c * k + dt) * ph + dy) * pw + dx;
-    const int64_t K = (int64_t)C * k * ph * pw;
-    cols[(row * K + col) / VEC] = x[src];
+    cols[((dst_row0 + px) * K + col0 + dx) / VEC] = x[(src_row + xpix) / VEC];
   }
 }
 
@@ -58,24 +58,25 @@ embed_tokens_kernel(const T* __restrict__ patches, const T* __restrict__ spatial
     const int64_t tokrow = i / dv;
     const int64_t b = tokrow / L;
     const int64_t l = tokrow % L;
-    float v[VEC];
+    // whole-vector loads / stores (VEC elements = 16 bytes on the aligned path, 1 element otherwise)
+    struct alignas(sizeof(T) * VEC) Vec { T e[VEC]; };
+    Vec o;
     if (has_cls && l == 0) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) v[e] = to_f32<T>(cls_row[d + e]);
+      o = *reinterpret_cast<const Vec*>(cls_row + d);
     } else {
       const int64_t p = l - has_cls;
       const int tp = (int)(p / hw), s = (int)(p % hw);
-      const T* src = patches + ((b * t + tp) * hw + s) * D + d;
+      const Vec a = *reinterpret_cast<const Vec*>(patches + ((b * t + tp) * hw + s) * D + d);
+      const Vec sp = *reinterpret_cast<const Vec*>(spatial + (int64_t)s * D + d);
+      const Vec te = *reinterpret_cast<const Vec*>(temporal + (int64_t)tp * D + d);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         // two roundings, as the reference's two separate adds in the model dtype
-        const float a = to_f32<T>(from_f32<T>(to_f32<T>(src[e]) + to_f32<T>(spatial[(int64_t)s * D + d + e])));
-        v[e] = a + to_f32<T>(temporal[(int64_t)tp * D + d + e]);
+        const float first = to_f32<T>(from_f32<T>(to_f32<T>(a.e[e]) + to_f32<T>(sp.e[e])));
+        o.e[e] = from_f32<T>(first + to_f32<T>(te.e[e]));
       }
     }
-    T* dst = out + tokrow * D + d;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) dst[e] = from_f32<T>(v[e]);
+    *reinterpret_cast<Vec*>(out + tokrow * D + d) = o;
   }
 }
 
@@ -94,16 +95,14 @@ extern "C" int vmb_patchify(const void* x, void* cols, int64_t B, int C, int T, 
   VMB_CHECK_ARG(x && cols, "patchify: null pointer");
   cudaStream_t st = as_stream(stream);
   const int es = dtype_size(dtype);
-  const int64_t used = B * C * (int64_t)(t * k) * (h * ph) * (w * pw);
-  auto grid_for = [](int64_t n) { return (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16); };
+  auto grid_for = [](int64_t rows) { return (unsigned)((rows + 7) / 8); };
   // widest vector that divides the patch width and keeps every source / destination run aligned
   int vec_bytes = 16;
   while (vec_bytes > es && ((pw * es) % vec_bytes != 0 || (W * es) % vec_bytes != 0 ||
                             reinterpret_cast<uintptr_t>(x) % vec_bytes != 0 ||
                             reinterpret_cast<uintptr_t>(cols) % vec_bytes != 0))
     vec_bytes /= 2;
-  const int vec = vec_bytes / es;
-  const int64_t nv = used / vec;
+  const int64_t nv = B * C * (int64_t)(t * k) * (h * ph);     // used image rows, one warp each
   // the element type only matters through its size: move raw words
   if (vec_bytes == 16) {
     if (es == 2) patchify_kernel<uint4, 8><<<grid_for(nv), 256, 0, st>>>((const uint4*)x, (uint4*)cols, C, T, H, W, k, ph, pw, t, h, w, nv);

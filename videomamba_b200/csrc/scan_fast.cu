@@ -32,6 +32,14 @@
 //     the parallelism (long-clip configuration, 25 089 tokens at batch 1).
 //   * reverse = 1 walks the sequence back to front (tile rows are gathered in logical order), which
 //     is what the flipped branch of BiMambaRefinerBlock needs without any torch.flip copy.
+//
+// Four layouts of the same kernel live in this file (measured against each other in
+// profiles/r01_scan_ncu_full_summary.txt); VMB_SCAN_VARIANT picks one:
+//   0 / 9  v9 (default)  lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one HMMA
+//   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
+//   1      v4            lane = 2 channels x 4 states, two shuffles per token (this header describes it)
+//   4      v6            v7's lanes, phase A of tile k+1 overlapped with tile k (149 registers, 19 KB)
+//   2      none of them: the any-shape kernel of scan_generic.cu
 #include <algorithm>
 #include <cstdlib>
 
@@ -866,6 +874,274 @@ scan7_kernel(const FastScanArgs a) {
 
 }  // namespace v7
 
+// =================================================================================================
+// v9: the <C_t, h_t> contraction on the tensor pipe.  Getting B_t and C_t into every lane is the
+// largest cost of v7 (timing ablation in profiles/: the shared-memory loads are ~41 % of the kernel,
+// the exponentials ~20 %).  Here a lane owns the 2 channels x 4 states of an mma.m16n8k16 A fragment
+// (rows = the warp's 16 channels, k = the 16 states): channels g, g + 8 and states 2 tig + {0, 1},
+// 2 tig + 8 + {0, 1} (g = lane >> 2, tig = lane & 3).  After the state update the fp32 states are
+// rounded once to bf16 pairs (exactly the fragment registers) and one HMMA multiplies them with C_t,
+// which stays in its bf16 form and is replicated over the 8 columns of the B operand -- so every
+// lane of a channel receives the finished sum: no shuffle, no fp32 expansion of C_t, half the B_t
+// bytes per lane.  The products C*h are exact in fp32; the only extra rounding is h -> bf16 inside
+// the contraction (2^-9 relative per term; the state itself stays fp32).
+// =================================================================================================
+namespace v9 {
+
+struct Plan {
+  int u0, z0, x0, b, dd, y, total, xrow;
+  __host__ __device__ int u(int s) const { return u0 + s * (kTT * kRowBytes); }
+  __host__ __device__ int z(int s) const { return z0 + s * (kTT * kRowBytes); }
+  __host__ __device__ int x(int s) const { return x0 + s * (kTT * xrow); }
+};
+__host__ __device__ inline Plan plan(int Xp) {
+  Plan p;
+  int off = 0;
+  p.xrow = x_row_bytes(Xp);
+  p.u0 = off; off += 2 * kTT * kRowBytes;
+  p.z0 = off; off += 2 * kTT * kRowBytes;
+  p.x0 = off; off += 2 * kTT * p.xrow;            // double buffered: C_t is read from the raw rows
+  p.b = off; off += kTT * kN * 4;                 // [token][tig][B(2tig), B(2tig+1), B(2tig+8), B(2tig+9)] fp32
+  p.dd = off; off += kTT * 8 * 16;                // [token][g ^ (token & 1)]{delta_g, du_g, delta_g+8, du_g+8}
+  p.y = off; off += kTT * kRowBytes;
+  p.total = off;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int R, bool kStateOnly>
+__global__ void __launch_bounds__(kThreads, 18)
+scan9_kernel(const FastScanArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int KST = (R + 15) / 16;
+  const Plan sp = plan(a.Xp);
+  const int xrow = sp.xrow;
+  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  using bf16 = __nv_bfloat16;
+
+  const int lane = threadIdx.x;
+  const int g = lane >> 2, tig = lane & 3;        // mma fragment coordinates (both phases)
+  const int cw = blockIdx.x * kCh;
+  const int b = blockIdx.y;
+  const int seg = blockIdx.z;
+  const int tbeg = seg * a.seg_len;
+  const int L = min(a.L, tbeg + a.seg_len);
+  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
+  float* const wsH = a.seg_ws;
+  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
+  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
+
+  // states of this lane: channel ca = cw + g -> ha[0] = (2 tig, 2 tig + 1), ha[1] = (2 tig + 8, + 9);
+  // channel cb = ca + 8 -> hb likewise
+  float2 Aa[2], Ab[2], ha[2], hb[2];
+  const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
+  const int64_t hoff_b = hoff_a + 8 * kN;
+  {
+    const float* pa = a.A2 + (int64_t)(cw + g) * kN + 2 * tig;
+    Aa[0] = *reinterpret_cast<const float2*>(pa);
+    Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
+    Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
+    Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
+    auto ld = [&](int64_t off) -> float {
+      if (kStateOnly) return 0.f;
+      if (seg > 0) return wsHin[seg * seg_stride + off];
+      return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
+    };
+    ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
+    ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
+    hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
+    hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
+  }
+  const float Da = a.D ? a.D[cw + g] : 0.f, Db = a.D ? a.D[cw + g + 8] : 0.f;
+  // phase A (dt projection): accumulator rows = tokens g, g + 8; columns = channels 8 n + 2 tig + {0, 1}
+  uint32_t bfrag[2][KST][2];
+  float bias[2][2];
+  {
+    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const bf16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
+        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
+      }
+      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
+      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
+    }
+  }
+
+  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
+  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
+  const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
+  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
+  const int xchunks = a.Xp / 8;
+  const int dir = a.reverse ? -1 : 1;
+  const int p0 = a.reverse ? a.L - 1 : 0;
+  const int u_ts = (int)a.u_ts, z_ts = (int)a.z_ts, x_ts = (int)a.x_ts, y_ts = (int)a.y_ts;
+
+  auto issue_tile = [&](int tile, int st) {
+    const int row = lane >> 1, ch = lane & 1;
+    const int t = tile * kTT + row;
+    const bool ok = t < L;
+    const int prow = ok ? p0 + dir * t : 0;
+    cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + (prow * u_ts + ch * 8), ok);
+    if (!kStateOnly)
+      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + (prow * z_ts + ch * 8), ok);
+    const bf16* src = xg + prow * x_ts;
+    for (int k = ch; k < xchunks; k += 2) cp_async16(sbase + sp.x(st) + row * xrow + k * 16, src + k * 8, ok);
+  };
+
+  const int tile_lo = tbeg / kTT;
+  const int ntiles = (L + kTT - 1) / kTT;
+  issue_tile(tile_lo, 0);
+  cp_async_commit();
+  float sum_a = 0.f, sum_b = 0.f;
+  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
+
+  for (int tile = tile_lo; tile < ntiles; ++tile) {
+    const int st = (tile - tile_lo) & 1;
+    const int t0 = tile * kTT;
+    cp_async_wait<0>();
+    __syncwarp();                                  // tile landed; last tile's smem readers are done
+    if (tile + 1 < ntiles) issue_tile(tile + 1, st ^ 1);   // the other raw stage is free: prefetch now
+    cp_async_commit();
+
+    const uint8_t* su = smem + sp.u(st);
+    const uint8_t* sz = smem + sp.z(st);
+    const uint8_t* sx = smem + sp.x(st);
+
+    // ---- B_t of the tile to fp32, in fragment order (a lane's 4 states contiguous) --------------
+#pragma unroll
+    for (int i = 0; i < (kTT * kN / 2) / kThreads; ++i) {         // 16 tokens x 8 bf16 pairs
+      const int e = lane + i * kThreads;
+      const int row = e >> 3, p = e & 7;                          // pair p = states 2p, 2p + 1
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(sx + row * xrow + (R + 2 * p) * 2);
+      // states 2 tig + e -> slot 4 tig + e; states 2 tig + 8 + e -> slot 4 tig + 2 + e
+      const int slot = (p & 3) * 4 + (p >> 2) * 2;
+      *reinterpret_cast<float2*>(smem + sp.b + row * (kN * 4) + slot * 4) = make_float2(bf16lo(v), bf16hi(v));
+    }
+    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
+    {
+      float acc[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        uint32_t af[4];
+        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
+        ldmatrix_x4(sbase + sp.x(st) + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
+        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int tl = g + 8 * half;                              // token row within the tile
+        const bool pad = t0 + tl >= L;
+        const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + tl * kRowBytes + (2 * tig) * 2);
+        const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + tl * kRowBytes + (8 + 2 * tig) * 2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                             // channels 2 tig + i and 8 + 2 tig + i
+          float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
+          float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
+          if (pad) { da = 0.f; db = 0.f; }                        // padding: decay 1, drive 0
+          const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
+          *reinterpret_cast<float4*>(smem + sp.dd + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
+              make_float4(da, da * uav, db, db * ubv);
+        }
+      }
+    }
+    __syncwarp();                                  // B / dd tiles visible
+
+    // ---- phase B: the recurrence; <C, h> by one HMMA per token -------------------------------------
+    const uint8_t* sdd0 = smem + sp.dd + (g << 4);                // even tokens
+    const uint8_t* sdd1 = smem + sp.dd + ((g ^ 1) << 4);          // odd tokens
+    const uint8_t* sb = smem + sp.b + tig * 16;
+    const uint8_t* sc = sx + (R + kN + 2 * tig) * 2;              // C_t words (2 tig, 2 tig + 1) of the raw rows
+#pragma unroll
+    for (int tg = 0; tg < kTT; tg += 4) {
+      float ya = 0.f, yb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = tg + i;
+        const float4 dd = *reinterpret_cast<const float4*>(((t & 1) ? sdd1 : sdd0) + t * 128);
+        const float4 Bv = *reinterpret_cast<const float4*>(sb + t * (kN * 4));
+        const float2 da2 = make_float2(dd.x, dd.x), db2 = make_float2(dd.z, dd.z);
+        const float2 xa0 = __fmul2_rn(da2, Aa[0]), xa1 = __fmul2_rn(da2, Aa[1]);
+        const float2 xb0 = __fmul2_rn(db2, Ab[0]), xb1 = __fmul2_rn(db2, Ab[1]);
+        const float2 ea0 = make_float2(ex2_approx(xa0.x), ex2_approx(xa0.y));
+        const float2 ea1 = make_float2(ex2_approx(xa1.x), ex2_approx(xa1.y));
+        const float2 eb0 = make_float2(ex2_approx(xb0.x), ex2_approx(xb0.y));
+        const float2 eb1 = make_float2(ex2_approx(xb1.x), ex2_approx(xb1.y));
+        const float2 dua = make_float2(dd.y, dd.y), dub = make_float2(dd.w, dd.w);
+        const float2 B01 = make_float2(Bv.x, Bv.y), B89 = make_float2(Bv.z, Bv.w);
+        ha[0] = __ffma2_rn(ea0, ha[0], __fmul2_rn(dua, B01));
+        ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
+        hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
+        hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
+        if constexpr (kStateOnly) {
+          sum_a += dd.x;
+          sum_b += dd.z;
+        } else {
+          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * xrow);
+          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * xrow + 16);
+          const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
+                                  pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(d, af, c0, c1);           // every column of the B operand is C_t: d[0] = y(ca), d[2] = y(cb)
+          if (tig == i) { ya = d[0]; yb = d[2]; }
+        }
+      }
+      if constexpr (!kStateOnly) {
+        // lane tig finalises token tg + tig of its two channels
+        const int tf = tg + tig;
+        const float ua = __bfloat162float(*reinterpret_cast<const bf16*>(su + tf * kRowBytes + g * 2));
+        const float ub = __bfloat162float(*reinterpret_cast<const bf16*>(su + tf * kRowBytes + (g + 8) * 2));
+        const float za = __bfloat162float(*reinterpret_cast<const bf16*>(sz + tf * kRowBytes + g * 2));
+        const float zb = __bfloat162float(*reinterpret_cast<const bf16*>(sz + tf * kRowBytes + (g + 8) * 2));
+        sy[tf * (kRowBytes / 2) + g] = __float2bfloat16_rn(fmaf(Da, ua, ya) * silu_fast(za));
+        sy[tf * (kRowBytes / 2) + g + 8] = __float2bfloat16_rn(fmaf(Db, ub, yb) * silu_fast(zb));
+      }
+    }
+    if constexpr (!kStateOnly) {
+      __syncwarp();
+      const int row = lane >> 1, ch = lane & 1;
+      const int t = t0 + row;
+      if (t < L)
+        *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
+            *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
+    }
+    // the __syncwarp at the top of the next iteration orders these reads before the next writes
+  }
+
+  auto st_h = [&](float* dst) {
+    *reinterpret_cast<float2*>(dst + hoff_a) = ha[0];
+    *reinterpret_cast<float2*>(dst + hoff_a + 8) = ha[1];
+    *reinterpret_cast<float2*>(dst + hoff_b) = hb[0];
+    *reinterpret_cast<float2*>(dst + hoff_b + 8) = hb[1];
+  };
+  if constexpr (kStateOnly) {
+    st_h(wsH + seg * seg_stride);
+    if (tig == 0) {
+      float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + cw + g;
+      ss[0] = sum_a;
+      ss[8] = sum_b;
+    }
+    return;
+  }
+  if (seg != a.nseg - 1) return;
+  if (a.h_last != nullptr) st_h(a.h_last);
+}
+
+}  // namespace v9
+
 int variant() {
   static int v = [] {
     const char* e = std::getenv("VMB_SCAN_VARIANT");
@@ -936,6 +1212,33 @@ int launch(const FastScanArgs& a0, cudaStream_t st) {
 }
 
 template <int R>
+int launch9(const FastScanArgs& a0, cudaStream_t st) {
+  FastScanArgs a = a0;
+  plan_segments(a, &a.nseg, &a.seg_len);
+  const v9::Plan sp = v9::plan(a.Xp);
+  if (sp.total > 48 * 1024) VMB_UNSUPPORTED("scan_fast: x_dbl rows too wide for the staging buffers");
+  if (a.nseg > 1) {
+    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
+    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
+      a.nseg = 1;
+      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
+    }
+  }
+  if (a.nseg > 1) {
+    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
+    v9::scan9_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
+    VMB_LAUNCH_CHECK("scan9_kernel<state>");
+    const int64_t n = (int64_t)a.B * a.Di * kN;
+    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    VMB_LAUNCH_CHECK("scan_carry_kernel");
+  }
+  dim3 grid(a.Di / kCh, a.B, a.nseg);
+  v9::scan9_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
+  VMB_LAUNCH_CHECK("scan9_kernel");
+  return VMB_OK;
+}
+
+template <int R>
 int launch6(const FastScanArgs& a0, cudaStream_t st) {
   FastScanArgs a = a0;
   plan_segments(a, &a.nseg, &a.seg_len);
@@ -974,7 +1277,7 @@ bool scan_fast_supported(const FastScanArgs& a) {
          (a.h_last == nullptr || al16(a.h_last)) &&
          a.u_bs % 8 == 0 && a.u_ts % 8 == 0 && a.z_bs % 8 == 0 && a.z_ts % 8 == 0 &&
          a.x_bs % 8 == 0 && a.x_ts % 8 == 0 && a.y_bs % 8 == 0 && a.y_ts % 8 == 0 &&
-         (variant() & 2) == 0;
+         variant() != 2;                       // VMB_SCAN_VARIANT=2: never use the fused kernels
 }
 
 int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
@@ -987,6 +1290,14 @@ int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {
+  if (variant() == 0 || variant() == 9) {   // default: v9, <C, h> on the tensor pipe
+    switch (a.R) {
+      case 12: return launch9<12>(a, st);
+      case 24: return launch9<24>(a, st);
+      case 36: return launch9<36>(a, st);
+      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
+    }
+  }
   if (variant() == 4) {        // VMB_SCAN_VARIANT=4 (v6 layout): faster alone, but fills the SM (see profiles/)
     switch (a.R) {
       case 12: return launch6<12>(a, st);
@@ -995,7 +1306,7 @@ int scan_fast(const FastScanArgs& a, cudaStream_t st) {
       default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
     }
   }
-  if (variant() != 1) {        // default: v7; VMB_SCAN_VARIANT=1: v4 (2 channels x 4 states per lane)
+  if (variant() == 7) {        // VMB_SCAN_VARIANT=7: v7 (1 channel x 8 states per lane, fp32 contraction); =1: v4
     switch (a.R) {
       case 12: return launch<12, true>(a, st);
       case 24: return launch<24, true>(a, st);
