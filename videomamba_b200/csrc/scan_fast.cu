@@ -38,7 +38,8 @@
 //   0 / 9  v9 (default)  lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one HMMA
 //   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
 //   1      v4            lane = 2 channels x 4 states, two shuffles per token (this header describes it)
-//   4      v6            v7's lanes, phase A of tile k+1 overlapped with tile k (149 registers, 19 KB)
+//   (v6 -- v7's lanes with phase A of tile k+1 overlapped with tile k, 149 registers, 19 KB -- was measured and
+//    removed: faster alone, slower with steps in flight; git history and profiles/ keep it)
 //   2      none of them: the any-shape kernel of scan_generic.cu
 #include <algorithm>
 #include <cstdlib>
@@ -363,296 +364,8 @@ scan_fast_kernel(const FastScanArgs a) {
 
 
 // =================================================================================================
-// v6: a lane owns ONE channel x 8 states (2 lanes per channel): one shuffle per token pair and every
-// delta / B / C load is shared by 8 state updates.  Phase A of tile k+1 (dt projection on the tensor
-// pipe, softplus, delta*u, D*u, SiLU(z)) is issued inside the straight-line block of the recurrence
-// of tile k, so its MUFU / HMMA / LDS latencies hide behind the recurrence instead of forming a
-// per-tile bubble; everything the output needs per (token, channel) is precomputed there as one
-// float4 {delta, delta*u, D*u, SiLU(z)}.  u / z / dt_low rows are staged by 16-byte cp.async two
-// tiles ahead (fire and forget: a warp issues in order, so a register prefetch from global would
-// expose the L2 latency at its first use); B_t / C_t are expanded to fp32 once per tile.
-// =================================================================================================
-namespace v6 {
-
-constexpr int kDdPitch = kCh * 16 + 16;           // bytes per token row of the {delta,du,Du,sz} tile
-constexpr int kBcPitch = 2 * kN * 4;              // [B0..15 | C0..15] fp32
-
-template <int R> struct Plan {
-  static constexpr int KST = (R + 15) / 16;
-  static constexpr int xrow = KST * 32 + 16;      // dt_low columns only; odd number of 16-B chunks
-  static constexpr int raw_u = 0;
-  static constexpr int raw_z = kTT * kRowBytes;
-  static constexpr int raw_x = 2 * kTT * kRowBytes;
-  static constexpr int raw_stride = 2 * kTT * kRowBytes + kTT * xrow;
-  static constexpr int dd0 = 2 * raw_stride;
-  static constexpr int dd_stride = kTT * kDdPitch;
-  static constexpr int bc0 = dd0 + 2 * dd_stride;
-  static constexpr int bc_stride = kTT * kBcPitch;
-  static constexpr int y0 = bc0 + 2 * bc_stride;
-  static constexpr int total = y0 + kTT * kRowBytes;
-};
-
-template <int R, bool kStateOnly>
-__global__ void __launch_bounds__(kThreads, 11)
-scan6_kernel(const FastScanArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  using P = Plan<R>;
-  constexpr int KST = P::KST;
-  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  using bf16 = __nv_bfloat16;
-
-  const int lane = threadIdx.x;
-  const int j4 = lane & 3, pr = lane >> 2;        // phase A: accumulator column pair / row
-  const int c = lane >> 1, jh = lane & 1;         // phase B: channel within the CTA / state half
-  const int cw = blockIdx.x * kCh;
-  const int b = blockIdx.y;
-  const int seg = blockIdx.z;
-  const int tbeg = seg * a.seg_len;
-  const int L = min(a.L, tbeg + a.seg_len);
-  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
-  float* const wsH = a.seg_ws;
-  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
-  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
-
-  // ---- per-lane constants -------------------------------------------------------------------
-  float2 Ap[4], hp[4];
-  const int64_t hoff = ((int64_t)b * a.Di + cw + c) * kN + 8 * jh;
-  {
-    const float4 v0 = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(cw + c) * kN + 8 * jh);
-    const float4 v1 = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(cw + c) * kN + 8 * jh + 4);
-    Ap[0] = make_float2(v0.x, v0.y); Ap[1] = make_float2(v0.z, v0.w);
-    Ap[2] = make_float2(v1.x, v1.y); Ap[3] = make_float2(v1.z, v1.w);
-    float h[8];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (kStateOnly) h[n] = 0.f;
-      else if (seg > 0) h[n] = wsHin[seg * seg_stride + hoff + n];
-      else h[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) hp[k] = make_float2(h[2 * k], h[2 * k + 1]);
-  }
-  uint32_t bfrag[2][KST][2];
-  float bias[2][2], Dv[2][2];
-  {
-    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const bf16* wr = wd + (int64_t)(cw + 8 * n + pr) * a.Rp;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * j4);
-        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * j4);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        bias[n][i] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j4 + i] : 0.f;
-        Dv[n][i] = a.D ? a.D[cw + 8 * n + 2 * j4 + i] : 0.f;
-      }
-    }
-  }
-
-  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
-  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
-  const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
-  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
-  // token t of the logical sequence lives at row p0 + dir * t; offsets inside one batch entry fit 32 bits
-  const int dir = a.reverse ? -1 : 1;
-  const int p0 = a.reverse ? a.L - 1 : 0;
-  const int u_ts = (int)a.u_ts, z_ts = (int)a.z_ts, x_ts = (int)a.x_ts, y_ts = (int)a.y_ts;
-
-  // raw tile: u, z (16 rows x 32 B) and the dt_low columns of x_dbl, by 16-byte cp.async
-  auto issue_raw = [&](int tile, int st) {
-    const uint32_t base = sbase + st * P::raw_stride;
-    {
-      const int row = lane >> 1, ch = lane & 1;
-      const int t = tile * kTT + row;
-      const bool ok = t < L;
-      const int prow = ok ? p0 + dir * t : 0;
-      cp_async16(base + P::raw_u + row * kRowBytes + ch * 16, ug + (prow * u_ts + ch * 8), ok);
-      if (!kStateOnly)
-        cp_async16(base + P::raw_z + row * kRowBytes + ch * 16, zg + (prow * z_ts + ch * 8), ok);
-    }
-#pragma unroll
-    for (int i = 0; i < KST; ++i) {
-      const int e = lane + 32 * i;
-      const int row = e / (2 * KST), ch = e % (2 * KST);
-      const int t = tile * kTT + row;
-      const bool ok = t < L;
-      cp_async16(base + P::raw_x + row * P::xrow + ch * 16, xg + ((ok ? p0 + dir * t : 0) * x_ts + ch * 8), ok);
-    }
-  };
-  // B_t / C_t of a tile: 16 rows x 64 B straight from global as 8-byte loads (4 per lane: rows
-  // (lane >> 3) + 4 i, 8 bytes at part = lane & 7); they are only needed at the end of the tile ...
-  auto load_bc = [&](int tile, uint2 (&r)[4]) {
-    const int t = tile * kTT + (lane >> 3);
-    const int off = (p0 + dir * t) * x_ts + R + 4 * (lane & 7);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      r[i] = make_uint2(0u, 0u);
-      if (t + 4 * i < L) r[i] = __ldg(reinterpret_cast<const uint2*>(xg + (off + 4 * i * dir * x_ts)));
-    }
-  };
-  // ... where they are expanded to fp32 in shared memory
-  auto store_bc = [&](int st, const uint2 (&r)[4]) {
-    uint8_t* dst = smem + P::bc0 + st * P::bc_stride + (lane >> 3) * kBcPitch + (lane & 7) * 16;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(dst + 4 * i * kBcPitch) =
-          make_float4(bf16lo(r[i].x), bf16hi(r[i].x), bf16lo(r[i].y), bf16hi(r[i].y));
-  };
-  // phase A, part 1: dt projection of a raw tile on the tensor pipe
-  auto phase_a_mma = [&](int st, float (&acc)[2][4]) {
-#pragma unroll
-    for (int n = 0; n < 2; ++n)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < KST; ++ks) {
-      uint32_t af[4];
-      const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-      ldmatrix_x4(sbase + st * P::raw_stride + P::raw_x + row * P::xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
-      mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-      mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-    }
-  };
-  // phase A, part 2 (one of four): two (token, channel) entries {delta, delta*u, D*u, SiLU(z)}
-  auto phase_a_pair = [&](int n, int half, const float (&acc)[2][4], int st, int t0) {
-    const int tl = pr + 8 * half;
-    float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
-    float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
-    if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }                    // padding: decay 1, drive 0
-    const uint8_t* raw = smem + st * P::raw_stride + tl * kRowBytes + (8 * n + 2 * j4) * 2;
-    const uint32_t uv = *reinterpret_cast<const uint32_t*>(raw + P::raw_u);
-    const float u0 = bf16lo(uv), u1 = bf16hi(uv);
-    float4 v0 = make_float4(d0, d0 * u0, Dv[n][0] * u0, 0.f);
-    float4 v1 = make_float4(d1, d1 * u1, Dv[n][1] * u1, 0.f);
-    if (!kStateOnly) {
-      const uint32_t zv = *reinterpret_cast<const uint32_t*>(raw + P::raw_z);
-      v0.w = silu_fast(bf16lo(zv));
-      v1.w = silu_fast(bf16hi(zv));
-    }
-    float4* dst = reinterpret_cast<float4*>(smem + P::dd0 + st * P::dd_stride + tl * kDdPitch + (8 * n + 2 * j4) * 16);
-    dst[0] = v0;
-    dst[1] = v1;
-  };
-
-  // y tile out: 16 rows x 32 bytes from the staging rows as 16-byte stores
-  bf16* const sy = reinterpret_cast<bf16*>(smem + P::y0);
-  auto store_y = [&](int tile) {
-    const int row = lane >> 1, ch = lane & 1;
-    const int t = tile * kTT + row;
-    if (t < L)
-      *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
-          *reinterpret_cast<const uint4*>(smem + P::y0 + row * kRowBytes + ch * 16);
-  };
-
-  const int tile_lo = tbeg / kTT;
-  const int ntiles = (L + kTT - 1) / kTT;
-  float sum_d = 0.f;
-
-  // ---- prologue: tile_lo staged and through phase A ------------------------------------------------
-  {
-    issue_raw(tile_lo, tile_lo & 1);
-    cp_async_commit();
-    uint2 bc[4];
-    load_bc(tile_lo, bc);
-    cp_async_wait<0>();
-    __syncwarp();
-    issue_raw(tile_lo + 1, (tile_lo + 1) & 1);
-    cp_async_commit();
-    float acc[2][4];
-    phase_a_mma(tile_lo & 1, acc);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) phase_a_pair(q >> 1, q & 1, acc, tile_lo & 1, tile_lo * kTT);
-    store_bc(tile_lo & 1, bc);
-  }
-
-  for (int tile = tile_lo; tile < ntiles; ++tile) {
-    const int st = tile & 1, sn = st ^ 1;
-    const int t0 = tile * kTT;
-    cp_async_wait<0>();                            // raw tile + 1 landed
-    __syncwarp();                                  // dd / bc of this tile visible; stage st raw is free
-    issue_raw(tile + 2, st);
-    cp_async_commit();
-    if (!kStateOnly && tile > tile_lo) {
-      store_y(tile - 1);
-      __syncwarp();                                // the staging rows are rewritten further down
-    }
-
-    uint2 bc[4];
-    load_bc(tile + 1, bc);
-    float acc[2][4];
-    phase_a_mma(sn, acc);
-
-    const uint8_t* sdd = smem + P::dd0 + st * P::dd_stride + c * 16;
-    const uint8_t* sbc = smem + P::bc0 + st * P::bc_stride + jh * 32;
-    float qs0 = 0.f, fz0 = 0.f, fw0 = 0.f;
-#pragma unroll
-    for (int t = 0; t < kTT; ++t) {
-      const float4 dd = *reinterpret_cast<const float4*>(sdd + t * kDdPitch);
-      const float4 B0 = *reinterpret_cast<const float4*>(sbc + t * kBcPitch);
-      const float4 B1 = *reinterpret_cast<const float4*>(sbc + t * kBcPitch + 16);
-      const float2 d2 = make_float2(dd.x, dd.x), du2 = make_float2(dd.y, dd.y);
-      float2 e[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 x = __fmul2_rn(d2, Ap[k]);
-        e[k] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-      }
-      hp[0] = __ffma2_rn(e[0], hp[0], __fmul2_rn(du2, make_float2(B0.x, B0.y)));
-      hp[1] = __ffma2_rn(e[1], hp[1], __fmul2_rn(du2, make_float2(B0.z, B0.w)));
-      hp[2] = __ffma2_rn(e[2], hp[2], __fmul2_rn(du2, make_float2(B1.x, B1.y)));
-      hp[3] = __ffma2_rn(e[3], hp[3], __fmul2_rn(du2, make_float2(B1.z, B1.w)));
-      if constexpr (kStateOnly) {
-        sum_d += dd.x;
-      } else {
-        const float4 C0 = *reinterpret_cast<const float4*>(sbc + t * kBcPitch + 64);
-        const float4 C1 = *reinterpret_cast<const float4*>(sbc + t * kBcPitch + 80);
-        float2 q = __fmul2_rn(hp[0], make_float2(C0.x, C0.y));
-        q = __ffma2_rn(hp[1], make_float2(C0.z, C0.w), q);
-        q = __ffma2_rn(hp[2], make_float2(C1.x, C1.y), q);
-        q = __ffma2_rn(hp[3], make_float2(C1.z, C1.w), q);
-        const float s = q.x + q.y;
-        if (t & 1) {                               // lane jh finalises token t - 1 + jh
-          const float mine = jh ? s : qs0, send = jh ? qs0 : s;
-          const float yv = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-          const float du_ = jh ? dd.z : fz0;
-          const float sz_ = jh ? dd.w : fw0;
-          sy[(t - 1 + jh) * (kRowBytes / 2) + c] = __float2bfloat16_rn((yv + du_) * sz_);
-        } else {
-          qs0 = s; fz0 = dd.z; fw0 = dd.w;
-        }
-      }
-      if ((t & 3) == 3) phase_a_pair(t >> 3, (t >> 2) & 1, acc, sn, t0 + kTT);
-    }
-    store_bc(sn, bc);
-  }
-  if (!kStateOnly && ntiles > tile_lo) {
-    __syncwarp();
-    store_y(ntiles - 1);
-  }
-
-  if constexpr (kStateOnly) {
-    float* hs = wsH + seg * seg_stride + hoff;
-    *reinterpret_cast<float4*>(hs) = make_float4(hp[0].x, hp[0].y, hp[1].x, hp[1].y);
-    *reinterpret_cast<float4*>(hs + 4) = make_float4(hp[2].x, hp[2].y, hp[3].x, hp[3].y);
-    if (jh == 0) wsS[((int64_t)seg * a.B + b) * a.Di + cw + c] = sum_d;
-    return;
-  }
-  if (seg != a.nseg - 1) return;
-  if (a.h_last != nullptr) {
-    float* hl = a.h_last + hoff;
-    *reinterpret_cast<float4*>(hl) = make_float4(hp[0].x, hp[0].y, hp[1].x, hp[1].y);
-    *reinterpret_cast<float4*>(hl + 4) = make_float4(hp[2].x, hp[2].y, hp[3].x, hp[3].y);
-  }
-}
-
-}  // namespace v6
-
-// =================================================================================================
 // v7: v4's small footprint (one-warp CTAs, <= 96 registers, 10 KB of shared memory, so two launches
-// can share an SM) with v6's lane layout: a lane owns ONE channel x 8 states (2 lanes per channel),
+// can share an SM) and a lane that owns ONE channel x 8 states (2 lanes per channel),
 // one shuffle per token PAIR, 32-bit address arithmetic.  Phase A is not overlapped with the
 // recurrence inside a warp; the other resident warps cover it.
 // =================================================================================================
@@ -1238,32 +951,6 @@ int launch9(const FastScanArgs& a0, cudaStream_t st) {
   return VMB_OK;
 }
 
-template <int R>
-int launch6(const FastScanArgs& a0, cudaStream_t st) {
-  FastScanArgs a = a0;
-  plan_segments(a, &a.nseg, &a.seg_len);
-  constexpr int smem = v6::Plan<R>::total;
-  if (a.nseg > 1) {
-    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
-    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
-      a.nseg = 1;
-      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
-    }
-  }
-  if (a.nseg > 1) {
-    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
-    v6::scan6_kernel<R, true><<<g1, kThreads, smem, st>>>(a);
-    VMB_LAUNCH_CHECK("scan6_kernel<state>");
-    const int64_t n = (int64_t)a.B * a.Di * kN;
-    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
-    VMB_LAUNCH_CHECK("scan_carry_kernel");
-  }
-  dim3 grid(a.Di / kCh, a.B, a.nseg);
-  v6::scan6_kernel<R, false><<<grid, kThreads, smem, st>>>(a);
-  VMB_LAUNCH_CHECK("scan6_kernel");
-  return VMB_OK;
-}
-
 }  // namespace
 
 bool scan_fast_supported(const FastScanArgs& a) {
@@ -1295,14 +982,6 @@ int scan_fast(const FastScanArgs& a, cudaStream_t st) {
       case 12: return launch9<12>(a, st);
       case 24: return launch9<24>(a, st);
       case 36: return launch9<36>(a, st);
-      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
-    }
-  }
-  if (variant() == 4) {        // VMB_SCAN_VARIANT=4 (v6 layout): faster alone, but fills the SM (see profiles/)
-    switch (a.R) {
-      case 12: return launch6<12>(a, st);
-      case 24: return launch6<24>(a, st);
-      case 36: return launch6<36>(a, st);
       default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
     }
   }
