@@ -8,39 +8,35 @@
 // :109-172; semantics of _selective_scan_ref :30-106).  Difference in rounding points: the
 // reference rounds delta_raw to bf16 between the two ops, here it stays fp32 (closer to exact).
 //
-// The kernel is bound by MUFU ex2 throughput, instruction issue and shared-memory bandwidth, not
-// by HBM (DESIGN.md "scan"), so the layout minimises instructions and smem bytes per (token,
-// channel):
+// The kernel is bound by instruction issue, MUFU ex2 and the register-file write-back of its
+// shared-memory loads, not by HBM (profiles/r01_scan_ncu_full_summary.txt).  Common
+// to all layouts below:
 //   * CTA = ONE warp = (batch b, 16 channels); the sequence is walked in tiles of 16 tokens staged
-//     with 16-byte cp.async copies (u / z double buffered).  One-warp CTAs need no block barriers,
-//     drift out of phase with each other (so some warp always has MUFU work ready), and 1536 of
-//     them spread over 148 SMs within 6 % of even (768 two-warp CTAs: 14 % idle tail).
-//   * phase A (per tile, per warp): the dt projection of the tile, delta_raw[16 tokens x 16
-//     channels] = dt_low[32 x R] * w_dt^T, runs on the tensor pipe (mma.sync m16n8k16, the A
-//     fragments come straight from the staged bf16 x_dbl rows via ldmatrix, w_dt fragments stay in
-//     registers); softplus and delta*u are applied to the accumulator fragments, which are
-//     written to shared memory as {delta0, delta1, du0, du1} per channel pair.
-//   * phase B: a thread owns a 2-channel x 4-state block of the recurrence (4 adjacent lanes
-//     cover the 16 states), so one 128-bit broadcast load each of B_t, C_t and the pair's
-//     {delta, du} feeds 8 state updates; the 4 lanes' partial outputs are combined with two
-//     shuffles, and every lane finalises one (token, channel) of a 2-token step: + D*u, * SiLU(z).
-//   * B_t / C_t are expanded to fp32 once per tile; y leaves through shared memory as 16-byte stores.
+//     with 16-byte cp.async copies (double buffered).  One-warp CTAs need no block barriers and
+//     1536 of them spread over 148 SMs within 6 % of even (768 two-warp CTAs: 14 % idle tail).
+//   * phase A (per tile): the dt projection of the tile, delta_raw[16 tokens x 16 channels] =
+//     dt_low[16 x R] * w_dt^T, runs on the tensor pipe (mma.sync m16n8k16, the A fragments come
+//     straight from the staged bf16 x_dbl rows via ldmatrix, w_dt fragments stay in registers);
+//     softplus and delta*u are applied to the accumulator fragments and written to shared memory.
+//   * phase B (per token): the recurrence on packed fp32 (fma.rn.f32x2), then + D*u, * SiLU(z).
 //   * small batches (fewer warps than the GPU needs) split the sequence into segments: a first
 //     pass computes every segment's end state from a zero start (recurrence only, no outputs) and
 //     its total decay exp(A * sum(delta)); a tiny kernel chains the carries; the second pass runs
-//     all segments concurrently from their true initial states.  Exact, 1.6x the work, up to 24x
+//     all segments concurrently from their true initial states.  Exact, ~1.5x the work, up to 24x
 //     the parallelism (long-clip configuration, 25 089 tokens at batch 1).
 //   * reverse = 1 walks the sequence back to front (tile rows are gathered in logical order), which
 //     is what the flipped branch of BiMambaRefinerBlock needs without any torch.flip copy.
 //
-// Four layouts of the same kernel live in this file (measured against each other in
-// profiles/r01_scan_ncu_full_summary.txt); VMB_SCAN_VARIANT picks one:
-//   0 / 9  v9 (default)  lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one HMMA
+// Three lane layouts of phase B live in this file (measured against each other in profiles/);
+// VMB_SCAN_VARIANT picks one:
+//   0 / 9  v9 (default)  lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one
+//                        HMMA per token on bf16-rounded states: no shuffle, C_t stays bf16
 //   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
-//   1      v4            lane = 2 channels x 4 states, two shuffles per token (this header describes it)
-//   (v6 -- v7's lanes with phase A of tile k+1 overlapped with tile k, 149 registers, 19 KB -- was measured and
-//    removed: faster alone, slower with steps in flight; git history and profiles/ keep it)
+//   1      v4            lane = 2 channels x 4 states, fp32 contraction, two shuffles per token
+//                        (the first kernel below)
 //   2      none of them: the any-shape kernel of scan_generic.cu
+// (v6 -- v7's lanes with phase A of tile k+1 overlapped with tile k, 149 registers, 19 KB -- was
+//  measured and removed: faster alone, slower with steps in flight.)
 #include <algorithm>
 #include <cstdlib>
 
