@@ -598,19 +598,22 @@ scan7_kernel(const FastScanArgs a) {
 namespace v9 {
 
 struct Plan {
-  int u0, z0, x0, b, dd, y, total, xrow;
-  __host__ __device__ int u(int s) const { return u0 + s * (kTT * kRowBytes); }
-  __host__ __device__ int z(int s) const { return z0 + s * (kTT * kRowBytes); }
-  __host__ __device__ int x(int s) const { return x0 + s * (kTT * xrow); }
+  int u0, z0, x0, b, c, dd, y, total, xrow;
+  __host__ __device__ constexpr int u(int s) const { return u0 + s * (kTT * kRowBytes); }
+  __host__ __device__ constexpr int z(int s) const { return z0 + s * (kTT * kRowBytes); }
 };
-__host__ __device__ inline Plan plan(int Xp) {
-  Plan p;
+// x_dbl row pitch the host packs for dt_rank R (ops.xdbl_pitch): a compile-time constant here, so
+// every shared-memory offset of the kernel is an immediate
+__host__ __device__ constexpr int xp_of(int R) { return (R + 2 * kN + 15) / 16 * 16; }
+__host__ __device__ constexpr Plan plan(int Xp) {
+  Plan p{};
   int off = 0;
   p.xrow = x_row_bytes(Xp);
   p.u0 = off; off += 2 * kTT * kRowBytes;
   p.z0 = off; off += 2 * kTT * kRowBytes;
-  p.x0 = off; off += 2 * kTT * p.xrow;            // double buffered: C_t is read from the raw rows
+  p.x0 = off; off += kTT * p.xrow;                // raw x_dbl rows: consumed by phase A, then refilled
   p.b = off; off += kTT * kN * 4;                 // [token][tig][B(2tig), B(2tig+1), B(2tig+8), B(2tig+9)] fp32
+  p.c = off; off += kTT * kN * 2;                 // [token][C0..15] bf16, as in the row
   p.dd = off; off += kTT * 8 * 16;                // [token][g ^ (token & 1)]{delta_g, du_g, delta_g+8, du_g+8}
   p.y = off; off += kTT * kRowBytes;
   p.total = off;
@@ -624,12 +627,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <int R, bool kStateOnly>
-__global__ void __launch_bounds__(kThreads, 18)
+__global__ void __launch_bounds__(kThreads, 18)   // cap 112: it takes 96, so 21 CTAs fit an SM
 scan9_kernel(const FastScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int KST = (R + 15) / 16;
-  const Plan sp = plan(a.Xp);
-  const int xrow = sp.xrow;
+  constexpr Plan sp = plan(xp_of(R));
+  constexpr int xrow = sp.xrow;
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   using bf16 = __nv_bfloat16;
 
@@ -689,12 +692,12 @@ scan9_kernel(const FastScanArgs a) {
   const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
   const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
   bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
-  const int xchunks = a.Xp / 8;
+  constexpr int xchunks = xp_of(R) / 8;
   const int dir = a.reverse ? -1 : 1;
   const int p0 = a.reverse ? a.L - 1 : 0;
   const int u_ts = (int)a.u_ts, z_ts = (int)a.z_ts, x_ts = (int)a.x_ts, y_ts = (int)a.y_ts;
 
-  auto issue_tile = [&](int tile, int st) {
+  auto issue_uz = [&](int tile, int st) {
     const int row = lane >> 1, ch = lane & 1;
     const int t = tile * kTT + row;
     const bool ok = t < L;
@@ -702,13 +705,20 @@ scan9_kernel(const FastScanArgs a) {
     cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + (prow * u_ts + ch * 8), ok);
     if (!kStateOnly)
       cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + (prow * z_ts + ch * 8), ok);
-    const bf16* src = xg + prow * x_ts;
-    for (int k = ch; k < xchunks; k += 2) cp_async16(sbase + sp.x(st) + row * xrow + k * 16, src + k * 8, ok);
+  };
+  auto issue_x = [&](int tile) {
+    const int row = lane >> 1, ch = lane & 1;
+    const int t = tile * kTT + row;
+    const bool ok = t < L;
+    const bf16* src = xg + (ok ? p0 + dir * t : 0) * x_ts;
+#pragma unroll
+    for (int k = ch; k < xchunks; k += 2) cp_async16(sbase + sp.x0 + row * xrow + k * 16, src + k * 8, ok);
   };
 
   const int tile_lo = tbeg / kTT;
   const int ntiles = (L + kTT - 1) / kTT;
-  issue_tile(tile_lo, 0);
+  issue_uz(tile_lo, 0);
+  issue_x(tile_lo);
   cp_async_commit();
   float sum_a = 0.f, sum_b = 0.f;
   bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
@@ -718,12 +728,9 @@ scan9_kernel(const FastScanArgs a) {
     const int t0 = tile * kTT;
     cp_async_wait<0>();
     __syncwarp();                                  // tile landed; last tile's smem readers are done
-    if (tile + 1 < ntiles) issue_tile(tile + 1, st ^ 1);   // the other raw stage is free: prefetch now
-    cp_async_commit();
-
     const uint8_t* su = smem + sp.u(st);
     const uint8_t* sz = smem + sp.z(st);
-    const uint8_t* sx = smem + sp.x(st);
+    const uint8_t* sx = smem + sp.x0;
 
     // ---- B_t of the tile to fp32, in fragment order (a lane's 4 states contiguous) --------------
 #pragma unroll
@@ -734,6 +741,15 @@ scan9_kernel(const FastScanArgs a) {
       // states 2 tig + e -> slot 4 tig + e; states 2 tig + 8 + e -> slot 4 tig + 2 + e
       const int slot = (p & 3) * 4 + (p >> 2) * 2;
       *reinterpret_cast<float2*>(smem + sp.b + row * (kN * 4) + slot * 4) = make_float2(bf16lo(v), bf16hi(v));
+    }
+    if constexpr (!kStateOnly) {                   // C_t stays bf16: keep a copy, the raw rows are refilled
+#pragma unroll
+      for (int i = 0; i < (kTT * kN / 2) / kThreads; ++i) {
+        const int e = lane + i * kThreads;
+        const int row = e >> 3, p = e & 7;
+        *reinterpret_cast<uint32_t*>(smem + sp.c + row * (kN * 2) + p * 4) =
+            *reinterpret_cast<const uint32_t*>(sx + row * xrow + (R + kN + 2 * p) * 2);
+      }
     }
     // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
     {
@@ -746,7 +762,7 @@ scan9_kernel(const FastScanArgs a) {
       for (int ks = 0; ks < KST; ++ks) {
         uint32_t af[4];
         const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-        ldmatrix_x4(sbase + sp.x(st) + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
+        ldmatrix_x4(sbase + sp.x0 + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
         mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
         mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
       }
@@ -767,13 +783,18 @@ scan9_kernel(const FastScanArgs a) {
         }
       }
     }
-    __syncwarp();                                  // B / dd tiles visible
+    __syncwarp();                                  // B / C / dd tiles visible; raw x_dbl rows no longer needed
+    if (tile + 1 < ntiles) {                       // prefetch the next tile behind the recurrence
+      issue_uz(tile + 1, st ^ 1);
+      issue_x(tile + 1);
+    }
+    cp_async_commit();
 
     // ---- phase B: the recurrence; <C, h> by one HMMA per token -------------------------------------
     const uint8_t* sdd0 = smem + sp.dd + (g << 4);                // even tokens
     const uint8_t* sdd1 = smem + sp.dd + ((g ^ 1) << 4);          // odd tokens
     const uint8_t* sb = smem + sp.b + tig * 16;
-    const uint8_t* sc = sx + (R + kN + 2 * tig) * 2;              // C_t words (2 tig, 2 tig + 1) of the raw rows
+    const uint8_t* sc = smem + sp.c + tig * 4;                    // C_t words (2 tig, 2 tig + 1), (2 tig + 8, + 9)
 #pragma unroll
     for (int tg = 0; tg < kTT; tg += 4) {
       float ya = 0.f, yb = 0.f;
@@ -799,8 +820,8 @@ scan9_kernel(const FastScanArgs a) {
           sum_a += dd.x;
           sum_b += dd.z;
         } else {
-          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * xrow);
-          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * xrow + 16);
+          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
+          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
           const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
                                   pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
           float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -922,9 +943,10 @@ int launch(const FastScanArgs& a0, cudaStream_t st) {
 
 template <int R>
 int launch9(const FastScanArgs& a0, cudaStream_t st) {
+  if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);   // unusual x_dbl pitch: v7 takes any
   FastScanArgs a = a0;
   plan_segments(a, &a.nseg, &a.seg_len);
-  const v9::Plan sp = v9::plan(a.Xp);
+  constexpr v9::Plan sp = v9::plan(v9::xp_of(R));
   if (sp.total > 48 * 1024) VMB_UNSUPPORTED("scan_fast: x_dbl rows too wide for the staging buffers");
   if (a.nseg > 1) {
     const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
