@@ -286,6 +286,169 @@ conv1d_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_bs, int64_t 
   }
 }
 
+// Ring-staged variant of the streaming kernel: the rows a thread is going to consume are brought
+// in by 16-byte cp.async into a private ring of shared-memory slots ([slot][thread], conflict free),
+// kRing rows deep, so the bytes in flight per SM no longer depend on registers: 6 CTAs x 96 threads
+// x 20 rows x 16 B = 184 KB outstanding per SM against the ~60 KB the HBM latency-bandwidth product
+// needs.  A thread only ever reads slots it filled itself, so cp.async.wait_group is the only
+// synchronisation.  Groups of kGrp rows are committed together; group k + kRing / kGrp is issued
+// into the slots of group k right after group k has been consumed.
+constexpr int kGrp = 4;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+template <int kPending> __device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+template <bool kSilu, int kRing>
+__global__ void __launch_bounds__(96, 5)
+conv1d_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_bs, int64_t x_ts,
+                   const __nv_bfloat16* __restrict__ weight, const __nv_bfloat16* __restrict__ bias,
+                   const void* __restrict__ cs_in, int cs_in_dtype, __nv_bfloat16* __restrict__ y,
+                   int64_t y_bs, int64_t y_ts, void* __restrict__ cs_out, int cs_out_dtype, int L,
+                   int Di, int reverse, int tok) {
+  constexpr int W = 4;
+  constexpr int kAhead = kRing / kGrp;              // groups in flight
+  extern __shared__ __align__(16) uint8_t ring_smem[];
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c0 >= Di) return;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * tok;
+  const int tend = min(L, t0 + tok);                // tokens [t0, tend)
+  const __nv_bfloat16* xb = x + (int64_t)b * x_bs + c0;
+  __nv_bfloat16* yb = y + (int64_t)b * y_bs + c0;
+  const int dir = reverse ? -1 : 1;
+  const int r0 = reverse ? L - 1 : 0;               // logical token t lives at row r0 + dir * t
+  const int xs = (int)x_ts, ys = (int)y_ts;
+  const uint32_t slot0 = static_cast<uint32_t>(__cvta_generic_to_shared(ring_smem)) + threadIdx.x * 16;
+  const uint32_t slot_pitch = blockDim.x * 16;
+  const uint8_t* const my = ring_smem + threadIdx.x * 16;
+  auto issue_group = [&](int grp, int pos) {        // rows t0 + grp * kGrp + i -> slots pos * kGrp + i
+#pragma unroll
+    for (int i = 0; i < kGrp; ++i) {
+      const int t = t0 + grp * kGrp + i;
+      const bool ok = t < tend;
+      cp_async16_zfill(slot0 + (pos * kGrp + i) * slot_pitch, xb + (int64_t)(r0 + dir * (ok ? t : t0)) * xs, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int ngroups = (tend - t0 + kGrp - 1) / kGrp;
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) issue_group(k, k);   // groups beyond the chunk are zero fills
+
+  auto ldrow = [&](int t) -> uint4 {
+    return (t >= 0 && t < L) ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)(r0 + dir * t) * xs))
+                             : make_uint4(0u, 0u, 0u, 0u);
+  };
+  uint4 hist[W - 1];
+#pragma unroll
+  for (int k = 0; k < W - 1; ++k) hist[k] = ldrow(t0 - (W - 1) + k);
+
+  float2 w2[4][W], b2[4];
+  {
+    const uint4 wv[4] = {__ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W)),
+                         __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W + 8)),
+                         __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W + 16)),
+                         __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W + 24))};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {                   // 8 bf16: channel 2p taps 0..3, channel 2p+1 taps 0..3
+      const uint32_t q[4] = {wv[p].x, wv[p].y, wv[p].z, wv[p].w};
+      const float e0[4] = {__uint_as_float(q[0] << 16), __uint_as_float(q[0] & 0xffff0000u),
+                           __uint_as_float(q[1] << 16), __uint_as_float(q[1] & 0xffff0000u)};
+      const float e1[4] = {__uint_as_float(q[2] << 16), __uint_as_float(q[2] & 0xffff0000u),
+                           __uint_as_float(q[3] << 16), __uint_as_float(q[3] & 0xffff0000u)};
+#pragma unroll
+      for (int k = 0; k < W; ++k) w2[p][k] = make_float2(e0[k], e1[k]);
+    }
+    if (bias) {
+      float2 t[4];
+      unpack_pairs(__ldg(reinterpret_cast<const uint4*>(bias + c0)), t);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) b2[p] = t[p];
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) b2[p] = make_float2(0.f, 0.f);
+    }
+  }
+
+  float2 win[W - 1][4];                             // rows t-3, t-2, t-1
+#pragma unroll
+  for (int k = 0; k < W - 1; ++k) {
+    const int t = t0 - (W - 1) + k;
+    if (t < 0 && cs_in != nullptr) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        win[k][p] = make_float2(
+            load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p) * W + (W + t), cs_in_dtype),
+            load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p + 1) * W + (W + t), cs_in_dtype));
+    } else {
+      unpack_pairs(hist[k], win[k]);
+    }
+  }
+
+  int pos = 0;
+#pragma unroll 1
+  for (int grp = 0; grp < ngroups; ++grp) {
+    cp_async_wait_group<kAhead - 1>();              // group grp has landed (own writes: no barrier needed)
+    uint4 cur[kGrp];
+#pragma unroll
+    for (int i = 0; i < kGrp; ++i)
+      cur[i] = *reinterpret_cast<const uint4*>(my + (size_t)(pos * kGrp + i) * slot_pitch);
+    issue_group(grp + kAhead, pos);                 // refill the slots just read (program order: after the loads)
+    pos = pos + 1 == kAhead ? 0 : pos + 1;
+    const int ts = t0 + grp * kGrp;
+#pragma unroll
+    for (int i = 0; i < kGrp; ++i) {
+      float2 xin[4];
+      unpack_pairs(cur[i], xin);
+      uint32_t o[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float2 acc = __ffma2_rn(w2[p][0], win[0][p], b2[p]);
+        acc = __ffma2_rn(w2[p][1], win[1][p], acc);
+        acc = __ffma2_rn(w2[p][2], win[2][p], acc);
+        acc = __ffma2_rn(w2[p][3], xin[p], acc);
+        if (kSilu) { acc.x = silu_fast(acc.x); acc.y = silu_fast(acc.y); }
+        const __nv_bfloat162 h = __floats2bfloat162_rn(acc.x, acc.y);
+        o[p] = *reinterpret_cast<const uint32_t*>(&h);
+        win[0][p] = win[1][p]; win[1][p] = win[2][p]; win[2][p] = xin[p];
+      }
+      if (ts + i < tend)
+        *reinterpret_cast<uint4*>(yb + (int64_t)(r0 + dir * (ts + i)) * ys) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  cp_async_wait_group<0>();                         // nothing of ours may still be landing when the CTA retires
+
+  // The thread that owns the final chunk also emits the next conv state: hist[L-W .. L-1] (pre-conv x).
+  if (cs_out != nullptr && t0 < L && t0 + tok >= L) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const int t = L - W + k;
+      float2 f[4];
+      if (t >= 0) {
+        unpack_pairs(ldrow(t), f);
+      } else if (cs_in != nullptr) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          f[p] = make_float2(
+              load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p) * W + (W + t), cs_in_dtype),
+              load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p + 1) * W + (W + t), cs_in_dtype));
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) f[p] = make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        store_from_f32(cs_out, ((int64_t)b * Di + c0 + 2 * p) * W + k, cs_out_dtype, f[p].x);
+        store_from_f32(cs_out, ((int64_t)b * Di + c0 + 2 * p + 1) * W + k, cs_out_dtype, f[p].y);
+      }
+    }
+  }
+}
+
 template <typename T, int W>
 __global__ void conv1d_update_kernel(const T* __restrict__ x, int64_t x_bs, void* __restrict__ cs,
                                      int cs_dtype, const T* __restrict__ weight,
@@ -318,11 +481,28 @@ int launch_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, co
                cudaStream_t st) {
   const int cthreads = (Di + VEC - 1) / VEC;
   if constexpr (sizeof(T) == 2 && VEC == 8 && W == 4) {
-    static const bool old = std::getenv("VMB_CONV_VARIANT") && std::atoi(std::getenv("VMB_CONV_VARIANT")) == 1;
+    static const int variant = std::getenv("VMB_CONV_VARIANT") ? std::atoi(std::getenv("VMB_CONV_VARIANT")) : 0;
+    const bool old = variant == 1;
     if (!old && reinterpret_cast<uintptr_t>(weight) % 16 == 0 &&
         (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0) && L >= 2 * kSub) {
       const int blk = cthreads >= 96 ? 96 : ((cthreads + 31) / 32) * 32;
       const int gx = (cthreads + blk - 1) / blk;
+      if (variant != 2) {                                 // default: ring-staged streaming kernel
+        constexpr int kRing = 24;
+        const int tokr = 40;   // tokens per thread; measured 24 .. 128 at batch 32: 56.3 us at 40, 58.4 at 64, 64.8 at 128
+        const size_t smem = (size_t)kRing * blk * 16;
+        dim3 g(gx, (L + tokr - 1) / tokr, B);
+        if (silu)
+          conv1d_ring_kernel<true, kRing><<<g, blk, smem, st>>>((const T*)x, x_bs, x_ts, (const T*)weight,
+                                                                (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
+                                                                y_ts, cs_out, cs_out_dtype, L, Di, reverse, tokr);
+        else
+          conv1d_ring_kernel<false, kRing><<<g, blk, smem, st>>>((const T*)x, x_bs, x_ts, (const T*)weight,
+                                                                 (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
+                                                                 y_ts, cs_out, cs_out_dtype, L, Di, reverse, tokr);
+        VMB_LAUNCH_CHECK("conv1d_ring_kernel");
+        return VMB_OK;
+      }
       const int tok = 64;        // tokens per thread (88 = two exact waves at batch 32 measured slower: 66.6 vs 63.6 us)
       dim3 g(gx, (L + tok - 1) / tok, B);
       if (silu)
