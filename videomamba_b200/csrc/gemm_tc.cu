@@ -347,6 +347,253 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ---- CTA-pair variant (cta_group::2) ---------------------------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) work on one 256 x BN tile: CTA r owns rows
+// [128 r, 128 r + 128) of the tile (its A rows in its shared memory, its accumulator rows in its
+// TMEM) and HALF of the W tile (rows [r BN/2, (r+1) BN/2)); the tensor cores of both SMs read both
+// halves.  Per 128 x BN of output an SM therefore ingests 128 A rows + BN/2 W rows instead of
+// 128 + BN: the 1-CTA kernel is bound by the ~12.4 TB/s the L2 can deliver (in_proj: 288 KB per
+// 128 x 256 tile -> 109 us; out_proj: 491 KB per 128 x 192 tile -> 62 us, both exactly what is
+// measured), and the pair needs 1.5x / 1.43x less.
+//   * both CTAs run a TMA producer; every load signals the LEADER's (rank 0) full barrier
+//     (cp.async.bulk.tensor .cta_group::2), the leader expects the bytes of both CTAs;
+//   * only the leader issues tcgen05.mma.cta_group::2 (M = 256); its commits are multicast to the
+//     empty / accumulator-full barriers of both CTAs;
+//   * the epilogue warps of both CTAs hand the accumulator back on the leader's barrier
+//     (remote mbarrier.arrive for rank 1);  TMEM is allocated / freed by warp 1 of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default .release.cta semantics: the hand-over orders TMEM reads (tcgen05 fences), not generic memory;
+  // a cluster-scope release here costs a memory barrier per thread per tile (measured: +20 % kernel time)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__host__ __device__ constexpr size_t smem_bytes_pair(int bn, int stages) {
+  return 1024 + (size_t)stages * (BM * BK * 2 + (bn / 2) * BK * 2) + 2 * (BM * kSubN * 2) + 256;
+}
+__host__ __device__ constexpr int stages_pair(int) { return 6; }   // 6 x (16 KB A + <= 16 KB W half)
+
+template <int BN, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ bias,
+                    int M, int N, int K) {
+  constexpr int kTmemCols = tmem_cols_for(BN);
+  constexpr uint32_t kABytes = BM * BK * 2;
+  constexpr uint32_t kWBytes = (BN / 2) * BK * 2;          // this CTA's half of the W tile
+  constexpr uint32_t kSubBytes = BM * kSubN * 2;
+  constexpr uint32_t kIdesc = umma_idesc_bf16(2 * BM, BN);  // M = 256 across the pair
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_w = smem_a + kStages * kABytes;
+  const uint32_t smem_c = smem_w + kStages * kWBytes;
+  const uint32_t bars = smem_c + 2 * kSubBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = (N + BN - 1) / BN;
+  const int k_blocks = (K + BK - 1) / BK;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_c);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);       // leader: its own arrive.expect_tx; bytes come from both CTAs
+      mbar_init(empty_bar(s), 1);      // one multicast commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);     // leader: the 4 epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                  // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * (kABytes + kWBytes));
+          const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
+          tma_load_2d_pair(smem_a + stage * kABytes, &map_a, lbar, kb * BK, m0);
+          tma_load_2d_pair(smem_w + stage * kWBytes, &map_w, lbar, kb * BK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // both epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem_a + stage * kABytes);
+          const uint64_t b_desc = umma_desc_sw128(smem_w + stage * kWBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb | k) != 0);
+          tc_commit_pair(empty_bar(stage));          // frees the slot in both CTAs
+          if (kb == k_blocks - 1) tc_commit_pair(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue (both CTAs, own 128 rows) =====
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const bool issuer = threadIdx.x == kEpiWarp0 * 32;
+    int local = 0;
+    int buf = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int sub = 0; sub < BN / kSubN; ++sub) {
+        const bool beyond = n0 + sub * kSubN >= N;   // whole sub-tile beyond N (uniform)
+        uint32_t v0[32], v1[32];
+        if (!beyond) {
+          tc_ld_32x32(t_row + sub * kSubN, v0);
+          tc_ld_32x32(t_row + sub * kSubN + 32, v1);
+          tc_wait_ld();
+        }
+        if (sub == BN / kSubN - 1) {                 // accumulator fully read: one arrival per warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        }
+        if (beyond) continue;
+        if (bias != nullptr) {
+          const int nb = n0 + sub * kSubN;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float b0 = nb + j < N ? __bfloat162float(bias[nb + j]) : 0.f;
+            const float b1 = nb + 32 + j < N ? __bfloat162float(bias[nb + 32 + j]) : 0.f;
+            v0[j] = __float_as_uint(__uint_as_float(v0[j]) + b0);
+            v1[j] = __float_as_uint(__uint_as_float(v1[j]) + b1);
+          }
+        }
+        if (issuer) tma_store_wait_read<1>();
+        epi_bar_sync();
+        uint8_t* dst = smem_gen + (smem_c - smem_base) + buf * kSubBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t p[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = c * 8 + q * 2;
+            const float lo = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+            const float hi = __uint_as_float(j + 1 < 32 ? v0[j + 1] : v1[j + 1 - 32]);
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            p[q] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (issuer) {
+          tma_store_2d(&map_c, smem_c + buf * kSubBytes, n0 + sub * kSubN, m0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  __syncwarp();                        // the elected lanes rejoin their warps before the aligned barrier
+  tc_fence_before();
+  cluster_sync_all();                  // the leader's MMAs read the peer's shared memory and TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
 // ---- host side: tensor maps ----------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -431,6 +678,41 @@ int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* b
   return VMB_OK;
 }
 
+template <int BN, int kStages>
+int launch_pair(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+                int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+  CUtensorMap ma, mw, mc;
+  int rc;
+  if ((rc = make_map(&ma, A, M, K, lda, BM))) return rc;
+  if ((rc = make_map(&mw, W, N, K, ldw, BN / 2))) return rc;
+  if ((rc = make_map(&mc, C, M, N, ldc, BM))) return rc;
+  static bool attr_set[64] = {false};
+  constexpr size_t smem = smem_bytes_pair(BN, kStages);
+  static_assert(smem <= 227 * 1024, "pair kernel: shared memory budget");
+  int dev = 0;
+  VMB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    VMB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, kStages>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const int pairs = (int)std::min<int64_t>(tiles, sm_count() / 2);
+  gemm_tc_pair_kernel<BN, kStages><<<2 * pairs, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias,
+                                                                      (int)M, N, K);
+  VMB_LAUNCH_CHECK("gemm_tc_pair_kernel");
+  return VMB_OK;
+}
+
+// VMB_GEMM_PAIR=0 keeps every projection on the 1-CTA kernel.
+int pair_mode() {
+  static int v = [] {
+    const char* e = std::getenv("VMB_GEMM_PAIR");
+    return e ? std::atoi(e) : 1;
+  }();
+  return v;
+}
+
 // 0: stand-alone tiles (default).  1: small-footprint tiles (co-residency with the scan).
 int footprint() {
   static int v = [] {
@@ -456,6 +738,10 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* 
   if (footprint() == 1) {
     if (N <= 64) return launch<64, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
     return launch<128, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  }
+  if (pair_mode() != 0 && M >= 4 * BM) {   // CTA pairs: 256-row tiles, half a W tile per SM
+    if (N % 256 == 0) return launch_pair<256, stages_pair(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    if (N % 192 == 0) return launch_pair<192, stages_pair(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   }
   if (N <= 64) return launch<64, stages_for(64)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   if (N <= 128) return launch<128, stages_for(128)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
