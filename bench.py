@@ -391,7 +391,7 @@ def run_ours(args):
     if fused:
         # fused dt_proj+softplus+scan+gate kernel: reads u (conv output), z, the x_dbl row; writes y
         bytes_per_token = 3 * Di * es + w.Xp * es
-        kernel = "scan9_kernel (dt_proj + softplus + S6 scan + D skip + SiLU gate, fused)"
+        kernel = "scan10_kernel (TMA-staged tiles; dt_proj + softplus + S6 scan + D skip + SiLU gate, fused)"
     else:
         # op-level selective_scan_fn: reads u, delta, z, B, C; writes y
         bytes_per_token = 4 * Di * es + 2 * N * es

@@ -653,6 +653,55 @@ int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int6
   return VMB_OK;
 }
 
+}  // namespace
+
+// 3-D bf16 tensor map (innermost dimension contiguous), box = box0 x box1 x 1, used by the scan's
+// TMA staging (scan_fast.cu).  Cached like the 2-D maps.
+int make_tensor_map_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
+                            uint32_t box1, bool swizzle128) {
+  struct Key {
+    const void* ptr; uint64_t d0, d1, d2, s1, s2; uint32_t b0, b1; bool sw;
+    bool operator==(const Key& o) const {
+      return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 &&
+             b0 == o.b0 && b1 == o.b1 && sw == o.sw;
+    }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      size_t h = std::hash<const void*>()(k.ptr);
+      auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+      mix(k.d0); mix(k.d1); mix(k.d2); mix(k.s1); mix(k.s2); mix(k.b0); mix(k.b1); mix(k.sw);
+      return h;
+    }
+  };
+  static std::mutex mu;
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  const Key key{ptr, d0, d1, d2, stride1_bytes, stride2_bytes, box0, box1, swizzle128};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return VMB_OK; }
+  }
+  EncodeFn fn = encode_fn();
+  if (!fn) { set_error("tensor map: cuTensorMapEncodeTiled entry point not available"); return VMB_ERR_CUDA; }
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tensor map: cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r); return VMB_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return VMB_OK;
+}
+
+namespace {
+
 template <int BN, int kStages>
 int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
            int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {

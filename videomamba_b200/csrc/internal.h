@@ -1,5 +1,7 @@
 // Internal (non-ABI) entry points shared between the translation units of libvmb200.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vmb {
@@ -14,6 +16,12 @@ bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, c
                        int64_t ldc, int64_t M, int N, int K);
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
             int64_t ldc, int64_t M, int N, int K, cudaStream_t st);
+
+// gemm_tc.cu -- cached 3-D bf16 tensor map (dims d0 (contiguous) x d1 x d2, byte strides of d1 / d2,
+// box0 x box1 x 1 boxes, optional 128-byte swizzle) for TMA staging outside the GEMM.
+int make_tensor_map_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
+                            uint32_t box1, bool swizzle128);
 
 // scan_generic.cu
 int scan_generic(const vmb_scan_args& a, cudaStream_t st);

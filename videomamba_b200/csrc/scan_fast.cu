@@ -29,7 +29,9 @@
 //
 // Three lane layouts of phase B live in this file (measured against each other in profiles/);
 // VMB_SCAN_VARIANT picks one:
-//   0 / 9  v9 (default)  lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one
+//   0 / 10 v10 (default) v9's lanes, tiles staged by TMA box copies on an mbarrier instead of
+//                        cp.async row gathers (62 % fewer shared-memory wavefronts)
+//   9      v9            lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one
 //                        HMMA per token on bf16-rounded states: no shuffle, C_t stays bf16
 //   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
 //   1      v4            lane = 2 channels x 4 states, fp32 contraction, two shuffles per token
@@ -872,6 +874,327 @@ scan9_kernel(const FastScanArgs a) {
 
 }  // namespace v9
 
+// =================================================================================================
+// v10 = v9 with the tiles staged by TMA.  ncu on v9: 62 % of all shared-memory wavefronts are the
+// cp.async row gathers (24 wavefronts per LDGSTS: every 32-byte sector that returns from L2 is its
+// own write), and the LSU / MIO path is the resource the recurrence's own loads queue on.  Here one
+// lane issues three cp.async.bulk.tensor box copies per tile (u 16 x 16, z 16 x 16, x_dbl Xp x 16)
+// that complete on an mbarrier; rows beyond the sequence are zero-filled by the TMA unit, the
+// reversed direction loads the box in memory order and the consumers mirror the row index
+// (compile-time kRev, so every shared-memory offset stays an immediate).  The x_dbl tile is dense
+// (128-byte rows at dt_rank 24: loaded with the 128-byte swizzle and read through the same XOR, so
+// ldmatrix and the B / C gathers stay conflict free); u / z rows are dense 32-byte rows.
+// =================================================================================================
+namespace v10 {
+
+struct Plan {
+  int x0, u0, z0, b, c, dd, y, bar, total, xb;
+  __host__ __device__ constexpr int u(int s) const { return u0 + s * (kTT * 32); }
+  __host__ __device__ constexpr int z(int s) const { return z0 + s * (kTT * 32); }
+};
+__host__ __device__ constexpr Plan plan(int Xp) {
+  Plan p{};
+  int off = 0;
+  p.xb = Xp * 2;                                  // dense x_dbl rows
+  p.x0 = off; off += kTT * p.xb;                  // 1024-byte aligned (swizzle atom) -- base of the carve-up
+  p.u0 = off; off += 2 * kTT * 32;
+  p.z0 = off; off += 2 * kTT * 32;
+  p.b = off; off += kTT * kN * 4;
+  p.c = off; off += kTT * kN * 2;
+  p.dd = off; off += kTT * 8 * 16;
+  p.y = off; off += kTT * kRowBytes;
+  p.bar = off; off += 16;                         // two mbarriers (one per stage)
+  p.total = off + 1024;                           // + alignment slack
+  return p;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int R, bool kStateOnly, bool kRev>
+__global__ void __launch_bounds__(kThreads, 18)
+scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
+              const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int KST = (R + 15) / 16;
+  constexpr Plan sp = plan(v9::xp_of(R));
+  constexpr int XB = sp.xb;
+  constexpr bool kSwz = XB == 128;                // 128-byte rows: TMA 128B swizzle
+  const uint32_t sbase = (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) + 1023u) & ~1023u;
+  uint8_t* const smem = smem_raw + (sbase - static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)));
+  using bf16 = __nv_bfloat16;
+  using v9::pack_bf16x2;
+
+  const int lane = threadIdx.x;
+  const int g = lane >> 2, tig = lane & 3;
+  const int cw = blockIdx.x * kCh;
+  const int b = blockIdx.y;
+  const int seg = blockIdx.z;
+  const int tbeg = seg * a.seg_len;
+  const int L = min(a.L, tbeg + a.seg_len);
+  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
+  float* const wsH = a.seg_ws;
+  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
+  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
+
+  float2 Aa[2], Ab[2], ha[2], hb[2];
+  const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
+  const int64_t hoff_b = hoff_a + 8 * kN;
+  {
+    const float* pa = a.A2 + (int64_t)(cw + g) * kN + 2 * tig;
+    Aa[0] = *reinterpret_cast<const float2*>(pa);
+    Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
+    Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
+    Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
+    auto ld = [&](int64_t off) -> float {
+      if (kStateOnly) return 0.f;
+      if (seg > 0) return wsHin[seg * seg_stride + off];
+      return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
+    };
+    ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
+    ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
+    hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
+    hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
+  }
+  const float Da = a.D ? a.D[cw + g] : 0.f, Db = a.D ? a.D[cw + g + 8] : 0.f;
+  uint32_t bfrag[2][KST][2];
+  float bias[2][2];
+  {
+    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const bf16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
+        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
+      }
+      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
+      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
+    }
+  }
+
+  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
+  const int dir = kRev ? -1 : 1;
+  const int p0 = kRev ? a.L - 1 : 0;
+  const int y_ts = (int)a.y_ts;
+
+  // shared-memory row of logical tile row r: the reversed direction holds the box in memory order
+  auto srow = [](int r) { return kRev ? kTT - 1 - r : r; };
+  // byte address (relative to the tile) of byte offset o in logical row r of the x_dbl tile
+  auto xoff = [&](int r, int o) {
+    const int sr = srow(r);
+    return kSwz ? sr * XB + ((((o >> 4) ^ (sr & 7)) << 4) | (o & 15)) : sr * XB + o;
+  };
+
+  const uint32_t bar0 = sbase + sp.bar;
+  constexpr uint32_t kTileBytes = kTT * 32 * (kStateOnly ? 1 : 2) + kTT * XB;
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int tile, int st) {              // lane 0 only
+    const int row0 = kRev ? a.L - kTT - tile * kTT : tile * kTT;   // first memory row of the box (may be < 0)
+    const uint32_t bar = bar0 + 8 * st;
+    mbar_expect_tx(bar, kTileBytes);
+    tma_load_3d(sbase + sp.x0, &map_x, bar, 0, row0, b);
+    tma_load_3d(sbase + sp.u(st), &map_u, bar, cw, row0, b);
+    if (!kStateOnly) tma_load_3d(sbase + sp.z(st), &map_z, bar, cw, row0, b);
+  };
+
+  const int tile_lo = tbeg / kTT;
+  const int ntiles = (L + kTT - 1) / kTT;
+  if (lane == 0) issue(tile_lo, 0);
+  float sum_a = 0.f, sum_b = 0.f;
+  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
+
+  // loop-invariant per-lane offsets
+  uint32_t xa_addr[KST];                            // ldmatrix rows of phase A
+  {
+    const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+    for (int ks = 0; ks < KST; ++ks) xa_addr[ks] = sbase + sp.x0 + xoff(row, 32 * ks + 16 * (lane >> 4));
+  }
+  // B / C gathers: element e = lane + 32 i -> row (lane >> 3) + 4 i, pair p = lane & 7
+  const int gp = lane & 7, gr = lane >> 3;
+  // rows r and r + 8 share their swizzle phase, so two offsets (rows gr, gr + 4) cover all four
+  int xb_off[2], xc_off[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    xb_off[i] = xoff(gr + 4 * i, (R + 2 * gp) * 2);
+    xc_off[i] = xoff(gr + 4 * i, (R + kN + 2 * gp) * 2);
+  }
+  constexpr int kRow8 = kRev ? -8 * XB : 8 * XB;    // logical row + 8 in shared-memory bytes
+  const int bslot = (gp & 3) * 4 + (gp >> 2) * 2;
+
+  for (int tile = tile_lo; tile < ntiles; ++tile) {
+    const int it = tile - tile_lo;
+    const int st = it & 1;
+    const int t0 = tile * kTT;
+    mbar_wait(bar0 + 8 * st, (it >> 1) & 1);
+    __syncwarp();                                  // tile landed; last tile's smem readers are done
+    const uint8_t* su = smem + sp.u(st);
+    const uint8_t* sz = smem + sp.z(st);
+    const uint8_t* sx = smem + sp.x0;
+
+    // ---- B_t of the tile to fp32, in fragment order (a lane's 4 states contiguous) --------------
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(sx + xb_off[i & 1] + (i >> 1) * kRow8);
+      *reinterpret_cast<float2*>(smem + sp.b + (gr + 4 * i) * (kN * 4) + bslot * 4) =
+          make_float2(bf16lo(v), bf16hi(v));
+    }
+    if constexpr (!kStateOnly) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint32_t*>(smem + sp.c + (gr + 4 * i) * (kN * 2) + gp * 4) =
+            *reinterpret_cast<const uint32_t*>(sx + xc_off[i & 1] + (i >> 1) * kRow8);
+    }
+    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
+    {
+      float acc[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        uint32_t af[4];
+        ldmatrix_x4(xa_addr[ks], af);
+        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int tl = g + 8 * half;                              // token row within the tile
+        const bool pad = t0 + tl >= L;
+        const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (2 * tig) * 2);
+        const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (8 + 2 * tig) * 2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
+          float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
+          if (pad) { da = 0.f; db = 0.f; }
+          const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
+          *reinterpret_cast<float4*>(smem + sp.dd + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
+              make_float4(da, da * uav, db, db * ubv);
+        }
+      }
+    }
+    __syncwarp();                                  // B / C / dd tiles visible; raw x_dbl rows no longer needed
+    if (tile + 1 < ntiles && lane == 0) {          // prefetch the next tile behind the recurrence
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our reads before the TMA's writes
+      issue(tile + 1, st ^ 1);
+    }
+
+    // ---- phase B: the recurrence; <C, h> by one HMMA per token -------------------------------------
+    const uint8_t* sdd0 = smem + sp.dd + (g << 4);
+    const uint8_t* sdd1 = smem + sp.dd + ((g ^ 1) << 4);
+    const uint8_t* sb = smem + sp.b + tig * 16;
+    const uint8_t* sc = smem + sp.c + tig * 4;
+#pragma unroll
+    for (int tg = 0; tg < kTT; tg += 4) {
+      float ya = 0.f, yb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = tg + i;
+        const float4 dd = *reinterpret_cast<const float4*>(((t & 1) ? sdd1 : sdd0) + t * 128);
+        const float4 Bv = *reinterpret_cast<const float4*>(sb + t * (kN * 4));
+        const float2 da2 = make_float2(dd.x, dd.x), db2 = make_float2(dd.z, dd.z);
+        const float2 xa0 = __fmul2_rn(da2, Aa[0]), xa1 = __fmul2_rn(da2, Aa[1]);
+        const float2 xb0 = __fmul2_rn(db2, Ab[0]), xb1 = __fmul2_rn(db2, Ab[1]);
+        const float2 ea0 = make_float2(ex2_approx(xa0.x), ex2_approx(xa0.y));
+        const float2 ea1 = make_float2(ex2_approx(xa1.x), ex2_approx(xa1.y));
+        const float2 eb0 = make_float2(ex2_approx(xb0.x), ex2_approx(xb0.y));
+        const float2 eb1 = make_float2(ex2_approx(xb1.x), ex2_approx(xb1.y));
+        const float2 dua = make_float2(dd.y, dd.y), dub = make_float2(dd.w, dd.w);
+        const float2 B01 = make_float2(Bv.x, Bv.y), B89 = make_float2(Bv.z, Bv.w);
+        ha[0] = __ffma2_rn(ea0, ha[0], __fmul2_rn(dua, B01));
+        ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
+        hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
+        hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
+        if constexpr (kStateOnly) {
+          sum_a += dd.x;
+          sum_b += dd.z;
+        } else {
+          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
+          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
+          const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
+                                  pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(d, af, c0, c1);
+          if (tig == i) { ya = d[0]; yb = d[2]; }
+        }
+      }
+      if constexpr (!kStateOnly) {
+        // lane tig finalises token tg + tig of its two channels; its shared-memory row is
+        // tg + tig (forward) or 15 - tg - tig (reversed)
+        const int tf = tg + tig;
+        const int so = (kRev ? (kTT - 1 - tg) * 32 : tg * 32) + (kRev ? -tig * 32 : tig * 32) + g * 2;
+        const float ua = __bfloat162float(*reinterpret_cast<const bf16*>(su + so));
+        const float ub = __bfloat162float(*reinterpret_cast<const bf16*>(su + so + 16));
+        const float za = __bfloat162float(*reinterpret_cast<const bf16*>(sz + so));
+        const float zb = __bfloat162float(*reinterpret_cast<const bf16*>(sz + so + 16));
+        sy[tf * (kRowBytes / 2) + g] = __float2bfloat16_rn(fmaf(Da, ua, ya) * silu_fast(za));
+        sy[tf * (kRowBytes / 2) + g + 8] = __float2bfloat16_rn(fmaf(Db, ub, yb) * silu_fast(zb));
+      }
+    }
+    if constexpr (!kStateOnly) {
+      __syncwarp();
+      const int row = lane >> 1, ch = lane & 1;
+      const int t = t0 + row;
+      if (t < L)
+        *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
+            *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
+    }
+  }
+
+  auto st_h = [&](float* dst) {
+    *reinterpret_cast<float2*>(dst + hoff_a) = ha[0];
+    *reinterpret_cast<float2*>(dst + hoff_a + 8) = ha[1];
+    *reinterpret_cast<float2*>(dst + hoff_b) = hb[0];
+    *reinterpret_cast<float2*>(dst + hoff_b + 8) = hb[1];
+  };
+  if constexpr (kStateOnly) {
+    st_h(wsH + seg * seg_stride);
+    if (tig == 0) {
+      float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + cw + g;
+      ss[0] = sum_a;
+      ss[8] = sum_b;
+    }
+    return;
+  }
+  if (seg != a.nseg - 1) return;
+  if (a.h_last != nullptr) st_h(a.h_last);
+}
+
+}  // namespace v10
+
 int variant() {
   static int v = [] {
     const char* e = std::getenv("VMB_SCAN_VARIANT");
@@ -969,6 +1292,49 @@ int launch9(const FastScanArgs& a0, cudaStream_t st) {
   return VMB_OK;
 }
 
+// v10 needs dense, 16-byte aligned rows for its tensor maps; everything else takes v9.
+template <int R>
+int launch10(const FastScanArgs& a0, cudaStream_t st) {
+  if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);
+  FastScanArgs a = a0;
+  plan_segments(a, &a.nseg, &a.seg_len);
+  constexpr v10::Plan sp = v10::plan(v9::xp_of(R));
+  if (a.nseg > 1) {
+    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
+    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
+      a.nseg = 1;
+      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
+    }
+  }
+  CUtensorMap mu, mz, mx;
+  const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B;
+  auto bs = [&](int64_t v, int64_t ts) { return (uint64_t)((a.B > 1 ? v : ts * a.L) * 2); };
+  int rc;
+  if ((rc = make_tensor_map_3d_bf16(&mu, a.u, (uint64_t)a.Di, L, B, (uint64_t)a.u_ts * 2, bs(a.u_bs, a.u_ts),
+                                    kCh, kTT, false)))
+    return rc;
+  if ((rc = make_tensor_map_3d_bf16(&mz, a.z, (uint64_t)a.Di, L, B, (uint64_t)a.z_ts * 2, bs(a.z_bs, a.z_ts),
+                                    kCh, kTT, false)))
+    return rc;
+  if ((rc = make_tensor_map_3d_bf16(&mx, a.xdbl, (uint64_t)a.Xp, L, B, (uint64_t)a.x_ts * 2,
+                                    bs(a.x_bs, a.x_ts), (uint32_t)a.Xp, kTT, a.Xp * 2 == 128)))
+    return rc;
+  if (a.nseg > 1) {
+    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
+    if (a.reverse) v10::scan10_kernel<R, true, true><<<g1, kThreads, sp.total, st>>>(a, mu, mz, mx);
+    else v10::scan10_kernel<R, true, false><<<g1, kThreads, sp.total, st>>>(a, mu, mz, mx);
+    VMB_LAUNCH_CHECK("scan10_kernel<state>");
+    const int64_t n = (int64_t)a.B * a.Di * kN;
+    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    VMB_LAUNCH_CHECK("scan_carry_kernel");
+  }
+  dim3 grid(a.Di / kCh, a.B, a.nseg);
+  if (a.reverse) v10::scan10_kernel<R, false, true><<<grid, kThreads, sp.total, st>>>(a, mu, mz, mx);
+  else v10::scan10_kernel<R, false, false><<<grid, kThreads, sp.total, st>>>(a, mu, mz, mx);
+  VMB_LAUNCH_CHECK("scan10_kernel");
+  return VMB_OK;
+}
+
 }  // namespace
 
 bool scan_fast_supported(const FastScanArgs& a) {
@@ -995,7 +1361,15 @@ int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {
-  if (variant() == 0 || variant() == 9) {   // default: v9, <C, h> on the tensor pipe
+  if (variant() == 0 || variant() == 10) {  // default: v10 = v9's lanes + TMA-staged tiles
+    switch (a.R) {
+      case 12: return launch10<12>(a, st);
+      case 24: return launch10<24>(a, st);
+      case 36: return launch10<36>(a, st);
+      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
+    }
+  }
+  if (variant() == 9) {                     // v9: cp.async staging
     switch (a.R) {
       case 12: return launch9<12>(a, st);
       case 24: return launch9<24>(a, st);
