@@ -47,7 +47,9 @@ add_norm_kernel(const TX* __restrict__ x, int64_t ldx, const TR* __restrict__ re
                 const TW* __restrict__ weight, const TW* __restrict__ bias, TX* __restrict__ y,
                 TO* __restrict__ residual_out, int64_t rows, int dim, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  // CTAs walk the rows back to front: the producer (out_proj) wrote the last rows most recently, so
+  // they are the ones still in L2; the consumer (in_proj) starts at row 0, which this kernel writes last
+  const int64_t row = (int64_t)(gridDim.x - 1 - blockIdx.x) * kRowsPerCta + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = dim >> 2;
   float v[kIters][4];

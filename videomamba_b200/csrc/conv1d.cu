@@ -315,8 +315,11 @@ conv1d_ring_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_bs, int64_t x_
   extern __shared__ __align__(16) uint8_t ring_smem[];
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (c0 >= Di) return;
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.y * tok;
+  // CTAs are dispatched x-, then y-, then z-fastest: walk batch and chunks back to front, so the kernel
+  // starts on the rows in_proj wrote last (still in L2) and x_proj, which starts at row 0, finds
+  // this kernel's most recent output there
+  const int b = gridDim.z - 1 - blockIdx.z;
+  const int t0 = (gridDim.y - 1 - blockIdx.y) * tok;
   const int tend = min(L, t0 + tok);                // tokens [t0, tend)
   const __nv_bfloat16* xb = x + (int64_t)b * x_bs + c0;
   __nv_bfloat16* yb = y + (int64_t)b * y_bs + c0;
