@@ -106,6 +106,28 @@ def test_tensor_core_projection_exact_integers(mnk):
     assert torch.equal(out[:, :N], want) and bool((out[:, N:] == 7.0).all())
 
 
+@pytest.mark.parametrize("m", [512, 513, 640, 767, 1025, 2049])
+@pytest.mark.parametrize("nk", [(192, 16), (256, 72), (384, 384), (512, 40), (768, 136)])
+def test_projection_cta_pair_tile_edges(m, nk):
+    """The CTA-pair kernel (cta_group::2, 256-row tiles) at its edges: the second CTA of the last pair
+    owns 0, 1, 127 or 128 valid rows, K is not a multiple of the 64-wide k-block, N takes one to four
+    tiles of 192 / 256.  Integer operands: the result must equal the exact product rounded once."""
+    n, k = nk
+    gen = torch.Generator().manual_seed(m * 7 + n + k)
+    a = torch.randint(-2, 3, (m, k), generator=gen).to(torch.bfloat16).to(DEV)
+    w = torch.randint(-2, 3, (n, k), generator=gen).to(torch.bfloat16).to(DEV)
+    bias = torch.randint(-4, 5, (n,), generator=gen).to(torch.bfloat16).to(DEV)
+    guard = torch.full((m + 300, n), 5.0, dtype=torch.bfloat16, device=DEV)   # rows beyond M stay untouched
+    from videomamba_b200 import _lib
+    lib = _lib.load()
+    rc = lib.vmb_linear_fwd(ops._p(a), k, ops._p(w), k, ops._p(bias), ops._p(guard), n, m, n, k,
+                            _lib.VMB_BF16, ops._stream(a))
+    _lib.check(rc, "vmb_linear_fwd")
+    want = (a.double() @ w.double().t() + bias.double()).to(torch.float32).to(torch.bfloat16)
+    assert torch.equal(guard[:m], want)
+    assert bool((guard[m:] == 5.0).all())
+
+
 def test_tensor_core_projection_random_values():
     """Random bf16 operands against a float64 product of the same bf16 values: the only error left
     is the fp32 accumulation order and the final rounding (<= 1 bf16 ulp of the result)."""
@@ -192,6 +214,47 @@ def test_causal_conv1d(dtype, geom, reverse):
         assert rel_err(got, want) <= _tol(dtype)
         assert got_state.shape == (B, Di, W)
         assert torch.equal(got_state.cpu(), want_state.contiguous())   # pre-conv inputs: bit exact
+
+
+@pytest.mark.parametrize("L", [16, 17, 39, 40, 41, 79, 81, 163])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_causal_conv1d_ring_kernel_chunk_edges(L, reverse):
+    """bf16 production kernel (ring-staged, 40 tokens per thread, groups of 4 rows): lengths around the
+    chunk and group boundaries, x as the strided first half of xz, with and without carried state.
+    Chunked execution (state carried across two calls) must equal the single pass bit for bit."""
+    B, Di, W = 2, 768, 4
+    bf = torch.bfloat16
+    gen = torch.Generator().manual_seed(L)
+    xz = _rand(gen, B, L, 2 * Di, dtype=bf)
+    w = _rand(gen, Di, W, dtype=bf, scale=0.5)
+    b = _rand(gen, Di, dtype=bf, scale=0.5)
+    cs = _rand(gen, B, Di, W, dtype=bf)
+    x = xz[..., :Di]
+    for state in (None, cs):
+        xl = torch.flip(x, dims=[1]) if reverse else x
+        xcm = xl.transpose(1, 2)
+        if state is not None:
+            cat = torch.cat([state, xcm], dim=-1)
+            want = orc.causal_conv1d_ref(cat, w, b, "silu")[..., -L:]
+            want_state = cat[..., -W:]
+        else:
+            want = orc.causal_conv1d_ref(xcm, w, b, "silu")
+            want_state = torch.nn.functional.pad(xcm, (W - L, 0))[..., -W:]
+        want = want.transpose(1, 2)
+        if reverse:
+            want = torch.flip(want, dims=[1])
+        got, got_state = ops.causal_conv1d_tokens(
+            xz.to(DEV)[..., :Di], w.to(DEV), b.to(DEV), None if state is None else state.to(DEV),
+            want_state=True, reverse=reverse)
+        assert rel_err(got, want) <= _tol(bf)
+        assert torch.equal(got_state.cpu(), want_state.contiguous())
+    if not reverse and L >= 32:
+        xd = xz.to(DEV)[..., :Di]
+        full, st_full = ops.causal_conv1d_tokens(xd, w.to(DEV), b.to(DEV), None, want_state=True)
+        cut = L // 2 + 1
+        y0, s0 = ops.causal_conv1d_tokens(xd[:, :cut], w.to(DEV), b.to(DEV), None, want_state=True)
+        y1, s1 = ops.causal_conv1d_tokens(xd[:, cut:], w.to(DEV), b.to(DEV), s0, want_state=True)
+        assert torch.equal(torch.cat([y0, y1], dim=1), full) and torch.equal(s1, st_full)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
