@@ -67,6 +67,17 @@ VMB_API int vmb_add_norm_fwd(const void* x, int x_dtype, int64_t ldx,
                      int64_t rows, int dim, float eps, int is_rms, vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Refiner fusion gate: out = s * fwd + (1 - s) * bwd with s = sigmoid(g1 (+ g2)), element-wise over
+ * n contiguous elements (n % 4 == 0).  Replaces the nn.Sigmoid of `fusion_gate` and the blend
+ * `gate * out_fwd + (1.0 - gate) * out_bwd` of BiMambaRefinerBlock.forward
+ * (models/refiner_backbone.py:40-43, :129-134).  g1 / g2 are the two halves of
+ * Linear(cat[out_fwd, out_bwd]) (g2 nullable when the caller projected the concatenation itself).
+ * fp32 math, one rounding to `dtype`.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_gate_blend_fwd(const void* g1, const void* g2 /* nullable */, const void* fwd,
+                       const void* bwd, void* out, int64_t n, int dtype, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dense projection  C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]),  fp32 accumulate.
  * Replaces the cuBLAS calls behind in_proj / x_proj / dt_proj / out_proj:
  * models/videomamba/mamba_simple.py:333-339, :409, :413, :445-446 (and :464, :476-479, :496).

@@ -33,6 +33,11 @@ def linear(x, weight, bias=None):
     return orc._linear(x, weight.to(x.dtype), bias)
 
 
+def gate_blend(g1, g2, fwd, bwd):
+    s = torch.sigmoid((g1.float() + g2.float()) if g2 is not None else g1.float())
+    return (s * fwd.float() + (1.0 - s) * bwd.float()).to(fwd.dtype)
+
+
 def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None):
     return orc.causal_conv1d_update_ref(x, conv_state, weight.reshape(x.shape[1], -1), bias,
                                         activation)
@@ -72,6 +77,7 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "mixer_fwd", mixer_fwd)
     monkeypatch.setattr(ops, "add_norm", add_norm)
     monkeypatch.setattr(ops, "linear", linear)
+    monkeypatch.setattr(ops, "gate_blend", gate_blend)
     monkeypatch.setattr(ops, "patchify", patchify)
     monkeypatch.setattr(ops, "embed_tokens", embed_tokens)
     monkeypatch.setattr(ops, "causal_conv1d_update", causal_conv1d_update)

@@ -487,6 +487,23 @@ def test_single_step_ops(dtype):
     assert rel_err(got, want) <= _tol(dtype) and rel_err(st_dev, st_ref) <= 1e-5
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 37, 384), (1, 5, 16), (3, 200, 576), (0, 4, 8)])
+def test_gate_blend(dtype, shape):
+    """Refiner fusion gate (refiner_backbone.py:129-134): s * fwd + (1 - s) * bwd, s = sigmoid(g1 + g2),
+    against the torch expression in float64; one- and two-logit forms."""
+    gen = torch.Generator().manual_seed(sum(shape))
+    g1, g2, f, b = (_rand(gen, *shape, dtype=dtype) for _ in range(4))
+    for second in (g2, None):
+        lg = g1.double() + (second.double() if second is not None else 0.0)
+        sg = torch.sigmoid(lg)
+        want = sg * f.double() + (1.0 - sg) * b.double()
+        got = ops.gate_blend(g1.to(DEV), None if second is None else second.to(DEV), f.to(DEV), b.to(DEV))
+        assert got.dtype == dtype and got.shape == f.shape
+        if f.numel():
+            assert rel_err(got, want) <= (1e-6 if dtype == torch.float32 else 8e-3)
+
+
 def test_state_gather_scatter_roundtrip():
     pool = torch.randn(9, 24, 16, device=DEV)
     idx = torch.tensor([7, 0, 3], device=DEV)

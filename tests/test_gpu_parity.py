@@ -364,3 +364,31 @@ def test_run_to_run_determinism():
         a = mx(x)
         b = mx(x)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_refiner_oracle_parity_production_width(dtype, tol):
+    """BiMambaRefinerBlock (refiner_backbone.py:92-135) at the Small width against the oracle: the
+    backward block walks the tokens back to front (no flip copies for 3-D input), the fusion gate is
+    two projections + one sigmoid/blend kernel, out_proj the tensor-core projection; 4-D input flips
+    frames only."""
+    torch.manual_seed(0)
+    dim = 384
+    blk = video_mamba.BiMambaRefinerBlock(dim=dim, ssm_cfg={"use_fast_path": False}, layer_idx=0).eval()
+    with torch.no_grad():
+        for m in (blk.block_fwd.mixer, blk.block_bwd.mixer):
+            m.A_log.add_(0.1 * torch.randn_like(m.A_log))
+    sd = {k: v.detach().clone().to(dtype) for k, v in blk.state_dict().items()}
+    blk.load_state_dict(sd)
+    blk = blk.to(dtype).to(DEV)
+    gen = torch.Generator().manual_seed(1)
+    x3 = torch.randn(2, 300, dim, generator=gen).to(dtype)
+    x4 = torch.randn(2, 5, 49, dim, generator=gen).to(dtype)
+    for x in (x3, x4):
+        want, want_state = orc.refiner_ref(sd, x)
+        with torch.no_grad():
+            got, got_state = blk(x.to(DEV))
+        assert got.shape == want.shape and got.dtype == dtype
+        _close(got, want, tol)
+        for a, b in zip(got_state, want_state):
+            _close(a, b, tol)

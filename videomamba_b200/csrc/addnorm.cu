@@ -192,3 +192,58 @@ extern "C" int vmb_add_norm_fwd(const void* x, int x_dtype, int64_t ldx, const v
   }
 #undef VMB_AN_CASE
 }
+
+// ---- refiner fusion gate --------------------------------------------------------------------
+// out = s * fwd + (1 - s) * bwd,  s = sigmoid(g1 (+ g2)):  the sigmoid and the blend of
+// BiMambaRefinerBlock (models/refiner_backbone.py:129-134) in one pass; g1 / g2 are the two halves of
+// Linear(cat[fwd, bwd]) computed as two projections, so the concatenated tensor never exists.
+namespace vmb {
+namespace {
+template <typename T, bool kAccurate>
+__global__ void __launch_bounds__(256)
+gate_blend_kernel(const T* __restrict__ g1, const T* __restrict__ g2, const T* __restrict__ fwd,
+                  const T* __restrict__ bwd, T* __restrict__ out, int64_t nvec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  using V = typename Vec4<T>::type;
+  float a[4], b[4], f[4], r[4], o[4];
+  Vec4<T>::unpack(reinterpret_cast<const V*>(g1)[i], a);
+  if (g2 != nullptr) {
+    Vec4<T>::unpack(reinterpret_cast<const V*>(g2)[i], b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] += b[j];
+  }
+  Vec4<T>::unpack(reinterpret_cast<const V*>(fwd)[i], f);
+  Vec4<T>::unpack(reinterpret_cast<const V*>(bwd)[i], r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float s = kAccurate ? 1.f / (1.f + expf(-a[j])) : fmaf(tanh_approx(0.5f * a[j]), 0.5f, 0.5f);
+    o[j] = s * f[j] + (1.f - s) * r[j];
+  }
+  reinterpret_cast<V*>(out)[i] = Vec4<T>::pack(o);
+}
+}  // namespace
+}  // namespace vmb
+
+extern "C" int vmb_gate_blend_fwd(const void* g1, const void* g2, const void* fwd, const void* bwd,
+                                  void* out, int64_t n, int dtype, vmb_stream_t stream) {
+  using namespace vmb;
+  VMB_CHECK_ARG(dtype_ok(dtype), "gate_blend: bad dtype");
+  VMB_CHECK_ARG(n >= 0, "gate_blend: bad size %lld", (long long)n);
+  if (n == 0) return VMB_OK;
+  VMB_CHECK_ARG(g1 && fwd && bwd && out, "gate_blend: null g1 / fwd / bwd / out");
+  if (n % 4 != 0) VMB_UNSUPPORTED("gate_blend: element count must be a multiple of 4");
+  const int64_t nvec = n / 4;
+  const unsigned grid = (unsigned)((nvec + 255) / 256);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == VMB_BF16)
+    gate_blend_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)fwd,
+        (const __nv_bfloat16*)bwd, (__nv_bfloat16*)out, nvec);
+  else
+    gate_blend_kernel<float, true><<<grid, 256, 0, st>>>((const float*)g1, (const float*)g2,
+                                                          (const float*)fwd, (const float*)bwd,
+                                                          (float*)out, nvec);
+  VMB_LAUNCH_CHECK("gate_blend_kernel");
+  return VMB_OK;
+}

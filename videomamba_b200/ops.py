@@ -145,6 +145,24 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     return out.reshape(*x.shape[:-1], N)
 
 
+def gate_blend(g1: Tensor, g2: Optional[Tensor], fwd: Tensor, bwd: Tensor) -> Tensor:
+    """``s * fwd + (1 - s) * bwd`` with ``s = sigmoid(g1 (+ g2))`` in one pass (refiner fusion gate,
+    reference models/refiner_backbone.py:129-134)."""
+    _require_cuda(fwd)
+    lib = _lib.load()
+    if not (g1.shape == fwd.shape == bwd.shape) or (g2 is not None and g2.shape != fwd.shape):
+        raise ValueError("gate_blend: shape mismatch")
+    g1, fwd, bwd = g1.contiguous(), fwd.contiguous(), bwd.contiguous()
+    if g2 is not None:
+        g2 = g2.contiguous()
+    out = torch.empty_like(fwd)
+    with _on_device(fwd):
+        rc = lib.vmb_gate_blend_fwd(_p(g1), _p(g2), _p(fwd), _p(bwd), _p(out), fwd.numel(), _dt(fwd),
+                                    _stream(fwd))
+    _lib.check(rc, "vmb_gate_blend_fwd")
+    return out
+
+
 def patchify(x: Tensor, tubelet: int, ph: int, pw: int) -> Tensor:
     """Clip ``(B, C, T, H, W)`` -> patch rows ``(B*t*h*w, C*tubelet*ph*pw)`` (im2col of a Conv3d whose
     kernel equals its stride; rows ordered (b, t, y, x), columns (c, dt, dy, dx))."""

@@ -96,6 +96,18 @@ class BiMambaRefinerBlock(nn.Module):
         bwd_state = self._ensure_state(self.block_bwd, state_bwd_init, bsz, x_seq.device)
         out_bwd = self._backward_block(x_seq, bwd_state, packed)
 
-        gate = self.fusion_gate(torch.cat([out_fwd, out_bwd], dim=-1))
-        out = self.out_proj(gate * out_fwd + (1.0 - gate) * out_bwd)
+        out = self._fuse(out_fwd, out_bwd)
         return self._unpack_tokens(out, packed), new_state_fwd
+
+    def _fuse(self, out_fwd: Tensor, out_bwd: Tensor) -> Tensor:
+        """``out_proj(gate * out_fwd + (1 - gate) * out_bwd)``, ``gate = sigmoid(Linear(cat))``
+        (refiner_backbone.py:129-134) through the library: the gate projection runs as two
+        projections over the two halves of its weight (no concatenated tensor), the sigmoid and
+        the blend are one kernel, ``out_proj`` is the tensor-core projection."""
+        lin = self.fusion_gate[0]
+        dim = out_fwd.shape[-1]
+        w = lin.weight
+        g1 = ops.linear(out_fwd, w[:, :dim], lin.bias)
+        g2 = ops.linear(out_bwd, w[:, dim:], None)
+        mixed = ops.gate_blend(g1, g2, out_fwd, out_bwd)
+        return ops.linear(mixed, self.out_proj.weight, self.out_proj.bias)
