@@ -392,3 +392,40 @@ def test_refiner_oracle_parity_production_width(dtype, tol):
         _close(got, want, tol)
         for a, b in zip(got_state, want_state):
             _close(a, b, tol)
+
+
+def test_graphed_stream_equals_eager_chunks():
+    """videomamba_b200.graphed.GraphedStream: continuation chunks replayed from one CUDA graph (state
+    fed back inside the graph, temporal rows of the current offset in a fixed buffer) are
+    bit-identical to the eager ``model(x, ssm_state=prev, temporal_pos_offset=off)`` chain."""
+    from videomamba_b200.graphed import GraphedStream
+    torch.manual_seed(0)
+    bf = torch.bfloat16
+    m = video_mamba.PretrainVideoMamba(img_size=64, patch_size=16, depth=3, embed_dim=192, channels=3,
+                                       ssm_cfg={"use_fast_path": False}, num_frames=16,
+                                       pool_type="avg").eval()
+    with torch.no_grad():
+        m.temporal_pos_embedding.normal_(0, 0.02)
+    m = m.to(bf).to(DEV)
+    B, T = 3, 2
+    gen = torch.Generator().manual_seed(3)
+    chunks = [torch.rand(B, 3, T, 64, 64, generator=gen).to(bf).to(DEV) for _ in range(5)]
+    with torch.no_grad():
+        st = m.allocate_state(B, dtype=bf, device=DEV)
+        eager = []
+        for i, x in enumerate(chunks):
+            vis, pool, st = m(x, ssm_state=st, temporal_pos_offset=i * T)
+            eager.append((vis.clone(), pool.clone()))
+    runner = GraphedStream(m)
+    vis, pool = runner.first(chunks[0])
+    assert torch.equal(vis, eager[0][0]) and torch.equal(pool, eager[0][1])
+    for i in range(1, 5):
+        vis, pool = runner.step(chunks[i])
+        assert runner.offset == (i + 1) * T
+        assert torch.equal(vis, eager[i][0]), i
+        assert torch.equal(pool, eager[i][1]), i
+    for (c, s), (ec, es) in zip(runner.state, st):
+        assert torch.equal(c, ec) and torch.equal(s, es)
+    with pytest.raises(ValueError, match="pool_type='avg'"):
+        GraphedStream(video_mamba.PretrainVideoMamba(img_size=32, patch_size=16, depth=1, embed_dim=32,
+                                                     channels=3, num_frames=4, pool_type="cls+avg"))

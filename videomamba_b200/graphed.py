@@ -1,0 +1,128 @@
+"""CUDA-graph replay of continuation chunks for small-chunk streaming.
+
+A continuation chunk of a few frames is launch bound: ~146 kernel launches per forward cost ~2.3 ms
+eager at 196 tokens while the kernels themselves need ~1.3 ms (tools/graph_probe.py).  The library
+only enqueues on the caller's stream and allocates nothing, so a whole forward captures as is; this
+runner adds what a stream needs around it: replay-stable input / state buffers, the state fed back
+inside the graph, and the temporal position rows of the current offset (reference
+videomamba.py:655-675, computed eagerly per chunk so the interpolation rule is untouched) written
+into a fixed buffer before each replay.
+
+Semantics are those of ``model(x, ssm_state=state, temporal_pos_offset=offset)`` with the state of
+the previous call (streaming contract 1.0.0): the first chunk runs eagerly (it carries the CLS
+token, so its shapes differ), every later chunk is one graph launch.  Results are bit-identical to
+the eager calls (same kernels, same order).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+LayerState = Tuple[Tensor, Tensor]
+
+
+class GraphedStream:
+    """One batch of concurrent streams advancing ``chunk_frames`` frames per call."""
+
+    def __init__(self, model, warmup: int = 2):
+        if getattr(model, "add_pool_norm", True) and getattr(model, "pool_type", "avg") != "avg":
+            raise ValueError("continuation chunks carry no CLS token: build the model with "
+                             "pool_type='avg' (or add_pool_norm=False) for graphed streaming.")
+        self.model = model
+        self.warmup = int(warmup)
+        self.offset = 0                       # temporal tokens consumed so far
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._x: Optional[Tensor] = None
+        self._rows: Optional[Tensor] = None
+        self._state: Optional[List[LayerState]] = None
+        self._out = None
+
+    # ---- public -------------------------------------------------------------------------
+    @property
+    def state(self) -> Optional[List[LayerState]]:
+        """The carried ``[(conv_state, ssm_state)] * depth`` (live buffers; clone to keep)."""
+        return self._state
+
+    def first(self, x: Tensor, state=None):
+        """First chunk of the streams (offset 0, CLS included): eager.  Returns what
+        ``model(x, ssm_state=state, temporal_pos_offset=0)`` returns, minus the state."""
+        m = self.model
+        if state is None:
+            p = next(m.parameters())
+            state = m.allocate_state(x.shape[0], dtype=p.dtype, device=x.device)
+        with torch.no_grad():
+            out = m(x, ssm_state=state, temporal_pos_offset=0)
+        self._state = [(c.clone(), s.clone()) for c, s in self._as_list(out[-1])]
+        self.offset = m._validate_temporal_length(x.shape[2])
+        self._graph = None
+        return out[:-1] if len(out) > 2 else out[0]
+
+    def step(self, x: Tensor):
+        """Next chunk: one graph launch.  The returned tensors are the graph's output buffers and
+        are overwritten by the next ``step`` (clone to keep)."""
+        if self._state is None:
+            raise RuntimeError("call first() before step().")
+        m = self.model
+        t_tokens = m._validate_temporal_length(x.shape[2])
+        rows = self._temporal_rows(t_tokens, x)
+        if self._graph is None or self._x.shape != x.shape or self._x.dtype != x.dtype:
+            self._capture(x, rows)
+        else:
+            self._x.copy_(x)
+            self._rows.copy_(rows)
+            self._graph.replay()
+        self.offset += t_tokens
+        out = self._out
+        return out[:-1] if len(out) > 2 else out[0]
+
+    # ---- internals ----------------------------------------------------------------------
+    @staticmethod
+    def _as_list(state) -> List[LayerState]:
+        if isinstance(state, dict):
+            return [state[i] for i in range(len(state))]
+        return list(state)
+
+    def _temporal_rows(self, t_tokens: int, x: Tensor) -> Tensor:
+        m = self.model
+        m._temporal_rows_override = None
+        dtype = next(m.parameters()).dtype
+        return m._get_temporal_pos_embedding(t_tokens, offset=self.offset, dtype=dtype,
+                                             device=x.device).contiguous()
+
+    def _run(self):
+        m = self.model
+        out = m(self._x, ssm_state=self._state, temporal_pos_offset=max(self.offset, 1))
+        for (c, s), (nc, ns) in zip(self._state, self._as_list(out[-1])):
+            c.copy_(nc)
+            s.copy_(ns)
+        return out
+
+    def _capture(self, x: Tensor, rows: Tensor) -> None:
+        m = self.model
+        self._x = x.clone()
+        self._rows = rows.clone()
+        keep = [(c.clone(), s.clone()) for c, s in self._state]
+        m._temporal_rows_override = self._rows
+        try:
+            with torch.no_grad():
+                side = torch.cuda.Stream(device=x.device)
+                side.wait_stream(torch.cuda.current_stream(x.device))
+                with torch.cuda.stream(side):
+                    for _ in range(self.warmup):        # warm the allocator and the tensor-map caches
+                        self._run()
+                torch.cuda.current_stream(x.device).wait_stream(side)
+                for (c, s), (kc, ks) in zip(self._state, keep):   # warm-up advanced the state: restore
+                    c.copy_(kc)
+                    s.copy_(ks)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._out = self._run()
+                for (c, s), (kc, ks) in zip(self._state, keep):
+                    c.copy_(kc)
+                    s.copy_(ks)
+                graph.replay()
+            self._graph = graph
+        finally:
+            m._temporal_rows_override = None

@@ -294,6 +294,11 @@ class PretrainVideoMamba(nn.Module):
         linearly stretched to length offset+seqlen (the reference's behaviour, :655-675)."""
         if offset < 0:
             raise ValueError("temporal_pos_offset must be non-negative.")
+        override = getattr(self, "_temporal_rows_override", None)
+        if override is not None:        # graphed streaming: rows live in a replay-stable buffer
+            if override.shape[1] != seqlen:
+                raise ValueError("temporal row buffer does not match the chunk length.")
+            return override
         device = self.temporal_pos_embedding.device if device is None else device
         dtype = self.temporal_pos_embedding.dtype if dtype is None else dtype
         table = self.temporal_pos_embedding.to(device=device, dtype=dtype)
