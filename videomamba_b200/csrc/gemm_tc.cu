@@ -408,7 +408,7 @@ __host__ __device__ constexpr size_t smem_bytes_pair(int bn, int stages) {
 __host__ __device__ constexpr int stages_pair(int) { return 6; }   // 6 x (16 KB A + <= 16 KB W half)
 
 template <int BN, int kStages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, kStages <= 3 ? 3 : 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ bias,
                     int M, int N, int K) {
@@ -786,6 +786,16 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* 
             int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
   if (footprint() == 1) {
     if (N <= 64) return launch<64, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    return launch<128, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  }
+  if (footprint() == 2 || footprint() == 3) {   // small-footprint CTA pairs: 2 stages (97 KB) / 3 stages (129 KB)
+    if (N <= 64) return launch<64, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    if (M >= 4 * BM && N % 256 == 0)
+      return footprint() == 2 ? launch_pair<256, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st)
+                              : launch_pair<256, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    if (M >= 4 * BM && N % 192 == 0)
+      return footprint() == 2 ? launch_pair<192, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st)
+                              : launch_pair<192, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
     return launch<128, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   }
   if (pair_mode() != 0 && M >= 4 * BM) {   // CTA pairs: 256-row tiles, half a W tile per SM
