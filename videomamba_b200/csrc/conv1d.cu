@@ -5,6 +5,11 @@
 // A thread owns VEC consecutive channels (one 128-bit load per token) and slides a W-tap
 // window down a chunk of tokens, so x is read once (+ W-1 halo rows per chunk) and y written once.
 // Algorithmic bytes per token: 2 * Di * sizeof(T).
+// Three kernels: conv1d_fwd_kernel (any dtype / width, all loads of a 16-token chunk up front),
+// conv1d_stream_kernel (bf16, d_conv 4: register double-buffered sub-chunks; VMB_CONV_VARIANT=2) and
+// conv1d_ring_kernel (bf16, d_conv 4, the default: rows staged by cp.async into a private ring of
+// shared-memory slots, 0.83 of the HBM peak; CTAs walk batch and chunks back to front so the
+// kernel starts on the rows in_proj wrote last -- DESIGN.md 3.3, 3.4).
 #include <cstdlib>
 
 #include "common.cuh"

@@ -4,6 +4,10 @@
 // (models/videomamba/mamba_simple.py:333-339 in_proj, :409 x_proj, :445-446 out_proj) and behind
 // the Conv3d patch embedding (models/videomamba/videomamba.py:359-368, kernel == stride).
 //
+// Two kernels share the design below: gemm_tc_kernel (one CTA per tile of 128 x BN) and
+// gemm_tc_pair_kernel (cta_group::2: the two CTAs of a cluster share a 256 x BN tile, each holding
+// half of the W tile -- the default for N % 256 == 0 or N % 192 == 0, see its header further down).
+//
 // Design (B200 / sm_100a, one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0   TMA producer: A tile (128 x 64) and W tile (BN x 64) per k-block into a kStages-deep
 //            ring of 128B-swizzled shared-memory buffers (cp.async.bulk.tensor + mbarrier tx).

@@ -12,7 +12,8 @@
 // shared-memory loads, not by HBM (profiles/r01_scan_ncu_full_summary.txt).  Common
 // to all layouts below:
 //   * CTA = ONE warp = (batch b, 16 channels); the sequence is walked in tiles of 16 tokens staged
-//     with 16-byte cp.async copies (double buffered).  One-warp CTAs need no block barriers and
+//     in shared memory one tile ahead (v10: TMA box copies on an mbarrier; earlier layouts: 16-byte
+//     cp.async copies, double buffered).  One-warp CTAs need no block barriers and
 //     1536 of them spread over 148 SMs within 6 % of even (768 two-warp CTAs: 14 % idle tail).
 //   * phase A (per tile): the dt projection of the tile, delta_raw[16 tokens x 16 channels] =
 //     dt_low[16 x R] * w_dt^T, runs on the tensor pipe (mma.sync m16n8k16, the A fragments come
