@@ -420,11 +420,15 @@ def run_ours(args):
     # conv reads x and writes xc; add+norm reads hidden (bf16) + residual (fp32), writes both)
     hbm_kernels = {}
     Dm = mixer.d_model
-    for k, bpt in (("conv", 2 * Di * es), ("add_norm", Dm * es + 4 * Dm + 4 * Dm + Dm * es)):
+    # conv alone reads x and writes xc; fused with x_proj (no separate x_proj stage) it also writes x_dbl
+    conv_fused = "x_proj" not in stages or not stages["x_proj"]["launches_per_step"]
+    conv_bpt = (2 * Di + w.Xp) * es if conv_fused else 2 * Di * es
+    for k, bpt in (("conv", conv_bpt), ("add_norm", Dm * es + 4 * Dm + 4 * Dm + Dm * es)):
         if k in stages and stages[k]["launches_per_step"]:
             per = stages[k]["ms_per_step"] / stages[k]["launches_per_step"]
             gbs = tokens * bpt / (per * 1e-3) / 1e9
-            hbm_kernels[k] = {"achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak, "ms_per_launch": per}
+            name = "conv_xproj" if (k == "conv" and conv_fused) else k
+            hbm_kernels[name] = {"achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak, "ms_per_launch": per}
     # projections against the tensor roofline (reported beside, not the dominant-kernel object)
     tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     D = mixer.d_model

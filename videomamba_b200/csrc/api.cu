@@ -256,16 +256,6 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
                         p->dtype, stream);
   }
   if (rc) return rc;
-  // causal conv + SiLU with optional history (mamba_simple.py:381-404)
-  {
-    ProfScope ps(VMB_PROF_CONV, st);
-    rc = vmb_causal_conv1d_fwd(xz, (int64_t)L * 2 * Di, 2 * Di, p->w_conv, p->b_conv,
-                               p->conv_state_in, p->cs_in_dtype, xc, (int64_t)L * Di, Di,
-                               p->conv_state_out, p->cs_out_dtype, B, L, Di, p->W, 1, p->reverse,
-                               p->dtype, stream);
-  }
-  if (rc) return rc;
-
   FastScanArgs f;
   f.u = xc; f.u_bs = (int64_t)L * Di; f.u_ts = Di;
   f.z = (char*)xz + (int64_t)Di * es; f.z_bs = (int64_t)L * 2 * Di; f.z_ts = 2 * Di;
@@ -281,13 +271,34 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   if (p->path == 2 && !fast_ok) VMB_UNSUPPORTED("mixer: fast path requested but not available");
   const bool fast = fast_ok && p->path != 1;
 
+  // Stateless forward walk on the fast path: the conv runs inside the x_proj projection (its output
+  // tile goes from the conv warps to the tensor cores through shared memory and to HBM once).
+  const bool fused_conv = fast && p->W == 4 && !p->reverse && p->conv_state_in == nullptr &&
+                          p->conv_state_out == nullptr &&
+                          conv_xproj_supported(xz, 2 * Di, p->w_conv, p->b_conv, p->w_x_pad, Di, xc, Di,
+                                               xdbl, Xw, M, Xw, Di, L);
+  if (fused_conv) {
+    ProfScope ps(VMB_PROF_CONV, st);
+    rc = conv_xproj_tc(xz, 2 * Di, p->w_conv, p->b_conv, p->w_x_pad, Di, xc, Di, xdbl, Xw, M, Xw, Di, L,
+                       1, st);
+    if (rc) return rc;
+  } else {
+    // causal conv + SiLU with optional history (mamba_simple.py:381-404)
+    ProfScope ps(VMB_PROF_CONV, st);
+    rc = vmb_causal_conv1d_fwd(xz, (int64_t)L * 2 * Di, 2 * Di, p->w_conv, p->b_conv,
+                               p->conv_state_in, p->cs_in_dtype, xc, (int64_t)L * Di, Di,
+                               p->conv_state_out, p->cs_out_dtype, B, L, Di, p->W, 1, p->reverse,
+                               p->dtype, stream);
+    if (rc) return rc;
+  }
+
   if (fast) {
     // x_proj with zero-padded weight rows: x_dbl (M, Xp) = [dt_low | B | C | 0]
-    {
+    if (!fused_conv) {
       ProfScope ps(VMB_PROF_X_PROJ, st);
       rc = vmb_linear_fwd(xc, Di, p->w_x_pad, Di, nullptr, xdbl, Xw, M, Xw, Di, p->dtype, stream);
+      if (rc) return rc;
     }
-    if (rc) return rc;
     {
       ProfScope ps(VMB_PROF_SCAN, st);
       rc = scan_fast(f, st);

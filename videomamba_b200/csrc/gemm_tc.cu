@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 #include <mutex>
 #include <unordered_map>
 
@@ -598,6 +599,318 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ---- causal conv1d + SiLU fused into the x_proj projection ------------------------------------
+// x_dbl[M, BN] = SiLU(conv(x))[M, K] * W[BN, K]^T, and xc = SiLU(conv(x)) is written on the way (the
+// scan reads it as u).  Stands in for the causal_conv1d_fn -> rearrange -> x_proj sequence of
+// models/videomamba/mamba_simple.py:381-409 for the stateless forward walk (no conv_state in / out,
+// no reversal: those keep the separate kernels).  The conv output tile never returns from HBM:
+//   warp 0     TMA producer: per k-block (64 channels) the RAW x rows [m0 - 3, m0 + 128) x 64
+//              (unswizzled box; rows before the tensor start are zero-filled) and the W tile.
+//   warps 6-21 conv (two groups of 8 warps, alternate k-blocks): thread = 4 channels x 8 rows; slides
+//              the 4-tap window over its 11 raw rows
+//              (same FFMA2 order as conv1d_ring_kernel: bit-identical xc), writes the bf16 results
+//              to the k-block's A stage in the UMMA 128-byte-swizzle layout AND to xc in HBM, then
+//              fence.proxy.async + mbarrier arrive.  Rows where a new sequence starts (row % L < 3)
+//              drop the taps that would reach into the previous clip.
+//   warp 1     MMA issuer (tcgen05.mma M 128 x N BN x K 16 from the A stage and the W tile).
+//   warps 2-5  epilogue: TMEM -> bf16 -> staging -> TMA store of the x_dbl tile.
+// HBM traffic per token: x read once, xc written once, x_dbl written once (the separate kernels
+// re-read xc: + Di * 2 bytes).
+#ifndef VMB_CX_GROUPS
+#define VMB_CX_GROUPS 2
+#endif
+constexpr int kCxGroups = VMB_CX_GROUPS;                                 // conv warp groups (8 warps each)
+constexpr int kCxThreads = 192 + 256 * kCxGroups;   // TMA, MMA, 4 epilogue warps, kCxGroups x 8 conv warps
+constexpr int kCxRawRows = BM + 3;
+constexpr uint32_t kCxRawBytes = kCxRawRows * BK * 2;                       // 16 768
+constexpr uint32_t kCxRawStage = (kCxRawBytes + 1023u) / 1024u * 1024u;     // 17 408
+constexpr int kCxAStages = 2;            // conv-output (A operand) ring: held only from conv to MMA
+__host__ __device__ constexpr size_t smem_bytes_cx(int bn, int stages, int K) {
+  return 1024 + (size_t)stages * (kCxRawStage + bn * BK * 2) + (size_t)kCxAStages * (BM * BK * 2) +
+         BM * kSubN * 2 + 512 + (size_t)K * 10;       // conv taps (K x 4) and bias (K), bf16
+}
+
+template <int BN, int kStages, bool kSilu>
+__global__ void __launch_bounds__(kCxThreads, 1)
+conv_xproj_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ cw,
+                  const __nv_bfloat16* __restrict__ cb, __nv_bfloat16* __restrict__ xc, int64_t xc_ld,
+                  int M, int K, int L) {
+  static_assert(BN <= kSubN, "conv_xproj: one epilogue sub-tile");
+  constexpr int kTmemCols = tmem_cols_for(BN);
+  constexpr uint32_t kABytes = BM * BK * 2;
+  constexpr uint32_t kWBytes = BN * BK * 2;
+  constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_x = smem_base;                                   // raw x stages
+  const uint32_t smem_w = smem_x + kStages * kCxRawStage;
+  const uint32_t smem_a = smem_w + kStages * kWBytes;
+  const uint32_t smem_c = smem_a + kCxAStages * kABytes;
+  const uint32_t bars = smem_c + BM * kSubN * 2;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (kStages + s); };
+  auto a_full = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto a_empty = [&](int s) { return bars + 8u * (2 * kStages + kCxAStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 * kCxAStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 * kCxAStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 2 * kCxAStages + 4);
+  const uint32_t smem_cw = bars + 512;                                 // conv taps, then bias
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int k_blocks = K / BK;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_c);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(raw_empty(s), 256 + 1);     // the conv threads (raw rows read) + the MMA commit (W read)
+    }
+    for (int s = 0; s < kCxAStages; ++s) {
+      mbar_init(a_full(s), 256);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {   // conv taps (K x 4) and bias (K) into shared memory, once per CTA
+    uint4* dst = reinterpret_cast<uint4*>(smem_gen + (smem_cw - smem_base));
+    const int nw = K / 2;                            // 16-byte chunks of taps (4 taps x 2 channels each)
+    for (int q = threadIdx.x; q < nw; q += blockDim.x) dst[q] = __ldg(reinterpret_cast<const uint4*>(cw) + q);
+    const int nb = K / 8;
+    for (int q = threadIdx.x; q < nb; q += blockDim.x)
+      dst[nw + q] = cb != nullptr ? __ldg(reinterpret_cast<const uint4*>(cb) + q) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // tiles are walked back to front: in_proj wrote the last rows of x most recently
+  auto tile_m0 = [&](int i) { return (m_tiles - 1 - i) * BM; };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = blockIdx.x; i < m_tiles; i += gridDim.x) {
+        const int m0 = tile_m0(i);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(raw_empty(stage), phase ^ 1);
+          mbar_expect_tx(raw_full(stage), kCxRawBytes + kWBytes);
+          tma_load_2d(smem_x + stage * kCxRawStage, &map_x, raw_full(stage), kb * BK, m0 - 3);
+          tma_load_2d(smem_w + stage * kWBytes, &map_w, raw_full(stage), kb * BK, 0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      int n = 0;                                     // running k-block counter
+      int local = 0;
+      for (int i = blockIdx.x; i < m_tiles; i += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++n) {
+          const int rs = n % kStages, as = n % kCxAStages;
+          mbar_wait(raw_full(rs), (uint32_t)(n / kStages) & 1u);        // W tile landed
+          mbar_wait(a_full(as), (uint32_t)(n / kCxAStages) & 1u);       // conv output of this k-block staged
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem_a + as * kABytes);
+          const uint64_t b_desc = umma_desc_sw128(smem_w + rs * kWBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb | k) != 0);
+          tc_commit(a_empty(as));
+          tc_commit(raw_empty(rs));
+          if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue: one 128 x BN tile of x_dbl =====
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const bool issuer = threadIdx.x == kEpiWarp0 * 32;
+    int local = 0;
+    for (int i = blockIdx.x; i < m_tiles; i += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m0 = tile_m0(i);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      uint32_t v0[32], v1[32];
+      tc_ld_32x32(t_row, v0);
+      if (BN > 32) tc_ld_32x32(t_row + 32, v1);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (issuer) tma_store_wait_read<0>();          // the previous tile's store has read the staging buffer
+      epi_bar_sync();
+      uint8_t* dst = smem_gen + (smem_c - smem_base) + row * 128;
+#pragma unroll
+      for (int c = 0; c < BN / 8; ++c) {
+        uint32_t p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = c * 8 + q * 2;
+          const float lo = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+          const float hi = __uint_as_float(j + 1 < 32 ? v0[j + 1] : v1[j + 1 - 32]);
+          __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+          p[q] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (issuer) {
+        tma_store_2d(&map_c, smem_c, 0, m0);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_all();
+  } else {
+    // ===== conv warps: kCxGroups groups of 256 threads take the k-blocks round robin.  A conv warp issues
+    // about one instruction per 6 cycles (dependent FFMA2 / MUFU chains), so throughput scales with the
+    // number of resident conv warps: thread = 4 channels (quad q4 of the k-block) x rows [8 rg, 8 rg + 8),
+    // 16 conv warps per SM at <= 88 registers =====
+    const int ct = threadIdx.x - 6 * 32;
+    const int grp = ct >> 8;
+    const int q4 = ct & 15, rg = (ct & 255) >> 4;
+    const uint4* cws = reinterpret_cast<const uint4*>(smem_gen + (smem_cw - smem_base));
+    int n = 0;                                       // running k-block counter (all roles agree on it)
+    for (int i = blockIdx.x; i < m_tiles; i += gridDim.x) {
+      const int m0 = tile_m0(i);
+      const int mrow = m0 + rg * 8;                  // first output row of this thread
+      const int t_first = mrow % L;                  // its position in its sequence
+      for (int kb = 0; kb < k_blocks; ++kb, ++n) {
+        if (n % kCxGroups != grp) continue;
+        const int stage = n % kStages;                          // raw ring
+        const uint32_t phase = (uint32_t)(n / kStages) & 1u;
+        const int as = n % kCxAStages;                          // A ring
+        const uint32_t aphase = (uint32_t)(n / kCxAStages) & 1u;
+        const int c0 = kb * BK + q4 * 4;             // first of this thread's 4 channels
+        float2 w2[2][4], b2[2];
+        {
+          const uint4 wv[2] = {cws[c0 / 2], cws[c0 / 2 + 1]};
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {              // 8 bf16: channel 2p taps 0..3, channel 2p+1 taps 0..3
+            const uint32_t q[4] = {wv[p].x, wv[p].y, wv[p].z, wv[p].w};
+            const float e0[4] = {__uint_as_float(q[0] << 16), __uint_as_float(q[0] & 0xffff0000u),
+                                 __uint_as_float(q[1] << 16), __uint_as_float(q[1] & 0xffff0000u)};
+            const float e1[4] = {__uint_as_float(q[2] << 16), __uint_as_float(q[2] & 0xffff0000u),
+                                 __uint_as_float(q[3] << 16), __uint_as_float(q[3] & 0xffff0000u)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w2[p][k] = make_float2(e0[k], e1[k]);
+          }
+          const uint2 bv = reinterpret_cast<const uint2*>(cws + K / 2)[c0 / 4];
+          b2[0] = make_float2(__uint_as_float(bv.x << 16), __uint_as_float(bv.x & 0xffff0000u));
+          b2[1] = make_float2(__uint_as_float(bv.y << 16), __uint_as_float(bv.y & 0xffff0000u));
+        }
+        mbar_wait(raw_full(stage), phase);
+        mbar_wait(a_empty(as), aphase ^ 1);
+        const uint8_t* rawp = smem_gen + (smem_x - smem_base) + stage * kCxRawStage + q4 * 8;
+        uint8_t* ap = smem_gen + (smem_a - smem_base) + as * kABytes;
+        auto unpack = [](const uint2& v, float2 (&f)[2]) {
+          f[0] = make_float2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+          f[1] = make_float2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+        };
+        // raw row j of the stage is tensor row m0 - 3 + j: this thread's window starts at 8 rg.
+        // kEdge: a sequence starts inside (or just before) these rows -- taps that would reach into the
+        // previous clip are dropped; the common case has no such row and no checks.
+        auto run_rows = [&](auto edge_tag) {
+          constexpr bool kEdge = decltype(edge_tag)::value;
+          float2 win[3][2];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            unpack(*reinterpret_cast<const uint2*>(rawp + (rg * 8 + k) * 128), win[k]);
+            if (kEdge && t_first - 3 + k < 0) {
+              win[k][0] = make_float2(0.f, 0.f);
+              win[k][1] = make_float2(0.f, 0.f);
+            }
+          }
+          int t = t_first;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float2 xin[2];
+            unpack(*reinterpret_cast<const uint2*>(rawp + (rg * 8 + 3 + j) * 128), xin);
+            if (kEdge && t == L) {                   // a new sequence starts at this row
+              t = 0;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                win[k][0] = make_float2(0.f, 0.f);
+                win[k][1] = make_float2(0.f, 0.f);
+              }
+            }
+            uint32_t ov[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              float2 acc = __ffma2_rn(w2[q][0], win[0][q], b2[q]);
+              acc = __ffma2_rn(w2[q][1], win[1][q], acc);
+              acc = __ffma2_rn(w2[q][2], win[2][q], acc);
+              acc = __ffma2_rn(w2[q][3], xin[q], acc);
+              if (kSilu) {   // x * (0.5 * tanh(x / 2) + 0.5), packed: same per-lane arithmetic as silu_fast
+                const float2 hx = __fmul2_rn(acc, make_float2(0.5f, 0.5f));
+                const float2 th = make_float2(tanh_approx(hx.x), tanh_approx(hx.y));
+                acc = __fmul2_rn(acc, __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)));
+              }
+              const __nv_bfloat162 h = __floats2bfloat162_rn(acc.x, acc.y);
+              ov[q] = *reinterpret_cast<const uint32_t*>(&h);
+              win[0][q] = win[1][q]; win[1][q] = win[2][q]; win[2][q] = xin[q];
+            }
+            const int r = rg * 8 + j;                // row of the tile
+            const uint2 out = make_uint2(ov[0], ov[1]);
+            // 128B swizzle of the A stage: 16-byte chunk (q4 >> 1) XOR (row mod 8), this quad's half of it
+            *reinterpret_cast<uint2*>(ap + r * 128 + ((((q4 >> 1) ^ (r & 7)) << 4) | ((q4 & 1) << 3))) = out;
+            if (!kEdge || m0 + r < M) *reinterpret_cast<uint2*>(xc + (int64_t)(m0 + r) * xc_ld + c0) = out;
+            if (kEdge) ++t;
+          }
+        };
+        if (t_first < 3 || t_first + 8 > L || m0 + BM > M) run_rows(std::true_type{});
+        else run_rows(std::false_type{});
+        fence_proxy_async_smem();                    // generic-proxy writes of the A stage -> tensor core reads
+        mbar_arrive(a_full(as));
+        mbar_arrive(raw_empty(stage));
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
 // ---- host side: tensor maps ----------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -757,6 +1070,57 @@ int launch_pair(const void* A, int64_t lda, const void* W, int64_t ldw, const vo
   return VMB_OK;
 }
 
+// 2-D bf16 row-major tensor, box = box_rows x 64 columns, NO swizzle (raw rows for the conv warps).
+int make_map_plain(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeFn fn = encode_fn();
+  if (!fn) { set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available"); return VMB_ERR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled (plain) failed (%d)", (int)r); return VMB_ERR_CUDA; }
+  return VMB_OK;
+}
+
+template <int BN, int kStages>
+int launch_cx(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W, int64_t ldw,
+              void* xc, int64_t xc_ld, void* C, int64_t ldc, int64_t M, int N, int K, int L, int silu,
+              cudaStream_t st) {
+  CUtensorMap mx, mw, mc;
+  int rc;
+  if ((rc = make_map_plain(&mx, x, M, K, x_ld, kCxRawRows))) return rc;
+  if ((rc = make_map(&mw, W, N, K, ldw, BN))) return rc;
+  if ((rc = make_map(&mc, C, M, N, ldc, BM))) return rc;
+  const size_t smem = smem_bytes_cx(BN, kStages, K);
+  if (smem > 227 * 1024) VMB_UNSUPPORTED("conv_xproj: K too large for the shared-memory budget");
+  static bool attr_set[64][2] = {};
+  int dev = 0;
+  VMB_CUDA(cudaGetDevice(&dev));
+  const int si = silu ? 1 : 0;
+  if (dev < 0 || dev >= 64 || !attr_set[dev][si]) {
+    if (silu)
+      VMB_CUDA(cudaFuncSetAttribute(conv_xproj_kernel<BN, kStages, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else
+      VMB_CUDA(cudaFuncSetAttribute(conv_xproj_kernel<BN, kStages, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (dev >= 0 && dev < 64) attr_set[dev][si] = true;
+  }
+  const int64_t tiles = (M + BM - 1) / BM;
+  const int grid = (int)std::min<int64_t>(tiles, sm_count());
+  if (silu)
+    conv_xproj_kernel<BN, kStages, true><<<grid, kCxThreads, smem, st>>>(
+        mx, mw, mc, (const __nv_bfloat16*)cw, (const __nv_bfloat16*)cb, (__nv_bfloat16*)xc, xc_ld, (int)M, K, L);
+  else
+    conv_xproj_kernel<BN, kStages, false><<<grid, kCxThreads, smem, st>>>(
+        mx, mw, mc, (const __nv_bfloat16*)cw, (const __nv_bfloat16*)cb, (__nv_bfloat16*)xc, xc_ld, (int)M, K, L);
+  VMB_LAUNCH_CHECK("conv_xproj_kernel");
+  return VMB_OK;
+}
+
 // VMB_GEMM_PAIR=0 keeps every projection on the 1-CTA kernel.
 int pair_mode() {
   static int v = [] {
@@ -812,6 +1176,26 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* 
   if (N % 192 == 0 || N < 256)
     return launch<192, stages_for(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+}
+
+// VMB_CONV_XPROJ=0 keeps the conv and x_proj as separate kernels.
+bool conv_xproj_supported(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W,
+                          int64_t ldw, const void* xc, int64_t xc_ld, const void* C, int64_t ldc,
+                          int64_t M, int N, int K, int L) {
+  static const bool on = [] {
+    const char* e = std::getenv("VMB_CONV_XPROJ");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  return on && N == 64 && K % BK == 0 && K >= BK && smem_bytes_cx(64, 6, K) <= 227 * 1024 && M >= 4 * BM && M < (1ll << 31) - 2 * BM && L >= 4 &&
+         al16(x) && al16(cw) && (cb == nullptr || al16(cb)) && al16(W) && al16(xc) && al16(C) &&
+         x_ld % 8 == 0 && ldw % 8 == 0 && xc_ld % 8 == 0 && ldc % 8 == 0;
+}
+
+int conv_xproj_tc(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W,
+                  int64_t ldw, void* xc, int64_t xc_ld, void* C, int64_t ldc, int64_t M, int N, int K,
+                  int L, int silu, cudaStream_t st) {
+  return launch_cx<64, 6>(x, x_ld, cw, cb, W, ldw, xc, xc_ld, C, ldc, M, N, K, L, silu, st);
 }
 
 }  // namespace vmb

@@ -23,6 +23,16 @@ int make_tensor_map_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint
                             uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                             uint32_t box1, bool swizzle128);
 
+// gemm_tc.cu -- causal conv (d_conv 4, bf16) + SiLU fused into the x_proj projection: x (M rows of K
+// channels, row pitch x_ld; rows are (batch, token) flattened, L tokens per sequence), conv taps cw
+// (K, 4) / bias cb (K), W (N = 64, K) -> xc (M, K) and C = xc * W^T (M, N).  Stateless forward walk only.
+bool conv_xproj_supported(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W,
+                          int64_t ldw, const void* xc, int64_t xc_ld, const void* C, int64_t ldc,
+                          int64_t M, int N, int K, int L);
+int conv_xproj_tc(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W,
+                  int64_t ldw, void* xc, int64_t xc_ld, void* C, int64_t ldc, int64_t M, int N, int K,
+                  int L, int silu, cudaStream_t st);
+
 // scan_generic.cu
 int scan_generic(const vmb_scan_args& a, cudaStream_t st);
 
