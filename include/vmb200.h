@@ -91,6 +91,21 @@ VMB_API int vmb_linear_fwd(const void* A, int64_t lda, const void* W, int64_t ld
                    vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Causal conv1d (d_conv 4) + SiLU fused into the x_proj projection (bf16, stateless forward walk):
+ *   xc[m, :]    = SiLU(bias + sum_k w[:, k] * x[m + k - 3, :])   with x[row before its sequence] = 0,
+ *   x_dbl[m, :] = xc[m, :] * w_x^T                                (fp32 accumulate, one rounding).
+ * Replaces causal_conv1d_fn + rearrange + x_proj at models/videomamba/mamba_simple.py:381-409 when no
+ * conv_state is carried: the conv output goes to the tensor cores through shared memory and to HBM
+ * once.  Rows are (batch, token) flattened: M = B * L rows of Di channels with row pitch x_ld; L tokens
+ * per sequence.  w_conv (Di, 4), b_conv (Di) nullable, w_x (N, Di) with N == 64 (x_proj weight zero
+ * padded to the x_dbl pitch).  Results are bit-identical to vmb_causal_conv1d_fwd followed by
+ * vmb_linear_fwd.  Returns VMB_ERR_UNSUPPORTED for shapes outside that (callers then use the pair).
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int vmb_conv_xproj_fwd(const void* x, int64_t x_ld, const void* w_conv, const void* b_conv,
+                       const void* w_x, int64_t w_x_ld, void* xc, int64_t xc_ld, void* x_dbl,
+                       int64_t x_dbl_ld, int64_t M, int N, int Di, int L, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Depthwise causal conv1d (+ optional SiLU), token-major, with streaming history.
  * Replaces causal_conv1d.causal_conv1d_fn at models/videomamba/mamba_simple.py:383-399 together
  * with the torch.cat / F.pad state handling around it (:381-404):

@@ -487,6 +487,33 @@ def test_single_step_ops(dtype):
     assert rel_err(got, want) <= _tol(dtype) and rel_err(st_dev, st_ref) <= 1e-5
 
 
+@pytest.mark.parametrize("geom", [(4, 130, 768), (64, 9, 384), (3, 777, 768), (128, 5, 64), (2, 3137, 768),
+                                  (1, 512, 1152), (5, 131, 128)])
+def test_conv_xproj_fused_equals_separate_kernels(geom):
+    """conv1d + SiLU fused into the x_proj projection (vmb_conv_xproj_fwd) against the separate kernels,
+    bit for bit: sequences far shorter than a 128-row tile (several clip starts inside one tile and
+    inside one thread's 8 rows), lengths that put clip starts at every row phase, a ragged last tile,
+    x as the strided first half of xz."""
+    B, L, Di = geom
+    bf = torch.bfloat16
+    gen = torch.Generator().manual_seed(B * L + Di)
+    xz = _rand(gen, B, L, 2 * Di, dtype=bf).to(DEV)
+    w = _rand(gen, Di, 4, dtype=bf, scale=0.5).to(DEV)
+    b = _rand(gen, Di, dtype=bf, scale=0.5).to(DEV)
+    wx = _rand(gen, 64, Di, dtype=bf, scale=Di ** -0.5).to(DEV)
+    x = xz[..., :Di]
+    for bias in (b, None):
+        want_xc = ops.causal_conv1d_tokens(x, w, bias)
+        want_xd = ops.linear(want_xc, wx)
+        xc, xd = ops.conv_xproj_tokens(x, w, bias, wx)
+        assert torch.equal(xc, want_xc), float((xc.float() - want_xc.float()).abs().max())
+        assert torch.equal(xd, want_xd), float((xd.float() - want_xd.float()).abs().max())
+    # and against the oracle conv (fp32 math) at the bf16 tolerance
+    ref = orc.causal_conv1d_ref(x.cpu().transpose(1, 2), w.cpu(), b.cpu(), "silu").transpose(1, 2)
+    xc, _ = ops.conv_xproj_tokens(x, w, b, wx)
+    assert rel_err(xc, ref) <= _tol(bf)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 37, 384), (1, 5, 16), (3, 200, 576), (0, 4, 8)])
 def test_gate_blend(dtype, shape):

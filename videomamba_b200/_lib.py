@@ -79,6 +79,8 @@ SIGNATURES = {
     "vmb_add_norm_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                  c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_int,
                                  c_void_p]),
+    "vmb_conv_xproj_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                   c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "vmb_gate_blend_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                    c_void_p]),
     "vmb_linear_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,

@@ -6,6 +6,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace vmb {
@@ -273,7 +275,14 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
 
   // Stateless forward walk on the fast path: the conv runs inside the x_proj projection (its output
   // tile goes from the conv warps to the tensor cores through shared memory and to HBM once).
-  const bool fused_conv = fast && p->W == 4 && !p->reverse && p->conv_state_in == nullptr &&
+  // Opt-in (VMB_CONV_XPROJ=1): alone it saves 14 us per layer, but it is a persistent kernel that fills
+  // the SM's shared memory, so with several forwards in flight it cannot share SMs with another step's
+  // scan the way the small conv CTAs do (bench.py: serial 20.6 -> 20.2 ms, 3 in flight 17.6 -> 18.5 ms).
+  static const bool fuse_conv_xproj = [] {
+    const char* e = std::getenv("VMB_CONV_XPROJ");
+    return e != nullptr && std::atoi(e) != 0;
+  }();
+  const bool fused_conv = fuse_conv_xproj && fast && p->W == 4 && !p->reverse && p->conv_state_in == nullptr &&
                           p->conv_state_out == nullptr &&
                           conv_xproj_supported(xz, 2 * Di, p->w_conv, p->b_conv, p->w_x_pad, Di, xc, Di,
                                                xdbl, Xw, M, Xw, Di, L);
@@ -336,6 +345,22 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   // out_proj (mamba_simple.py:445-446)
   return vmb_linear_fwd(y, Di, p->w_out, Di, p->b_out, p->out, p->o_tstride, M, D, Di, p->dtype,
                         stream);
+}
+
+extern "C" int vmb_conv_xproj_fwd(const void* x, int64_t x_ld, const void* w_conv, const void* b_conv,
+                                  const void* w_x, int64_t w_x_ld, void* xc, int64_t xc_ld, void* x_dbl,
+                                  int64_t x_dbl_ld, int64_t M, int N, int Di, int L, vmb_stream_t stream) {
+  using namespace vmb;
+  VMB_CHECK_ARG(M >= 0 && N > 0 && Di > 0 && L > 0, "conv_xproj: bad sizes");
+  if (M == 0) return VMB_OK;
+  VMB_CHECK_ARG(x && w_conv && w_x && xc && x_dbl, "conv_xproj: null pointer");
+  VMB_CHECK_ARG(M % L == 0, "conv_xproj: M must be a whole number of sequences of L tokens");
+  if (!conv_xproj_supported(x, x_ld, w_conv, b_conv, w_x, w_x_ld, xc, xc_ld, x_dbl, x_dbl_ld, M, N, Di, L))
+    VMB_UNSUPPORTED("conv_xproj: shape / alignment outside the fused kernel (N == 64, Di %% 64 == 0, "
+                    "M >= 512, 16-byte aligned rows)");
+  cudaStream_t st = as_stream(stream);
+  ProfScope ps(VMB_PROF_CONV, st);
+  return conv_xproj_tc(x, x_ld, w_conv, b_conv, w_x, w_x_ld, xc, xc_ld, x_dbl, x_dbl_ld, M, N, Di, L, 1, st);
 }
 
 extern "C" int vmb_state_gather(const void* pool, const int32_t* index, void* batch, int n_rows,

@@ -1178,16 +1178,11 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* 
   return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
 }
 
-// VMB_CONV_XPROJ=0 keeps the conv and x_proj as separate kernels.
 bool conv_xproj_supported(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W,
                           int64_t ldw, const void* xc, int64_t xc_ld, const void* C, int64_t ldc,
                           int64_t M, int N, int K, int L) {
-  static const bool on = [] {
-    const char* e = std::getenv("VMB_CONV_XPROJ");
-    return e ? std::atoi(e) != 0 : true;
-  }();
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
-  return on && N == 64 && K % BK == 0 && K >= BK && smem_bytes_cx(64, 6, K) <= 227 * 1024 && M >= 4 * BM && M < (1ll << 31) - 2 * BM && L >= 4 &&
+  return N == 64 && K % BK == 0 && K >= BK && smem_bytes_cx(64, 6, K) <= 227 * 1024 && M >= 4 * BM && M < (1ll << 31) - 2 * BM && L >= 4 &&
          al16(x) && al16(cw) && (cb == nullptr || al16(cb)) && al16(W) && al16(xc) && al16(C) &&
          x_ld % 8 == 0 && ldw % 8 == 0 && xc_ld % 8 == 0 && ldc % 8 == 0;
 }

@@ -145,6 +145,29 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     return out.reshape(*x.shape[:-1], N)
 
 
+def conv_xproj_tokens(x: Tensor, conv_weight: Tensor, conv_bias: Optional[Tensor], w_x_pad: Tensor):
+    """Stateless causal conv (d_conv 4) + SiLU over ``x (B, L, Di)`` (may be a strided view) fused with
+    the x_proj projection: returns ``(xc (B, L, Di), x_dbl (B, L, N))``, bit-identical to
+    ``causal_conv1d_tokens`` followed by ``linear`` (reference mamba_simple.py:381-409)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    B, L, Di = x.shape
+    if x.stride(-1) != 1 or x.stride(0) != L * x.stride(1):
+        x = x.contiguous()
+    N = w_x_pad.shape[0]
+    conv_weight = conv_weight.reshape(Di, -1).to(x.dtype).contiguous()
+    if conv_bias is not None:
+        conv_bias = conv_bias.to(x.dtype).contiguous()
+    w_x_pad = w_x_pad.to(x.dtype).contiguous()
+    xc = torch.empty((B, L, Di), dtype=x.dtype, device=x.device)
+    xdbl = torch.empty((B, L, N), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        rc = lib.vmb_conv_xproj_fwd(_p(x), x.stride(1), _p(conv_weight), _p(conv_bias), _p(w_x_pad), Di,
+                                    _p(xc), Di, _p(xdbl), N, B * L, N, Di, L, _stream(x))
+    _lib.check(rc, "vmb_conv_xproj_fwd")
+    return xc, xdbl
+
+
 def gate_blend(g1: Tensor, g2: Optional[Tensor], fwd: Tensor, bwd: Tensor) -> Tensor:
     """``s * fwd + (1 - s) * bwd`` with ``s = sigmoid(g1 (+ g2))`` in one pass (refiner fusion gate,
     reference models/refiner_backbone.py:129-134)."""
