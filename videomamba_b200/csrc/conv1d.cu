@@ -293,9 +293,9 @@ conv1d_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_bs, int64_t 
 
 // Ring-staged variant of the streaming kernel: the rows a thread is going to consume are brought
 // in by 16-byte cp.async into a private ring of shared-memory slots ([slot][thread], conflict free),
-// kRing rows deep, so the bytes in flight per SM no longer depend on registers: 6 CTAs x 96 threads
-// x 20 rows x 16 B = 184 KB outstanding per SM against the ~60 KB the HBM latency-bandwidth product
-// needs.  A thread only ever reads slots it filled itself, so cp.async.wait_group is the only
+// kRing rows deep, so the bytes in flight per SM no longer depend on registers: 5 CTAs x 96 threads
+// x 8-12 rows x 16 B = 60-90 KB outstanding per SM at the shipped depth of 12, what the HBM
+// latency-bandwidth product needs.  A thread only ever reads slots it filled itself, so cp.async.wait_group is the only
 // synchronisation.  Groups of kGrp rows are committed together; group k + kRing / kGrp is issued
 // into the slots of group k right after group k has been consumed.
 constexpr int kGrp = 4;
