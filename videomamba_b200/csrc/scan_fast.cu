@@ -1225,7 +1225,11 @@ __global__ void scan_carry_kernel(const FastScanArgs a) {
 // Segments only when the batch alone cannot fill the GPU (one warp per 16 channels of a sequence).
 void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   const int64_t warps = (int64_t)a.B * (a.Di / kCh);
-  const int64_t want = 12ll * sm_count();      // 3 warps per scheduler
+  static const int per_sm = [] {
+    const char* e = std::getenv("VMB_SCAN_SPLIT_WARPS");
+    return e ? std::atoi(e) : 12;
+  }();
+  const int64_t want = (int64_t)per_sm * sm_count();      // 12 = 3 warps per scheduler
   *nseg = 1;
   *seg_len = (a.L + kTT - 1) / kTT * kTT;
   if (warps >= want || a.L < 768) return;       // a lone warp needs ~230 clk per token, 3 per scheduler ~120 each
