@@ -30,8 +30,11 @@
 //
 // Three lane layouts of phase B live in this file (measured against each other in profiles/);
 // VMB_SCAN_VARIANT picks one:
-//   0 / 10 v10 (default) v9's lanes, tiles staged by TMA box copies on an mbarrier instead of
+//   0      auto          v11 between 2 and 9.5 units per SM, v10 otherwise (see scan_fast())
+//   10     v10           v9's lanes, tiles staged by TMA box copies on an mbarrier instead of
 //                        cp.async row gathers (62 % fewer shared-memory wavefronts)
+//   11     v11           v10 split over a helper warp (TMA, gathers, dt projection, finalisation)
+//                        and a consumer warp (recurrence + contraction); unsplit sequences
 //   9      v9            lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one
 //                        HMMA per token on bf16-rounded states: no shuffle, C_t stays bf16
 //   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
@@ -1196,6 +1199,322 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
 
 }  // namespace v10
 
+// =================================================================================================
+// v11 = v10 split over TWO warps per CTA.  In v10 one warp runs, per 16-token tile, the B / C
+// gathers, phase A (dt projection + softplus), the recurrence and the finalisation one after the
+// other; the recurrence is latency bound (dependent MUFU / FFMA2 chains) and everything else sits
+// in the same in-order instruction stream.  Here a HELPER warp does everything that does not
+// depend on the state -- TMA issue, gathers, phase A for tile i, then + D*u, * SiLU(z) and the
+// store of tile i - 1 -- while the CONSUMER warp only runs the recurrence and the <C, h>
+// contraction, handing the raw sums back through shared memory.  dd / B / C / y_raw tiles are double
+// buffered, u / z triple buffered (read by the helper one tile later), two mbarrier pairs carry the
+// hand-over.  Unsplit sequences only (the sequence split keeps v10).
+// =================================================================================================
+namespace v11 {
+
+struct Plan {
+  int x0, u0, z0, b, c, dd, yr, bar, total, xb;
+  __host__ __device__ constexpr int x(int s) const { return x0 + s * (kTT * xb); }
+  __host__ __device__ constexpr int u(int s) const { return u0 + s * (kTT * 32); }
+  __host__ __device__ constexpr int z(int s) const { return z0 + s * (kTT * 32); }
+  __host__ __device__ constexpr int B(int s) const { return b + s * (kTT * kN * 4); }
+  __host__ __device__ constexpr int C(int s) const { return c + s * (kTT * kN * 2); }
+  __host__ __device__ constexpr int D(int s) const { return dd + s * (kTT * 8 * 16); }
+  __host__ __device__ constexpr int Y(int s) const { return yr + s * (kTT * kCh * 4); }
+};
+__host__ __device__ constexpr Plan plan(int Xp) {
+  Plan p{};
+  int off = 0;
+  p.xb = Xp * 2;
+  const int xt = (kTT * p.xb + 1023) / 1024 * 1024;   // keep both x tiles on swizzle-atom boundaries
+  p.x0 = off; off += 2 * xt;
+  p.u0 = off; off += 3 * kTT * 32;
+  p.z0 = off; off += 3 * kTT * 32;
+  p.b = off; off += 2 * kTT * kN * 4;
+  p.c = off; off += 2 * kTT * kN * 2;
+  p.dd = off; off += 2 * kTT * 8 * 16;
+  p.yr = off; off += 2 * kTT * kCh * 4;               // raw <C, h> sums, fp32 [token][channel]
+  p.bar = off; off += 64;                             // tma[3], full[2], done[2]
+  p.total = off + 1024;
+  return p;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// wait with back-off: a helper warp that is ahead must not spin on the issue slots the consumer needs
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
+}
+
+template <int R, bool kRev>
+__global__ void __launch_bounds__(64, 11)
+scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
+              const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int KST = (R + 15) / 16;
+  constexpr int XB = v9::xp_of(R) * 2;
+  constexpr int XT = (kTT * XB + 1023) / 1024 * 1024;
+  constexpr Plan sp = plan(v9::xp_of(R));
+  constexpr bool kSwz = XB == 128;
+  const uint32_t sbase = (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) + 1023u) & ~1023u;
+  uint8_t* const smem = smem_raw + (sbase - static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)));
+  using bf16 = __nv_bfloat16;
+  using v9::pack_bf16x2;
+  using v10::mbar_expect_tx;
+  using v10::mbar_init;
+  using v10::mbar_wait;
+  using v10::tma_load_3d;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int cw = blockIdx.x * kCh;
+  const int b = blockIdx.y;
+  const int L = a.L;
+  const int ntiles = (L + kTT - 1) / kTT;
+
+  const uint32_t bar0 = sbase + sp.bar;
+  auto tma_bar = [&](int s) { return bar0 + 8u * s; };          // tile % 3
+  auto full_bar = [&](int s) { return bar0 + 24u + 8u * s; };   // helper -> consumer, tile & 1
+  auto done_bar = [&](int s) { return bar0 + 40u + 8u * s; };   // consumer -> helper, tile & 1
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 3; ++s) mbar_init(tma_bar(s), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(full_bar(s), 1); mbar_init(done_bar(s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Roles by hardware warp slot: a CTA's two warps sit on neighbouring schedulers (slot % 4); if warp 1
+  // were always the consumer, every MUFU-heavy warp of the SM would share two of the four schedulers.
+  // Both warps derive the roles from the same two slot numbers, so they always agree.
+  volatile uint32_t* slot_ids = reinterpret_cast<volatile uint32_t*>(smem + sp.bar + 56);
+  {
+    uint32_t wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    if (lane == 0) slot_ids[warp] = wid;
+  }
+  __syncthreads();
+  bool is_helper;
+  {
+    const uint32_t w0 = slot_ids[0], w1 = slot_ids[1];
+    const uint32_t lo = min(w0, w1), hi = max(w0, w1);
+    const uint32_t consumer = ((lo >> 2) & 1u) ? hi : lo;
+    is_helper = slot_ids[warp] != consumer;        // compares the STORED numbers: the two warps always differ
+  }
+
+  auto srow = [](int r) { return kRev ? kTT - 1 - r : r; };
+  auto xoff = [&](int r, int o) {
+    const int sr = srow(r);
+    return kSwz ? sr * XB + ((((o >> 4) ^ (sr & 7)) << 4) | (o & 15)) : sr * XB + o;
+  };
+  const int dir = kRev ? -1 : 1;
+  const int p0 = kRev ? a.L - 1 : 0;
+
+  if (is_helper) {
+    // ================================ helper ================================
+    uint32_t bfrag[2][KST][2];
+    float bias[2][2];
+    {
+      const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const bf16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
+#pragma unroll
+        for (int ks = 0; ks < KST; ++ks) {
+          bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
+          bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
+        }
+        bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
+        bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
+      }
+    }
+    // finalisation: lane = (token row lane >> 1, channel half lane & 1): 8 channels of one token
+    const int frow = lane >> 1, fch = (lane & 1) * 8;
+    float Dv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Dv[j] = a.D ? a.D[cw + fch + j] : 0.f;
+    bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw + fch;
+    const int y_ts = (int)a.y_ts;
+
+    constexpr uint32_t kTileBytes = kTT * 32 * 2 + kTT * XB;
+    auto issue = [&](int tile) {                    // lane 0 only
+      const int row0 = kRev ? a.L - kTT - tile * kTT : tile * kTT;
+      const uint32_t bar = tma_bar(tile % 3);
+      mbar_expect_tx(bar, kTileBytes);
+      tma_load_3d(sbase + sp.x(tile & 1), &map_x, bar, 0, row0, b);
+      tma_load_3d(sbase + sp.u(tile % 3), &map_u, bar, cw, row0, b);
+      tma_load_3d(sbase + sp.z(tile % 3), &map_z, bar, cw, row0, b);
+    };
+    if (lane == 0) {
+      issue(0);
+      if (ntiles > 1) issue(1);
+    }
+    const int gp = lane & 7, gr = lane >> 3;
+    const int bslot = (gp & 3) * 4 + (gp >> 2) * 2;
+    constexpr int kRow8 = kRev ? -8 * XB : 8 * XB;
+
+    auto finalize = [&](int tile) {                 // + D*u, * SiLU(z), store: tile's raw sums are in Y(tile & 1)
+      const int pb = tile & 1;
+      mbar_wait_sleep(done_bar(pb), (uint32_t)(tile >> 1) & 1u);
+      const int t = tile * kTT + frow;
+      const uint8_t* su = smem + sp.u(tile % 3) + srow(frow) * 32 + fch * 2;
+      const uint8_t* sz = smem + sp.z(tile % 3) + srow(frow) * 32 + fch * 2;
+      const float* yr = reinterpret_cast<const float*>(smem + sp.Y(pb)) + frow * kCh + fch;
+      const uint4 uv = *reinterpret_cast<const uint4*>(su);
+      const uint4 zv = *reinterpret_cast<const uint4*>(sz);
+      const float4 y0 = *reinterpret_cast<const float4*>(yr), y1 = *reinterpret_cast<const float4*>(yr + 4);
+      const uint32_t uw[4] = {uv.x, uv.y, uv.z, uv.w}, zw[4] = {zv.x, zv.y, zv.z, zv.w};
+      const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float lo = fmaf(Dv[2 * q], bf16lo(uw[q]), yv[2 * q]) * silu_fast(bf16lo(zw[q]));
+        const float hi = fmaf(Dv[2 * q + 1], bf16hi(uw[q]), yv[2 * q + 1]) * silu_fast(bf16hi(zw[q]));
+        o[q] = pack_bf16x2(lo, hi);
+      }
+      if (t < L)
+        *reinterpret_cast<uint4*>(yg + (int64_t)(p0 + dir * t) * y_ts) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int pb = tile & 1;
+      const int t0 = tile * kTT;
+      mbar_wait(tma_bar(tile % 3), (uint32_t)(tile / 3) & 1u);
+      // buffers pb were last read by the consumer for tile - 2, which finalize(tile - 2) has waited for
+      const uint8_t* sx = smem + sp.x(pb);
+      const uint8_t* su = smem + sp.u(tile % 3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(sx + xoff(gr + 4 * (i & 1), (R + 2 * gp) * 2) + (i >> 1) * kRow8);
+        *reinterpret_cast<float2*>(smem + sp.B(pb) + (gr + 4 * i) * (kN * 4) + bslot * 4) =
+            make_float2(bf16lo(v), bf16hi(v));
+        *reinterpret_cast<uint32_t*>(smem + sp.C(pb) + (gr + 4 * i) * (kN * 2) + gp * 4) =
+            *reinterpret_cast<const uint32_t*>(sx + xoff(gr + 4 * (i & 1), (R + kN + 2 * gp) * 2) + (i >> 1) * kRow8);
+      }
+      {
+        float acc[2][4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KST; ++ks) {
+          uint32_t af[4];
+          const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
+          ldmatrix_x4(sbase + sp.x(pb) + xoff(row, 32 * ks + 16 * (lane >> 4)), af);
+          mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+          mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int tl = g + 8 * half;
+          const bool pad = t0 + tl >= L;
+          const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (2 * tig) * 2);
+          const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (8 + 2 * tig) * 2);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
+            float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
+            if (pad) { da = 0.f; db = 0.f; }
+            const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
+            *reinterpret_cast<float4*>(smem + sp.D(pb) + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
+                make_float4(da, da * uav, db, db * ubv);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(pb));    // tile staged for the consumer
+      if (tile > 0) finalize(tile - 1);
+      __syncwarp();
+      // x(pb) has been read by this tile's gathers, u / z slot (tile + 2) % 3 by finalize(tile - 1) just now:
+      // refill them for tile + 2 (one whole iteration ahead of their use)
+      if (lane == 0 && tile + 2 < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(tile + 2);
+      }
+    }
+    finalize(ntiles - 1);
+  } else {
+    // ================================ consumer ================================
+    float2 Aa[2], Ab[2], ha[2], hb[2];
+    const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
+    const int64_t hoff_b = hoff_a + 8 * kN;
+    {
+      const float* pa = a.A2 + (int64_t)(cw + g) * kN + 2 * tig;
+      Aa[0] = *reinterpret_cast<const float2*>(pa);
+      Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
+      Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
+      Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
+      auto ld = [&](int64_t off) -> float { return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f; };
+      ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
+      ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
+      hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
+      hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
+    }
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int pb = tile & 1;
+      mbar_wait(full_bar(pb), (uint32_t)(tile >> 1) & 1u);
+      const uint8_t* sdd0 = smem + sp.D(pb) + (g << 4);
+      const uint8_t* sdd1 = smem + sp.D(pb) + ((g ^ 1) << 4);
+      const uint8_t* sb = smem + sp.B(pb) + tig * 16;
+      const uint8_t* sc = smem + sp.C(pb) + tig * 4;
+      float* yr = reinterpret_cast<float*>(smem + sp.Y(pb));
+#pragma unroll
+      for (int tg = 0; tg < kTT; tg += 4) {
+        float ya = 0.f, yb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = tg + i;
+          const float4 dd = *reinterpret_cast<const float4*>(((t & 1) ? sdd1 : sdd0) + t * 128);
+          const float4 Bv = *reinterpret_cast<const float4*>(sb + t * (kN * 4));
+          const float2 da2 = make_float2(dd.x, dd.x), db2 = make_float2(dd.z, dd.z);
+          const float2 xa0 = __fmul2_rn(da2, Aa[0]), xa1 = __fmul2_rn(da2, Aa[1]);
+          const float2 xb0 = __fmul2_rn(db2, Ab[0]), xb1 = __fmul2_rn(db2, Ab[1]);
+          const float2 ea0 = make_float2(ex2_approx(xa0.x), ex2_approx(xa0.y));
+          const float2 ea1 = make_float2(ex2_approx(xa1.x), ex2_approx(xa1.y));
+          const float2 eb0 = make_float2(ex2_approx(xb0.x), ex2_approx(xb0.y));
+          const float2 eb1 = make_float2(ex2_approx(xb1.x), ex2_approx(xb1.y));
+          const float2 dua = make_float2(dd.y, dd.y), dub = make_float2(dd.w, dd.w);
+          const float2 B01 = make_float2(Bv.x, Bv.y), B89 = make_float2(Bv.z, Bv.w);
+          ha[0] = __ffma2_rn(ea0, ha[0], __fmul2_rn(dua, B01));
+          ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
+          hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
+          hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
+          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
+          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
+          const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
+                                  pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(d, af, c0, c1);
+          if (tig == i) { ya = d[0]; yb = d[2]; }
+        }
+        yr[(tg + tig) * kCh + g] = ya;               // lane tig hands over token tg + tig of its two channels
+        yr[(tg + tig) * kCh + g + 8] = yb;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done_bar(pb));      // raw sums written, dd / B / C tiles pb free
+    }
+    if (a.h_last != nullptr) {
+      *reinterpret_cast<float2*>(a.h_last + hoff_a) = ha[0];
+      *reinterpret_cast<float2*>(a.h_last + hoff_a + 8) = ha[1];
+      *reinterpret_cast<float2*>(a.h_last + hoff_b) = hb[0];
+      *reinterpret_cast<float2*>(a.h_last + hoff_b + 8) = hb[1];
+    }
+  }
+}
+
+}  // namespace v11
+
 int variant() {
   static int v = [] {
     const char* e = std::getenv("VMB_SCAN_VARIANT");
@@ -1340,6 +1659,34 @@ int launch10(const FastScanArgs& a0, cudaStream_t st) {
   return VMB_OK;
 }
 
+// v11 (two warps per CTA) for unsplit sequences; the sequence split and odd pitches take v10.
+template <int R>
+int launch11(const FastScanArgs& a0, cudaStream_t st) {
+  if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);
+  FastScanArgs a = a0;
+  a.nseg = 1;
+  a.seg_len = (a.L + kTT - 1) / kTT * kTT;
+  constexpr v11::Plan sp = v11::plan(v9::xp_of(R));
+  CUtensorMap mu, mz, mx;
+  const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B;
+  auto bs = [&](int64_t v, int64_t ts) { return (uint64_t)((a.B > 1 ? v : ts * a.L) * 2); };
+  int rc;
+  if ((rc = make_tensor_map_3d_bf16(&mu, a.u, (uint64_t)a.Di, L, B, (uint64_t)a.u_ts * 2, bs(a.u_bs, a.u_ts),
+                                    kCh, kTT, false)))
+    return rc;
+  if ((rc = make_tensor_map_3d_bf16(&mz, a.z, (uint64_t)a.Di, L, B, (uint64_t)a.z_ts * 2, bs(a.z_bs, a.z_ts),
+                                    kCh, kTT, false)))
+    return rc;
+  if ((rc = make_tensor_map_3d_bf16(&mx, a.xdbl, (uint64_t)a.Xp, L, B, (uint64_t)a.x_ts * 2,
+                                    bs(a.x_bs, a.x_ts), (uint32_t)a.Xp, kTT, a.Xp * 2 == 128)))
+    return rc;
+  dim3 grid(a.Di / kCh, a.B, 1);
+  if (a.reverse) v11::scan11_kernel<R, true><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
+  else v11::scan11_kernel<R, false><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
+  VMB_LAUNCH_CHECK("scan11_kernel");
+  return VMB_OK;
+}
+
 }  // namespace
 
 bool scan_fast_supported(const FastScanArgs& a) {
@@ -1366,6 +1713,21 @@ int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {
+  // Auto (variant 0): between 2 and 9.5 (batch, 16-channel) units per SM the two-warp kernel wins
+  // without splitting the sequence (B200, L = 3137 / 6273: -12 % at 7.8 units per SM, -26 % at 2.6, -30 % at
+  // 3.9 for the Middle width); fewer units need the sequence split (v10), more fill the schedulers anyway
+  // and v10's smaller footprint lets two launches share the SMs (profiles/r01_scan_ncu_full_summary.txt).
+  const int64_t units = (int64_t)a.B * (a.Di / kCh);
+  const bool two_warp = variant() == 11 ||
+                        (variant() == 0 && units >= 2ll * sm_count() && 2 * units < 19ll * sm_count());
+  if (two_warp) {
+    switch (a.R) {
+      case 12: return launch11<12>(a, st);
+      case 24: return launch11<24>(a, st);
+      case 36: return launch11<36>(a, st);
+      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
+    }
+  }
   if (variant() == 0 || variant() == 10) {  // default: v10 = v9's lanes + TMA-staged tiles
     switch (a.R) {
       case 12: return launch10<12>(a, st);
