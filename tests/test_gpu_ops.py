@@ -325,7 +325,10 @@ def _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, h0, reverse, R, N):
 
 
 @pytest.mark.parametrize("geom", [(2, 777, 768, 24, 64), (1, 100, 384, 12, 48), (3, 33, 1152, 36, 80),
-                                  (2, 1, 768, 24, 64), (1, 31, 768, 24, 56)])
+                                  (2, 1, 768, 24, 64), (1, 31, 768, 24, 56),
+                                  # 300-1400 (batch, 16-channel) units: the two-warp kernel (scan v11)
+                                  (8, 100, 768, 24, 64), (5, 333, 1152, 36, 80), (16, 50, 384, 12, 48),
+                                  (7, 15, 768, 24, 64), (24, 17, 768, 24, 64)])
 @pytest.mark.parametrize("reverse", [False, True])
 def test_fused_scan_against_float64(geom, reverse):
     """The fused dt_proj + scan kernel (bf16) against float64 on identical inputs, with and without an
