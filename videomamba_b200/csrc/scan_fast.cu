@@ -30,11 +30,12 @@
 //
 // Three lane layouts of phase B live in this file (measured against each other in profiles/);
 // VMB_SCAN_VARIANT picks one:
-//   0      auto          v11 between 2 and 9.5 units per SM, v10 otherwise (see scan_fast())
+//   0      auto          v11 below 9.5 units per SM (with the sequence split below 2), v10 above
 //   10     v10           v9's lanes, tiles staged by TMA box copies on an mbarrier instead of
 //                        cp.async row gathers (62 % fewer shared-memory wavefronts)
-//   11     v11           v10 split over a helper warp (TMA, gathers, dt projection, finalisation)
-//                        and a consumer warp (recurrence + contraction); unsplit sequences
+//   11 / 12 v11          v10 split over a helper warp (TMA, gathers, dt projection, finalisation)
+//                        and a consumer warp (recurrence + contraction); 11 never splits the
+//                        sequence, 12 splits like v10
 //   9      v9            lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one
 //                        HMMA per token on bf16-rounded states: no shuffle, C_t stays bf16
 //   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
@@ -1258,7 +1259,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int R, bool kRev>
+template <int R, bool kStateOnly, bool kRev>
 __global__ void __launch_bounds__(64, 11)
 scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
@@ -1282,8 +1283,15 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   const int g = lane >> 2, tig = lane & 3;
   const int cw = blockIdx.x * kCh;
   const int b = blockIdx.y;
-  const int L = a.L;
-  const int ntiles = (L + kTT - 1) / kTT;
+  const int seg = blockIdx.z;                      // sequence split: segment [tbeg, L) of the sequence
+  const int tbeg = seg * a.seg_len;
+  const int L = min(a.L, tbeg + a.seg_len);
+  const int tile_lo = tbeg / kTT;
+  const int ntiles = (L + kTT - 1) / kTT;          // global tile indices [tile_lo, ntiles)
+  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
+  float* const wsH = a.seg_ws;
+  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
+  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
 
   const uint32_t bar0 = sbase + sp.bar;
   auto tma_bar = [&](int s) { return bar0 + 8u * s; };          // tile % 3
@@ -1346,29 +1354,33 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw + fch;
     const int y_ts = (int)a.y_ts;
 
-    constexpr uint32_t kTileBytes = kTT * 32 * 2 + kTT * XB;
-    auto issue = [&](int tile) {                    // lane 0 only
+    // `it` = tile - tile_lo indexes the buffers and barrier phases; TMA coordinates use the global tile
+    constexpr uint32_t kTileBytes = kTT * 32 * (kStateOnly ? 1 : 2) + kTT * XB;
+    auto issue = [&](int it) {                      // lane 0 only
+      const int tile = tile_lo + it;
       const int row0 = kRev ? a.L - kTT - tile * kTT : tile * kTT;
-      const uint32_t bar = tma_bar(tile % 3);
+      const uint32_t bar = tma_bar(it % 3);
       mbar_expect_tx(bar, kTileBytes);
-      tma_load_3d(sbase + sp.x(tile & 1), &map_x, bar, 0, row0, b);
-      tma_load_3d(sbase + sp.u(tile % 3), &map_u, bar, cw, row0, b);
-      tma_load_3d(sbase + sp.z(tile % 3), &map_z, bar, cw, row0, b);
+      tma_load_3d(sbase + sp.x(it & 1), &map_x, bar, 0, row0, b);
+      tma_load_3d(sbase + sp.u(it % 3), &map_u, bar, cw, row0, b);
+      if (!kStateOnly) tma_load_3d(sbase + sp.z(it % 3), &map_z, bar, cw, row0, b);
     };
+    const int nit = ntiles - tile_lo;
     if (lane == 0) {
       issue(0);
-      if (ntiles > 1) issue(1);
+      if (nit > 1) issue(1);
     }
     const int gp = lane & 7, gr = lane >> 3;
     const int bslot = (gp & 3) * 4 + (gp >> 2) * 2;
     constexpr int kRow8 = kRev ? -8 * XB : 8 * XB;
 
-    auto finalize = [&](int tile) {                 // + D*u, * SiLU(z), store: tile's raw sums are in Y(tile & 1)
-      const int pb = tile & 1;
-      mbar_wait_sleep(done_bar(pb), (uint32_t)(tile >> 1) & 1u);
-      const int t = tile * kTT + frow;
-      const uint8_t* su = smem + sp.u(tile % 3) + srow(frow) * 32 + fch * 2;
-      const uint8_t* sz = smem + sp.z(tile % 3) + srow(frow) * 32 + fch * 2;
+    auto finalize = [&](int it) {                   // + D*u, * SiLU(z), store: the tile's raw sums are in Y(it & 1)
+      const int pb = it & 1;
+      mbar_wait_sleep(done_bar(pb), (uint32_t)(it >> 1) & 1u);
+      if (kStateOnly) return;                       // first pass of the split: only the buffer hand-back matters
+      const int t = (tile_lo + it) * kTT + frow;
+      const uint8_t* su = smem + sp.u(it % 3) + srow(frow) * 32 + fch * 2;
+      const uint8_t* sz = smem + sp.z(it % 3) + srow(frow) * 32 + fch * 2;
       const float* yr = reinterpret_cast<const float*>(smem + sp.Y(pb)) + frow * kCh + fch;
       const uint4 uv = *reinterpret_cast<const uint4*>(su);
       const uint4 zv = *reinterpret_cast<const uint4*>(sz);
@@ -1386,20 +1398,21 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         *reinterpret_cast<uint4*>(yg + (int64_t)(p0 + dir * t) * y_ts) = make_uint4(o[0], o[1], o[2], o[3]);
     };
 
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int pb = tile & 1;
-      const int t0 = tile * kTT;
-      mbar_wait(tma_bar(tile % 3), (uint32_t)(tile / 3) & 1u);
-      // buffers pb were last read by the consumer for tile - 2, which finalize(tile - 2) has waited for
+    for (int it = 0; it < nit; ++it) {
+      const int pb = it & 1;
+      const int t0 = (tile_lo + it) * kTT;
+      mbar_wait(tma_bar(it % 3), (uint32_t)(it / 3) & 1u);
+      // buffers pb were last read by the consumer for tile it - 2, which finalize(it - 2) has waited for
       const uint8_t* sx = smem + sp.x(pb);
-      const uint8_t* su = smem + sp.u(tile % 3);
+      const uint8_t* su = smem + sp.u(it % 3);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t v = *reinterpret_cast<const uint32_t*>(sx + xoff(gr + 4 * (i & 1), (R + 2 * gp) * 2) + (i >> 1) * kRow8);
         *reinterpret_cast<float2*>(smem + sp.B(pb) + (gr + 4 * i) * (kN * 4) + bslot * 4) =
             make_float2(bf16lo(v), bf16hi(v));
-        *reinterpret_cast<uint32_t*>(smem + sp.C(pb) + (gr + 4 * i) * (kN * 2) + gp * 4) =
-            *reinterpret_cast<const uint32_t*>(sx + xoff(gr + 4 * (i & 1), (R + kN + 2 * gp) * 2) + (i >> 1) * kRow8);
+        if (!kStateOnly)
+          *reinterpret_cast<uint32_t*>(smem + sp.C(pb) + (gr + 4 * i) * (kN * 2) + gp * 4) =
+              *reinterpret_cast<const uint32_t*>(sx + xoff(gr + 4 * (i & 1), (R + kN + 2 * gp) * 2) + (i >> 1) * kRow8);
       }
       {
         float acc[2][4];
@@ -1434,16 +1447,16 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(pb));    // tile staged for the consumer
-      if (tile > 0) finalize(tile - 1);
+      if (it > 0) finalize(it - 1);
       __syncwarp();
-      // x(pb) has been read by this tile's gathers, u / z slot (tile + 2) % 3 by finalize(tile - 1) just now:
-      // refill them for tile + 2 (one whole iteration ahead of their use)
-      if (lane == 0 && tile + 2 < ntiles) {
+      // x(pb) has been read by this tile's gathers, u / z slot (it + 2) % 3 by finalize(it - 1) just now:
+      // refill them for tile it + 2 (one whole iteration ahead of their use)
+      if (lane == 0 && it + 2 < nit) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(tile + 2);
+        issue(it + 2);
       }
     }
-    finalize(ntiles - 1);
+    finalize(nit - 1);
   } else {
     // ================================ consumer ================================
     float2 Aa[2], Ab[2], ha[2], hb[2];
@@ -1455,15 +1468,21 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
       Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
       Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
       Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
-      auto ld = [&](int64_t off) -> float { return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f; };
+      auto ld = [&](int64_t off) -> float {
+        if (kStateOnly) return 0.f;
+        if (seg > 0) return wsHin[seg * seg_stride + off];
+        return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
+      };
       ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
       ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
       hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
       hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
     }
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int pb = tile & 1;
-      mbar_wait(full_bar(pb), (uint32_t)(tile >> 1) & 1u);
+    float sum_a = 0.f, sum_b = 0.f;
+    const int nit = ntiles - tile_lo;
+    for (int it = 0; it < nit; ++it) {
+      const int pb = it & 1;
+      mbar_wait(full_bar(pb), (uint32_t)(it >> 1) & 1u);
       const uint8_t* sdd0 = smem + sp.D(pb) + (g << 4);
       const uint8_t* sdd1 = smem + sp.D(pb) + ((g ^ 1) << 4);
       const uint8_t* sb = smem + sp.B(pb) + tig * 16;
@@ -1490,25 +1509,42 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
           ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
           hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
           hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
-          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
-          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
-          const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
-                                  pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
-          float d[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(d, af, c0, c1);
-          if (tig == i) { ya = d[0]; yb = d[2]; }
+          if constexpr (kStateOnly) {
+            sum_a += dd.x;
+            sum_b += dd.z;
+          } else {
+            const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
+            const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
+            const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
+                                    pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(d, af, c0, c1);
+            if (tig == i) { ya = d[0]; yb = d[2]; }
+          }
         }
-        yr[(tg + tig) * kCh + g] = ya;               // lane tig hands over token tg + tig of its two channels
-        yr[(tg + tig) * kCh + g + 8] = yb;
+        if constexpr (!kStateOnly) {
+          yr[(tg + tig) * kCh + g] = ya;             // lane tig hands over token tg + tig of its two channels
+          yr[(tg + tig) * kCh + g + 8] = yb;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(done_bar(pb));      // raw sums written, dd / B / C tiles pb free
     }
-    if (a.h_last != nullptr) {
-      *reinterpret_cast<float2*>(a.h_last + hoff_a) = ha[0];
-      *reinterpret_cast<float2*>(a.h_last + hoff_a + 8) = ha[1];
-      *reinterpret_cast<float2*>(a.h_last + hoff_b) = hb[0];
-      *reinterpret_cast<float2*>(a.h_last + hoff_b + 8) = hb[1];
+    auto st_h = [&](float* dst) {
+      *reinterpret_cast<float2*>(dst + hoff_a) = ha[0];
+      *reinterpret_cast<float2*>(dst + hoff_a + 8) = ha[1];
+      *reinterpret_cast<float2*>(dst + hoff_b) = hb[0];
+      *reinterpret_cast<float2*>(dst + hoff_b + 8) = hb[1];
+    };
+    if constexpr (kStateOnly) {
+      st_h(wsH + seg * seg_stride);
+      if (tig == 0) {
+        float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + cw + g;
+        ss[0] = sum_a;
+        ss[8] = sum_b;
+      }
+    } else if (seg == a.nseg - 1 && a.h_last != nullptr) {
+      st_h(a.h_last);
     }
   }
 }
@@ -1659,13 +1695,17 @@ int launch10(const FastScanArgs& a0, cudaStream_t st) {
   return VMB_OK;
 }
 
-// v11 (two warps per CTA) for unsplit sequences; the sequence split and odd pitches take v10.
+// v11 (two warps per CTA); odd x_dbl pitches take v7.  split = false forces one segment.
 template <int R>
-int launch11(const FastScanArgs& a0, cudaStream_t st) {
+int launch11(const FastScanArgs& a0, cudaStream_t st, bool split) {
   if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);
   FastScanArgs a = a0;
-  a.nseg = 1;
-  a.seg_len = (a.L + kTT - 1) / kTT * kTT;
+  plan_segments(a, &a.nseg, &a.seg_len);
+  if (!split || (a.nseg > 1 && (a.seg_ws == nullptr ||
+                                a.seg_ws_bytes < scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N)))) {
+    a.nseg = 1;
+    a.seg_len = (a.L + kTT - 1) / kTT * kTT;
+  }
   constexpr v11::Plan sp = v11::plan(v9::xp_of(R));
   CUtensorMap mu, mz, mx;
   const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B;
@@ -1680,9 +1720,18 @@ int launch11(const FastScanArgs& a0, cudaStream_t st) {
   if ((rc = make_tensor_map_3d_bf16(&mx, a.xdbl, (uint64_t)a.Xp, L, B, (uint64_t)a.x_ts * 2,
                                     bs(a.x_bs, a.x_ts), (uint32_t)a.Xp, kTT, a.Xp * 2 == 128)))
     return rc;
-  dim3 grid(a.Di / kCh, a.B, 1);
-  if (a.reverse) v11::scan11_kernel<R, true><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
-  else v11::scan11_kernel<R, false><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
+  if (a.nseg > 1) {
+    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
+    if (a.reverse) v11::scan11_kernel<R, true, true><<<g1, 64, sp.total, st>>>(a, mu, mz, mx);
+    else v11::scan11_kernel<R, true, false><<<g1, 64, sp.total, st>>>(a, mu, mz, mx);
+    VMB_LAUNCH_CHECK("scan11_kernel<state>");
+    const int64_t n = (int64_t)a.B * a.Di * kN;
+    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    VMB_LAUNCH_CHECK("scan_carry_kernel");
+  }
+  dim3 grid(a.Di / kCh, a.B, a.nseg);
+  if (a.reverse) v11::scan11_kernel<R, false, true><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
+  else v11::scan11_kernel<R, false, false><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
   VMB_LAUNCH_CHECK("scan11_kernel");
   return VMB_OK;
 }
@@ -1718,13 +1767,14 @@ int scan_fast(const FastScanArgs& a, cudaStream_t st) {
   // 3.9 for the Middle width); fewer units need the sequence split (v10), more fill the schedulers anyway
   // and v10's smaller footprint lets two launches share the SMs (profiles/r01_scan_ncu_full_summary.txt).
   const int64_t units = (int64_t)a.B * (a.Di / kCh);
-  const bool two_warp = variant() == 11 ||
-                        (variant() == 0 && units >= 2ll * sm_count() && 2 * units < 19ll * sm_count());
-  if (two_warp) {
+  const bool two_warp = variant() == 11 || (variant() == 0 && 2 * units < 19ll * sm_count());
+  if (two_warp || variant() == 12) {        // 12: v11 everywhere, with the sequence split
+    // below 2 units per SM the sequence split supplies the parallelism (v11 is 2-6 % ahead of v10 there)
+    const bool split = variant() == 12 || (variant() == 0 && units < 2ll * sm_count());
     switch (a.R) {
-      case 12: return launch11<12>(a, st);
-      case 24: return launch11<24>(a, st);
-      case 36: return launch11<36>(a, st);
+      case 12: return launch11<12>(a, st, split);
+      case 24: return launch11<24>(a, st, split);
+      case 36: return launch11<36>(a, st, split);
       default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
     }
   }
