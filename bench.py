@@ -391,7 +391,11 @@ def run_ours(args):
     if fused:
         # fused dt_proj+softplus+scan+gate kernel: reads u (conv output), z, the x_dbl row; writes y
         bytes_per_token = 3 * Di * es + w.Xp * es
-        kernel = "scan10_kernel (TMA-staged tiles; dt_proj + softplus + S6 scan + D skip + SiLU gate, fused)"
+        # scan_fast() picks the two-warp kernel below 9.5 (batch, 16-channel) units per SM
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        two_warp = 2 * B * (Di // 16) < 19 * sms and os.environ.get("VMB_SCAN_VARIANT", "0") in ("0", "11", "12")
+        kernel = ("scan11_kernel (helper + consumer warps" if two_warp else "scan10_kernel (one warp per unit") + \
+                 "; TMA-staged tiles; dt_proj + softplus + S6 scan + D skip + SiLU gate, fused)"
     else:
         # op-level selective_scan_fn: reads u, delta, z, B, C; writes y
         bytes_per_token = 4 * Di * es + 2 * N * es
