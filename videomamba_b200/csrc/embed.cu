@@ -13,32 +13,33 @@
 namespace vmb {
 namespace {
 
-// One thread moves VEC consecutive pixels of one image row (they stay consecutive inside a patch row
-// because VEC divides pw).  Reads are coalesced along x; writes are VEC-element runs, pw-element
-// segments per (patch, c, dt, dy).
+// One warp builds ONE patch row (C*k*ph*pw contiguous elements): lanes walk its VEC-element vectors, so
+// the stores are fully coalesced runs and every output line is written once, completely, by one warp
+// (the first kernel walked image rows: coalesced reads, but every 32-byte piece of a patch row arrived
+// from a different warp at a different time -- 120 us for 308 MB).  The reads are pw-element segments
+// (32 bytes at patch 16 / bf16) whose neighbours along x belong to the next patch, i.e. the next warp.
 template <typename V, int VEC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const V* __restrict__ x, V* __restrict__ cols, int C, int T, int H, int W, int k,
                 int ph, int pw, int t, int h, int w, int64_t rows) {
-  // a warp walks one used image row (b, c, tt, y); lanes take consecutive VEC-pixel vectors
-  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);   // patch row (b, tp, py, px)
   if (r >= rows) return;
-  const int wv = (w * pw) / VEC;                   // vectors per used image row
   int64_t q = r;
-  const int y = (int)(q % (h * ph)); q /= (h * ph);
-  const int tt = (int)(q % (t * k)); q /= (t * k);
-  const int c = (int)(q % C);
-  const int64_t b = q / C;
-  const int py = y / ph, dy = y % ph;
-  const int tp = tt / k, dt = tt % k;
-  const int64_t K = (int64_t)C * k * ph * pw;
-  const int64_t src_row = (((b * C + c) * T + tt) * H + y) * (int64_t)W;
-  const int64_t dst_row0 = ((b * t + tp) * h + py) * (int64_t)w;            // patch row of px = 0
-  const int64_t col0 = (((int64_t)c * k + dt) * ph + dy) * pw;
-  for (int xv = threadIdx.x & 31; xv < wv; xv += 32) {
-    const int xpix = xv * VEC;
-    const int px = xpix / pw, dx = xpix % pw;
-    cols[((dst_row0 + px) * K + col0 + dx) / VEC] = x[(src_row + xpix) / VEC];
+  const int px = (int)(q % w); q /= w;
+  const int py = (int)(q % h); q /= h;
+  const int tp = (int)(q % t);
+  const int64_t b = q / t;
+  const int vpw = pw / VEC;                        // vectors per pw-element segment
+  const int nseg = C * k * ph;                     // segments (c, dt, dy) of the patch row
+  const int nvec = nseg * vpw;
+  const int64_t dst = r * (int64_t)nvec;
+  for (int i = threadIdx.x & 31; i < nvec; i += 32) {
+    const int sgm = i / vpw, dx = (i % vpw) * VEC;
+    const int dy = sgm % ph;
+    const int dt = (sgm / ph) % k;
+    const int c = sgm / (ph * k);
+    const int64_t src = ((((b * C + c) * T + (tp * k + dt)) * H + (py * ph + dy)) * (int64_t)W + px * pw + dx);
+    cols[dst + i] = x[src / VEC];
   }
 }
 
@@ -102,7 +103,7 @@ extern "C" int vmb_patchify(const void* x, void* cols, int64_t B, int C, int T, 
                             reinterpret_cast<uintptr_t>(x) % vec_bytes != 0 ||
                             reinterpret_cast<uintptr_t>(cols) % vec_bytes != 0))
     vec_bytes /= 2;
-  const int64_t nv = B * C * (int64_t)(t * k) * (h * ph);     // used image rows, one warp each
+  const int64_t nv = B * (int64_t)t * h * w;                  // patch rows, one warp each
   // the element type only matters through its size: move raw words
   if (vec_bytes == 16) {
     if (es == 2) patchify_kernel<uint4, 8><<<grid_for(nv), 256, 0, st>>>((const uint4*)x, (uint4*)cols, C, T, H, W, k, ph, pw, t, h, w, nv);
