@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VMB_ABI_VERSION 1
+#define VMB_ABI_VERSION 2
 
 /* element types */
 #define VMB_F32 0
@@ -187,6 +187,16 @@ typedef struct vmb_fused_scan_args {
    * small batches split the sequence into concurrently processed segments (exact two-pass carry);
    * without it the call still works, one warp per 16 channels of a sequence. */
   void* workspace;    int64_t workspace_bytes;
+  /* a_geometric != 0: the caller guarantees A2[d][n] == (n+1) * A2[d][0] for every channel (the exact
+   * S4D-real structure of the reference's initialisation, models/videomamba/mamba_simple.py:265-272;
+   * check it when the weights are loaded): the decay factors of a channel then come from two
+   * exponentials and packed multiplies instead of sixteen exponentials.  0 = general A. */
+  int32_t a_geometric;
+  /* measurement aid, 0 = automatic: 10 * layout (1 one warp per unit, 2 two warps, 3 two warps + sequence
+   * split) + evaluator (1 = MUFU only, 2..5 = 1..4 of a lane's four state pairs on the FMA-pipe
+   * polynomial, 9 = geometric).  Evaluators other than the built default and 9 exist only in
+   * measurement builds (-DVMB_SCAN_LAB) and return VMB_ERR_UNSUPPORTED otherwise. */
+  int32_t tune;
 } vmb_fused_scan_args;
 VMB_API int64_t vmb_fused_scan_workspace_bytes(int B, int L, int Di, int N);
 VMB_API int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* args, vmb_stream_t stream);
@@ -238,6 +248,8 @@ typedef struct vmb_mixer_args {
   int32_t dtype;
   int32_t reverse;     /* walk tokens L-1..0 (conv and scan) */
   int32_t path;        /* 0 = auto, 1 = force generic kernels, 2 = force fast kernels */
+  int32_t a_geometric; /* as in vmb_fused_scan_args */
+  int32_t scan_tune;   /* as vmb_fused_scan_args.tune */
 } vmb_mixer_args;
 VMB_API int64_t vmb_mixer_workspace_bytes(int B, int L, int D, int Di, int N, int R, int dtype);
 VMB_API int vmb_mixer_fwd(const vmb_mixer_args* args, vmb_stream_t stream);

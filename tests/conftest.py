@@ -33,8 +33,9 @@ def golden():
 
     def load(name):
         if name not in cache:
+            # plain containers of tensors / numbers / strings: nothing in a fixture is executed
             cache[name] = torch.load(os.path.join(GOLDEN, name), map_location="cpu",
-                                     weights_only=False)
+                                     weights_only=True)
         return cache[name]
 
     return load

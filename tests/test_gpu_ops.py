@@ -324,42 +324,101 @@ def _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, h0, reverse, R, N):
     return (y.flip(1) if reverse else y), h
 
 
-@pytest.mark.parametrize("geom", [(2, 777, 768, 24, 64), (1, 100, 384, 12, 48), (3, 33, 1152, 36, 80),
-                                  (2, 1, 768, 24, 64), (1, 31, 768, 24, 56),
-                                  # 300-1400 (batch, 16-channel) units: the two-warp kernel (scan v11)
-                                  (8, 100, 768, 24, 64), (5, 333, 1152, 36, 80), (16, 50, 384, 12, 48),
-                                  (7, 15, 768, 24, 64), (24, 17, 768, 24, 64)])
-@pytest.mark.parametrize("reverse", [False, True])
-def test_fused_scan_against_float64(geom, reverse):
-    """The fused dt_proj + scan kernel (bf16) against float64 on identical inputs, with and without an
-    initial state, ragged lengths (tile tails), all three production dt ranks."""
+SCAN_GEOMS = [(2, 777, 768, 24, 64), (1, 100, 384, 12, 48), (3, 33, 1152, 36, 80), (2, 1, 768, 24, 64),
+              # 300-1400 (batch, 16-channel) units: the two-warp kernel (scan2w)
+              (8, 100, 768, 24, 64), (5, 333, 1152, 36, 80), (16, 50, 384, 12, 48),
+              (7, 15, 768, 24, 64), (24, 17, 768, 24, 64),
+              # >= 1406 units: the one-warp kernel (scan1w) -- what bench.py times at batch 32
+              (32, 17, 768, 24, 64), (32, 64, 768, 24, 64), (32, 777, 768, 24, 64),
+              (20, 100, 1152, 36, 80), (64, 40, 384, 12, 48)]
+
+
+def _fused_scan_case(geom, geometric):
     Bsz, L, Di, R, Xp = geom
     N = 16
-    gen = torch.Generator().manual_seed(L + Di)
+    gen = torch.Generator().manual_seed(L + Di + (7 if geometric else 0))
     bf = torch.bfloat16
     u = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
     z = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
     xdbl = _rand(gen, Bsz, L, Xp, dtype=bf).to(DEV)
     w_dt = _rand(gen, Di, R, dtype=bf, scale=R ** -0.5).to(DEV)
-    A = -torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Di, 1)
-                   + 0.1 * torch.randn(Di, N, generator=gen)).to(DEV)
+    if geometric:       # A[d, n] = (n + 1) * A[d, 0] with a per-channel base (S4D-real has base -1)
+        base = -torch.exp(0.5 * torch.randn(Di, 1, generator=gen))
+        A = (base * torch.arange(1, N + 1).float()).to(DEV)
+    else:
+        A = -torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Di, 1)
+                       + 0.1 * torch.randn(Di, N, generator=gen)).to(DEV)
     Dp = torch.randn(Di, generator=gen).to(DEV)
     bias = (torch.randn(Di, generator=gen) - 3.0).to(DEV)
     h0 = torch.randn(Bsz, Di, N, generator=gen).to(DEV)
+    return u, z, xdbl, w_dt, A, Dp, bias, h0, gen
+
+
+@pytest.mark.parametrize("geom", SCAN_GEOMS)
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("geometric", [False, True])
+def test_fused_scan_against_float64(geom, reverse, geometric):
+    """The fused dt_proj + scan kernels (bf16) against float64 on identical inputs, with and without an
+    initial state, ragged lengths (tile tails), all three production dt ranks, unit counts on both
+    sides of the one-warp / two-warp switch, general A and the geometric-A evaluator."""
+    Bsz, L, Di, R, Xp = geom
+    N = 16
+    bf = torch.bfloat16
+    u, z, xdbl, w_dt, A, Dp, bias, h0, gen = _fused_scan_case(geom, geometric)
     A2 = (A * ops.LOG2E).contiguous()
+    assert ops.is_geometric(A2) == geometric
     for init in (None, h0):
         want, want_h = _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, init, reverse, R, N)
         got, got_h = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, init,
-                                                     want_last=True, reverse=reverse)
+                                                     want_last=True, reverse=reverse, a_geometric=geometric)
         assert got.dtype == bf and got_h.dtype == torch.float32
         assert rel_err(got, want) <= 6e-3, rel_err(got, want)
         assert rel_err(got_h, want_h) <= 2e-3, rel_err(got_h, want_h)
+    if geometric:       # the general evaluator on the same structured A agrees too
+        plain = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, reverse=reverse)
+        want, _ = _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, None, reverse, R, N)
+        assert rel_err(plain, want) <= 6e-3
     # strided views: z living in the second half of an xz buffer, u / y with a wider pitch
     xz = _rand(gen, Bsz, L, 2 * Di, dtype=bf).to(DEV)
     want, _ = _fused_scan_ref64(xz[..., :Di], xz[..., Di:], xdbl, w_dt, A, Dp, bias, None, reverse, R, N)
     got = ops.selective_scan_fused_tokens(xz[..., :Di], xz[..., Di:], xdbl, w_dt, A2, R, N, Dp, bias,
-                                          reverse=reverse)
+                                          reverse=reverse, a_geometric=geometric)
     assert rel_err(got, want) <= 6e-3
+
+
+def test_fused_scan_layouts_agree_bitwise():
+    """The one-warp and two-warp kernels (forced through the tune field) run the same arithmetic in the
+    same order: identical bits; the sequence split re-associates the carry and is merely close."""
+    run = lambda args, **kw: ops.selective_scan_fused_tokens(*args[:4], args[4], 24, 16, args[5], args[6],
+                                                             want_last=True, **kw)
+    short = _scan_inputs(6, 700)                     # below the split threshold (768 tokens)
+    auto, h_auto = run(short)
+    for tune in (10, 20, 30):
+        got, h = run(short, tune=tune)
+        assert torch.equal(got, auto) and torch.equal(h, h_auto), tune
+    long = _scan_inputs(2, 3000, seed=13)            # 96 units: split into segments when allowed
+    one, h_one = run(long, tune=10)
+    two, h_two = run(long, tune=30)
+    assert torch.equal(one, two) and torch.equal(h_one, h_two)
+    whole, h_whole = run(long, tune=20)              # two warps, never split
+    assert rel_err(one, whole) <= 4e-3 and rel_err(h_one, h_whole) <= 1e-4
+
+
+def test_fused_scan_rejects_other_pitches_and_unbuilt_evaluators():
+    """x_dbl rows must have the pitch ops.xdbl_pitch(R, N) (every shared-memory offset of the kernels is
+    an immediate); evaluators that only exist in measurement builds are refused, not emulated."""
+    u, z, xdbl, w_dt, A2, Dp, bias = _scan_inputs(1, 31, Xp=56)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, 24, 16, Dp, bias)
+    u, z, xdbl, w_dt, A2, Dp, bias = _scan_inputs(1, 31)
+    lab = ops.selective_scan_fused_tokens
+    outs = []
+    for tune in (1, 2, 3, 4, 5):         # general-A evaluators: the built default succeeds, others refuse
+        try:
+            outs.append(lab(u, z, xdbl, w_dt, A2, 24, 16, Dp, bias, tune=tune))
+        except RuntimeError as e:
+            assert "not part of this build" in str(e)
+    assert len(outs) >= 1
 
 
 def _scan_inputs(Bsz, L, Di=768, R=24, Xp=64, N=16, seed=9):

@@ -75,6 +75,30 @@ def test_golden_model_forward(golden, name):
         _close(mp, g["x_pool_masked"], _tol(dt))
 
 
+def test_golden_temporal_table_interpolation(golden):
+    """a.9 with a NON-ZERO temporal table walked beyond its length (reference videomamba.py:655-675):
+    full clip and two chunked walks against the live-reference fixture."""
+    g = golden("model_fp32_temporal_interp.pt")
+    m = _model_from(g["cfg"], g["sd"], torch.float32)
+    x = g["x"].to(DEV)
+    with torch.no_grad():
+        vis, pool = m(x)
+        _close(vis, g["full_vis"], 1e-5); _close(pool, g["full_pool"], 1e-5)
+        for n in (4, 6, 8):
+            rows = m._get_temporal_pos_embedding(n - 2, offset=2, dtype=torch.float32, device=x.device)
+            _close(rows, g[f"rows_{n}"], 1e-6)
+        for tag, cuts in (("c44", (0, 4, 8)), ("c33", (0, 3, 6))):
+            state = m.allocate_state(2, dtype=torch.float32, device=x.device)
+            for i in range(len(cuts) - 1):
+                lo, hi = cuts[i], cuts[i + 1]
+                m.pool_type = "cls+avg" if lo == 0 else "avg"
+                v, p_, state = m(x[:, :, lo:hi], ssm_state=state, temporal_pos_offset=lo)
+                _close(v, g[f"{tag}_vis{i}"], 1e-5); _close(p_, g[f"{tag}_pool{i}"], 1e-5)
+            m.pool_type = "cls+avg"
+            for (c, s), (rc, rs) in zip(state, g[f"{tag}_state"]):
+                _close(c, rc, 1e-5); _close(s, rs, 1e-5)
+
+
 @pytest.mark.parametrize("name", GOLD)
 @pytest.mark.parametrize("container", ["list", "tuple", "dict"])
 def test_golden_streaming(golden, name, container):
@@ -199,6 +223,37 @@ def test_oracle_parity_production_widths(dtype, width, perturbed):
     if not perturbed:
         stitched = torch.cat([g1[0], g2[0]], dim=1)
         assert rel_err(stitched, got_vis) <= (2e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("frames", [1, 2])
+@pytest.mark.parametrize("weights", ["general", "geometric"])
+def test_oracle_parity_small_width_batch32(frames, weights):
+    """VideoMamba-Small width at the BENCH batch (32 clips @224: 1536 (batch, 16-channel) units, the
+    one-warp scan kernel and the CTA-pair projections that bench.py times), 1-2 frames, bf16, against
+    the CPU oracle.  `geometric`: S4D-real A with A_log kept in fp32 (a bf16 cast of log(n) breaks the
+    structure), which selects the geometric-A evaluator of the scan."""
+    dtype, dim, depth, batch = torch.bfloat16, 384, 2, 32
+    cfg = dict(img_size=224, patch_size=16, depth=depth, embed_dim=dim, kernel_size=1, num_frames=frames,
+               norm_epsilon=1e-5, rms_norm=True, fused_add_norm=True, residual_in_fp32=True,
+               pool_type="cls+avg", add_pool_norm=True)
+    general = weights == "general"
+    sd32 = orc.synthetic_state_dict(cfg, seed=11, dtype=torch.float32, perturbed=general)
+    sd = {k: v.to(dtype) for k, v in sd32.items()}
+    m = _model_from(cfg, sd, dtype)
+    if not general:
+        for i, layer in enumerate(m.layers):
+            exact = sd32[f"layers.{i}.mixer.A_log"]
+            sd[f"layers.{i}.mixer.A_log"] = exact
+            layer.mixer.A_log = torch.nn.Parameter(exact.to(DEV))
+        assert all(layer.mixer._kernel_weights().a_geometric for layer in m.layers)
+    else:
+        assert not any(layer.mixer._kernel_weights().a_geometric for layer in m.layers)
+    x = torch.rand(batch, 3, frames, 224, 224, generator=torch.Generator().manual_seed(3)).to(dtype)
+    with torch.no_grad():
+        want_vis, want_pool = orc.OracleVideoMamba(cfg, sd).forward(x)
+        got_vis, got_pool = m(x.to(DEV))
+    _close(got_vis, want_vis, 2e-2)
+    _close(got_pool, want_pool, 2e-2)
 
 
 @pytest.mark.parametrize("case", ["configs0_tiny_8f_fp32_b2", "configs1_small_16f_bf16_b1"])

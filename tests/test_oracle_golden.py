@@ -60,6 +60,32 @@ def test_streaming_chunks_match_reference(golden, name):
         assert s.dtype == torch.float32  # last ssm state is fp32 whatever the model dtype
 
 
+def test_temporal_table_interpolation_quirk_matches_reference(golden):
+    """a.9: NON-ZERO temporal table walked beyond its length (reference videomamba.py:655-675):
+    the table is interpolated to offset + T rows, then sliced, so chunk rows depend on the chunk end."""
+    g = golden("model_fp32_temporal_interp.pt")
+    o = orc.OracleVideoMamba(g["cfg"], g["sd"])
+    x = g["x"]
+    vis, pool = o.forward(x)
+    _check(vis, g["full_vis"]); _check(pool, g["full_pool"])
+    for n in (4, 6, 8):
+        _check(o._temporal_pos(n - 2, 2, torch.float32), g[f"rows_{n}"], 1e-6)
+    di = 2 * g["cfg"]["embed_dim"]
+    for tag, cuts in (("c44", (0, 4, 8)), ("c33", (0, 3, 6))):
+        state = [(torch.zeros(2, di, 4), torch.zeros(2, di, 16)) for _ in range(g["cfg"]["depth"])]
+        for i in range(len(cuts) - 1):
+            lo, hi = cuts[i], cuts[i + 1]
+            o.pool_type = "cls+avg" if lo == 0 else "avg"
+            v, p_, state = o.forward(x[:, :, lo:hi], ssm_state=state, temporal_pos_offset=lo)
+            _check(v, g[f"{tag}_vis{i}"]); _check(p_, g[f"{tag}_pool{i}"])
+        o.pool_type = "cls+avg"
+        for (c, s), (rc, rs) in zip(state, g[f"{tag}_state"]):
+            _check(c, rc); _check(s, rs)
+    # the quirk itself: the first chunk sees the raw rows 0..3, the single pass rows 0..3 of the table
+    # stretched to 8 -- with a non-zero table the chunked walk is NOT the single pass
+    assert orc.rel_err(g["c44_vis0"], g["full_vis"][:, :4 * 4]) > 1e-2
+
+
 def test_legacy_ssm_only_state(golden):
     g = golden("model_fp32_rms_fused.pt")
     o = orc.OracleVideoMamba(g["cfg"], g["sd"])

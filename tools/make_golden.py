@@ -88,6 +88,44 @@ def model_case(vm, dtype, name, rms, fused):
     return case
 
 
+def temporal_interp_case(vm):
+    """Temporal position table with NON-ZERO rows, walked beyond its length: the reference
+    interpolates the table to ``offset + T`` rows and slices (models/videomamba/videomamba.py:655-675),
+    so the rows a continuation chunk sees depend on where the chunk ends.  Pins that rule: full clip of
+    8 frames on a 4-row table, chunks 4 | 4 (second one interpolates to 8), and a ragged 3 | 3 walk
+    (second chunk interpolates to 6)."""
+    cfg = dict(img_size=16, patch_size=8, depth=2, embed_dim=32, channels=3, kernel_size=1,
+               num_frames=4, norm_epsilon=1e-5, rms_norm=True, fused_add_norm=True,
+               residual_in_fp32=True, pool_type="cls+avg", add_pool_norm=True)
+    torch.manual_seed(4321)
+    model = vm.PretrainVideoMamba(
+        img_size=16, patch_size=8, depth=2, embed_dim=32, channels=3,
+        ssm_cfg={"use_fast_path": False}, rms_norm=True, fused_add_norm=True,
+        residual_in_fp32=True, kernel_size=1, num_frames=4, pool_type="cls+avg").eval()
+    gen = torch.Generator().manual_seed(77)
+    _perturb(model, gen)
+    with torch.no_grad():       # rows of visibly different size, so a wrong row is a large error
+        model.temporal_pos_embedding.copy_(torch.randn(model.temporal_pos_embedding.shape, generator=gen))
+    x = torch.rand(2, 3, 8, 16, 16, generator=gen)
+    case = {"cfg": cfg, "sd": _clone_sd(model), "x": x,
+            "source": "_get_temporal_pos_embedding models/videomamba/videomamba.py:655-675"}
+    with torch.no_grad():
+        case["full_vis"], case["full_pool"] = model(x)
+        for tag, cuts in (("c44", (0, 4, 8)), ("c33", (0, 3, 6))):
+            state = model.allocate_state(2, dtype=torch.float32)
+            for i in range(len(cuts) - 1):
+                lo, hi = cuts[i], cuts[i + 1]
+                model.pool_type = "cls+avg" if lo == 0 else "avg"
+                vis, pool, state = model(x[:, :, lo:hi], ssm_state=state, temporal_pos_offset=lo)
+                case[f"{tag}_vis{i}"], case[f"{tag}_pool{i}"] = vis, pool
+            model.pool_type = "cls+avg"
+            case[f"{tag}_state"] = [(c.clone(), s.clone()) for c, s in state]
+        for n in (4, 6, 8):
+            case[f"rows_{n}"] = model._get_temporal_pos_embedding(
+                n - 2, offset=2, dtype=torch.float32, device=x.device).clone()
+    torch.save(case, os.path.join(OUT, "model_fp32_temporal_interp.pt"))
+
+
 def mixer_case(ms):
     """scripts/check_streaming_state.py:33-55 configuration (d_model 16, d_state 8, 12 = 5 | 7)."""
     torch.manual_seed(7)
@@ -167,6 +205,7 @@ def main():
     model_case(vm, torch.float32, "model_fp32_rms_fused.pt", rms=True, fused=True)
     model_case(vm, torch.bfloat16, "model_bf16_rms_fused.pt", rms=True, fused=True)
     model_case(vm, torch.float32, "model_fp32_ln_unfused.pt", rms=False, fused=False)
+    temporal_interp_case(vm)
     mixer_case(ms)
     scan_case(ms)
     refiner_case(rb)

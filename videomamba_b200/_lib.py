@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvmb200.so")
 
 VMB_F32, VMB_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 
@@ -48,6 +48,7 @@ class FusedScanArgs(C.Structure):
         ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32), ("R", c_int32),
         ("Rp", c_int32), ("Xp", c_int32), ("reverse", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("a_geometric", c_int32), ("tune", c_int32),
     ]
 
 
@@ -68,6 +69,7 @@ class MixerArgs(C.Structure):
         ("B", c_int32), ("L", c_int32), ("D", c_int32), ("Di", c_int32), ("N", c_int32),
         ("R", c_int32), ("W", c_int32),
         ("dtype", c_int32), ("reverse", c_int32), ("path", c_int32),
+        ("a_geometric", c_int32), ("scan_tune", c_int32),
     ]
 
 

@@ -170,6 +170,15 @@ extern "C" int vmb_add_norm_fwd(const void* x, int x_dtype, int64_t ldx, const v
   if (!residual) residual_dtype = VMB_F32;
   if (!residual_out) residual_out_dtype = VMB_F32;
   VMB_CHECK_ARG(dtype_ok(residual_dtype) && dtype_ok(residual_out_dtype), "add_norm: bad dtype");
+  {
+    // rows are read and written as 4-element vectors: 16 B for fp32, 8 B for bf16
+    auto aligned = [](const void* p, int dt) {
+      return p == nullptr || reinterpret_cast<uintptr_t>(p) % (dt == VMB_F32 ? 16 : 8) == 0;
+    };
+    if (!aligned(x, x_dtype) || !aligned(y, x_dtype) || !aligned(residual, residual_dtype) ||
+        !aligned(residual_out, residual_out_dtype) || !aligned(weight, w_dtype) || !aligned(bias, w_dtype))
+      VMB_UNSUPPORTED("add_norm: base pointers must be aligned to 4 elements (16 B fp32 / 8 B bf16)");
+  }
   cudaStream_t st = as_stream(stream);
   ProfScope ps(VMB_PROF_ADD_NORM, st);
   const bool rms = is_rms != 0;
@@ -233,6 +242,13 @@ extern "C" int vmb_gate_blend_fwd(const void* g1, const void* g2, const void* fw
   if (n == 0) return VMB_OK;
   VMB_CHECK_ARG(g1 && fwd && bwd && out, "gate_blend: null g1 / fwd / bwd / out");
   if (n % 4 != 0) VMB_UNSUPPORTED("gate_blend: element count must be a multiple of 4");
+  {
+    const uintptr_t al = dtype == VMB_F32 ? 16 : 8;
+    const void* ptrs[5] = {g1, g2, fwd, bwd, out};
+    for (const void* p : ptrs)
+      if (p != nullptr && reinterpret_cast<uintptr_t>(p) % al != 0)
+        VMB_UNSUPPORTED("gate_blend: pointers must be aligned to 4 elements (16 B fp32 / 8 B bf16)");
+  }
   const int64_t nvec = n / 4;
   const unsigned grid = (unsigned)((nvec + 255) / 256);
   cudaStream_t st = as_stream(stream);

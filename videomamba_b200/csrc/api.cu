@@ -201,7 +201,7 @@ extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_st
   f.h0 = a->h0; f.h0_dtype = a->h0_dtype;
   f.y = a->y; f.y_bs = a->y_bstride; f.y_ts = a->y_tstride; f.h_last = a->h_last;
   f.B = a->B; f.L = a->L; f.Di = a->Di; f.N = a->N; f.R = a->R; f.Rp = a->Rp; f.Xp = a->Xp;
-  f.reverse = a->reverse;
+  f.reverse = a->reverse; f.a_geometric = a->a_geometric; f.tune = a->tune;
   f.seg_ws = reinterpret_cast<float*>(a->workspace);
   f.seg_ws_bytes = a->workspace ? a->workspace_bytes : 0;
   VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->workspace) % 16 == 0, "fused_scan: workspace not 16-byte aligned");
@@ -266,6 +266,7 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   f.h0 = p->ssm_state_in; f.h0_dtype = p->ss_in_dtype;
   f.y = y; f.y_bs = (int64_t)L * Di; f.y_ts = Di; f.h_last = p->ssm_state_out;
   f.B = B; f.L = L; f.Di = Di; f.N = N; f.R = R; f.Rp = p->Rp; f.Xp = p->Xp; f.reverse = p->reverse;
+  f.a_geometric = p->a_geometric; f.tune = p->scan_tune;
   f.seg_ws = ws.seg_bytes ? reinterpret_cast<float*>(base + ws.seg) : nullptr;
   f.seg_ws_bytes = ws.seg_bytes;
   const bool fast_ok = p->dtype == VMB_BF16 && p->w_x_pad && p->w_dt_pad && p->Xp == Xw &&

@@ -8,90 +8,63 @@
 // :109-172; semantics of _selective_scan_ref :30-106).  Difference in rounding points: the
 // reference rounds delta_raw to bf16 between the two ops, here it stays fp32 (closer to exact).
 //
-// The kernel is bound by instruction issue, MUFU ex2 and the register-file write-back of its
-// shared-memory loads, not by HBM (profiles/r01_scan_ncu_full_summary.txt).  Common
-// to all layouts below:
-//   * CTA = ONE warp = (batch b, 16 channels); the sequence is walked in tiles of 16 tokens staged
-//     in shared memory one tile ahead (v10: TMA box copies on an mbarrier; earlier layouts: 16-byte
-//     cp.async copies, double buffered).  One-warp CTAs need no block barriers and
-//     1536 of them spread over 148 SMs within 6 % of even (768 two-warp CTAs: 14 % idle tail).
-//   * phase A (per tile): the dt projection of the tile, delta_raw[16 tokens x 16 channels] =
-//     dt_low[16 x R] * w_dt^T, runs on the tensor pipe (mma.sync m16n8k16, the A fragments come
-//     straight from the staged bf16 x_dbl rows via ldmatrix, w_dt fragments stay in registers);
-//     softplus and delta*u are applied to the accumulator fragments and written to shared memory.
-//   * phase B (per token): the recurrence on packed fp32 (fma.rn.f32x2), then + D*u, * SiLU(z).
-//   * small batches (fewer warps than the GPU needs) split the sequence into segments: a first
-//     pass computes every segment's end state from a zero start (recurrence only, no outputs) and
-//     its total decay exp(A * sum(delta)); a tiny kernel chains the carries; the second pass runs
-//     all segments concurrently from their true initial states.  Exact, ~1.5x the work, up to 24x
-//     the parallelism (long-clip configuration, 25 089 tokens at batch 1).
-//   * reverse = 1 walks the sequence back to front (tile rows are gathered in logical order), which
-//     is what the flipped branch of BiMambaRefinerBlock needs without any torch.flip copy.
-//
-// Three lane layouts of phase B live in this file (measured against each other in profiles/);
-// VMB_SCAN_VARIANT picks one:
-//   0      auto          v11 below 9.5 units per SM (with the sequence split below 2), v10 above
-//   10     v10           v9's lanes, tiles staged by TMA box copies on an mbarrier instead of
-//                        cp.async row gathers (62 % fewer shared-memory wavefronts)
-//   11 / 12 v11          v10 split over a helper warp (TMA, gathers, dt projection, finalisation)
-//                        and a consumer warp (recurrence + contraction); 11 never splits the
-//                        sequence, 12 splits like v10
-//   9      v9            lane = the 2 channels x 4 states of an mma A fragment; <C_t, h_t> by one
-//                        HMMA per token on bf16-rounded states: no shuffle, C_t stays bf16
-//   7      v7            lane = 1 channel x 8 states, fp32 contraction, one shuffle per token pair
-//   1      v4            lane = 2 channels x 4 states, fp32 contraction, two shuffles per token
-//                        (the first kernel below)
-//   2      none of them: the any-shape kernel of scan_generic.cu
-// (v6 -- v7's lanes with phase A of tile k+1 overlapped with tile k, 149 registers, 19 KB -- was
-//  measured and removed: faster alone, slower with steps in flight.)
+// The kernel is bound by instruction issue and the XU (MUFU) pipe, not by HBM: 16 exponentials per
+// (token, channel) in fp32 state (profiles/).  Layout:
+//   * unit = (batch b, 16 channels); the sequence is walked in tiles of 16 tokens.  One lane issues
+//     three cp.async.bulk.tensor box copies per tile (u 16 x 16, z 16 x 16, x_dbl Xp x 16) that
+//     complete on an mbarrier; rows beyond the sequence are zero-filled by the TMA unit; the
+//     reversed direction loads the box in memory order and the consumers mirror the row index
+//     (compile-time kRev, so every shared-memory offset stays an immediate).  128-byte x_dbl rows
+//     (dt_rank 24) use the 128-byte swizzle and are read through the same XOR.
+//   * phase A (per tile): delta_raw[16 tokens x 16 channels] = dt_low[16 x R] * w_dt^T on the tensor
+//     pipe (mma.sync m16n8k16, A fragments by ldmatrix straight from the staged bf16 rows, w_dt
+//     fragments in registers); softplus and delta*u on the accumulator fragments -> shared memory
+//     entries {delta_a, delta_b, du_a, du_b} for the channel pair (a, b) = (g, g + 8).
+//   * phase B (per token): a lane owns the 2 channels x 4 states of an mma A fragment whose rows are
+//     the unit's 16 channels and whose k index is the 16 states (channels g, g+8; states
+//     2*tig + {0,1}, 2*tig + 8 + {0,1}).  The pair (a, b) of one state shares a packed register:
+//     decay and update run on fma.rn.f32x2, the states are rounded once to bf16 pairs -- exactly the
+//     fragment registers -- and ONE HMMA multiplies them with C_t (replicated over the 8 columns of
+//     the B operand), so every lane of a channel receives <C_t, h_t>: no shuffle.
+//   * the decay factors exp2(delta * A2[n]) come from one of three evaluators (template kExp):
+//       general, MUFU:  one MUFU.EX2 per factor (8 per lane-token);
+//       general, split: kExp of the lane's four state pairs use a Cody-Waite range reduction +
+//                       degree-3 polynomial on the FMA pipe (packed), the rest MUFU -- same issue
+//                       slots, fewer XU cycles, which is what the recurrence phase queues on;
+//       geometric A:    A[d][n] = (n+1) * A[d][0] (exact S4D-real structure, reference
+//                       mamba_simple.py:265-272): two MUFU per channel (r = e^(delta*A0) and
+//                       r^(2*tig+1)), the other factors by packed multiplies.  Selected by the caller
+//                       (weights are checked when they are loaded), never guessed in the kernel.
+//   * two kernels share that code: scan1w (one warp per unit: tile staging, phase A, recurrence and
+//     finalisation in one instruction stream; small footprint, two launches can share an SM) and
+//     scan2w (helper warp: TMA, gathers, phase A, finalisation; consumer warp: recurrence only --
+//     faster when the batch alone leaves the schedulers short of warps).
+//   * small batches split the sequence into segments: a first pass computes every segment's end
+//     state from a zero start (recurrence only) and sum(delta); a tiny kernel chains the carries;
+//     the second pass runs all segments concurrently from their true initial states.  Exact.
+//   * reverse = 1 walks the sequence back to front (the flipped branch of BiMambaRefinerBlock,
+//     models/refiner_backbone.py:61-68, :92-135, without flip copies).
 #include <algorithm>
-#include <cstdlib>
 
 #include "internal.h"
 
 namespace vmb {
 namespace {
 
-constexpr int kCh = 16;                 // channels per CTA (one warp: 8 channel pairs x 4 state quads)
-constexpr int kThreads = 32;
+constexpr int kCh = 16;                 // channels per unit (8 channel pairs x 4 state quads)
 constexpr int kTT = 16;                 // tokens per tile
-constexpr int kRowBytes = 48;           // u / z / y tile rows: 32 B of channels + 16 B pad
+constexpr int kRowBytes = 48;           // y tile rows: 32 B of channels + 16 B pad
 constexpr int kN = 16;
-#ifndef VMB_SCAN_MIN_CTAS
-#define VMB_SCAN_MIN_CTAS 20
+constexpr int kExpGeo = 8;              // kExp value of the geometric-A evaluator
+#ifndef VMB_SCAN_POLY_PAIRS
+#define VMB_SCAN_POLY_PAIRS 0           // general-A default: state pairs per lane on the FMA pipe
 #endif
-constexpr int kMinCtas = VMB_SCAN_MIN_CTAS;   // register cap = 65536 / (32 * kMinCtas)
+constexpr int kExpDefault = VMB_SCAN_POLY_PAIRS;
 
-// x_dbl tile row pitch in bytes: an odd number of 16-byte chunks keeps ldmatrix conflict free
-__host__ __device__ constexpr int x_row_bytes(int Xp) { return ((Xp / 8) % 2 == 1) ? Xp * 2 : Xp * 2 + 16; }
+// x_dbl row pitch the host packs for dt_rank R (ops.xdbl_pitch): a compile-time constant here, so
+// every shared-memory offset of the kernels is an immediate
+__host__ __device__ constexpr int xp_of(int R) { return (R + 2 * kN + 15) / 16 * 16; }
 
-struct Smem {   // byte offsets; u / z are double buffered (stage s at base + s * stride); the raw
-                // x_dbl rows are consumed at the start of a tile, so one buffer is refilled right after
-  int u0, z0, x0, bc, dd, y, total;
-  __host__ __device__ int u(int s) const { return u0 + s * (kTT * kRowBytes); }
-  __host__ __device__ int z(int s) const { return z0 + s * (kTT * kRowBytes); }
-};
-__host__ __device__ inline Smem smem_plan(int Xp) {
-  Smem s;
-  int off = 0;
-  s.u0 = off; off += 2 * kTT * kRowBytes;
-  s.z0 = off; off += 2 * kTT * kRowBytes;
-  s.x0 = off; off += kTT * x_row_bytes(Xp);
-  s.bc = off; off += kTT * 2 * kN * 4;          // [token][B0..15 | C0..15] fp32
-  s.dd = off; off += kTT * (kCh / 2) * 16;      // [token][channel pair]{delta0, delta1, du0, du1}
-  s.y = off; off += kTT * kRowBytes;
-  s.total = off;
-  return s;
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
-}
 // softplus(x) = max(x, 0) + log1p(exp(-|x|)).  log1p through lg2(1 + e): its absolute error is
 // <= 1 ulp of 1.0 (6e-8), which is what matters for a step size that enters exp(delta*A) and
 // delta*u linearly; identity above 20 (the reference's threshold) falls out in fp32.
@@ -114,783 +87,212 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-
-// One channel's 4 states of this lane for one token: h <- exp2(delta*A2)*h + du*B ; returns <C, h>.
-__device__ __forceinline__ float step4(float (&h)[4], const float (&A2)[4], float delta, float du,
-                                       const float4& Bv, const float4& Cv) {
-  const float2 d2 = make_float2(delta, delta), du2 = make_float2(du, du);
-  const float2 x01 = __fmul2_rn(d2, make_float2(A2[0], A2[1]));
-  const float2 x23 = __fmul2_rn(d2, make_float2(A2[2], A2[3]));
-  const float2 e01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
-  const float2 e23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
-  const float2 b01 = __fmul2_rn(du2, make_float2(Bv.x, Bv.y));
-  const float2 b23 = __fmul2_rn(du2, make_float2(Bv.z, Bv.w));
-  const float2 h01 = __ffma2_rn(e01, make_float2(h[0], h[1]), b01);
-  const float2 h23 = __ffma2_rn(e23, make_float2(h[2], h[3]), b23);
-  h[0] = h01.x; h[1] = h01.y; h[2] = h23.x; h[3] = h23.y;
-  float2 q = __fmul2_rn(h01, make_float2(Cv.x, Cv.y));
-  q = __ffma2_rn(h23, make_float2(Cv.z, Cv.w), q);
-  return q.x + q.y;
-}
-
-// kStateOnly: first pass of the sequence split -- run the recurrence of one segment from a zero
-// state, emit its end state and sum(delta), skip everything that only the outputs need.
-template <int R, bool kStateOnly>
-__global__ void __launch_bounds__(kThreads, kMinCtas)
-scan_fast_kernel(const FastScanArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int KST = (R + 15) / 16;           // k-steps of the dt projection
-  const Smem sp = smem_plan(a.Xp);
-  const int xrow = x_row_bytes(a.Xp);
-  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-
-  const int lane = threadIdx.x;
-  const int j = lane & 3;                      // state quad [4j, 4j+4) (phase B) / column pair (phase A)
-  const int pr = lane >> 2;                    // channel pair (phase B) / accumulator row (phase A)
-  const int cw = blockIdx.x * kCh;             // first channel of this warp
-  const int b = blockIdx.y;
-  const int seg = blockIdx.z;                  // sequence segment [tbeg, L) of the logical sequence
-  const int tbeg = seg * a.seg_len;
-  const int L = min(a.L, tbeg + a.seg_len);    // end of this segment (tokens beyond it are padding)
-  using bf16 = __nv_bfloat16;
-  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;           // floats per segment of H / Hin
-  float* const wsH = a.seg_ws;
-  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
-  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
-
-  // ---- per-thread constants ---------------------------------------------------------------
-  // phase B: channels ca = cw + 2 pr and ca + 1, states 4j .. 4j+3
-  const int ca = cw + 2 * pr;
-  float A2a[4], A2b[4], ha[4], hb[4];
-  {
-    const float4 va = *reinterpret_cast<const float4*>(a.A2 + (int64_t)ca * kN + 4 * j);
-    const float4 vb = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(ca + 1) * kN + 4 * j);
-    A2a[0] = va.x; A2a[1] = va.y; A2a[2] = va.z; A2a[3] = va.w;
-    A2b[0] = vb.x; A2b[1] = vb.y; A2b[2] = vb.z; A2b[3] = vb.w;
-    const int64_t hoff = ((int64_t)b * a.Di + ca) * kN + 4 * j;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      if (kStateOnly) {
-        ha[n] = 0.f; hb[n] = 0.f;
-      } else if (seg > 0) {                    // carried in from the previous segments
-        ha[n] = wsHin[seg * seg_stride + hoff + n];
-        hb[n] = wsHin[seg * seg_stride + hoff + kN + n];
-      } else {
-        ha[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
-        hb[n] = a.h0 ? load_as_f32(a.h0, hoff + kN + n, a.h0_dtype) : 0.f;
-      }
-    }
-  }
-  // finalising lane: channel ca + (j & 1)
-  const int cf = 2 * pr + (j & 1);             // channel within the CTA
-  const float Dv = a.D ? a.D[cw + cf] : 0.f;
-  // phase A: B fragments of w_dt^T for the two 8-channel n-tiles, and the dt bias of this lane's
-  // 4 accumulator columns: channels cw + 8 n + 2 j + {0, 1}
-  uint32_t bfrag[2][KST][2];
-  float bias[2][2];
-  {
-    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const bf16* wr = wd + (int64_t)(cw + 8 * n + pr) * a.Rp;   // B operand column = channel row
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * j);
-        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * j);
-      }
-      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j] : 0.f;
-      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j + 1] : 0.f;
-    }
-  }
-
-  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
-  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
-  const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
-  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
-  const int xchunks = a.Xp / 8;                // 16-byte chunks per x_dbl row
-  auto phys = [&](int t) -> int64_t { return a.reverse ? (int64_t)(a.L - 1 - t) : (int64_t)t; };
-
-  // a lane copies one 16-byte chunk of u and of z (16 rows x 2 chunks) ...
-  auto issue_uz = [&](int tile, int st) {
-    const int row = lane >> 1, ch = lane & 1;
-    const int t = tile * kTT + row;
-    const bool ok = t < L;
-    const int64_t prow = ok ? phys(t) : 0;
-    cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + prow * a.u_ts + ch * 8, ok);
-    if (!kStateOnly)
-      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + prow * a.z_ts + ch * 8, ok);
-  };
-  // ... and every other chunk of one x_dbl row (16 rows x 2 lanes)
-  auto issue_x = [&](int tile) {
-    const int row = lane >> 1;
-    const int t = tile * kTT + row;
-    const bool ok = t < L;
-    const bf16* src = xg + (ok ? phys(t) : 0) * a.x_ts;
-    for (int ch = lane & 1; ch < xchunks; ch += 2)
-      cp_async16(sbase + sp.x0 + row * xrow + ch * 16, src + ch * 8, ok);
-  };
-
-  const int tile_lo = tbeg / kTT;              // seg_len is a multiple of the tile
-  const int ntiles = (L + kTT - 1) / kTT;
-  issue_uz(tile_lo, 0);
-  issue_x(tile_lo);
-  cp_async_commit();
-  float sum_a = 0.f, sum_b = 0.f;              // sum of delta over the segment (state-only pass)
-
-  float* const sbc = reinterpret_cast<float*>(smem + sp.bc);
-  float4* const sdd = reinterpret_cast<float4*>(smem + sp.dd);   // [token][8 pairs]
-  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
-
-  for (int tile = tile_lo; tile < ntiles; ++tile) {
-    const int st = (tile - tile_lo) & 1;
-    const int t0 = tile * kTT;
-    cp_async_wait<0>();
-    __syncwarp();                              // tile landed; last tile's smem readers are done
-
-    const bf16* su = reinterpret_cast<const bf16*>(smem + sp.u(st));
-    const bf16* sz = reinterpret_cast<const bf16*>(smem + sp.z(st));
-
-    // ---- expand B_t / C_t of the tile to fp32 ---------------------------------------------------
-    {
-      const uint8_t* xr = smem + sp.x0;
-#pragma unroll
-      for (int i = 0; i < (kTT * kN) / kThreads; ++i) {          // 16 tokens x 16 bf16 pairs
-        const int e = lane + i * kThreads;
-        const int row = e >> 4, p = e & 15;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(xr + row * xrow + (R + 2 * p) * 2);
-        *reinterpret_cast<float2*>(sbc + row * (2 * kN) + 2 * p) = make_float2(bf16lo(v), bf16hi(v));
-      }
-    }
-
-    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
-    {
-      float acc[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        uint32_t af[4];
-        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-        ldmatrix_x4(sbase + sp.x0 + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
-        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-      }
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int tl = pr + 8 * half;                          // token row within the tile
-          float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
-          float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
-          if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }              // padding: decay 1, drive 0
-          const uint32_t uv = *reinterpret_cast<const uint32_t*>(
-              reinterpret_cast<const uint8_t*>(su) + tl * kRowBytes + (8 * n + 2 * j) * 2);
-          sdd[tl * (kCh / 2) + 4 * n + j] = make_float4(d0, d1, d0 * bf16lo(uv), d1 * bf16hi(uv));
-        }
-    }
-    __syncwarp();                              // sBC / sDD visible; raw x_dbl rows no longer needed
-    if (tile + 1 < ntiles) {                   // prefetch the next tile behind the recurrence
-      issue_uz(tile + 1, st ^ 1);
-      issue_x(tile + 1);
-    }
-    cp_async_commit();
-
-    // ---- phase B: the recurrence, 2 tokens per step ----------------------------------------------
-    if constexpr (kStateOnly) {
-#pragma unroll 4
-      for (int t = 0; t < kTT; ++t) {
-        const float4 dd = sdd[t * (kCh / 2) + pr];
-        const float4 Bv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + 4 * j);
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        (void)step4(ha, A2a, dd.x, dd.z, Bv, zero);
-        (void)step4(hb, A2b, dd.y, dd.w, Bv, zero);
-        sum_a += dd.x;
-        sum_b += dd.y;
-      }
-      __syncwarp();
-    } else {
-#pragma unroll 2
-      for (int tt = 0; tt < kTT; tt += 2) {
-        float ys[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int t = tt + s;
-          const float4 dd = sdd[t * (kCh / 2) + pr];
-          const float4 Bv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + 4 * j);
-          const float4 Cv = *reinterpret_cast<const float4*>(sbc + t * (2 * kN) + kN + 4 * j);
-          const float pa = step4(ha, A2a, dd.x, dd.z, Bv, Cv);
-          const float pb = step4(hb, A2b, dd.y, dd.w, Bv, Cv);
-          const bool odd = j & 1;
-          float q = (odd ? pb : pa) + __shfl_xor_sync(0xffffffffu, odd ? pa : pb, 1);
-          q += __shfl_xor_sync(0xffffffffu, q, 2);
-          ys[s] = q;                           // y of channel ca + (j & 1) at token t, in all 4 lanes
-        }
-        const int tf = tt + (j >> 1);          // this lane finalises (token tf, channel cf)
-        const float yv = (j >> 1) ? ys[1] : ys[0];
-        const float uval = __bfloat162float(su[tf * (kRowBytes / 2) + cf]);
-        const float zval = __bfloat162float(sz[tf * (kRowBytes / 2) + cf]);
-        sy[tf * (kRowBytes / 2) + cf] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_fast(zval));
-      }
-      __syncwarp();
-
-      // ---- y tile out: 16 rows x 32 bytes as 16-byte stores ----------------------------------------
-      const int row = lane >> 1, ch = lane & 1;
-      const int t = t0 + row;
-      if (t < L) {
-        const uint4 v = *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
-        *reinterpret_cast<uint4*>(yg + phys(t) * a.y_ts + ch * 8) = v;
-      }
-    }
-    // the __syncwarp at the top of the next iteration orders these reads before the next writes
-  }
-
-  if constexpr (kStateOnly) {
-    float* hs = wsH + seg * seg_stride + ((int64_t)b * a.Di + ca) * kN + 4 * j;
-    *reinterpret_cast<float4*>(hs) = make_float4(ha[0], ha[1], ha[2], ha[3]);
-    *reinterpret_cast<float4*>(hs + kN) = make_float4(hb[0], hb[1], hb[2], hb[3]);
-    if (j == 0) {
-      float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + ca;
-      ss[0] = sum_a;
-      ss[1] = sum_b;
-    }
-    return;
-  }
-  if (seg != a.nseg - 1) return;               // only the last segment holds the final state
-  if (a.h_last != nullptr) {
-    float* hl = a.h_last + ((int64_t)b * a.Di + ca) * kN + 4 * j;
-    *reinterpret_cast<float4*>(hl) = make_float4(ha[0], ha[1], ha[2], ha[3]);
-    *reinterpret_cast<float4*>(hl + kN) = make_float4(hb[0], hb[1], hb[2], hb[3]);
-  }
-}
-
-
-// =================================================================================================
-// v7: v4's small footprint (one-warp CTAs, <= 96 registers, 10 KB of shared memory, so two launches
-// can share an SM) and a lane that owns ONE channel x 8 states (2 lanes per channel),
-// one shuffle per token PAIR, 32-bit address arithmetic.  Phase A is not overlapped with the
-// recurrence inside a warp; the other resident warps cover it.
-// =================================================================================================
-namespace v7 {
-
-constexpr int kDdRow = kCh * 8;                   // {delta, delta*u} per channel: 128 B per token
-
-template <int R, bool kStateOnly>
-__global__ void __launch_bounds__(kThreads, kMinCtas)
-scan7_kernel(const FastScanArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int KST = (R + 15) / 16;
-  const Smem sp = smem_plan(a.Xp);
-  const int xrow = x_row_bytes(a.Xp);
-  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  using bf16 = __nv_bfloat16;
-
-  const int lane = threadIdx.x;
-  const int j4 = lane & 3, pr = lane >> 2;        // phase A: accumulator column pair / row
-  const int c = lane >> 1, jh = lane & 1;         // phase B: channel within the CTA / state half
-  const int cw = blockIdx.x * kCh;
-  const int b = blockIdx.y;
-  const int seg = blockIdx.z;
-  const int tbeg = seg * a.seg_len;
-  const int L = min(a.L, tbeg + a.seg_len);
-  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
-  float* const wsH = a.seg_ws;
-  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
-  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
-
-  float2 Ap[4], hp[4];
-  const int64_t hoff = ((int64_t)b * a.Di + cw + c) * kN + 8 * jh;
-  {
-    const float4 v0 = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(cw + c) * kN + 8 * jh);
-    const float4 v1 = *reinterpret_cast<const float4*>(a.A2 + (int64_t)(cw + c) * kN + 8 * jh + 4);
-    Ap[0] = make_float2(v0.x, v0.y); Ap[1] = make_float2(v0.z, v0.w);
-    Ap[2] = make_float2(v1.x, v1.y); Ap[3] = make_float2(v1.z, v1.w);
-    float h[8];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (kStateOnly) h[n] = 0.f;
-      else if (seg > 0) h[n] = wsHin[seg * seg_stride + hoff + n];
-      else h[n] = a.h0 ? load_as_f32(a.h0, hoff + n, a.h0_dtype) : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) hp[k] = make_float2(h[2 * k], h[2 * k + 1]);
-  }
-  const float Dv = a.D ? a.D[cw + c] : 0.f;       // finalising lane: channel c, token of the pair = jh
-  uint32_t bfrag[2][KST][2];
-  float bias[2][2];
-  {
-    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const bf16* wr = wd + (int64_t)(cw + 8 * n + pr) * a.Rp;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * j4);
-        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * j4);
-      }
-      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j4] : 0.f;
-      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * j4 + 1] : 0.f;
-    }
-  }
-
-  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
-  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
-  const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
-  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
-  const int xchunks = a.Xp / 8;
-  // token t of the logical sequence lives at row p0 + dir * t; offsets inside one batch entry fit 32 bits
-  const int dir = a.reverse ? -1 : 1;
-  const int p0 = a.reverse ? a.L - 1 : 0;
-  const int u_ts = (int)a.u_ts, z_ts = (int)a.z_ts, x_ts = (int)a.x_ts, y_ts = (int)a.y_ts;
-
-  auto issue_tile = [&](int tile, int st) {
-    const int row = lane >> 1, ch = lane & 1;
-    const int t = tile * kTT + row;
-    const bool ok = t < L;
-    const int prow = ok ? p0 + dir * t : 0;
-    cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + (prow * u_ts + ch * 8), ok);
-    if (!kStateOnly)
-      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + (prow * z_ts + ch * 8), ok);
-    const bf16* src = xg + prow * x_ts;
-    for (int k = ch; k < xchunks; k += 2) cp_async16(sbase + sp.x0 + row * xrow + k * 16, src + k * 8, ok);
-  };
-
-  const int tile_lo = tbeg / kTT;
-  const int ntiles = (L + kTT - 1) / kTT;
-  issue_tile(tile_lo, 0);
-  cp_async_commit();
-  float sum_d = 0.f;
-
-  float* const sbc = reinterpret_cast<float*>(smem + sp.bc);
-  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
-
-  for (int tile = tile_lo; tile < ntiles; ++tile) {
-    const int st = (tile - tile_lo) & 1;
-    const int t0 = tile * kTT;
-    cp_async_wait<0>();
-    __syncwarp();                                  // tile landed; last tile's smem readers are done
-
-    const uint8_t* su = smem + sp.u(st);
-    const uint8_t* sz = smem + sp.z(st);
-
-    // ---- expand B_t / C_t of the tile to fp32 ---------------------------------------------------
-    {
-      const uint8_t* xr = smem + sp.x0;
-#pragma unroll
-      for (int i = 0; i < (kTT * kN) / kThreads; ++i) {          // 16 tokens x 16 bf16 pairs
-        const int e = lane + i * kThreads;
-        const int row = e >> 4, p = e & 15;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(xr + row * xrow + (R + 2 * p) * 2);
-        *reinterpret_cast<float2*>(sbc + row * (2 * kN) + 2 * p) = make_float2(bf16lo(v), bf16hi(v));
-      }
-    }
-    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
-    {
-      float acc[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        uint32_t af[4];
-        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-        ldmatrix_x4(sbase + sp.x0 + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
-        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-      }
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int tl = pr + 8 * half;
-          float d0 = softplus_mufu(acc[n][2 * half] + bias[n][0]);
-          float d1 = softplus_mufu(acc[n][2 * half + 1] + bias[n][1]);
-          if (t0 + tl >= L) { d0 = 0.f; d1 = 0.f; }              // padding: decay 1, drive 0
-          const uint32_t uv = *reinterpret_cast<const uint32_t*>(su + tl * kRowBytes + (8 * n + 2 * j4) * 2);
-          // 16-byte chunk (4 n + j4) of the row, swizzled by the row parity: the 8 lanes of a quarter
-          // warp (rows pr = 2k, 2k + 1) cover all 32 banks
-          *reinterpret_cast<float4*>(smem + sp.dd + tl * kDdRow + (((4 * n + j4) ^ ((tl & 1) << 2)) << 4)) =
-              make_float4(d0, d0 * bf16lo(uv), d1, d1 * bf16hi(uv));
-        }
-    }
-    __syncwarp();                                  // sBC / sDD visible; raw x_dbl rows no longer needed
-    if (tile + 1 < ntiles) issue_tile(tile + 1, st ^ 1);
-    cp_async_commit();
-
-    // ---- phase B: the recurrence ---------------------------------------------------------------------
-    const uint8_t* sdd0 = smem + sp.dd + (((c >> 1)) << 4) + (c & 1) * 8;          // even tokens
-    const uint8_t* sdd1 = smem + sp.dd + (((c >> 1) ^ 4) << 4) + (c & 1) * 8;      // odd tokens
-    const uint8_t* sb = smem + sp.bc + jh * 32;
-    float qs0 = 0.f;
-#pragma unroll
-    for (int t = 0; t < kTT; ++t) {
-      const float2 dd = *reinterpret_cast<const float2*>(((t & 1) ? sdd1 : sdd0) + t * kDdRow);
-      const float4 B0 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4));
-      const float4 B1 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4) + 16);
-      const float2 d2 = make_float2(dd.x, dd.x), du2 = make_float2(dd.y, dd.y);
-      float2 e[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 x = __fmul2_rn(d2, Ap[k]);
-        e[k] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-      }
-      hp[0] = __ffma2_rn(e[0], hp[0], __fmul2_rn(du2, make_float2(B0.x, B0.y)));
-      hp[1] = __ffma2_rn(e[1], hp[1], __fmul2_rn(du2, make_float2(B0.z, B0.w)));
-      hp[2] = __ffma2_rn(e[2], hp[2], __fmul2_rn(du2, make_float2(B1.x, B1.y)));
-      hp[3] = __ffma2_rn(e[3], hp[3], __fmul2_rn(du2, make_float2(B1.z, B1.w)));
-      if constexpr (kStateOnly) {
-        sum_d += dd.x;
-      } else {
-        const float4 C0 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4) + 64);
-        const float4 C1 = *reinterpret_cast<const float4*>(sb + t * (2 * kN * 4) + 80);
-        float2 q = __fmul2_rn(hp[0], make_float2(C0.x, C0.y));
-        q = __ffma2_rn(hp[1], make_float2(C0.z, C0.w), q);
-        q = __ffma2_rn(hp[2], make_float2(C1.x, C1.y), q);
-        q = __ffma2_rn(hp[3], make_float2(C1.z, C1.w), q);
-        const float s = q.x + q.y;
-        if (t & 1) {                               // lane jh finalises (token t - 1 + jh, channel c)
-          const float mine = jh ? s : qs0, send = jh ? qs0 : s;
-          const float yv = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-          const int tf = t - 1 + jh;
-          const float uval = __bfloat162float(*reinterpret_cast<const bf16*>(su + tf * kRowBytes + c * 2));
-          const float zval = __bfloat162float(*reinterpret_cast<const bf16*>(sz + tf * kRowBytes + c * 2));
-          sy[tf * (kRowBytes / 2) + c] = __float2bfloat16_rn(fmaf(Dv, uval, yv) * silu_fast(zval));
-        } else {
-          qs0 = s;
-        }
-      }
-    }
-    if constexpr (!kStateOnly) {
-      __syncwarp();
-      const int row = lane >> 1, ch = lane & 1;
-      const int t = t0 + row;
-      if (t < L)
-        *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
-            *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
-    }
-    // the __syncwarp at the top of the next iteration orders these reads before the next writes
-  }
-
-  if constexpr (kStateOnly) {
-    float* hs = wsH + seg * seg_stride + hoff;
-    *reinterpret_cast<float4*>(hs) = make_float4(hp[0].x, hp[0].y, hp[1].x, hp[1].y);
-    *reinterpret_cast<float4*>(hs + 4) = make_float4(hp[2].x, hp[2].y, hp[3].x, hp[3].y);
-    if (jh == 0) wsS[((int64_t)seg * a.B + b) * a.Di + cw + c] = sum_d;
-    return;
-  }
-  if (seg != a.nseg - 1) return;
-  if (a.h_last != nullptr) {
-    float* hl = a.h_last + hoff;
-    *reinterpret_cast<float4*>(hl) = make_float4(hp[0].x, hp[0].y, hp[1].x, hp[1].y);
-    *reinterpret_cast<float4*>(hl + 4) = make_float4(hp[2].x, hp[2].y, hp[3].x, hp[3].y);
-  }
-}
-
-}  // namespace v7
-
-// =================================================================================================
-// v9: the <C_t, h_t> contraction on the tensor pipe.  Getting B_t and C_t into every lane is the
-// largest cost of v7 (timing ablation in profiles/: the shared-memory loads are ~41 % of the kernel,
-// the exponentials ~20 %).  Here a lane owns the 2 channels x 4 states of an mma.m16n8k16 A fragment
-// (rows = the warp's 16 channels, k = the 16 states): channels g, g + 8 and states 2 tig + {0, 1},
-// 2 tig + 8 + {0, 1} (g = lane >> 2, tig = lane & 3).  After the state update the fp32 states are
-// rounded once to bf16 pairs (exactly the fragment registers) and one HMMA multiplies them with C_t,
-// which stays in its bf16 form and is replicated over the 8 columns of the B operand -- so every
-// lane of a channel receives the finished sum: no shuffle, no fp32 expansion of C_t, half the B_t
-// bytes per lane.  The products C*h are exact in fp32; the only extra rounding is h -> bf16 inside
-// the contraction (2^-9 relative per term; the state itself stays fp32).
-// =================================================================================================
-namespace v9 {
-
-struct Plan {
-  int u0, z0, x0, b, c, dd, y, total, xrow;
-  __host__ __device__ constexpr int u(int s) const { return u0 + s * (kTT * kRowBytes); }
-  __host__ __device__ constexpr int z(int s) const { return z0 + s * (kTT * kRowBytes); }
-};
-// x_dbl row pitch the host packs for dt_rank R (ops.xdbl_pitch): a compile-time constant here, so
-// every shared-memory offset of the kernel is an immediate
-__host__ __device__ constexpr int xp_of(int R) { return (R + 2 * kN + 15) / 16 * 16; }
-__host__ __device__ constexpr Plan plan(int Xp) {
-  Plan p{};
-  int off = 0;
-  p.xrow = x_row_bytes(Xp);
-  p.u0 = off; off += 2 * kTT * kRowBytes;
-  p.z0 = off; off += 2 * kTT * kRowBytes;
-  p.x0 = off; off += kTT * p.xrow;                // raw x_dbl rows: consumed by phase A, then refilled
-  p.b = off; off += kTT * kN * 4;                 // [token][tig][B(2tig), B(2tig+1), B(2tig+8), B(2tig+9)] fp32
-  p.c = off; off += kTT * kN * 2;                 // [token][C0..15] bf16, as in the row
-  p.dd = off; off += kTT * 8 * 16;                // [token][g ^ (token & 1)]{delta_g, du_g, delta_g+8, du_g+8}
-  p.y = off; off += kTT * kRowBytes;
-  p.total = off;
-  return p;
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 
-template <int R, bool kStateOnly>
-__global__ void __launch_bounds__(kThreads, 18)   // cap 112: it takes 96, so 21 CTAs fit an SM
-scan9_kernel(const FastScanArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int KST = (R + 15) / 16;
-  constexpr Plan sp = plan(xp_of(R));
-  constexpr int xrow = sp.xrow;
-  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
-  using bf16 = __nv_bfloat16;
-
-  const int lane = threadIdx.x;
-  const int g = lane >> 2, tig = lane & 3;        // mma fragment coordinates (both phases)
-  const int cw = blockIdx.x * kCh;
-  const int b = blockIdx.y;
-  const int seg = blockIdx.z;
-  const int tbeg = seg * a.seg_len;
-  const int L = min(a.L, tbeg + a.seg_len);
-  const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
-  float* const wsH = a.seg_ws;
-  float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
-  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
-
-  // states of this lane: channel ca = cw + g -> ha[0] = (2 tig, 2 tig + 1), ha[1] = (2 tig + 8, + 9);
-  // channel cb = ca + 8 -> hb likewise
-  float2 Aa[2], Ab[2], ha[2], hb[2];
-  const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
-  const int64_t hoff_b = hoff_a + 8 * kN;
-  {
-    const float* pa = a.A2 + (int64_t)(cw + g) * kN + 2 * tig;
-    Aa[0] = *reinterpret_cast<const float2*>(pa);
-    Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
-    Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
-    Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
-    auto ld = [&](int64_t off) -> float {
-      if (kStateOnly) return 0.f;
-      if (seg > 0) return wsHin[seg * seg_stride + off];
-      return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
-    };
-    ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
-    ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
-    hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
-    hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
-  }
-  const float Da = a.D ? a.D[cw + g] : 0.f, Db = a.D ? a.D[cw + g + 8] : 0.f;
-  // phase A (dt projection): accumulator rows = tokens g, g + 8; columns = channels 8 n + 2 tig + {0, 1}
-  uint32_t bfrag[2][KST][2];
-  float bias[2][2];
-  {
-    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const bf16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
-        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
-      }
-      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
-      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
-    }
-  }
-
-  const bf16* ug = reinterpret_cast<const bf16*>(a.u) + (int64_t)b * a.u_bs + cw;
-  const bf16* zg = reinterpret_cast<const bf16*>(a.z) + (int64_t)b * a.z_bs + cw;
-  const bf16* xg = reinterpret_cast<const bf16*>(a.xdbl) + (int64_t)b * a.x_bs;
-  bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
-  constexpr int xchunks = xp_of(R) / 8;
-  const int dir = a.reverse ? -1 : 1;
-  const int p0 = a.reverse ? a.L - 1 : 0;
-  const int u_ts = (int)a.u_ts, z_ts = (int)a.z_ts, x_ts = (int)a.x_ts, y_ts = (int)a.y_ts;
-
-  auto issue_uz = [&](int tile, int st) {
-    const int row = lane >> 1, ch = lane & 1;
-    const int t = tile * kTT + row;
-    const bool ok = t < L;
-    const int prow = ok ? p0 + dir * t : 0;
-    cp_async16(sbase + sp.u(st) + row * kRowBytes + ch * 16, ug + (prow * u_ts + ch * 8), ok);
-    if (!kStateOnly)
-      cp_async16(sbase + sp.z(st) + row * kRowBytes + ch * 16, zg + (prow * z_ts + ch * 8), ok);
-  };
-  auto issue_x = [&](int tile) {
-    const int row = lane >> 1, ch = lane & 1;
-    const int t = tile * kTT + row;
-    const bool ok = t < L;
-    const bf16* src = xg + (ok ? p0 + dir * t : 0) * x_ts;
-#pragma unroll
-    for (int k = ch; k < xchunks; k += 2) cp_async16(sbase + sp.x0 + row * xrow + k * 16, src + k * 8, ok);
-  };
-
-  const int tile_lo = tbeg / kTT;
-  const int ntiles = (L + kTT - 1) / kTT;
-  issue_uz(tile_lo, 0);
-  issue_x(tile_lo);
-  cp_async_commit();
-  float sum_a = 0.f, sum_b = 0.f;
-  bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
-
-  for (int tile = tile_lo; tile < ntiles; ++tile) {
-    const int st = (tile - tile_lo) & 1;
-    const int t0 = tile * kTT;
-    cp_async_wait<0>();
-    __syncwarp();                                  // tile landed; last tile's smem readers are done
-    const uint8_t* su = smem + sp.u(st);
-    const uint8_t* sz = smem + sp.z(st);
-    const uint8_t* sx = smem + sp.x0;
-
-    // ---- B_t of the tile to fp32, in fragment order (a lane's 4 states contiguous) --------------
-#pragma unroll
-    for (int i = 0; i < (kTT * kN / 2) / kThreads; ++i) {         // 16 tokens x 8 bf16 pairs
-      const int e = lane + i * kThreads;
-      const int row = e >> 3, p = e & 7;                          // pair p = states 2p, 2p + 1
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(sx + row * xrow + (R + 2 * p) * 2);
-      // states 2 tig + e -> slot 4 tig + e; states 2 tig + 8 + e -> slot 4 tig + 2 + e
-      const int slot = (p & 3) * 4 + (p >> 2) * 2;
-      *reinterpret_cast<float2*>(smem + sp.b + row * (kN * 4) + slot * 4) = make_float2(bf16lo(v), bf16hi(v));
-    }
-    if constexpr (!kStateOnly) {                   // C_t stays bf16: keep a copy, the raw rows are refilled
-#pragma unroll
-      for (int i = 0; i < (kTT * kN / 2) / kThreads; ++i) {
-        const int e = lane + i * kThreads;
-        const int row = e >> 3, p = e & 7;
-        *reinterpret_cast<uint32_t*>(smem + sp.c + row * (kN * 2) + p * 4) =
-            *reinterpret_cast<const uint32_t*>(sx + row * xrow + (R + kN + 2 * p) * 2);
-      }
-    }
-    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
-    {
-      float acc[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        uint32_t af[4];
-        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-        ldmatrix_x4(sbase + sp.x0 + row * xrow + (16 * ks + 8 * (lane >> 4)) * 2, af);
-        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int tl = g + 8 * half;                              // token row within the tile
-        const bool pad = t0 + tl >= L;
-        const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + tl * kRowBytes + (2 * tig) * 2);
-        const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + tl * kRowBytes + (8 + 2 * tig) * 2);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {                             // channels 2 tig + i and 8 + 2 tig + i
-          float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
-          float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
-          if (pad) { da = 0.f; db = 0.f; }                        // padding: decay 1, drive 0
-          const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
-          *reinterpret_cast<float4*>(smem + sp.dd + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
-              make_float4(da, da * uav, db, db * ubv);
-        }
-      }
-    }
-    __syncwarp();                                  // B / C / dd tiles visible; raw x_dbl rows no longer needed
-    if (tile + 1 < ntiles) {                       // prefetch the next tile behind the recurrence
-      issue_uz(tile + 1, st ^ 1);
-      issue_x(tile + 1);
-    }
-    cp_async_commit();
-
-    // ---- phase B: the recurrence; <C, h> by one HMMA per token -------------------------------------
-    const uint8_t* sdd0 = smem + sp.dd + (g << 4);                // even tokens
-    const uint8_t* sdd1 = smem + sp.dd + ((g ^ 1) << 4);          // odd tokens
-    const uint8_t* sb = smem + sp.b + tig * 16;
-    const uint8_t* sc = smem + sp.c + tig * 4;                    // C_t words (2 tig, 2 tig + 1), (2 tig + 8, + 9)
-#pragma unroll
-    for (int tg = 0; tg < kTT; tg += 4) {
-      float ya = 0.f, yb = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = tg + i;
-        const float4 dd = *reinterpret_cast<const float4*>(((t & 1) ? sdd1 : sdd0) + t * 128);
-        const float4 Bv = *reinterpret_cast<const float4*>(sb + t * (kN * 4));
-        const float2 da2 = make_float2(dd.x, dd.x), db2 = make_float2(dd.z, dd.z);
-        const float2 xa0 = __fmul2_rn(da2, Aa[0]), xa1 = __fmul2_rn(da2, Aa[1]);
-        const float2 xb0 = __fmul2_rn(db2, Ab[0]), xb1 = __fmul2_rn(db2, Ab[1]);
-        const float2 ea0 = make_float2(ex2_approx(xa0.x), ex2_approx(xa0.y));
-        const float2 ea1 = make_float2(ex2_approx(xa1.x), ex2_approx(xa1.y));
-        const float2 eb0 = make_float2(ex2_approx(xb0.x), ex2_approx(xb0.y));
-        const float2 eb1 = make_float2(ex2_approx(xb1.x), ex2_approx(xb1.y));
-        const float2 dua = make_float2(dd.y, dd.y), dub = make_float2(dd.w, dd.w);
-        const float2 B01 = make_float2(Bv.x, Bv.y), B89 = make_float2(Bv.z, Bv.w);
-        ha[0] = __ffma2_rn(ea0, ha[0], __fmul2_rn(dua, B01));
-        ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
-        hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
-        hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
-        if constexpr (kStateOnly) {
-          sum_a += dd.x;
-          sum_b += dd.z;
-        } else {
-          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
-          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
-          const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
-                                  pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
-          float d[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(d, af, c0, c1);           // every column of the B operand is C_t: d[0] = y(ca), d[2] = y(cb)
-          if (tig == i) { ya = d[0]; yb = d[2]; }
-        }
-      }
-      if constexpr (!kStateOnly) {
-        // lane tig finalises token tg + tig of its two channels
-        const int tf = tg + tig;
-        const float ua = __bfloat162float(*reinterpret_cast<const bf16*>(su + tf * kRowBytes + g * 2));
-        const float ub = __bfloat162float(*reinterpret_cast<const bf16*>(su + tf * kRowBytes + (g + 8) * 2));
-        const float za = __bfloat162float(*reinterpret_cast<const bf16*>(sz + tf * kRowBytes + g * 2));
-        const float zb = __bfloat162float(*reinterpret_cast<const bf16*>(sz + tf * kRowBytes + (g + 8) * 2));
-        sy[tf * (kRowBytes / 2) + g] = __float2bfloat16_rn(fmaf(Da, ua, ya) * silu_fast(za));
-        sy[tf * (kRowBytes / 2) + g + 8] = __float2bfloat16_rn(fmaf(Db, ub, yb) * silu_fast(zb));
-      }
-    }
-    if constexpr (!kStateOnly) {
-      __syncwarp();
-      const int row = lane >> 1, ch = lane & 1;
-      const int t = t0 + row;
-      if (t < L)
-        *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
-            *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
-    }
-    // the __syncwarp at the top of the next iteration orders these reads before the next writes
-  }
-
-  auto st_h = [&](float* dst) {
-    *reinterpret_cast<float2*>(dst + hoff_a) = ha[0];
-    *reinterpret_cast<float2*>(dst + hoff_a + 8) = ha[1];
-    *reinterpret_cast<float2*>(dst + hoff_b) = hb[0];
-    *reinterpret_cast<float2*>(dst + hoff_b + 8) = hb[1];
-  };
-  if constexpr (kStateOnly) {
-    st_h(wsH + seg * seg_stride);
-    if (tig == 0) {
-      float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + cw + g;
-      ss[0] = sum_a;
-      ss[8] = sum_b;
-    }
-    return;
-  }
-  if (seg != a.nseg - 1) return;
-  if (a.h_last != nullptr) st_h(a.h_last);
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) {}
+}
+// wait with back-off: a helper warp that is ahead must not spin on the issue slots the consumer needs
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) __nanosleep(256);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
-}  // namespace v9
+// ---- decay factors --------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ex2_pair(float2 x) { return make_float2(ex2_approx(x.x), ex2_approx(x.y)); }
+
+// 2^x for x <= 0 on the FMA / ALU pipes, two values per instruction: Cody-Waite split x = n + f with
+// n = round(x) (magic-number add), 2^f on [-0.5, 0.5] by the degree-3 minimax polynomial constrained to
+// p(0) = 1 (relative error 1.0e-4; the decay RATE log2(p) is within 4.5e-4 relative for every f, so
+// slowly decaying states keep their time constant), exponent inserted by an integer add.  The clamp
+// keeps n inside the exponent field (results below 2^-125 are indistinguishable from 0 here).
+__device__ __forceinline__ float2 exp2_poly_pair(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);          // 1.5 * 2^23
+  const float2 t = __fadd2_rn(x, magic);                             // low mantissa bits = round(x)
+  const float2 nf = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-nf.x, -nf.y));
+  float2 p = make_float2(0.05500893294811249f, 0.05500893294811249f);
+  p = __ffma2_rn(p, f, make_float2(0.2422109693288803f, 0.2422109693288803f));
+  p = __ffma2_rn(p, f, make_float2(0.6932829022407532f, 0.6932829022407532f));
+  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
+// The state a lane carries: its 2 channels (a = g, b = g + 8 of the unit) x 4 states, packed as
+// (a, b) pairs per state; A holds the matching A2 = A * log2(e) entries.
+template <int kExp, bool kStateOnly>
+struct Lane {
+  float2 A[4];      // general: A2 of states {2tig, 2tig+1, 2tig+8, 2tig+9}; geometric: [0] = state 2tig, [1] = state 0
+  float2 h[4];
+  float sum_a, sum_b;
+
+  __device__ __forceinline__ void init(const FastScanArgs& a, int ch_a, int tig, int64_t hoff_a,
+                                       const float* h_in /* fp32 carry or nullptr */) {
+    const float* pa = a.A2 + (int64_t)ch_a * kN;
+    const float* pb = pa + 8 * kN;
+    if constexpr (kExp == kExpGeo) {
+      A[0] = make_float2(pa[2 * tig], pb[2 * tig]);
+      A[1] = make_float2(pa[0], pb[0]);
+      A[2] = A[3] = make_float2(0.f, 0.f);
+    } else {
+      const int n[4] = {2 * tig, 2 * tig + 1, 2 * tig + 8, 2 * tig + 9};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) A[i] = make_float2(pa[n[i]], pb[n[i]]);
+    }
+    const int64_t hoff_b = hoff_a + 8 * kN;
+    auto ld = [&](int64_t off) -> float {
+      if (kStateOnly) return 0.f;
+      if (h_in) return h_in[off];
+      return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
+    };
+    h[0] = make_float2(ld(hoff_a), ld(hoff_b));
+    h[1] = make_float2(ld(hoff_a + 1), ld(hoff_b + 1));
+    h[2] = make_float2(ld(hoff_a + 8), ld(hoff_b + 8));
+    h[3] = make_float2(ld(hoff_a + 9), ld(hoff_b + 9));
+    sum_a = sum_b = 0.f;
+  }
+
+  __device__ __forceinline__ void store(float* dst, int64_t hoff_a) const {
+    const int64_t hoff_b = hoff_a + 8 * kN;
+    *reinterpret_cast<float2*>(dst + hoff_a) = make_float2(h[0].x, h[1].x);
+    *reinterpret_cast<float2*>(dst + hoff_a + 8) = make_float2(h[2].x, h[3].x);
+    *reinterpret_cast<float2*>(dst + hoff_b) = make_float2(h[0].y, h[1].y);
+    *reinterpret_cast<float2*>(dst + hoff_b + 8) = make_float2(h[2].y, h[3].y);
+  }
+
+  // dd = {delta_a, delta_b, du_a, du_b}; Bv = B_t of the lane's four states; c0 / c1 = the lane's
+  // bf16 pairs of C_t (mma B fragment).  d[0] / d[2] return <C_t, h_t> of channels a / b.
+  __device__ __forceinline__ void token(const float4 dd, const float4 Bv, uint32_t c0, uint32_t c1,
+                                        float (&d)[4]) {
+    const float2 dab = make_float2(dd.x, dd.y), du = make_float2(dd.z, dd.w);
+    float2 e[4];
+    if constexpr (kExp == kExpGeo) {
+      const float2 e1 = ex2_pair(__fmul2_rn(dab, A[0]));       // r^(2tig+1)
+      const float2 r = ex2_pair(__fmul2_rn(dab, A[1]));        // r = 2^(delta * A2[0])
+      const float2 r2 = __fmul2_rn(r, r), r4 = __fmul2_rn(r2, r2), r8 = __fmul2_rn(r4, r4);
+      e[0] = e1;
+      e[1] = __fmul2_rn(e1, r);
+      e[2] = __fmul2_rn(e1, r8);
+      e[3] = __fmul2_rn(e[1], r8);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = __fmul2_rn(dab, A[i]);
+        // the polynomial takes the high-index (usually fastest decaying) states first
+        if (i >= 4 - kExp) e[i] = exp2_poly_pair(x);
+        else e[i] = ex2_pair(x);
+      }
+    }
+    h[0] = __ffma2_rn(e[0], h[0], __fmul2_rn(du, make_float2(Bv.x, Bv.x)));
+    h[1] = __ffma2_rn(e[1], h[1], __fmul2_rn(du, make_float2(Bv.y, Bv.y)));
+    h[2] = __ffma2_rn(e[2], h[2], __fmul2_rn(du, make_float2(Bv.z, Bv.z)));
+    h[3] = __ffma2_rn(e[3], h[3], __fmul2_rn(du, make_float2(Bv.w, Bv.w)));
+    if constexpr (kStateOnly) {
+      sum_a += dd.x;
+      sum_b += dd.y;
+    } else {
+      const uint32_t af[4] = {pack_bf16x2(h[0].x, h[1].x), pack_bf16x2(h[0].y, h[1].y),
+                              pack_bf16x2(h[2].x, h[3].x), pack_bf16x2(h[2].y, h[3].y)};
+      d[0] = d[1] = d[2] = d[3] = 0.f;
+      mma_bf16_16816(d, af, c0, c1);
+    }
+  }
+};
+
+// phase A of one tile for one warp: dt projection on the tensor pipe, softplus, delta * u -> sdd.
+// xa_addr: ldmatrix addresses (per k-step) of the x_dbl tile; su: u tile (dense 32-byte rows).
+template <int KST, bool kRev>
+__device__ __forceinline__ void phase_a(const uint32_t (&xa_addr)[KST], const uint32_t (&bfrag)[2][KST][2],
+                                        const float (&bias)[2][2], const uint8_t* su, uint8_t* sdd,
+                                        int g, int tig, int t0, int L) {
+  float acc[2][4];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KST; ++ks) {
+    uint32_t af[4];
+    ldmatrix_x4(xa_addr[ks], af);
+    mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
+    mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int tl = g + 8 * half;                              // token row within the tile
+    const int sr = kRev ? kTT - 1 - tl : tl;
+    const bool pad = t0 + tl >= L;
+    const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + sr * 32 + (2 * tig) * 2);
+    const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + sr * 32 + (8 + 2 * tig) * 2);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
+      float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
+      if (pad) { da = 0.f; db = 0.f; }
+      const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
+      // entry of channel pair (2tig + i, 2tig + i + 8) of token tl; the XOR keeps the 128-bit reads of
+      // the recurrence (8 pairs x 16 B per token) and these writes conflict free
+      *reinterpret_cast<float4*>(sdd + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
+          make_float4(da, db, da * uav, db * ubv);
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void load_wdt(const FastScanArgs& a, int cw, int g, int tig,
+                                         uint32_t (&bfrag)[2][(R + 15) / 16][2], float (&bias)[2][2]) {
+  constexpr int KST = (R + 15) / 16;
+  const __nv_bfloat16* wd = reinterpret_cast<const __nv_bfloat16*>(a.w_dt_pad);
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    const __nv_bfloat16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
+#pragma unroll
+    for (int ks = 0; ks < KST; ++ks) {
+      bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
+      bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
+    }
+    bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
+    bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
+  }
+}
 
 // =================================================================================================
-// v10 = v9 with the tiles staged by TMA.  ncu on v9: 62 % of all shared-memory wavefronts are the
-// cp.async row gathers (24 wavefronts per LDGSTS: every 32-byte sector that returns from L2 is its
-// own write), and the LSU / MIO path is the resource the recurrence's own loads queue on.  Here one
-// lane issues three cp.async.bulk.tensor box copies per tile (u 16 x 16, z 16 x 16, x_dbl Xp x 16)
-// that complete on an mbarrier; rows beyond the sequence are zero-filled by the TMA unit, the
-// reversed direction loads the box in memory order and the consumers mirror the row index
-// (compile-time kRev, so every shared-memory offset stays an immediate).  The x_dbl tile is dense
-// (128-byte rows at dt_rank 24: loaded with the 128-byte swizzle and read through the same XOR, so
-// ldmatrix and the B / C gathers stay conflict free); u / z rows are dense 32-byte rows.
+// scan1w: one warp per unit.
 // =================================================================================================
-namespace v10 {
+namespace one_warp {
 
 struct Plan {
   int x0, u0, z0, b, c, dd, y, bar, total, xb;
@@ -904,54 +306,27 @@ __host__ __device__ constexpr Plan plan(int Xp) {
   p.x0 = off; off += kTT * p.xb;                  // 1024-byte aligned (swizzle atom) -- base of the carve-up
   p.u0 = off; off += 2 * kTT * 32;
   p.z0 = off; off += 2 * kTT * 32;
-  p.b = off; off += kTT * kN * 4;
-  p.c = off; off += kTT * kN * 2;
-  p.dd = off; off += kTT * 8 * 16;
+  p.b = off; off += kTT * kN * 4;                 // [token][tig][B(2tig), B(2tig+1), B(2tig+8), B(2tig+9)] fp32
+  p.c = off; off += kTT * kN * 2;                 // [token][C0..15] bf16, as in the row
+  p.dd = off; off += kTT * 8 * 16;                // [token][pair ^ (token & 1)]{delta_a, delta_b, du_a, du_b}
   p.y = off; off += kTT * kRowBytes;
   p.bar = off; off += 16;                         // two mbarriers (one per stage)
   p.total = off + 1024;                           // + alignment slack
   return p;
 }
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
-                                            int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-template <int R, bool kStateOnly, bool kRev>
-__global__ void __launch_bounds__(kThreads, 18)
-scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
+template <int R, bool kStateOnly, bool kRev, int kExp>
+__global__ void __launch_bounds__(32, 18)
+scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int KST = (R + 15) / 16;
-  constexpr Plan sp = plan(v9::xp_of(R));
+  constexpr Plan sp = plan(xp_of(R));
   constexpr int XB = sp.xb;
   constexpr bool kSwz = XB == 128;                // 128-byte rows: TMA 128B swizzle
   const uint32_t sbase = (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) + 1023u) & ~1023u;
   uint8_t* const smem = smem_raw + (sbase - static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)));
   using bf16 = __nv_bfloat16;
-  using v9::pack_bf16x2;
 
   const int lane = threadIdx.x;
   const int g = lane >> 2, tig = lane & 3;
@@ -965,42 +340,13 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
   const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
 
-  float2 Aa[2], Ab[2], ha[2], hb[2];
+  Lane<kExp, kStateOnly> st;
   const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
-  const int64_t hoff_b = hoff_a + 8 * kN;
-  {
-    const float* pa = a.A2 + (int64_t)(cw + g) * kN + 2 * tig;
-    Aa[0] = *reinterpret_cast<const float2*>(pa);
-    Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
-    Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
-    Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
-    auto ld = [&](int64_t off) -> float {
-      if (kStateOnly) return 0.f;
-      if (seg > 0) return wsHin[seg * seg_stride + off];
-      return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
-    };
-    ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
-    ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
-    hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
-    hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
-  }
+  st.init(a, cw + g, tig, hoff_a, seg > 0 ? wsHin + seg * seg_stride : nullptr);
   const float Da = a.D ? a.D[cw + g] : 0.f, Db = a.D ? a.D[cw + g + 8] : 0.f;
   uint32_t bfrag[2][KST][2];
   float bias[2][2];
-  {
-    const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
-#pragma unroll
-    for (int n = 0; n < 2; ++n) {
-      const bf16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
-        bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
-      }
-      bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
-      bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
-    }
-  }
+  load_wdt<R>(a, cw, g, tig, bfrag, bias);
 
   bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
   const int dir = kRev ? -1 : 1;
@@ -1023,19 +369,18 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue = [&](int tile, int st) {              // lane 0 only
+  auto issue = [&](int tile, int stg) {            // lane 0 only
     const int row0 = kRev ? a.L - kTT - tile * kTT : tile * kTT;   // first memory row of the box (may be < 0)
-    const uint32_t bar = bar0 + 8 * st;
+    const uint32_t bar = bar0 + 8 * stg;
     mbar_expect_tx(bar, kTileBytes);
     tma_load_3d(sbase + sp.x0, &map_x, bar, 0, row0, b);
-    tma_load_3d(sbase + sp.u(st), &map_u, bar, cw, row0, b);
-    if (!kStateOnly) tma_load_3d(sbase + sp.z(st), &map_z, bar, cw, row0, b);
+    tma_load_3d(sbase + sp.u(stg), &map_u, bar, cw, row0, b);
+    if (!kStateOnly) tma_load_3d(sbase + sp.z(stg), &map_z, bar, cw, row0, b);
   };
 
   const int tile_lo = tbeg / kTT;
   const int ntiles = (L + kTT - 1) / kTT;
   if (lane == 0) issue(tile_lo, 0);
-  float sum_a = 0.f, sum_b = 0.f;
   bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
 
   // loop-invariant per-lane offsets
@@ -1059,12 +404,12 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
 
   for (int tile = tile_lo; tile < ntiles; ++tile) {
     const int it = tile - tile_lo;
-    const int st = it & 1;
+    const int stg = it & 1;
     const int t0 = tile * kTT;
-    mbar_wait(bar0 + 8 * st, (it >> 1) & 1);
+    mbar_wait(bar0 + 8 * stg, (it >> 1) & 1);
     __syncwarp();                                  // tile landed; last tile's smem readers are done
-    const uint8_t* su = smem + sp.u(st);
-    const uint8_t* sz = smem + sp.z(st);
+    const uint8_t* su = smem + sp.u(stg);
+    const uint8_t* sz = smem + sp.z(stg);
     const uint8_t* sx = smem + sp.x0;
 
     // ---- B_t of the tile to fp32, in fragment order (a lane's 4 states contiguous) --------------
@@ -1080,41 +425,11 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         *reinterpret_cast<uint32_t*>(smem + sp.c + (gr + 4 * i) * (kN * 2) + gp * 4) =
             *reinterpret_cast<const uint32_t*>(sx + xc_off[i & 1] + (i >> 1) * kRow8);
     }
-    // ---- phase A: delta = softplus(dt_low . w_dt + bias), du = delta * u (tensor pipe) ----------
-    {
-      float acc[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KST; ++ks) {
-        uint32_t af[4];
-        ldmatrix_x4(xa_addr[ks], af);
-        mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-        mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int tl = g + 8 * half;                              // token row within the tile
-        const bool pad = t0 + tl >= L;
-        const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (2 * tig) * 2);
-        const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (8 + 2 * tig) * 2);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
-          float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
-          if (pad) { da = 0.f; db = 0.f; }
-          const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
-          *reinterpret_cast<float4*>(smem + sp.dd + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
-              make_float4(da, da * uav, db, db * ubv);
-        }
-      }
-    }
+    phase_a<KST, kRev>(xa_addr, bfrag, bias, su, smem + sp.dd, g, tig, t0, L);
     __syncwarp();                                  // B / C / dd tiles visible; raw x_dbl rows no longer needed
     if (tile + 1 < ntiles && lane == 0) {          // prefetch the next tile behind the recurrence
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our reads before the TMA's writes
-      issue(tile + 1, st ^ 1);
+      issue(tile + 1, stg ^ 1);
     }
 
     // ---- phase B: the recurrence; <C, h> by one HMMA per token -------------------------------------
@@ -1130,29 +445,14 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         const int t = tg + i;
         const float4 dd = *reinterpret_cast<const float4*>(((t & 1) ? sdd1 : sdd0) + t * 128);
         const float4 Bv = *reinterpret_cast<const float4*>(sb + t * (kN * 4));
-        const float2 da2 = make_float2(dd.x, dd.x), db2 = make_float2(dd.z, dd.z);
-        const float2 xa0 = __fmul2_rn(da2, Aa[0]), xa1 = __fmul2_rn(da2, Aa[1]);
-        const float2 xb0 = __fmul2_rn(db2, Ab[0]), xb1 = __fmul2_rn(db2, Ab[1]);
-        const float2 ea0 = make_float2(ex2_approx(xa0.x), ex2_approx(xa0.y));
-        const float2 ea1 = make_float2(ex2_approx(xa1.x), ex2_approx(xa1.y));
-        const float2 eb0 = make_float2(ex2_approx(xb0.x), ex2_approx(xb0.y));
-        const float2 eb1 = make_float2(ex2_approx(xb1.x), ex2_approx(xb1.y));
-        const float2 dua = make_float2(dd.y, dd.y), dub = make_float2(dd.w, dd.w);
-        const float2 B01 = make_float2(Bv.x, Bv.y), B89 = make_float2(Bv.z, Bv.w);
-        ha[0] = __ffma2_rn(ea0, ha[0], __fmul2_rn(dua, B01));
-        ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
-        hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
-        hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
-        if constexpr (kStateOnly) {
-          sum_a += dd.x;
-          sum_b += dd.z;
-        } else {
-          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
-          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
-          const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
-                                  pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
-          float d[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(d, af, c0, c1);
+        uint32_t c0 = 0, c1 = 0;
+        if constexpr (!kStateOnly) {
+          c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
+          c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
+        }
+        float d[4];
+        st.token(dd, Bv, c0, c1, d);
+        if constexpr (!kStateOnly) {
           if (tig == i) { ya = d[0]; yb = d[2]; }
         }
       }
@@ -1179,43 +479,36 @@ scan10_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     }
   }
 
-  auto st_h = [&](float* dst) {
-    *reinterpret_cast<float2*>(dst + hoff_a) = ha[0];
-    *reinterpret_cast<float2*>(dst + hoff_a + 8) = ha[1];
-    *reinterpret_cast<float2*>(dst + hoff_b) = hb[0];
-    *reinterpret_cast<float2*>(dst + hoff_b + 8) = hb[1];
-  };
   if constexpr (kStateOnly) {
-    st_h(wsH + seg * seg_stride);
+    st.store(wsH + seg * seg_stride, hoff_a);
     if (tig == 0) {
       float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + cw + g;
-      ss[0] = sum_a;
-      ss[8] = sum_b;
+      ss[0] = st.sum_a;
+      ss[8] = st.sum_b;
     }
     return;
   }
   if (seg != a.nseg - 1) return;
-  if (a.h_last != nullptr) st_h(a.h_last);
+  if (a.h_last != nullptr) st.store(a.h_last, hoff_a);
 }
 
-}  // namespace v10
+}  // namespace one_warp
 
 // =================================================================================================
-// v11 = v10 split over TWO warps per CTA.  In v10 one warp runs, per 16-token tile, the B / C
-// gathers, phase A (dt projection + softplus), the recurrence and the finalisation one after the
-// other; the recurrence is latency bound (dependent MUFU / FFMA2 chains) and everything else sits
-// in the same in-order instruction stream.  Here a HELPER warp does everything that does not
-// depend on the state -- TMA issue, gathers, phase A for tile i, then + D*u, * SiLU(z) and the
-// store of tile i - 1 -- while the CONSUMER warp only runs the recurrence and the <C, h>
-// contraction, handing the raw sums back through shared memory.  dd / B / C / y_raw tiles are double
-// buffered, u / z triple buffered (read by the helper one tile later), two mbarrier pairs carry the
-// hand-over.  Unsplit sequences only (the sequence split keeps v10).
+// scan2w: TWO warps per unit.  In scan1w one warp runs, per 16-token tile, the B / C gathers, phase A,
+// the recurrence and the finalisation one after the other; the recurrence is latency bound (dependent
+// MUFU / FFMA2 chains) and everything else sits in the same in-order instruction stream.  Here a
+// HELPER warp does everything that does not depend on the state -- TMA issue, gathers, phase A for
+// tile i, then + D*u, * SiLU(z) and the store of tile i - 1 -- while the CONSUMER warp only runs the
+// recurrence and the <C, h> contraction, handing the raw sums back through shared memory.  dd / B /
+// C / y_raw tiles are double buffered, u / z triple buffered (read by the helper one tile later), two
+// mbarrier pairs carry the hand-over.
 // =================================================================================================
-namespace v11 {
+namespace two_warp {
 
 struct Plan {
   int x0, u0, z0, b, c, dd, yr, bar, total, xb;
-  __host__ __device__ constexpr int x(int s) const { return x0 + s * (kTT * xb); }
+  __host__ __device__ constexpr int x(int s) const { return x0 + s * ((kTT * xb + 1023) / 1024 * 1024); }
   __host__ __device__ constexpr int u(int s) const { return u0 + s * (kTT * 32); }
   __host__ __device__ constexpr int z(int s) const { return z0 + s * (kTT * 32); }
   __host__ __device__ constexpr int B(int s) const { return b + s * (kTT * kN * 4); }
@@ -1235,48 +528,23 @@ __host__ __device__ constexpr Plan plan(int Xp) {
   p.c = off; off += 2 * kTT * kN * 2;
   p.dd = off; off += 2 * kTT * 8 * 16;
   p.yr = off; off += 2 * kTT * kCh * 4;               // raw <C, h> sums, fp32 [token][channel]
-  p.bar = off; off += 64;                             // tma[3], full[2], done[2]
+  p.bar = off; off += 64;                             // tma[3], full[2], done[2], warp slot ids
   p.total = off + 1024;
   return p;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// wait with back-off: a helper warp that is ahead must not spin on the issue slots the consumer needs
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(256);
-  }
-}
-
-template <int R, bool kStateOnly, bool kRev>
+template <int R, bool kStateOnly, bool kRev, int kExp>
 __global__ void __launch_bounds__(64, 11)
-scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
+scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int KST = (R + 15) / 16;
-  constexpr int XB = v9::xp_of(R) * 2;
-  constexpr int XT = (kTT * XB + 1023) / 1024 * 1024;
-  constexpr Plan sp = plan(v9::xp_of(R));
+  constexpr int XB = xp_of(R) * 2;
+  constexpr Plan sp = plan(xp_of(R));
   constexpr bool kSwz = XB == 128;
   const uint32_t sbase = (static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)) + 1023u) & ~1023u;
   uint8_t* const smem = smem_raw + (sbase - static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw)));
   using bf16 = __nv_bfloat16;
-  using v9::pack_bf16x2;
-  using v10::mbar_expect_tx;
-  using v10::mbar_init;
-  using v10::mbar_wait;
-  using v10::tma_load_3d;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1327,25 +595,13 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   };
   const int dir = kRev ? -1 : 1;
   const int p0 = kRev ? a.L - 1 : 0;
+  const int nit = ntiles - tile_lo;
 
   if (is_helper) {
     // ================================ helper ================================
     uint32_t bfrag[2][KST][2];
     float bias[2][2];
-    {
-      const bf16* wd = reinterpret_cast<const bf16*>(a.w_dt_pad);
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const bf16* wr = wd + (int64_t)(cw + 8 * n + g) * a.Rp;
-#pragma unroll
-        for (int ks = 0; ks < KST; ++ks) {
-          bfrag[n][ks][0] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 2 * tig);
-          bfrag[n][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 16 * ks + 8 + 2 * tig);
-        }
-        bias[n][0] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig] : 0.f;
-        bias[n][1] = a.dt_bias ? a.dt_bias[cw + 8 * n + 2 * tig + 1] : 0.f;
-      }
-    }
+    load_wdt<R>(a, cw, g, tig, bfrag, bias);
     // finalisation: lane = (token row lane >> 1, channel half lane & 1): 8 channels of one token
     const int frow = lane >> 1, fch = (lane & 1) * 8;
     float Dv[8];
@@ -1365,7 +621,6 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
       tma_load_3d(sbase + sp.u(it % 3), &map_u, bar, cw, row0, b);
       if (!kStateOnly) tma_load_3d(sbase + sp.z(it % 3), &map_z, bar, cw, row0, b);
     };
-    const int nit = ntiles - tile_lo;
     if (lane == 0) {
       issue(0);
       if (nit > 1) issue(1);
@@ -1415,35 +670,11 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               *reinterpret_cast<const uint32_t*>(sx + xoff(gr + 4 * (i & 1), (R + kN + 2 * gp) * 2) + (i >> 1) * kRow8);
       }
       {
-        float acc[2][4];
+        uint32_t xa_addr[KST];
+        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KST; ++ks) {
-          uint32_t af[4];
-          const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-          ldmatrix_x4(sbase + sp.x(pb) + xoff(row, 32 * ks + 16 * (lane >> 4)), af);
-          mma_bf16_16816(acc[0], af, bfrag[0][ks][0], bfrag[0][ks][1]);
-          mma_bf16_16816(acc[1], af, bfrag[1][ks][0], bfrag[1][ks][1]);
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int tl = g + 8 * half;
-          const bool pad = t0 + tl >= L;
-          const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (2 * tig) * 2);
-          const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + srow(tl) * 32 + (8 + 2 * tig) * 2);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            float da = softplus_mufu(acc[0][2 * half + i] + bias[0][i]);
-            float db = softplus_mufu(acc[1][2 * half + i] + bias[1][i]);
-            if (pad) { da = 0.f; db = 0.f; }
-            const float uav = i ? bf16hi(ua) : bf16lo(ua), ubv = i ? bf16hi(ub) : bf16lo(ub);
-            *reinterpret_cast<float4*>(smem + sp.D(pb) + tl * 128 + (((2 * tig + i) ^ (tl & 1)) << 4)) =
-                make_float4(da, da * uav, db, db * ubv);
-          }
-        }
+        for (int ks = 0; ks < KST; ++ks) xa_addr[ks] = sbase + sp.x(pb) + xoff(row, 32 * ks + 16 * (lane >> 4));
+        phase_a<KST, kRev>(xa_addr, bfrag, bias, su, smem + sp.D(pb), g, tig, t0, L);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(pb));    // tile staged for the consumer
@@ -1459,27 +690,9 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     finalize(nit - 1);
   } else {
     // ================================ consumer ================================
-    float2 Aa[2], Ab[2], ha[2], hb[2];
+    Lane<kExp, kStateOnly> st;
     const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
-    const int64_t hoff_b = hoff_a + 8 * kN;
-    {
-      const float* pa = a.A2 + (int64_t)(cw + g) * kN + 2 * tig;
-      Aa[0] = *reinterpret_cast<const float2*>(pa);
-      Aa[1] = *reinterpret_cast<const float2*>(pa + 8);
-      Ab[0] = *reinterpret_cast<const float2*>(pa + 8 * kN);
-      Ab[1] = *reinterpret_cast<const float2*>(pa + 8 * kN + 8);
-      auto ld = [&](int64_t off) -> float {
-        if (kStateOnly) return 0.f;
-        if (seg > 0) return wsHin[seg * seg_stride + off];
-        return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
-      };
-      ha[0] = make_float2(ld(hoff_a), ld(hoff_a + 1));
-      ha[1] = make_float2(ld(hoff_a + 8), ld(hoff_a + 9));
-      hb[0] = make_float2(ld(hoff_b), ld(hoff_b + 1));
-      hb[1] = make_float2(ld(hoff_b + 8), ld(hoff_b + 9));
-    }
-    float sum_a = 0.f, sum_b = 0.f;
-    const int nit = ntiles - tile_lo;
+    st.init(a, cw + g, tig, hoff_a, seg > 0 ? wsHin + seg * seg_stride : nullptr);
     for (int it = 0; it < nit; ++it) {
       const int pb = it & 1;
       mbar_wait(full_bar(pb), (uint32_t)(it >> 1) & 1u);
@@ -1496,29 +709,14 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
           const int t = tg + i;
           const float4 dd = *reinterpret_cast<const float4*>(((t & 1) ? sdd1 : sdd0) + t * 128);
           const float4 Bv = *reinterpret_cast<const float4*>(sb + t * (kN * 4));
-          const float2 da2 = make_float2(dd.x, dd.x), db2 = make_float2(dd.z, dd.z);
-          const float2 xa0 = __fmul2_rn(da2, Aa[0]), xa1 = __fmul2_rn(da2, Aa[1]);
-          const float2 xb0 = __fmul2_rn(db2, Ab[0]), xb1 = __fmul2_rn(db2, Ab[1]);
-          const float2 ea0 = make_float2(ex2_approx(xa0.x), ex2_approx(xa0.y));
-          const float2 ea1 = make_float2(ex2_approx(xa1.x), ex2_approx(xa1.y));
-          const float2 eb0 = make_float2(ex2_approx(xb0.x), ex2_approx(xb0.y));
-          const float2 eb1 = make_float2(ex2_approx(xb1.x), ex2_approx(xb1.y));
-          const float2 dua = make_float2(dd.y, dd.y), dub = make_float2(dd.w, dd.w);
-          const float2 B01 = make_float2(Bv.x, Bv.y), B89 = make_float2(Bv.z, Bv.w);
-          ha[0] = __ffma2_rn(ea0, ha[0], __fmul2_rn(dua, B01));
-          ha[1] = __ffma2_rn(ea1, ha[1], __fmul2_rn(dua, B89));
-          hb[0] = __ffma2_rn(eb0, hb[0], __fmul2_rn(dub, B01));
-          hb[1] = __ffma2_rn(eb1, hb[1], __fmul2_rn(dub, B89));
-          if constexpr (kStateOnly) {
-            sum_a += dd.x;
-            sum_b += dd.z;
-          } else {
-            const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
-            const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
-            const uint32_t af[4] = {pack_bf16x2(ha[0].x, ha[0].y), pack_bf16x2(hb[0].x, hb[0].y),
-                                    pack_bf16x2(ha[1].x, ha[1].y), pack_bf16x2(hb[1].x, hb[1].y)};
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_bf16_16816(d, af, c0, c1);
+          uint32_t c0 = 0, c1 = 0;
+          if constexpr (!kStateOnly) {
+            c0 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2));
+            c1 = *reinterpret_cast<const uint32_t*>(sc + t * (kN * 2) + 16);
+          }
+          float d[4];
+          st.token(dd, Bv, c0, c1, d);
+          if constexpr (!kStateOnly) {
             if (tig == i) { ya = d[0]; yb = d[2]; }
           }
         }
@@ -1530,34 +728,20 @@ scan11_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
       __syncwarp();
       if (lane == 0) mbar_arrive(done_bar(pb));      // raw sums written, dd / B / C tiles pb free
     }
-    auto st_h = [&](float* dst) {
-      *reinterpret_cast<float2*>(dst + hoff_a) = ha[0];
-      *reinterpret_cast<float2*>(dst + hoff_a + 8) = ha[1];
-      *reinterpret_cast<float2*>(dst + hoff_b) = hb[0];
-      *reinterpret_cast<float2*>(dst + hoff_b + 8) = hb[1];
-    };
     if constexpr (kStateOnly) {
-      st_h(wsH + seg * seg_stride);
+      st.store(wsH + seg * seg_stride, hoff_a);
       if (tig == 0) {
         float* ss = wsS + ((int64_t)seg * a.B + b) * a.Di + cw + g;
-        ss[0] = sum_a;
-        ss[8] = sum_b;
+        ss[0] = st.sum_a;
+        ss[8] = st.sum_b;
       }
     } else if (seg == a.nseg - 1 && a.h_last != nullptr) {
-      st_h(a.h_last);
+      st.store(a.h_last, hoff_a);
     }
   }
 }
 
-}  // namespace v11
-
-int variant() {
-  static int v = [] {
-    const char* e = std::getenv("VMB_SCAN_VARIANT");
-    return e ? std::atoi(e) : 0;
-  }();
-  return v;
-}
+}  // namespace two_warp
 
 // Chains the segment carries: Hin[0] = h0, Hin[s+1] = exp2(A2 * S[s]) * Hin[s] + H[s].
 __global__ void scan_carry_kernel(const FastScanArgs a) {
@@ -1580,11 +764,7 @@ __global__ void scan_carry_kernel(const FastScanArgs a) {
 // Segments only when the batch alone cannot fill the GPU (one warp per 16 channels of a sequence).
 void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   const int64_t warps = (int64_t)a.B * (a.Di / kCh);
-  static const int per_sm = [] {
-    const char* e = std::getenv("VMB_SCAN_SPLIT_WARPS");
-    return e ? std::atoi(e) : 12;
-  }();
-  const int64_t want = (int64_t)per_sm * sm_count();      // 12 = 3 warps per scheduler
+  const int64_t want = 12ll * sm_count();       // 3 warps per scheduler
   *nseg = 1;
   *seg_len = (a.L + kTT - 1) / kTT * kTT;
   if (warps >= want || a.L < 768) return;       // a lone warp needs ~230 clk per token, 3 per scheduler ~120 each
@@ -1595,145 +775,81 @@ void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   *seg_len = len;
 }
 
-template <int R, bool kV7>
-int launch(const FastScanArgs& a0, cudaStream_t st) {
-  FastScanArgs a = a0;
-  plan_segments(a, &a.nseg, &a.seg_len);
-  const Smem sp = smem_plan(a.Xp);
-  if (sp.total > 48 * 1024) VMB_UNSUPPORTED("scan_fast: x_dbl rows too wide for the staging buffers");
-  if (a.nseg > 1) {
-    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
-    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
-      a.nseg = 1;                              // no workspace given: run unsplit (still correct)
-      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
-    }
-  }
-  if (a.nseg > 1) {
-    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
-    if (kV7) v7::scan7_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
-    else scan_fast_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
-    VMB_LAUNCH_CHECK("scan_fast_kernel<state>");
-    const int64_t n = (int64_t)a.B * a.Di * kN;
-    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
-    VMB_LAUNCH_CHECK("scan_carry_kernel");
-  }
-  dim3 grid(a.Di / kCh, a.B, a.nseg);
-  if (kV7) v7::scan7_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
-  else scan_fast_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
-  VMB_LAUNCH_CHECK("scan_fast_kernel");
-  return VMB_OK;
-}
-
-template <int R>
-int launch9(const FastScanArgs& a0, cudaStream_t st) {
-  if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);   // unusual x_dbl pitch: v7 takes any
-  FastScanArgs a = a0;
-  plan_segments(a, &a.nseg, &a.seg_len);
-  constexpr v9::Plan sp = v9::plan(v9::xp_of(R));
-  if (sp.total > 48 * 1024) VMB_UNSUPPORTED("scan_fast: x_dbl rows too wide for the staging buffers");
-  if (a.nseg > 1) {
-    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
-    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
-      a.nseg = 1;
-      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
-    }
-  }
-  if (a.nseg > 1) {
-    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
-    v9::scan9_kernel<R, true><<<g1, kThreads, sp.total, st>>>(a);
-    VMB_LAUNCH_CHECK("scan9_kernel<state>");
-    const int64_t n = (int64_t)a.B * a.Di * kN;
-    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
-    VMB_LAUNCH_CHECK("scan_carry_kernel");
-  }
-  dim3 grid(a.Di / kCh, a.B, a.nseg);
-  v9::scan9_kernel<R, false><<<grid, kThreads, sp.total, st>>>(a);
-  VMB_LAUNCH_CHECK("scan9_kernel");
-  return VMB_OK;
-}
-
-// v10 needs dense, 16-byte aligned rows for its tensor maps; everything else takes v9.
-template <int R>
-int launch10(const FastScanArgs& a0, cudaStream_t st) {
-  if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);
-  FastScanArgs a = a0;
-  plan_segments(a, &a.nseg, &a.seg_len);
-  constexpr v10::Plan sp = v10::plan(v9::xp_of(R));
-  if (a.nseg > 1) {
-    const int64_t need = scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N);
-    if (a.seg_ws == nullptr || a.seg_ws_bytes < need) {
-      a.nseg = 1;
-      a.seg_len = (a.L + kTT - 1) / kTT * kTT;
-    }
-  }
-  CUtensorMap mu, mz, mx;
+int tensor_maps(const FastScanArgs& a, CUtensorMap* mu, CUtensorMap* mz, CUtensorMap* mx) {
   const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B;
   auto bs = [&](int64_t v, int64_t ts) { return (uint64_t)((a.B > 1 ? v : ts * a.L) * 2); };
   int rc;
-  if ((rc = make_tensor_map_3d_bf16(&mu, a.u, (uint64_t)a.Di, L, B, (uint64_t)a.u_ts * 2, bs(a.u_bs, a.u_ts),
+  if ((rc = make_tensor_map_3d_bf16(mu, a.u, (uint64_t)a.Di, L, B, (uint64_t)a.u_ts * 2, bs(a.u_bs, a.u_ts),
                                     kCh, kTT, false)))
     return rc;
-  if ((rc = make_tensor_map_3d_bf16(&mz, a.z, (uint64_t)a.Di, L, B, (uint64_t)a.z_ts * 2, bs(a.z_bs, a.z_ts),
+  if ((rc = make_tensor_map_3d_bf16(mz, a.z, (uint64_t)a.Di, L, B, (uint64_t)a.z_ts * 2, bs(a.z_bs, a.z_ts),
                                     kCh, kTT, false)))
     return rc;
-  if ((rc = make_tensor_map_3d_bf16(&mx, a.xdbl, (uint64_t)a.Xp, L, B, (uint64_t)a.x_ts * 2,
-                                    bs(a.x_bs, a.x_ts), (uint32_t)a.Xp, kTT, a.Xp * 2 == 128)))
-    return rc;
-  if (a.nseg > 1) {
-    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
-    if (a.reverse) v10::scan10_kernel<R, true, true><<<g1, kThreads, sp.total, st>>>(a, mu, mz, mx);
-    else v10::scan10_kernel<R, true, false><<<g1, kThreads, sp.total, st>>>(a, mu, mz, mx);
-    VMB_LAUNCH_CHECK("scan10_kernel<state>");
-    const int64_t n = (int64_t)a.B * a.Di * kN;
-    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
-    VMB_LAUNCH_CHECK("scan_carry_kernel");
-  }
-  dim3 grid(a.Di / kCh, a.B, a.nseg);
-  if (a.reverse) v10::scan10_kernel<R, false, true><<<grid, kThreads, sp.total, st>>>(a, mu, mz, mx);
-  else v10::scan10_kernel<R, false, false><<<grid, kThreads, sp.total, st>>>(a, mu, mz, mx);
-  VMB_LAUNCH_CHECK("scan10_kernel");
-  return VMB_OK;
+  return make_tensor_map_3d_bf16(mx, a.xdbl, (uint64_t)a.Xp, L, B, (uint64_t)a.x_ts * 2, bs(a.x_bs, a.x_ts),
+                                 (uint32_t)a.Xp, kTT, a.Xp * 2 == 128);
 }
 
-// v11 (two warps per CTA); odd x_dbl pitches take v7.  split = false forces one segment.
-template <int R>
-int launch11(const FastScanArgs& a0, cudaStream_t st, bool split) {
-  if (a0.Xp != v9::xp_of(R)) return launch<R, true>(a0, st);
+template <int R, int kExp, bool kTwoWarp>
+int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
   FastScanArgs a = a0;
   plan_segments(a, &a.nseg, &a.seg_len);
   if (!split || (a.nseg > 1 && (a.seg_ws == nullptr ||
                                 a.seg_ws_bytes < scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N)))) {
-    a.nseg = 1;
+    a.nseg = 1;                                // no workspace given: run unsplit (still correct)
     a.seg_len = (a.L + kTT - 1) / kTT * kTT;
   }
-  constexpr v11::Plan sp = v11::plan(v9::xp_of(R));
   CUtensorMap mu, mz, mx;
-  const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B;
-  auto bs = [&](int64_t v, int64_t ts) { return (uint64_t)((a.B > 1 ? v : ts * a.L) * 2); };
-  int rc;
-  if ((rc = make_tensor_map_3d_bf16(&mu, a.u, (uint64_t)a.Di, L, B, (uint64_t)a.u_ts * 2, bs(a.u_bs, a.u_ts),
-                                    kCh, kTT, false)))
-    return rc;
-  if ((rc = make_tensor_map_3d_bf16(&mz, a.z, (uint64_t)a.Di, L, B, (uint64_t)a.z_ts * 2, bs(a.z_bs, a.z_ts),
-                                    kCh, kTT, false)))
-    return rc;
-  if ((rc = make_tensor_map_3d_bf16(&mx, a.xdbl, (uint64_t)a.Xp, L, B, (uint64_t)a.x_ts * 2,
-                                    bs(a.x_bs, a.x_ts), (uint32_t)a.Xp, kTT, a.Xp * 2 == 128)))
-    return rc;
+  if (int rc = tensor_maps(a, &mu, &mz, &mx)) return rc;
+  constexpr int smem = kTwoWarp ? two_warp::plan(xp_of(R)).total : one_warp::plan(xp_of(R)).total;
+  constexpr int threads = kTwoWarp ? 64 : 32;
+  auto run = [&](dim3 grid, auto state_only) {
+    constexpr bool kSO = decltype(state_only)::value;
+    if constexpr (kTwoWarp) {
+      if (a.reverse) two_warp::scan2w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      else two_warp::scan2w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+    } else {
+      if (a.reverse) one_warp::scan1w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      else one_warp::scan1w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+    }
+  };
   if (a.nseg > 1) {
-    dim3 g1(a.Di / kCh, a.B, a.nseg - 1);
-    if (a.reverse) v11::scan11_kernel<R, true, true><<<g1, 64, sp.total, st>>>(a, mu, mz, mx);
-    else v11::scan11_kernel<R, true, false><<<g1, 64, sp.total, st>>>(a, mu, mz, mx);
-    VMB_LAUNCH_CHECK("scan11_kernel<state>");
+    run(dim3(a.Di / kCh, a.B, a.nseg - 1), std::true_type{});
+    VMB_LAUNCH_CHECK("scan kernel <state pass>");
     const int64_t n = (int64_t)a.B * a.Di * kN;
     scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
     VMB_LAUNCH_CHECK("scan_carry_kernel");
   }
-  dim3 grid(a.Di / kCh, a.B, a.nseg);
-  if (a.reverse) v11::scan11_kernel<R, false, true><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
-  else v11::scan11_kernel<R, false, false><<<grid, 64, sp.total, st>>>(a, mu, mz, mx);
-  VMB_LAUNCH_CHECK("scan11_kernel");
+  run(dim3(a.Di / kCh, a.B, a.nseg), std::false_type{});
+  VMB_LAUNCH_CHECK("scan kernel");
   return VMB_OK;
+}
+
+template <int R, int kExp>
+int launch_layout(const FastScanArgs& a, cudaStream_t st, bool two_warp, bool split) {
+  return two_warp ? launch<R, kExp, true>(a, st, split) : launch<R, kExp, false>(a, st, split);
+}
+
+template <int R>
+int launch_exp(const FastScanArgs& a, cudaStream_t st, int exp_sel, bool two_warp, bool split) {
+  switch (exp_sel) {
+    case kExpGeo: return launch_layout<R, kExpGeo>(a, st, two_warp, split);
+    case kExpDefault: return launch_layout<R, kExpDefault>(a, st, two_warp, split);
+    default: break;
+  }
+#ifdef VMB_SCAN_LAB
+  // measurement builds only: every general-A evaluator for the Small width (tools/scan_sweep.py)
+  if constexpr (R == 24) {
+    switch (exp_sel) {
+      case 0: return launch_layout<R, 0>(a, st, two_warp, split);
+      case 1: return launch_layout<R, 1>(a, st, two_warp, split);
+      case 2: return launch_layout<R, 2>(a, st, two_warp, split);
+      case 3: return launch_layout<R, 3>(a, st, two_warp, split);
+      case 4: return launch_layout<R, 4>(a, st, two_warp, split);
+      default: break;
+    }
+  }
+#endif
+  VMB_UNSUPPORTED("scan_fast: evaluator %d is not part of this build", exp_sel);
 }
 
 }  // namespace
@@ -1742,14 +858,13 @@ bool scan_fast_supported(const FastScanArgs& a) {
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   const bool r_ok = a.R == 12 || a.R == 24 || a.R == 36;
   const int kst16 = (a.R + 15) / 16 * 16;      // dt projection reads x_dbl / w_dt columns [0, kst16)
-  return a.N == kN && r_ok && a.Di % kCh == 0 && a.Xp % 8 == 0 && a.Xp >= a.R + 2 * kN &&
-         a.Xp >= kst16 && a.Rp >= kst16 && a.Rp % 2 == 0 && a.B >= 1 && a.B <= 65535 && a.L >= 1 &&
+  return a.N == kN && r_ok && a.Di % kCh == 0 && a.Xp == xp_of(a.R) && a.Rp >= kst16 && a.Rp % 2 == 0 &&
+         a.B >= 1 && a.B <= 65535 && a.L >= 1 &&
          a.w_dt_pad != nullptr && reinterpret_cast<uintptr_t>(a.w_dt_pad) % 4 == 0 &&
          al16(a.u) && al16(a.z) && al16(a.xdbl) && al16(a.y) && al16(a.A2) &&
          (a.h_last == nullptr || al16(a.h_last)) &&
          a.u_bs % 8 == 0 && a.u_ts % 8 == 0 && a.z_bs % 8 == 0 && a.z_ts % 8 == 0 &&
-         a.x_bs % 8 == 0 && a.x_ts % 8 == 0 && a.y_bs % 8 == 0 && a.y_ts % 8 == 0 &&
-         variant() != 2;                       // VMB_SCAN_VARIANT=2: never use the fused kernels
+         a.x_bs % 8 == 0 && a.x_ts % 8 == 0 && a.y_bs % 8 == 0 && a.y_ts % 8 == 0;
 }
 
 int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
@@ -1762,50 +877,23 @@ int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {
-  // Auto (variant 0): between 2 and 9.5 (batch, 16-channel) units per SM the two-warp kernel wins
-  // without splitting the sequence (B200, L = 3137 / 6273: -12 % at 7.8 units per SM, -26 % at 2.6, -30 % at
-  // 3.9 for the Middle width); fewer units need the sequence split (v10), more fill the schedulers anyway
-  // and v10's smaller footprint lets two launches share the SMs (profiles/r01_scan_ncu_full_summary.txt).
+  // Layout (tune / 10: 0 automatic, 1 one warp per unit, 2 two warps per unit, 3 two warps + sequence
+  // split).  Automatic: between 2 and 9.5 units per SM the two-warp kernel wins without splitting the
+  // sequence (B200, L = 3137 / 6273: -12 % at 7.8 units per SM, -26 % at 2.6, -30 % at 3.9 for the
+  // Middle width); fewer units need the sequence split, more fill the schedulers anyway and the
+  // one-warp kernel's smaller footprint lets two launches share the SMs (profiles/).
+  const int layout = a.tune / 10, exp_tune = a.tune % 10;
   const int64_t units = (int64_t)a.B * (a.Di / kCh);
-  const bool two_warp = variant() == 11 || (variant() == 0 && 2 * units < 19ll * sm_count());
-  if (two_warp || variant() == 12) {        // 12: v11 everywhere, with the sequence split
-    // below 2 units per SM the sequence split supplies the parallelism (v11 is 2-6 % ahead of v10 there)
-    const bool split = variant() == 12 || (variant() == 0 && units < 2ll * sm_count());
-    switch (a.R) {
-      case 12: return launch11<12>(a, st, split);
-      case 24: return launch11<24>(a, st, split);
-      case 36: return launch11<36>(a, st, split);
-      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
-    }
-  }
-  if (variant() == 0 || variant() == 10) {  // default: v10 = v9's lanes + TMA-staged tiles
-    switch (a.R) {
-      case 12: return launch10<12>(a, st);
-      case 24: return launch10<24>(a, st);
-      case 36: return launch10<36>(a, st);
-      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
-    }
-  }
-  if (variant() == 9) {                     // v9: cp.async staging
-    switch (a.R) {
-      case 12: return launch9<12>(a, st);
-      case 24: return launch9<24>(a, st);
-      case 36: return launch9<36>(a, st);
-      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
-    }
-  }
-  if (variant() == 7) {        // VMB_SCAN_VARIANT=7: v7 (1 channel x 8 states per lane, fp32 contraction); =1: v4
-    switch (a.R) {
-      case 12: return launch<12, true>(a, st);
-      case 24: return launch<24, true>(a, st);
-      case 36: return launch<36, true>(a, st);
-      default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
-    }
-  }
+  const bool two_warp = layout == 2 || layout == 3 || (layout == 0 && 2 * units < 19ll * sm_count());
+  const bool split = layout == 0 ? (!two_warp || units < 2ll * sm_count()) : layout != 2;
+  // Evaluator (tune % 10: 0 automatic, 1..5 = general A with 0..4 polynomial pairs, 9 = geometric).
+  int exp_sel = a.a_geometric ? kExpGeo : kExpDefault;
+  if (exp_tune == 9) exp_sel = kExpGeo;
+  else if (exp_tune >= 1 && exp_tune <= 5) exp_sel = exp_tune - 1;
   switch (a.R) {
-    case 12: return launch<12, false>(a, st);
-    case 24: return launch<24, false>(a, st);
-    case 36: return launch<36, false>(a, st);
+    case 12: return launch_exp<12>(a, st, exp_sel, two_warp, split);
+    case 24: return launch_exp<24>(a, st, exp_sel, two_warp, split);
+    case 36: return launch_exp<36>(a, st, exp_sel, two_warp, split);
     default: VMB_UNSUPPORTED("scan_fast: dt_rank %d not built", a.R);
   }
 }

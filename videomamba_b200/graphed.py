@@ -38,6 +38,10 @@ class GraphedStream:
         self._rows: Optional[Tensor] = None
         self._state: Optional[List[LayerState]] = None
         self._out = None
+        # the graph bakes in the pointers of every mixer's kernel operands: keep those objects alive
+        # and recapture when any of them was rebuilt (parameter update, refresh_weights())
+        self._captured_keys: Optional[list] = None
+        self._captured_weights: Optional[list] = None
 
     # ---- public -------------------------------------------------------------------------
     @property
@@ -67,7 +71,8 @@ class GraphedStream:
         m = self.model
         t_tokens = m._validate_temporal_length(x.shape[2])
         rows = self._temporal_rows(t_tokens, x)
-        if self._graph is None or self._x.shape != x.shape or self._x.dtype != x.dtype:
+        if self._graph is None or self._x.shape != x.shape or self._x.dtype != x.dtype \
+                or self._captured_keys != self._mixer_keys():
             self._capture(x, rows)
         else:
             self._x.copy_(x)
@@ -83,6 +88,12 @@ class GraphedStream:
         if isinstance(state, dict):
             return [state[i] for i in range(len(state))]
         return list(state)
+
+    def _mixers(self):
+        return [mod for mod in self.model.modules() if hasattr(mod, "weights_key")]
+
+    def _mixer_keys(self) -> list:
+        return [mod.weights_key() for mod in self._mixers()]
 
     def _temporal_rows(self, t_tokens: int, x: Tensor) -> Tensor:
         m = self.model
@@ -124,5 +135,7 @@ class GraphedStream:
                     s.copy_(ks)
                 graph.replay()
             self._graph = graph
+            self._captured_keys = self._mixer_keys()
+            self._captured_weights = [mod._kernel_weights() for mod in self._mixers()]
         finally:
             m._temporal_rows_override = None

@@ -101,17 +101,52 @@ class Mamba(nn.Module):
 
         self._weights_key: Optional[tuple] = None
         self._weights: Optional[ops.MixerWeights] = None
+        # load_state_dict copies into the parameters in place: drop the derived copies with it
+        self.register_load_state_dict_post_hook(lambda module, _incompatible: module.refresh_weights())
 
     # ------------------------------------------------------------------------------------------
+    #: debugging aid: when True every forward re-derives the kernel operands and compares them with
+    #: the cached ones (one device sync per call); catches writes that bypass autograd's version
+    #: counter (``param.data.copy_()``, flat-parameter optimisers) without ``refresh_weights()``.
+    verify_weights: bool = False
+
+    def refresh_weights(self) -> None:
+        """Drop the kernel-ready copies derived from the parameters (``A2 = -exp(A_log)*log2(e)``,
+        fp32 ``D`` / ``dt_proj.bias``, zero-padded ``x_proj`` / ``dt_proj`` weights, the geometric-A
+        flag).  They are rebuilt on the next forward.  Called automatically after
+        ``load_state_dict`` and whenever a parameter's storage, dtype or autograd version changes;
+        call it yourself after writing through ``param.data`` (EMA / SWA averaging, flat-parameter
+        frameworks), which bumps no version counter."""
+        self._weights_key = None
+        self._weights = None
+
+    def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .bfloat16() replace the storages
+        self.refresh_weights()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _params(self):
+        return (self.in_proj.weight, self.in_proj.bias, self.conv1d.weight, self.conv1d.bias,
+                self.x_proj.weight, self.dt_proj.weight, self.dt_proj.bias, self.A_log, self.D,
+                self.out_proj.weight, self.out_proj.bias)
+
+    def weights_key(self) -> tuple:
+        """Identity of the parameter storages the cached kernel operands were derived from."""
+        return tuple(None if p is None else (p.data_ptr(), p._version, p.dtype) for p in self._params())
+
     def _kernel_weights(self) -> ops.MixerWeights:
-        """Kernel-ready weights, rebuilt when any parameter changed (value, dtype or device)."""
-        params = (self.in_proj.weight, self.in_proj.bias, self.conv1d.weight, self.conv1d.bias,
-                  self.x_proj.weight, self.dt_proj.weight, self.dt_proj.bias, self.A_log, self.D,
-                  self.out_proj.weight, self.out_proj.bias)
-        key = tuple(None if p is None else (p.data_ptr(), p._version, p.dtype) for p in params)
+        """Kernel-ready weights, rebuilt when any parameter changed (storage, version or dtype)."""
+        key = self.weights_key()
         if key != self._weights_key:
-            self._weights = ops.MixerWeights(*params)
+            self._weights = ops.MixerWeights(*self._params())
             self._weights_key = key
+        elif self.verify_weights:
+            fresh = ops.MixerWeights(*self._params())
+            for name in ("A2", "Dskip", "dt_bias", "w_x_pad", "w_dt_pad"):
+                a, b = getattr(self._weights, name), getattr(fresh, name)
+                if a is not None and not torch.equal(a, b):
+                    raise RuntimeError(
+                        f"Mamba(layer {self.layer_idx}): cached kernel operand {name} is stale -- a parameter "
+                        "was written through .data; call refresh_weights() after such writes.")
         return self._weights
 
     @staticmethod
