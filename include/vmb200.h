@@ -250,6 +250,9 @@ typedef struct vmb_mixer_args {
   int32_t path;        /* 0 = auto, 1 = force generic kernels, 2 = force fast kernels */
   int32_t a_geometric; /* as in vmb_fused_scan_args */
   int32_t scan_tune;   /* as vmb_fused_scan_args.tune */
+  int32_t fuse_conv_xproj; /* != 0: stateless forward walks run conv + x_proj as ONE kernel (vmb_conv_xproj_fwd):
+                            * less HBM traffic and faster for a single forward in flight, slower when several
+                            * forwards share the GPU (it fills the SMs' shared memory); bit-identical results */
 } vmb_mixer_args;
 VMB_API int64_t vmb_mixer_workspace_bytes(int B, int L, int D, int Di, int N, int R, int dtype);
 VMB_API int vmb_mixer_fwd(const vmb_mixer_args* args, vmb_stream_t stream);

@@ -14,7 +14,7 @@ def _params(w):
 
 
 def mixer_fwd(w, hidden, conv_state=None, ssm_state=None, want_conv_state=False,
-              want_ssm_state=False, reverse=False, path=0):
+              want_ssm_state=False, reverse=False, path=0, **_tuning):
     p = _params(w)
     x = torch.flip(hidden, dims=[1]) if reverse else hidden
     out, (new_conv, last) = orc.mixer_ref(p, x, conv_state, ssm_state, want_state=True)

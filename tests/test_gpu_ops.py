@@ -616,3 +616,59 @@ def test_unsupported_inputs_raise_python_errors():
         ops.linear(torch.randn(2, 4), torch.randn(3, 4))
     with pytest.raises(RuntimeError, match="d_conv"):
         ops.causal_conv1d_tokens(torch.randn(1, 4, 8, device=DEV), torch.randn(8, 7, device=DEV), None)
+
+
+def test_add_norm_and_gate_accept_misaligned_views():
+    """a last-dim slice big[..., 2:2+dim] is a view whose base is not 16-byte aligned; the
+    vector kernels must not fault on it (ops realigns; the C entry refuses instead of faulting)."""
+    from videomamba_b200 import _lib
+    dim = 384
+    gen = torch.Generator().manual_seed(3)
+    for dtype in DTYPES:
+        big = _rand(gen, 6, 10, dim + 8, dtype=dtype).to(DEV)
+        x = big[..., 2:2 + dim]
+        assert x.data_ptr() % 16 != 0
+        w = torch.ones(dim, dtype=dtype, device=DEV)
+        res = _rand(gen, 6, 10, dim, dtype=torch.float32).to(DEV)
+        y, r = ops.add_norm(x, w, None, res, 1e-5, True, True, True)
+        y2, r2 = ops.add_norm(x.contiguous(), w, None, res, 1e-5, True, True, True)
+        assert torch.equal(y, y2) and torch.equal(r, r2)
+        g = ops.gate_blend(x, None, x, x)
+        assert torch.equal(g, ops.gate_blend(x.contiguous(), None, x.contiguous(), x.contiguous()))
+    # the C entry itself: misaligned base -> VMB_ERR_UNSUPPORTED, never a fault
+    lib = _lib.load()
+    buf = torch.zeros(4 * dim + 8, dtype=torch.float32, device=DEV)
+    import ctypes as C
+    p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+    w32 = torch.ones(dim, device=DEV)
+    out = torch.zeros(4, dim, device=DEV)
+    rc = lib.vmb_add_norm_fwd(p(buf, 4), 0, dim, None, 0, p(w32), None, 0, p(out), None, 0, 4, dim, 1e-5, 1,
+                              None)
+    assert rc == -2 and b"aligned" in lib.vmb_last_error()
+    torch.cuda.synchronize()
+
+
+def test_mixer_refuses_silent_training_and_detects_stale_weights():
+    """backward through the kernels raises; writes through .data are caught by
+    verify_weights and cured by refresh_weights()."""
+    from video_mamba.mamba_simple import Mamba
+    torch.manual_seed(2)
+    mx = Mamba(d_model=64, use_fast_path=False).to(DEV)
+    x = torch.randn(2, 20, 64, device=DEV)
+    out = mx(x)                                   # grad enabled, parameters require grad
+    assert out.requires_grad
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        out.sum().backward()
+    with torch.no_grad():
+        base = mx(x)
+        assert not base.requires_grad
+        mx.A_log.data.add_(0.5)                   # no version bump: the derived A2 copy is now stale
+        stale = mx(x)
+        assert torch.equal(stale, base)
+        mx.verify_weights = True
+        with pytest.raises(RuntimeError, match="stale"):
+            mx(x)
+        mx.verify_weights = False
+        mx.refresh_weights()
+        fresh = mx(x)
+        assert not torch.equal(fresh, base)

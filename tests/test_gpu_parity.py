@@ -280,6 +280,74 @@ def test_oracle_parity_at_baseline_sizes(case):
     _close(got_pool, want_pool, _tol(dtype))
 
 
+def test_mixer_fused_conv_xproj_is_bit_identical():
+    """Mamba.fuse_conv_xproj routes stateless forward walks through the one-kernel conv + x_proj
+    (vmb_conv_xproj_fwd inside vmb_mixer_fwd): same bits as the two-kernel path, at the bench width."""
+    torch.manual_seed(9)
+    mx = Mamba(d_model=384, use_fast_path=False).eval().to(torch.bfloat16).to(DEV)
+    x = torch.randn(4, 700, 384, device=DEV).to(torch.bfloat16)
+    with torch.no_grad():
+        base = mx(x)
+        mx.fuse_conv_xproj = True
+        fused = mx(x)
+        # with state the fused kernel does not apply; the flag must not change anything
+        st = mx.allocate_state(4, dtype=torch.bfloat16, device=DEV)
+        o1, s1 = mx(x, state=st, return_state=True)
+        mx.fuse_conv_xproj = False
+        o2, s2 = mx(x, state=st, return_state=True)
+    assert torch.equal(base, fused)
+    assert torch.equal(o1, o2) and torch.equal(s1[0], s2[0]) and torch.equal(s1[1], s2[1])
+
+
+def test_oracle_parity_middle_32f_full_size():
+    """BASELINE.json configs[2] at full model / clip size: VideoMamba-Middle (embed 576, depth 32),
+    32 frames @224 (6 273 tokens), bf16, batch 1, general-A weights, against the CPU oracle."""
+    dtype, dim, frames = torch.bfloat16, 576, 32
+    cfg = dict(img_size=224, patch_size=16, depth=32, embed_dim=dim, kernel_size=1, num_frames=frames,
+               norm_epsilon=1e-5, rms_norm=True, fused_add_norm=True, residual_in_fp32=True,
+               pool_type="cls+avg", add_pool_norm=True)
+    sd = _synthetic(cfg, dtype, True, seed=17)
+    x = torch.rand(1, 3, frames, 224, 224, generator=torch.Generator().manual_seed(4)).to(dtype)
+    m = _model_from(cfg, sd, dtype)
+    with torch.no_grad():
+        want_vis, want_pool = orc.OracleVideoMamba(cfg, sd).forward(x)
+        got_vis, got_pool = m(x.to(DEV))
+    assert got_vis.shape == (1, frames * 196, dim)
+    _close(got_vis, want_vis, 2e-2)
+    _close(got_pool, want_pool, 2e-2)
+
+
+def test_oracle_parity_streaming_64_frame_chunks_full_size():
+    """BASELINE.json configs[3] at full chunk size: VideoMamba-Small, two 64-frame chunks @224
+    (12 545 tokens with CLS, then 12 544) with (conv_state, ssm_state) carry and temporal_pos_offset,
+    bf16, one stream, general-A weights and a non-zero temporal table, against the CPU oracle:
+    x_vis, x_pool and the next state of both chunks."""
+    dtype, dim, depth, chunk = torch.bfloat16, 384, 24, 64
+    cfg = dict(img_size=224, patch_size=16, depth=depth, embed_dim=dim, kernel_size=1, num_frames=2 * chunk,
+               norm_epsilon=1e-5, rms_norm=True, fused_add_norm=True, residual_in_fp32=True,
+               pool_type="cls+avg", add_pool_norm=True)
+    sd = _synthetic(cfg, dtype, True, seed=19)
+    x = torch.rand(1, 3, 2 * chunk, 224, 224, generator=torch.Generator().manual_seed(5)).to(dtype)
+    oracle = orc.OracleVideoMamba(cfg, sd)
+    m = _model_from(cfg, sd, dtype)
+    zero = [(torch.zeros(1, 2 * dim, 4, dtype=dtype), torch.zeros(1, 2 * dim, 16, dtype=dtype))
+            for _ in range(depth)]
+    with torch.no_grad():
+        w0 = oracle.forward(x[:, :, :chunk], ssm_state=zero, temporal_pos_offset=0)
+        oracle.pool_type = "avg"
+        w1 = oracle.forward(x[:, :, chunk:], ssm_state=w0[2], temporal_pos_offset=chunk)
+        st = m.allocate_state(1, dtype=dtype, device=DEV)
+        g0 = m(x[:, :, :chunk].to(DEV), ssm_state=st, temporal_pos_offset=0)
+        m.pool_type = "avg"
+        g1 = m(x[:, :, chunk:].to(DEV), ssm_state=g0[2], temporal_pos_offset=chunk)
+    assert g0[0].shape == (1, chunk * 196, dim) and g1[0].shape == (1, chunk * 196, dim)
+    for got, want in ((g0, w0), (g1, w1)):
+        _close(got[0], want[0], 2e-2); _close(got[1], want[1], 2e-2)
+        for (gc, gs), (wc, ws) in zip(got[2], want[2]):
+            assert gs.dtype == torch.float32 and gc.shape == wc.shape
+            assert rel_err(gc, wc) <= 2e-2 and rel_err(gs, ws) <= 2e-2
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_mixer_forced_generic_equals_auto_path(dtype):
     """Both kernel selections of vmb_mixer_fwd must agree with the oracle (and so each other)."""

@@ -262,3 +262,49 @@ def test_refiner_matches_reference(golden):
         blk(torch.randn(3, 4))
     f, b = blk.allocate_state(2)
     assert f[0].shape == (2, 32, 4) and b[1].shape == (2, 32, 16)
+
+
+def test_forward_only_guard_makes_backward_fail_loudly():
+    """every libvmb200 op writes into fresh buffers with no autograd node; outputs computed from
+    tensors that require grad must carry a node whose backward raises, instead of silently training only
+    the torch glue."""
+    import pytest
+    import torch
+    from videomamba_b200 import ops
+
+    w = torch.randn(4, 4, requires_grad=True)
+    out = torch.zeros(2, 4)                       # stands for a kernel output buffer
+    tagged = ops.forward_only(out, w)
+    assert tagged.requires_grad and torch.equal(tagged, out)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        tagged.sum().backward()
+    with torch.no_grad():                         # inference: nothing is attached
+        assert ops.forward_only(out, w) is out
+    assert ops.forward_only(out, w.detach()) is out
+    both = ops.forward_only((out, None, out), w)
+    assert both[0].requires_grad and both[1] is None and both[2] is out
+
+
+def test_mixer_weight_cache_invalidation_hooks():
+    """the kernel-ready copies of a mixer's parameters are dropped by load_state_dict, by
+    .to() / dtype casts and by refresh_weights(); the key follows storage, version and dtype."""
+    import torch
+    from videomamba_b200.mixer import Mamba
+
+    m = Mamba(d_model=16, d_state=4)
+    k0 = m.weights_key()
+    m._weights_key, m._weights = k0, object()
+    with torch.no_grad():
+        m.A_log.add_(1.0)                         # in-place through autograd's counter: key changes
+    assert m.weights_key() != k0
+    m._weights_key, m._weights = m.weights_key(), object()
+    m.load_state_dict(m.state_dict())
+    assert m._weights is None and m._weights_key is None
+    m._weights_key, m._weights = m.weights_key(), object()
+    m.to(torch.bfloat16)
+    assert m._weights is None
+    m._weights_key, m._weights = m.weights_key(), object()
+    m.A_log.data.mul_(2.0)                        # bypasses the version counter: needs refresh_weights()
+    assert m.weights_key() == m._weights_key
+    m.refresh_weights()
+    assert m._weights is None

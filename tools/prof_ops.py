@@ -44,7 +44,7 @@ if which == "scan":
                      + 0.1 * torch.randn(Di, N, generator=g, device=dev)) * ops.LOG2E).contiguous()
     Dp = torch.ones(Di, device=dev)
     bias = torch.full((Di,), -3.0, device=dev)
-    split = os.environ.get("PSPLIT", "1") != "0"
+    split = os.environ.get("PSPLIT", "1") != "0"      # tool-only switch: time the unsplit walk
     timeit(lambda: ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, allow_split=split),
            B * L * (3 * Di + Xp) * 2)
 elif which == "conv":

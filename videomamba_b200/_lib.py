@@ -69,7 +69,7 @@ class MixerArgs(C.Structure):
         ("B", c_int32), ("L", c_int32), ("D", c_int32), ("Di", c_int32), ("N", c_int32),
         ("R", c_int32), ("W", c_int32),
         ("dtype", c_int32), ("reverse", c_int32), ("path", c_int32),
-        ("a_geometric", c_int32), ("scan_tune", c_int32),
+        ("a_geometric", c_int32), ("scan_tune", c_int32), ("fuse_conv_xproj", c_int32),
     ]
 
 

@@ -6,8 +6,6 @@
 #include <mutex>
 #include <vector>
 
-#include <cstdlib>
-
 #include "internal.h"
 
 namespace vmb {
@@ -274,15 +272,12 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   if (p->path == 2 && !fast_ok) VMB_UNSUPPORTED("mixer: fast path requested but not available");
   const bool fast = fast_ok && p->path != 1;
 
-  // Stateless forward walk on the fast path: the conv runs inside the x_proj projection (its output
-  // tile goes from the conv warps to the tensor cores through shared memory and to HBM once).
-  // Opt-in (VMB_CONV_XPROJ=1): alone it saves 14 us per layer, but it is a persistent kernel that fills
-  // the SM's shared memory, so with several forwards in flight it cannot share SMs with another step's
-  // scan the way the small conv CTAs do (bench.py: serial 20.6 -> 20.2 ms, 3 in flight 17.6 -> 18.5 ms).
-  static const bool fuse_conv_xproj = [] {
-    const char* e = std::getenv("VMB_CONV_XPROJ");
-    return e != nullptr && std::atoi(e) != 0;
-  }();
+  // Stateless forward walk on the fast path, on request (fuse_conv_xproj): the conv runs inside the x_proj
+  // projection (its output tile goes from the conv warps to the tensor cores through shared memory and to
+  // HBM once).  Alone it saves 14 us per layer, but it is a persistent kernel that fills the SM's shared
+  // memory, so with several forwards in flight it cannot share SMs with another step's scan the way the
+  // small conv CTAs do (bench.py: serial 20.6 -> 20.2 ms, 3 in flight 17.6 -> 18.5 ms): the caller decides.
+  const bool fuse_conv_xproj = p->fuse_conv_xproj != 0;
   const bool fused_conv = fuse_conv_xproj && fast && p->W == 4 && !p->reverse && p->conv_state_in == nullptr &&
                           p->conv_state_out == nullptr &&
                           conv_xproj_supported(xz, 2 * Di, p->w_conv, p->b_conv, p->w_x_pad, Di, xc, Di,

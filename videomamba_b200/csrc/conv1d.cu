@@ -5,12 +5,10 @@
 // A thread owns VEC consecutive channels (one 128-bit load per token) and slides a W-tap
 // window down a chunk of tokens, so x is read once (+ W-1 halo rows per chunk) and y written once.
 // Algorithmic bytes per token: 2 * Di * sizeof(T).
-// Three kernels: conv1d_fwd_kernel (any dtype / width, all loads of a 16-token chunk up front),
-// conv1d_stream_kernel (bf16, d_conv 4: register double-buffered sub-chunks; VMB_CONV_VARIANT=2) and
-// conv1d_ring_kernel (bf16, d_conv 4, the default: rows staged by cp.async into a private ring of
-// shared-memory slots, 0.83 of the HBM peak; CTAs walk batch and chunks back to front so the
+// Two kernels: conv1d_fwd_kernel (any dtype / width, all loads of a 16-token chunk up front) and
+// conv1d_ring_kernel (bf16, d_conv 4, the production shape: rows staged by cp.async into a private
+// ring of shared-memory slots, 0.83 of the HBM peak; CTAs walk batch and chunks back to front so the
 // kernel starts on the rows in_proj wrote last -- DESIGN.md 3.3, 3.4).
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -150,10 +148,8 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* 
 }
 
 // Production shape (bf16, d_conv 4, 16-byte aligned rows): a thread owns 8 channels and STREAMS down
-// `tok` tokens (a multiple of kSub) in sub-chunks of kSub rows; the loads of sub-chunk i+1 are in flight while
-// sub-chunk i is computed, so a warp always has 4 KB outstanding and the halo is 3 rows per 64.
-// Channel pairs are processed with packed FFMA2.
-constexpr int kSub = 8;
+// `tok` tokens; channel pairs are processed with packed FFMA2.
+constexpr int kSub = 8;     // shortest sequence the streaming kernel takes is 2 * kSub tokens
 
 __device__ __forceinline__ void unpack_pairs(const uint4& v, float2 (&f)[4]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -162,136 +158,7 @@ __device__ __forceinline__ void unpack_pairs(const uint4& v, float2 (&f)[4]) {
     f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
 }
 
-template <bool kSilu>
-__global__ void __launch_bounds__(96)
-conv1d_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_bs, int64_t x_ts,
-                     const __nv_bfloat16* __restrict__ weight, const __nv_bfloat16* __restrict__ bias,
-                     const void* __restrict__ cs_in, int cs_in_dtype, __nv_bfloat16* __restrict__ y,
-                     int64_t y_bs, int64_t y_ts, void* __restrict__ cs_out, int cs_out_dtype, int L,
-                     int Di, int reverse, int tok) {
-  constexpr int W = 4;
-  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c0 >= Di) return;
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.y * tok;
-  const __nv_bfloat16* xb = x + (int64_t)b * x_bs + c0;
-  __nv_bfloat16* yb = y + (int64_t)b * y_bs + c0;
-  const int dir = reverse ? -1 : 1;
-  const int r0 = reverse ? L - 1 : 0;               // logical token t lives at row r0 + dir * t
-  const int xs = (int)x_ts, ys = (int)y_ts;
-  auto ldrow = [&](int t) -> uint4 {
-    return (t >= 0 && t < L) ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)(r0 + dir * t) * xs))
-                             : make_uint4(0u, 0u, 0u, 0u);
-  };
-
-  // first sub-chunk and the 3 history rows in flight before anything else
-  uint4 cur[kSub], hist[W - 1];
-#pragma unroll
-  for (int k = 0; k < W - 1; ++k) hist[k] = ldrow(t0 - (W - 1) + k);
-#pragma unroll
-  for (int i = 0; i < kSub; ++i) cur[i] = ldrow(t0 + i);
-
-  float2 w2[4][W], b2[4];
-  {
-    const uint4 wa = __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W));        // channels c0 .. c0+1
-    const uint4 wb = __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W + 8));
-    const uint4 wc = __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W + 16));
-    const uint4 wd = __ldg(reinterpret_cast<const uint4*>(weight + (int64_t)c0 * W + 24));
-    const uint4 wv[4] = {wa, wb, wc, wd};
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {                   // 8 bf16: channel 2p taps 0..3, channel 2p+1 taps 0..3
-      const uint32_t q[4] = {wv[p].x, wv[p].y, wv[p].z, wv[p].w};
-      const float e0[4] = {__uint_as_float(q[0] << 16), __uint_as_float(q[0] & 0xffff0000u),
-                           __uint_as_float(q[1] << 16), __uint_as_float(q[1] & 0xffff0000u)};
-      const float e1[4] = {__uint_as_float(q[2] << 16), __uint_as_float(q[2] & 0xffff0000u),
-                           __uint_as_float(q[3] << 16), __uint_as_float(q[3] & 0xffff0000u)};
-#pragma unroll
-      for (int k = 0; k < W; ++k) w2[p][k] = make_float2(e0[k], e1[k]);
-    }
-    if (bias) {
-      float2 t[4];
-      unpack_pairs(__ldg(reinterpret_cast<const uint4*>(bias + c0)), t);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) b2[p] = t[p];
-    } else {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) b2[p] = make_float2(0.f, 0.f);
-    }
-  }
-
-  float2 win[W - 1][4];                             // rows t-3, t-2, t-1
-#pragma unroll
-  for (int k = 0; k < W - 1; ++k) {
-    const int t = t0 - (W - 1) + k;
-    if (t < 0 && cs_in != nullptr) {
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-        win[k][p] = make_float2(
-            load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p) * W + (W + t), cs_in_dtype),
-            load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p + 1) * W + (W + t), cs_in_dtype));
-    } else {
-      unpack_pairs(hist[k], win[k]);
-    }
-  }
-
-#pragma unroll 1
-  for (int sc = 0; sc < tok / kSub; ++sc) {
-    const int ts = t0 + sc * kSub;
-    if (ts >= L) break;
-    uint4 nxt[kSub];
-#pragma unroll
-    for (int i = 0; i < kSub; ++i) nxt[i] = ldrow(ts + kSub + i < t0 + tok ? ts + kSub + i : L);
-#pragma unroll
-    for (int i = 0; i < kSub; ++i) {
-      float2 xin[4];
-      unpack_pairs(cur[i], xin);
-      uint32_t o[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float2 acc = __ffma2_rn(w2[p][0], win[0][p], b2[p]);
-        acc = __ffma2_rn(w2[p][1], win[1][p], acc);
-        acc = __ffma2_rn(w2[p][2], win[2][p], acc);
-        acc = __ffma2_rn(w2[p][3], xin[p], acc);
-        if (kSilu) { acc.x = silu_fast(acc.x); acc.y = silu_fast(acc.y); }
-        const __nv_bfloat162 h = __floats2bfloat162_rn(acc.x, acc.y);
-        o[p] = *reinterpret_cast<const uint32_t*>(&h);
-        win[0][p] = win[1][p]; win[1][p] = win[2][p]; win[2][p] = xin[p];
-      }
-      if (ts + i < L)
-        *reinterpret_cast<uint4*>(yb + (int64_t)(r0 + dir * (ts + i)) * ys) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-#pragma unroll
-    for (int i = 0; i < kSub; ++i) cur[i] = nxt[i];
-  }
-
-  // The thread that owns the final chunk also emits the next conv state: hist[L-W .. L-1] (pre-conv x).
-  if (cs_out != nullptr && t0 < L && t0 + tok >= L) {
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      const int t = L - W + k;
-      float2 f[4];
-      if (t >= 0) {
-        unpack_pairs(ldrow(t), f);
-      } else if (cs_in != nullptr) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-          f[p] = make_float2(
-              load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p) * W + (W + t), cs_in_dtype),
-              load_as_f32(cs_in, ((int64_t)b * Di + c0 + 2 * p + 1) * W + (W + t), cs_in_dtype));
-      } else {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) f[p] = make_float2(0.f, 0.f);
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        store_from_f32(cs_out, ((int64_t)b * Di + c0 + 2 * p) * W + k, cs_out_dtype, f[p].x);
-        store_from_f32(cs_out, ((int64_t)b * Di + c0 + 2 * p + 1) * W + k, cs_out_dtype, f[p].y);
-      }
-    }
-  }
-}
-
-// Ring-staged variant of the streaming kernel: the rows a thread is going to consume are brought
+// Ring staging: the rows a thread is going to consume are brought
 // in by 16-byte cp.async into a private ring of shared-memory slots ([slot][thread], conflict free),
 // kRing rows deep, so the bytes in flight per SM no longer depend on registers: 5 CTAs x 96 threads
 // x 8-12 rows x 16 B = 60-90 KB outstanding per SM at the shipped depth of 12, what the HBM
@@ -489,40 +356,24 @@ int launch_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, co
                cudaStream_t st) {
   const int cthreads = (Di + VEC - 1) / VEC;
   if constexpr (sizeof(T) == 2 && VEC == 8 && W == 4) {
-    static const int variant = std::getenv("VMB_CONV_VARIANT") ? std::atoi(std::getenv("VMB_CONV_VARIANT")) : 0;
-    const bool old = variant == 1;
-    if (!old && reinterpret_cast<uintptr_t>(weight) % 16 == 0 &&
+    if (reinterpret_cast<uintptr_t>(weight) % 16 == 0 &&
         (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0) && L >= 2 * kSub) {
       const int blk = cthreads >= 96 ? 96 : ((cthreads + 31) / 32) * 32;
       const int gx = (cthreads + blk - 1) / blk;
-      if (variant != 2) {                                 // default: ring-staged streaming kernel
-        constexpr int kRing = 12;   // 18 KB per CTA; 12 / 16 / 24 rows measured: 55.9 / 56.8 / 57.0 us alone, the
-                                    // smaller footprint shares SMs with another step's scan more easily
-        const int tokr = 40;   // tokens per thread; measured 24 .. 128 at batch 32: 56.3 us at 40, 58.4 at 64, 64.8 at 128
-        const size_t smem = (size_t)kRing * blk * 16;
-        dim3 g(gx, (L + tokr - 1) / tokr, B);
-        if (silu)
-          conv1d_ring_kernel<true, kRing><<<g, blk, smem, st>>>((const T*)x, x_bs, x_ts, (const T*)weight,
-                                                                (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
-                                                                y_ts, cs_out, cs_out_dtype, L, Di, reverse, tokr);
-        else
-          conv1d_ring_kernel<false, kRing><<<g, blk, smem, st>>>((const T*)x, x_bs, x_ts, (const T*)weight,
-                                                                 (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
-                                                                 y_ts, cs_out, cs_out_dtype, L, Di, reverse, tokr);
-        VMB_LAUNCH_CHECK("conv1d_ring_kernel");
-        return VMB_OK;
-      }
-      const int tok = 64;        // tokens per thread (88 = two exact waves at batch 32 measured slower: 66.6 vs 63.6 us)
-      dim3 g(gx, (L + tok - 1) / tok, B);
+      constexpr int kRing = 12;   // 18 KB per CTA; 12 / 16 / 24 rows measured: 55.9 / 56.8 / 57.0 us alone, the
+                                  // smaller footprint shares SMs with another step's scan more easily
+      const int tokr = 40;   // tokens per thread; measured 24 .. 128 at batch 32: 56.3 us at 40, 58.4 at 64, 64.8 at 128
+      const size_t smem = (size_t)kRing * blk * 16;
+      dim3 g(gx, (L + tokr - 1) / tokr, B);
       if (silu)
-        conv1d_stream_kernel<true><<<g, blk, 0, st>>>((const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias,
-                                                      cs_in, cs_in_dtype, (T*)y, y_bs, y_ts, cs_out,
-                                                      cs_out_dtype, L, Di, reverse, tok);
+        conv1d_ring_kernel<true, kRing><<<g, blk, smem, st>>>((const T*)x, x_bs, x_ts, (const T*)weight,
+                                                              (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
+                                                              y_ts, cs_out, cs_out_dtype, L, Di, reverse, tokr);
       else
-        conv1d_stream_kernel<false><<<g, blk, 0, st>>>((const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias,
-                                                       cs_in, cs_in_dtype, (T*)y, y_bs, y_ts, cs_out,
-                                                       cs_out_dtype, L, Di, reverse, tok);
-      VMB_LAUNCH_CHECK("conv1d_stream_kernel");
+        conv1d_ring_kernel<false, kRing><<<g, blk, smem, st>>>((const T*)x, x_bs, x_ts, (const T*)weight,
+                                                               (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
+                                                               y_ts, cs_out, cs_out_dtype, L, Di, reverse, tokr);
+      VMB_LAUNCH_CHECK("conv1d_ring_kernel");
       return VMB_OK;
     }
   }

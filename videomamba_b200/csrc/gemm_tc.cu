@@ -1121,24 +1121,6 @@ int launch_cx(const void* x, int64_t x_ld, const void* cw, const void* cb, const
   return VMB_OK;
 }
 
-// VMB_GEMM_PAIR=0 keeps every projection on the 1-CTA kernel.
-int pair_mode() {
-  static int v = [] {
-    const char* e = std::getenv("VMB_GEMM_PAIR");
-    return e ? std::atoi(e) : 1;
-  }();
-  return v;
-}
-
-// 0: stand-alone tiles (default).  1: small-footprint tiles (co-residency with the scan).
-int footprint() {
-  static int v = [] {
-    const char* e = std::getenv("VMB_GEMM_FOOTPRINT");
-    return e ? std::atoi(e) : 0;
-  }();
-  return v;
-}
-
 }  // namespace
 
 bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, const void* C,
@@ -1152,21 +1134,7 @@ bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, c
 
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
             int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
-  if (footprint() == 1) {
-    if (N <= 64) return launch<64, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-    return launch<128, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  }
-  if (footprint() == 2 || footprint() == 3) {   // small-footprint CTA pairs: 2 stages (97 KB) / 3 stages (129 KB)
-    if (N <= 64) return launch<64, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-    if (M >= 4 * BM && N % 256 == 0)
-      return footprint() == 2 ? launch_pair<256, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st)
-                              : launch_pair<256, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-    if (M >= 4 * BM && N % 192 == 0)
-      return footprint() == 2 ? launch_pair<192, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st)
-                              : launch_pair<192, 3>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-    return launch<128, 2>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  }
-  if (pair_mode() != 0 && M >= 4 * BM) {   // CTA pairs: 256-row tiles, half a W tile per SM
+  if (M >= 4 * BM) {   // CTA pairs: 256-row tiles, half a W tile per SM
     if (N % 256 == 0) return launch_pair<256, stages_pair(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
     if (N % 192 == 0) return launch_pair<192, stages_pair(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
   }

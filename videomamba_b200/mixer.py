@@ -110,6 +110,10 @@ class Mamba(nn.Module):
     #: counter (``param.data.copy_()``, flat-parameter optimisers) without ``refresh_weights()``.
     verify_weights: bool = False
 
+    #: stateless forward walks run conv + x_proj as one kernel (vmb_conv_xproj_fwd): bit-identical, less
+    #: HBM traffic, faster when ONE forward is in flight, slower when several share the GPU
+    fuse_conv_xproj: bool = False
+
     def refresh_weights(self) -> None:
         """Drop the kernel-ready copies derived from the parameters (``A2 = -exp(A_log)*log2(e)``,
         fp32 ``D`` / ``dt_proj.bias``, zero-padded ``x_proj`` / ``dt_proj`` weights, the geometric-A
@@ -197,7 +201,8 @@ class Mamba(nn.Module):
         inplace_ssm = ssm_state is not None and state is None and not return_state
         want = return_state or inplace_ssm
         out, new_conv, last = ops.mixer_fwd(w, hidden_states, conv_state, ssm_state,
-                                            want_conv_state=return_state, want_ssm_state=want)
+                                            want_conv_state=return_state, want_ssm_state=want,
+                                            fuse_conv_xproj=self.fuse_conv_xproj)
         if inplace_ssm:
             ssm_state.copy_(last)
         if return_state:

@@ -444,7 +444,7 @@ class MixerWeights:
 def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = None,
               ssm_state: Optional[Tensor] = None, want_conv_state: bool = False,
               want_ssm_state: bool = False, reverse: bool = False, path: int = 0,
-              scan_tune: int = 0):
+              scan_tune: int = 0, fuse_conv_xproj: bool = False):
     """Whole Mamba mixer on token-major ``hidden (B, L, D)``.
     Returns ``(out, new_conv_state | None, last_ssm_state | None)``."""
     _require_cuda(hidden)
@@ -513,6 +513,7 @@ def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = No
     a.B, a.L, a.D, a.Di, a.N, a.R, a.W = B, L, D, w.Di, w.N, w.R, w.W
     a.dtype, a.reverse, a.path = dt, 1 if reverse else 0, path
     a.a_geometric, a.scan_tune = 1 if w.a_geometric else 0, int(scan_tune)
+    a.fuse_conv_xproj = 1 if fuse_conv_xproj else 0
     with _on_device(hidden):
         rc = lib.vmb_mixer_fwd(C.byref(a), _stream(hidden))
     _lib.check(rc, "vmb_mixer_fwd")
