@@ -113,13 +113,17 @@ VMB_API int vmb_conv_xproj_fwd(const void* x, int64_t x_ld, const void* w_conv, 
  *   conv_state_out = last W columns of hist (pre-conv inputs).
  * reverse != 0: the logical sequence is the physical one read back to front (token i of the
  * logical sequence is row L-1-i); history and state columns are in logical order.
+ * reverse != 0 with frame_len > 0 (L a multiple of it): FRAME-AXIS reversal -- frames of frame_len
+ * tokens are walked back to front, the tokens inside a frame front to back (logical token i is row
+ * L - (i / frame_len + 1) * frame_len + i % frame_len): the 4-D flip of BiMambaRefinerBlock
+ * (models/refiner_backbone.py:61-68) without the two gather copies.  frame_len = 0 otherwise.
  * ---------------------------------------------------------------------------------------- */
 VMB_API int vmb_causal_conv1d_fwd(const void* x, int64_t x_bstride, int64_t x_tstride,
                           const void* weight /* (Di, W) */, const void* bias /* nullable */,
                           const void* conv_state_in, int cs_in_dtype,  /* nullable */
                           void* y, int64_t y_bstride, int64_t y_tstride,
                           void* conv_state_out, int cs_out_dtype,      /* nullable */
-                          int B, int L, int Di, int W, int silu, int reverse, int dtype,
+                          int B, int L, int Di, int W, int silu, int reverse, int frame_len, int dtype,
                           vmb_stream_t stream);
 
 /* Single-token conv step: rolls conv_state (B,Di,W) in place, returns act(conv).
@@ -156,6 +160,7 @@ typedef struct vmb_scan_args {
   int32_t dtype;          /* element type of u / delta / z / bc / y */
   int32_t softplus;       /* apply softplus to delta_raw + dt_bias */
   int32_t reverse;
+  int32_t frame_len;      /* with reverse != 0: frame-axis reversal (see vmb_causal_conv1d_fwd); else 0 */
 } vmb_scan_args;
 VMB_API int vmb_selective_scan_fwd(const vmb_scan_args* args, vmb_stream_t stream);
 
@@ -197,6 +202,7 @@ typedef struct vmb_fused_scan_args {
    * polynomial, 9 = geometric).  Evaluators other than the built default and 9 exist only in
    * measurement builds (-DVMB_SCAN_LAB) and return VMB_ERR_UNSUPPORTED otherwise. */
   int32_t tune;
+  int32_t frame_len;      /* with reverse != 0: frame-axis reversal (see vmb_causal_conv1d_fwd); else 0 */
 } vmb_fused_scan_args;
 VMB_API int64_t vmb_fused_scan_workspace_bytes(int B, int L, int Di, int N);
 VMB_API int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* args, vmb_stream_t stream);
@@ -250,6 +256,7 @@ typedef struct vmb_mixer_args {
   int32_t path;        /* 0 = auto, 1 = force generic kernels, 2 = force fast kernels */
   int32_t a_geometric; /* as in vmb_fused_scan_args */
   int32_t scan_tune;   /* as vmb_fused_scan_args.tune */
+  int32_t frame_len;   /* with reverse != 0: frame-axis reversal (see vmb_causal_conv1d_fwd); else 0 */
   int32_t fuse_conv_xproj; /* != 0: stateless forward walks run conv + x_proj as ONE kernel (vmb_conv_xproj_fwd):
                             * less HBM traffic and faster for a single forward in flight, slower when several
                             * forwards share the GPU (it fills the SMs' shared memory); bit-identical results */

@@ -14,12 +14,19 @@ def _params(w):
 
 
 def mixer_fwd(w, hidden, conv_state=None, ssm_state=None, want_conv_state=False,
-              want_ssm_state=False, reverse=False, path=0, **_tuning):
+              want_ssm_state=False, reverse=False, path=0, frame_len=0, **_tuning):
     p = _params(w)
-    x = torch.flip(hidden, dims=[1]) if reverse else hidden
-    out, (new_conv, last) = orc.mixer_ref(p, x, conv_state, ssm_state, want_state=True)
-    if reverse:
-        out = torch.flip(out, dims=[1])
+
+    def flip(t):            # whole-sequence reversal, or frame-axis reversal (frames of frame_len tokens)
+        if not reverse:
+            return t
+        if not frame_len:
+            return torch.flip(t, dims=[1])
+        b, l, c = t.shape
+        return torch.flip(t.reshape(b, l // frame_len, frame_len, c), dims=[1]).reshape(b, l, c)
+
+    out, (new_conv, last) = orc.mixer_ref(p, flip(hidden), conv_state, ssm_state, want_state=True)
+    out = flip(out)
     if want_conv_state and conv_state is not None:
         new_conv = new_conv.to(torch.promote_types(conv_state.dtype, hidden.dtype))
     return out, (new_conv if want_conv_state else None), (last if want_ssm_state else None)

@@ -672,3 +672,53 @@ def test_mixer_refuses_silent_training_and_detects_stale_weights():
         mx.refresh_weights()
         fresh = mx(x)
         assert not torch.equal(fresh, base)
+
+
+def _flip_frames(t, n):
+    b, l, c = t.shape
+    return torch.flip(t.reshape(b, l // n, n, c), dims=[1]).reshape(b, l, c)
+
+
+@pytest.mark.parametrize("geom", [(2, 5, 49, 768, 24), (3, 4, 16, 384, 12), (1, 7, 33, 1152, 36), (40, 3, 20, 768, 24)])
+def test_frame_axis_reversal_equals_flip_copies(geom):
+    """reverse + frame_len: frames walked back to front, tokens of a frame front to back -- the 4-D flip
+    of BiMambaRefinerBlock (models/refiner_backbone.py:61-68) without the two gather copies.  Must equal
+    flip -> forward kernel -> flip: bit for bit for the scans (same arithmetic per token), to rounding for
+    the conv (a different kernel carries the frame walk)."""
+    Bsz, T, n, Di, R = geom
+    L, N, bf = T * n, 16, torch.bfloat16
+    Xp = ops.xdbl_pitch(R, N)
+    gen = torch.Generator().manual_seed(Di + n)
+    u = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
+    z = _rand(gen, Bsz, L, Di, dtype=bf).to(DEV)
+    xdbl = _rand(gen, Bsz, L, Xp, dtype=bf).to(DEV)
+    w_dt = _rand(gen, Di, R, dtype=bf, scale=R ** -0.5).to(DEV)
+    A2 = (-torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Di, 1)
+                     + 0.1 * torch.randn(Di, N, generator=gen)) * ops.LOG2E).to(DEV)
+    Dp = torch.randn(Di, generator=gen).to(DEV)
+    bias = (torch.randn(Di, generator=gen) - 3.0).to(DEV)
+    h0 = torch.randn(Bsz, Di, N, generator=gen).to(DEV)
+    # fused scan (one-warp and two-warp kernels by unit count)
+    want, want_h = ops.selective_scan_fused_tokens(_flip_frames(u, n), _flip_frames(z, n), _flip_frames(xdbl, n),
+                                                   w_dt, A2, R, N, Dp, bias, h0, want_last=True)
+    got, got_h = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, h0, want_last=True,
+                                                 reverse=True, frame_len=n)
+    assert torch.equal(got, _flip_frames(want, n)) and torch.equal(got_h, want_h)
+    # op-level scan (generic kernel), bf16 and fp32
+    for dt in (bf, torch.float32):
+        delta = _rand(gen, Bsz, L, Di, dtype=dt).to(DEV)
+        uu, zz, bc = u.to(dt), z.to(dt), xdbl[..., :2 * N].contiguous().to(dt)
+        want, want_h = ops.selective_scan_tokens(_flip_frames(uu, n), _flip_frames(delta, n), A2, _flip_frames(bc, n),
+                                                 0, N, N, Dp, _flip_frames(zz, n), bias, True, h0, True)
+        got, got_h = ops.selective_scan_tokens(uu, delta, A2, bc, 0, N, N, Dp, zz, bias, True, h0, True,
+                                               reverse=True, frame_len=n)
+        assert torch.equal(got, _flip_frames(want, n)) and torch.equal(got_h, want_h)
+    # conv with history in, next state out
+    w = _rand(gen, Di, 4, dtype=bf, scale=0.5).to(DEV)
+    b = _rand(gen, Di, dtype=bf).to(DEV)
+    cs = _rand(gen, Bsz, Di, 4, dtype=bf).to(DEV)
+    want, want_cs = ops.causal_conv1d_tokens(_flip_frames(u, n), w, b, cs, True)
+    got, got_cs = ops.causal_conv1d_tokens(u, w, b, cs, True, reverse=True, frame_len=n)
+    assert rel_err(got, _flip_frames(want, n)) <= 1e-2 and torch.equal(got_cs, want_cs)
+    with pytest.raises(RuntimeError, match="whole number of frames"):
+        ops.causal_conv1d_tokens(u, w, b, reverse=True, frame_len=n + 1 if L % (n + 1) else n + 2)

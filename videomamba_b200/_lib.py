@@ -31,7 +31,7 @@ class ScanArgs(C.Structure):
         ("y", c_void_p), ("y_bstride", c_int64), ("y_tstride", c_int64),
         ("h_last", c_void_p),
         ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32),
-        ("dtype", c_int32), ("softplus", c_int32), ("reverse", c_int32),
+        ("dtype", c_int32), ("softplus", c_int32), ("reverse", c_int32), ("frame_len", c_int32),
     ]
 
 
@@ -48,7 +48,7 @@ class FusedScanArgs(C.Structure):
         ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32), ("R", c_int32),
         ("Rp", c_int32), ("Xp", c_int32), ("reverse", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
-        ("a_geometric", c_int32), ("tune", c_int32),
+        ("a_geometric", c_int32), ("tune", c_int32), ("frame_len", c_int32),
     ]
 
 
@@ -69,7 +69,8 @@ class MixerArgs(C.Structure):
         ("B", c_int32), ("L", c_int32), ("D", c_int32), ("Di", c_int32), ("N", c_int32),
         ("R", c_int32), ("W", c_int32),
         ("dtype", c_int32), ("reverse", c_int32), ("path", c_int32),
-        ("a_geometric", c_int32), ("scan_tune", c_int32), ("fuse_conv_xproj", c_int32),
+        ("a_geometric", c_int32), ("scan_tune", c_int32), ("frame_len", c_int32),
+        ("fuse_conv_xproj", c_int32),
     ]
 
 
@@ -89,7 +90,7 @@ SIGNATURES = {
                                c_int64, c_int, c_int, c_int, c_void_p]),
     "vmb_causal_conv1d_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
-                                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vmb_causal_conv1d_update": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                          c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p]),

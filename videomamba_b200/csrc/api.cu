@@ -173,6 +173,8 @@ extern "C" int vmb_selective_scan_fwd(const vmb_scan_args* a, vmb_stream_t strea
   VMB_CHECK_ARG(a->B >= 0 && a->L >= 0 && a->Di > 0 && a->N > 0, "selective_scan: bad sizes");
   VMB_CHECK_ARG(a->B <= 65535, "selective_scan: batch %d > 65535", a->B);
   VMB_CHECK_ARG(!a->h0 || dtype_ok(a->h0_dtype), "selective_scan: bad h0 dtype");
+  VMB_CHECK_ARG(a->frame_len >= 0 && (a->frame_len == 0 || a->L % a->frame_len == 0),
+                "selective_scan: L=%d is not a whole number of frames of %d tokens", a->L, a->frame_len);
   if (a->B == 0) return VMB_OK;
   return scan_generic(*a, as_stream(stream));
 }
@@ -200,6 +202,9 @@ extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_st
   f.y = a->y; f.y_bs = a->y_bstride; f.y_ts = a->y_tstride; f.h_last = a->h_last;
   f.B = a->B; f.L = a->L; f.Di = a->Di; f.N = a->N; f.R = a->R; f.Rp = a->Rp; f.Xp = a->Xp;
   f.reverse = a->reverse; f.a_geometric = a->a_geometric; f.tune = a->tune;
+  f.frame_len = a->reverse ? a->frame_len : 0;
+  VMB_CHECK_ARG(f.frame_len >= 0 && (f.frame_len == 0 || a->L % f.frame_len == 0),
+                "fused_scan: L=%d is not a whole number of frames of %d tokens", a->L, f.frame_len);
   f.seg_ws = reinterpret_cast<float*>(a->workspace);
   f.seg_ws_bytes = a->workspace ? a->workspace_bytes : 0;
   VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->workspace) % 16 == 0, "fused_scan: workspace not 16-byte aligned");
@@ -265,6 +270,9 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   f.y = y; f.y_bs = (int64_t)L * Di; f.y_ts = Di; f.h_last = p->ssm_state_out;
   f.B = B; f.L = L; f.Di = Di; f.N = N; f.R = R; f.Rp = p->Rp; f.Xp = p->Xp; f.reverse = p->reverse;
   f.a_geometric = p->a_geometric; f.tune = p->scan_tune;
+  f.frame_len = p->reverse ? p->frame_len : 0;
+  VMB_CHECK_ARG(f.frame_len >= 0 && (f.frame_len == 0 || L % f.frame_len == 0),
+                "mixer: L=%d is not a whole number of frames of %d tokens", L, f.frame_len);
   f.seg_ws = ws.seg_bytes ? reinterpret_cast<float*>(base + ws.seg) : nullptr;
   f.seg_ws_bytes = ws.seg_bytes;
   const bool fast_ok = p->dtype == VMB_BF16 && p->w_x_pad && p->w_dt_pad && p->Xp == Xw &&
@@ -293,7 +301,7 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
     rc = vmb_causal_conv1d_fwd(xz, (int64_t)L * 2 * Di, 2 * Di, p->w_conv, p->b_conv,
                                p->conv_state_in, p->cs_in_dtype, xc, (int64_t)L * Di, Di,
                                p->conv_state_out, p->cs_out_dtype, B, L, Di, p->W, 1, p->reverse,
-                               p->dtype, stream);
+                               f.frame_len, p->dtype, stream);
     if (rc) return rc;
   }
 
@@ -330,7 +338,7 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
     s.h0 = p->ssm_state_in; s.h0_dtype = p->ss_in_dtype;
     s.y = y; s.y_bstride = (int64_t)L * Di; s.y_tstride = Di; s.h_last = p->ssm_state_out;
     s.B = B; s.L = L; s.Di = Di; s.N = N; s.dtype = p->dtype; s.softplus = 1;
-    s.reverse = p->reverse;
+    s.reverse = p->reverse; s.frame_len = f.frame_len;
     {
       ProfScope ps(VMB_PROF_SCAN, st);
       rc = vmb_selective_scan_fwd(&s, stream);

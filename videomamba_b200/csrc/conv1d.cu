@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128)
 conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* __restrict__ weight,
                   const T* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
                   T* __restrict__ y, int64_t y_bs, int64_t y_ts, void* __restrict__ cs_out,
-                  int cs_out_dtype, int L, int Di, int silu, int reverse) {
+                  int cs_out_dtype, int L, int Di, int silu, int reverse, int frame_len) {
   using IO = VecIO<T, VEC>;
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c0 >= Di) return;
@@ -75,7 +75,15 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* 
   const int t0 = blockIdx.y * kChunk;
   const T* xb = x + (int64_t)b * x_bs + c0;
   T* yb = y + (int64_t)b * y_bs + c0;
-  auto row = [&](int i) -> int64_t { return reverse ? (int64_t)(L - 1 - i) : (int64_t)i; };
+  // physical row of logical token i: forward, whole-sequence reversal, or frame-axis reversal (frames of
+  // frame_len tokens back to front, tokens inside a frame front to back -- the 4-D flip of
+  // BiMambaRefinerBlock, models/refiner_backbone.py:61-68)
+  auto row = [&](int i) -> int64_t {
+    if (!reverse) return (int64_t)i;
+    if (frame_len <= 0) return (int64_t)(L - 1 - i);
+    const int f = i / frame_len;
+    return (int64_t)(L - (f + 1) * frame_len + (i - f * frame_len));
+  };
 
   // rows t0 - (W-1) .. t0 + kChunk - 1 of the logical sequence (negative: carried state / zeros)
   typename IO::raw raw[kChunk + W - 1];
@@ -353,10 +361,11 @@ template <typename T, int VEC, int W>
 int launch_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, const void* bias,
                const void* cs_in, int cs_in_dtype, void* y, int64_t y_bs, int64_t y_ts,
                void* cs_out, int cs_out_dtype, int B, int L, int Di, int silu, int reverse,
-               cudaStream_t st) {
+               int frame_len, cudaStream_t st) {
   const int cthreads = (Di + VEC - 1) / VEC;
   if constexpr (sizeof(T) == 2 && VEC == 8 && W == 4) {
-    if (reinterpret_cast<uintptr_t>(weight) % 16 == 0 &&
+    if (!(reverse && frame_len > 0) &&          // the frame-axis walk runs on the chunk kernel below
+        reinterpret_cast<uintptr_t>(weight) % 16 == 0 &&
         (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0) && L >= 2 * kSub) {
       const int blk = cthreads >= 96 ? 96 : ((cthreads + 31) / 32) * 32;
       const int gx = (cthreads + blk - 1) / blk;
@@ -382,7 +391,7 @@ int launch_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, co
   constexpr bool kAccurate = sizeof(T) == 4;
   conv1d_fwd_kernel<T, VEC, W, kAccurate><<<grid, block, 0, st>>>(
       (const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias, cs_in, cs_in_dtype, (T*)y, y_bs,
-      y_ts, cs_out, cs_out_dtype, L, Di, silu, reverse);
+      y_ts, cs_out, cs_out_dtype, L, Di, silu, reverse, frame_len);
   VMB_LAUNCH_CHECK("conv1d_fwd_kernel");
   return VMB_OK;
 }
@@ -391,11 +400,11 @@ template <typename T, int VEC>
 int dispatch_w(int W, const void* x, int64_t x_bs, int64_t x_ts, const void* weight,
                const void* bias, const void* cs_in, int cs_in_dtype, void* y, int64_t y_bs,
                int64_t y_ts, void* cs_out, int cs_out_dtype, int B, int L, int Di, int silu,
-               int reverse, cudaStream_t st) {
+               int reverse, int frame_len, cudaStream_t st) {
 #define VMB_CW(WW)                                                                             \
   case WW:                                                                                     \
     return launch_fwd<T, VEC, WW>(x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs,    \
-                                  y_ts, cs_out, cs_out_dtype, B, L, Di, silu, reverse, st)
+                                  y_ts, cs_out, cs_out_dtype, B, L, Di, silu, reverse, frame_len, st)
   switch (W) {
     VMB_CW(1); VMB_CW(2); VMB_CW(3); VMB_CW(4);
     default: VMB_UNSUPPORTED("causal_conv1d: d_conv=%d not supported (1..4)", W);
@@ -409,7 +418,8 @@ int dispatch_w(int W, const void* x, int64_t x_bs, int64_t x_ts, const void* wei
 extern "C" int vmb_causal_conv1d_fwd(const void* x, int64_t x_bs, int64_t x_ts, const void* weight,
                                      const void* bias, const void* cs_in, int cs_in_dtype, void* y,
                                      int64_t y_bs, int64_t y_ts, void* cs_out, int cs_out_dtype,
-                                     int B, int L, int Di, int W, int silu, int reverse, int dtype,
+                                     int B, int L, int Di, int W, int silu, int reverse, int frame_len,
+                                     int dtype,
                                      vmb_stream_t stream) {
   using namespace vmb;
   VMB_CHECK_ARG(x && weight && y, "causal_conv1d: null x / weight / y");
@@ -419,6 +429,8 @@ extern "C" int vmb_causal_conv1d_fwd(const void* x, int64_t x_bs, int64_t x_ts, 
   if (!cs_out) cs_out_dtype = VMB_F32;
   VMB_CHECK_ARG(dtype_ok(cs_in_dtype) && dtype_ok(cs_out_dtype), "causal_conv1d: bad state dtype");
   VMB_CHECK_ARG(B <= 65535, "causal_conv1d: batch %d > 65535", B);
+  VMB_CHECK_ARG(frame_len >= 0 && (frame_len == 0 || L % frame_len == 0),
+                "causal_conv1d: L=%d is not a whole number of frames of %d tokens", L, frame_len);
   if (B == 0) return VMB_OK;
   if (L == 0) {
     // nothing to convolve; the state just carries over (or stays zero)
@@ -443,15 +455,15 @@ extern "C" int vmb_causal_conv1d_fwd(const void* x, int64_t x_bs, int64_t x_ts, 
     if (aligned)
       return dispatch_w<__nv_bfloat16, 8>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y,
                                           y_bs, y_ts, cs_out, cs_out_dtype, B, L, Di, silu,
-                                          reverse, st);
+                                          reverse, frame_len, st);
     return dispatch_w<__nv_bfloat16, 1>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs,
-                                        y_ts, cs_out, cs_out_dtype, B, L, Di, silu, reverse, st);
+                                        y_ts, cs_out, cs_out_dtype, B, L, Di, silu, reverse, frame_len, st);
   }
   if (aligned)
     return dispatch_w<float, 4>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs, y_ts,
-                                cs_out, cs_out_dtype, B, L, Di, silu, reverse, st);
+                                cs_out, cs_out_dtype, B, L, Di, silu, reverse, frame_len, st);
   return dispatch_w<float, 1>(W, x, x_bs, x_ts, weight, bias, cs_in, cs_in_dtype, y, y_bs, y_ts,
-                              cs_out, cs_out_dtype, B, L, Di, silu, reverse, st);
+                              cs_out, cs_out_dtype, B, L, Di, silu, reverse, frame_len, st);
 }
 
 extern "C" int vmb_causal_conv1d_update(const void* x, int64_t x_bs, void* conv_state, int cs_dtype,

@@ -48,6 +48,7 @@ struct FastScanArgs {
   float* h_last;
   int B, L, Di, N, R, Rp, Xp;
   int reverse;
+  int frame_len = 0;     // with reverse: frame-axis reversal, frames of frame_len tokens (0 = whole-sequence reversal)
   int a_geometric = 0;   // caller's promise: A2[d][n] == (n+1) * A2[d][0] (checked when the weights are loaded)
   int tune = 0;          // measurement aid: 10 * layout + evaluator, 0 = automatic (see scan_fast())
   // sequence split for small batches (filled by scan_fast itself): nseg segments of seg_len tokens,

@@ -232,12 +232,31 @@ struct Lane {
   }
 };
 
+// Tile -> (first memory row of its 16-row box, how many of its logical rows belong to the walk).
+// Forward: rows [16 tile, +16).  kRev: the box is loaded in memory order and read mirrored.  Frame-axis
+// reversal (frame_len > 0, forward code path): frames of frame_len tokens back to front, every frame
+// cut into its own tiles so a tile never straddles two frames (the rows a box reads beyond the end of
+// its frame are treated like the rows beyond the end of a sequence).
+template <bool kRev>
+__device__ __forceinline__ void tile_geom(int tile, int L_total, int L_end, int frame_len, int tpf,
+                                          int& row0, int& valid) {
+  if (!kRev && frame_len > 0) {
+    const int f = tile / tpf, j = tile - f * tpf;
+    row0 = L_total - (f + 1) * frame_len + j * kTT;
+    valid = min(kTT, frame_len - j * kTT);
+  } else {
+    const int t0 = tile * kTT;
+    row0 = kRev ? L_total - kTT - t0 : t0;                    // may be < 0: the TMA unit zero-fills
+    valid = min(kTT, L_end - t0);
+  }
+}
+
 // phase A of one tile for one warp: dt projection on the tensor pipe, softplus, delta * u -> sdd.
 // xa_addr: ldmatrix addresses (per k-step) of the x_dbl tile; su: u tile (dense 32-byte rows).
 template <int KST, bool kRev>
 __device__ __forceinline__ void phase_a(const uint32_t (&xa_addr)[KST], const uint32_t (&bfrag)[2][KST][2],
                                         const float (&bias)[2][2], const uint8_t* su, uint8_t* sdd,
-                                        int g, int tig, int t0, int L) {
+                                        int g, int tig, int valid) {
   float acc[2][4];
 #pragma unroll
   for (int n = 0; n < 2; ++n)
@@ -254,7 +273,7 @@ __device__ __forceinline__ void phase_a(const uint32_t (&xa_addr)[KST], const ui
   for (int half = 0; half < 2; ++half) {
     const int tl = g + 8 * half;                              // token row within the tile
     const int sr = kRev ? kTT - 1 - tl : tl;
-    const bool pad = t0 + tl >= L;
+    const bool pad = tl >= valid;                             // rows beyond the walk: delta = 0 keeps the state
     const uint32_t ua = *reinterpret_cast<const uint32_t*>(su + sr * 32 + (2 * tig) * 2);
     const uint32_t ub = *reinterpret_cast<const uint32_t*>(su + sr * 32 + (8 + 2 * tig) * 2);
 #pragma unroll
@@ -349,8 +368,6 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   load_wdt<R>(a, cw, g, tig, bfrag, bias);
 
   bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
-  const int dir = kRev ? -1 : 1;
-  const int p0 = kRev ? a.L - 1 : 0;
   const int y_ts = (int)a.y_ts;
 
   // shared-memory row of logical tile row r: the reversed direction holds the box in memory order
@@ -369,8 +386,11 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  const int F = kRev ? 0 : a.frame_len;
+  const int tpf = F > 0 ? (F + kTT - 1) / kTT : 0;
   auto issue = [&](int tile, int stg) {            // lane 0 only
-    const int row0 = kRev ? a.L - kTT - tile * kTT : tile * kTT;   // first memory row of the box (may be < 0)
+    int row0, valid;
+    tile_geom<kRev>(tile, a.L, L, F, tpf, row0, valid);
     const uint32_t bar = bar0 + 8 * stg;
     mbar_expect_tx(bar, kTileBytes);
     tma_load_3d(sbase + sp.x0, &map_x, bar, 0, row0, b);
@@ -379,7 +399,7 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   };
 
   const int tile_lo = tbeg / kTT;
-  const int ntiles = (L + kTT - 1) / kTT;
+  const int ntiles = F > 0 ? (a.L / F) * tpf : (L + kTT - 1) / kTT;
   if (lane == 0) issue(tile_lo, 0);
   bf16* const sy = reinterpret_cast<bf16*>(smem + sp.y);
 
@@ -405,7 +425,8 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   for (int tile = tile_lo; tile < ntiles; ++tile) {
     const int it = tile - tile_lo;
     const int stg = it & 1;
-    const int t0 = tile * kTT;
+    int row0, valid;
+    tile_geom<kRev>(tile, a.L, L, F, tpf, row0, valid);
     mbar_wait(bar0 + 8 * stg, (it >> 1) & 1);
     __syncwarp();                                  // tile landed; last tile's smem readers are done
     const uint8_t* su = smem + sp.u(stg);
@@ -425,7 +446,7 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         *reinterpret_cast<uint32_t*>(smem + sp.c + (gr + 4 * i) * (kN * 2) + gp * 4) =
             *reinterpret_cast<const uint32_t*>(sx + xc_off[i & 1] + (i >> 1) * kRow8);
     }
-    phase_a<KST, kRev>(xa_addr, bfrag, bias, su, smem + sp.dd, g, tig, t0, L);
+    phase_a<KST, kRev>(xa_addr, bfrag, bias, su, smem + sp.dd, g, tig, valid);
     __syncwarp();                                  // B / C / dd tiles visible; raw x_dbl rows no longer needed
     if (tile + 1 < ntiles && lane == 0) {          // prefetch the next tile behind the recurrence
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our reads before the TMA's writes
@@ -472,9 +493,8 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     if constexpr (!kStateOnly) {
       __syncwarp();
       const int row = lane >> 1, ch = lane & 1;
-      const int t = t0 + row;
-      if (t < L)
-        *reinterpret_cast<uint4*>(yg + ((p0 + dir * t) * y_ts + ch * 8)) =
+      if (row < valid)
+        *reinterpret_cast<uint4*>(yg + ((row0 + (kRev ? kTT - 1 - row : row)) * y_ts + ch * 8)) =
             *reinterpret_cast<const uint4*>(smem + sp.y + row * kRowBytes + ch * 16);
     }
   }
@@ -554,8 +574,10 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   const int seg = blockIdx.z;                      // sequence split: segment [tbeg, L) of the sequence
   const int tbeg = seg * a.seg_len;
   const int L = min(a.L, tbeg + a.seg_len);
+  const int F = kRev ? 0 : a.frame_len;
+  const int tpf = F > 0 ? (F + kTT - 1) / kTT : 0;
   const int tile_lo = tbeg / kTT;
-  const int ntiles = (L + kTT - 1) / kTT;          // global tile indices [tile_lo, ntiles)
+  const int ntiles = F > 0 ? (a.L / F) * tpf : (L + kTT - 1) / kTT;   // global tile indices [tile_lo, ntiles)
   const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
   float* const wsH = a.seg_ws;
   float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
@@ -593,8 +615,6 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     const int sr = srow(r);
     return kSwz ? sr * XB + ((((o >> 4) ^ (sr & 7)) << 4) | (o & 15)) : sr * XB + o;
   };
-  const int dir = kRev ? -1 : 1;
-  const int p0 = kRev ? a.L - 1 : 0;
   const int nit = ntiles - tile_lo;
 
   if (is_helper) {
@@ -613,8 +633,8 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     // `it` = tile - tile_lo indexes the buffers and barrier phases; TMA coordinates use the global tile
     constexpr uint32_t kTileBytes = kTT * 32 * (kStateOnly ? 1 : 2) + kTT * XB;
     auto issue = [&](int it) {                      // lane 0 only
-      const int tile = tile_lo + it;
-      const int row0 = kRev ? a.L - kTT - tile * kTT : tile * kTT;
+      int row0, valid;
+      tile_geom<kRev>(tile_lo + it, a.L, L, F, tpf, row0, valid);
       const uint32_t bar = tma_bar(it % 3);
       mbar_expect_tx(bar, kTileBytes);
       tma_load_3d(sbase + sp.x(it & 1), &map_x, bar, 0, row0, b);
@@ -633,7 +653,8 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
       const int pb = it & 1;
       mbar_wait_sleep(done_bar(pb), (uint32_t)(it >> 1) & 1u);
       if (kStateOnly) return;                       // first pass of the split: only the buffer hand-back matters
-      const int t = (tile_lo + it) * kTT + frow;
+      int row0, valid;
+      tile_geom<kRev>(tile_lo + it, a.L, L, F, tpf, row0, valid);
       const uint8_t* su = smem + sp.u(it % 3) + srow(frow) * 32 + fch * 2;
       const uint8_t* sz = smem + sp.z(it % 3) + srow(frow) * 32 + fch * 2;
       const float* yr = reinterpret_cast<const float*>(smem + sp.Y(pb)) + frow * kCh + fch;
@@ -649,13 +670,15 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         const float hi = fmaf(Dv[2 * q + 1], bf16hi(uw[q]), yv[2 * q + 1]) * silu_fast(bf16hi(zw[q]));
         o[q] = pack_bf16x2(lo, hi);
       }
-      if (t < L)
-        *reinterpret_cast<uint4*>(yg + (int64_t)(p0 + dir * t) * y_ts) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (frow < valid)
+        *reinterpret_cast<uint4*>(yg + (int64_t)(row0 + (kRev ? kTT - 1 - frow : frow)) * y_ts) =
+            make_uint4(o[0], o[1], o[2], o[3]);
     };
 
     for (int it = 0; it < nit; ++it) {
       const int pb = it & 1;
-      const int t0 = (tile_lo + it) * kTT;
+      int row0, valid;
+      tile_geom<kRev>(tile_lo + it, a.L, L, F, tpf, row0, valid);
       mbar_wait(tma_bar(it % 3), (uint32_t)(it / 3) & 1u);
       // buffers pb were last read by the consumer for tile it - 2, which finalize(it - 2) has waited for
       const uint8_t* sx = smem + sp.x(pb);
@@ -674,7 +697,7 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
 #pragma unroll
         for (int ks = 0; ks < KST; ++ks) xa_addr[ks] = sbase + sp.x(pb) + xoff(row, 32 * ks + 16 * (lane >> 4));
-        phase_a<KST, kRev>(xa_addr, bfrag, bias, su, smem + sp.D(pb), g, tig, t0, L);
+        phase_a<KST, kRev>(xa_addr, bfrag, bias, su, smem + sp.D(pb), g, tig, valid);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(pb));    // tile staged for the consumer
@@ -792,8 +815,9 @@ int tensor_maps(const FastScanArgs& a, CUtensorMap* mu, CUtensorMap* mz, CUtenso
 template <int R, int kExp, bool kTwoWarp>
 int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
   FastScanArgs a = a0;
+  if (!a.reverse) a.frame_len = 0;
   plan_segments(a, &a.nseg, &a.seg_len);
-  if (!split || (a.nseg > 1 && (a.seg_ws == nullptr ||
+  if (!split || a.frame_len > 0 || (a.nseg > 1 && (a.seg_ws == nullptr ||
                                 a.seg_ws_bytes < scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N)))) {
     a.nseg = 1;                                // no workspace given: run unsplit (still correct)
     a.seg_len = (a.L + kTT - 1) / kTT * kTT;
@@ -805,10 +829,10 @@ int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
   auto run = [&](dim3 grid, auto state_only) {
     constexpr bool kSO = decltype(state_only)::value;
     if constexpr (kTwoWarp) {
-      if (a.reverse) two_warp::scan2w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      if (a.reverse && a.frame_len == 0) two_warp::scan2w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else two_warp::scan2w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
     } else {
-      if (a.reverse) one_warp::scan1w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      if (a.reverse && a.frame_len == 0) one_warp::scan1w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else one_warp::scan1w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
     }
   };

@@ -43,12 +43,20 @@ scan_generic_kernel(const vmb_scan_args a) {
   const T* z = a.z ? reinterpret_cast<const T*>(a.z) + (int64_t)b * a.z_bstride + d : nullptr;
   T* y = reinterpret_cast<T*>(a.y) + (int64_t)b * a.y_bstride + d;
   const T* bc = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride;
+  // physical row of logical token i (forward / whole-sequence reversal / frame-axis reversal)
+  const int F = a.frame_len;
+  auto row = [&](int i) -> int64_t {
+    if (!a.reverse) return (int64_t)i;
+    if (F <= 0) return (int64_t)(L - 1 - i);
+    const int f = i / F;
+    return (int64_t)(L - (f + 1) * F + (i - f * F));
+  };
 
   for (int c0 = 0; c0 < L; c0 += kTok) {
     const int nt = min(kTok, L - c0);
     for (int e = tid; e < nt * N; e += kThreads) {
       const int t = e / N, n = e % N;
-      const int64_t r = a.reverse ? (int64_t)(L - 1 - (c0 + t)) : (int64_t)(c0 + t);
+      const int64_t r = row(c0 + t);
       sB[t][n] = to_f32<T>(bc[r * a.bc_tstride + a.b_off + n]);
       sC[t][n] = to_f32<T>(bc[r * a.bc_tstride + a.c_off + n]);
     }
@@ -56,7 +64,7 @@ scan_generic_kernel(const vmb_scan_args a) {
     if (valid) {
 #pragma unroll 2
       for (int t = 0; t < nt; ++t) {
-        const int64_t r = a.reverse ? (int64_t)(L - 1 - (c0 + t)) : (int64_t)(c0 + t);
+        const int64_t r = row(c0 + t);
         const float uv = to_f32<T>(u[r * a.u_tstride]);
         float dv = to_f32<T>(dl[r * a.d_tstride]) + bias;
         if (a.softplus) dv = softplus_f<kAccurate>(dv);

@@ -267,8 +267,10 @@ def _token_major(t: Tensor) -> Tensor:
 
 def causal_conv1d_tokens(x: Tensor, weight: Tensor, bias: Optional[Tensor],
                          conv_state: Optional[Tensor] = None, want_state: bool = False,
-                         silu: bool = True, reverse: bool = False):
+                         silu: bool = True, reverse: bool = False, frame_len: int = 0):
     """Depthwise causal conv on token-major ``x (B, L, Di)``; ``weight (Di, W)``.
+    ``reverse``: walk the tokens back to front; with ``frame_len > 0`` only the FRAME axis is reversed
+    (frames of ``frame_len`` tokens back to front, tokens inside a frame front to back).
     Returns ``y`` or ``(y, new_conv_state (B, Di, W))``."""
     _require_cuda(x)
     lib = _lib.load()
@@ -294,7 +296,8 @@ def causal_conv1d_tokens(x: Tensor, weight: Tensor, bias: Optional[Tensor],
             _p(cs_in), _dt(cs_in) if cs_in is not None else VMB_F32,
             _p(y), y.stride(0), y.stride(1),
             _p(cs_out), _dt(cs_out) if cs_out is not None else VMB_F32,
-            B, L, Di, W, 1 if silu else 0, 1 if reverse else 0, _dt(x), _stream(x))
+            B, L, Di, W, 1 if silu else 0, 1 if reverse else 0, int(frame_len) if reverse else 0,
+            _dt(x), _stream(x))
     _lib.check(rc, "vmb_causal_conv1d_fwd")
     return forward_only((y, cs_out) if want_state else y, x, weight, bias, conv_state)
 
@@ -303,7 +306,7 @@ def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_of
                           d_state: int, D: Optional[Tensor] = None, z: Optional[Tensor] = None,
                           dt_bias: Optional[Tensor] = None, softplus: bool = True,
                           h0: Optional[Tensor] = None, want_last: bool = False,
-                          reverse: bool = False):
+                          reverse: bool = False, frame_len: int = 0):
     """Token-major selective scan.  ``u, delta, z: (B, L, Di)``; ``bc: (B, L, >=c_off+N)`` holds
     B_t at ``[b_off, b_off+N)`` and C_t at ``[c_off, c_off+N)``; ``A2 = A*log2(e)`` fp32 (Di, N)."""
     _require_cuda(u)
@@ -332,6 +335,7 @@ def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_of
     a.h_last = None if h_last is None else h_last.data_ptr()
     a.B, a.L, a.Di, a.N = B, L, Di, d_state
     a.dtype, a.softplus, a.reverse = _dt(u), 1 if softplus else 0, 1 if reverse else 0
+    a.frame_len = int(frame_len) if reverse else 0
     with _on_device(u):
         rc = lib.vmb_selective_scan_fwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_fwd")
@@ -342,7 +346,8 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
                                 dt_rank: int, d_state: int, D: Optional[Tensor] = None,
                                 dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
                                 want_last: bool = False, reverse: bool = False,
-                                allow_split: bool = True, a_geometric: bool = False, tune: int = 0):
+                                allow_split: bool = True, a_geometric: bool = False, tune: int = 0,
+                                frame_len: int = 0):
     """Fused dt_proj + softplus + scan + D skip + SiLU(z) gate (bf16, d_state 16).
     ``u, z: (B, L, Di)``; ``xdbl: (B, L, Xp)`` rows ``[dt_low (R) | B (N) | C (N) | pad]`` with
     ``Xp = xdbl_pitch(R, N)``; ``w_dt: (Di, R)`` bf16, or already zero-padded to ``(Di, Rp)`` with
@@ -375,6 +380,7 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
     a.B, a.L, a.Di, a.N, a.R = B, L, Di, d_state, dt_rank
     a.Rp, a.Xp, a.reverse = w_dt.stride(0), xdbl.shape[-1], 1 if reverse else 0
     a.a_geometric, a.tune = 1 if a_geometric else 0, int(tune)
+    a.frame_len = int(frame_len) if reverse else 0
     if u.dtype != torch.bfloat16 or z.dtype != u.dtype or xdbl.dtype != u.dtype \
             or w_dt.dtype != u.dtype:
         raise TypeError("the fused scan is a bf16 kernel")
@@ -444,7 +450,7 @@ class MixerWeights:
 def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = None,
               ssm_state: Optional[Tensor] = None, want_conv_state: bool = False,
               want_ssm_state: bool = False, reverse: bool = False, path: int = 0,
-              scan_tune: int = 0, fuse_conv_xproj: bool = False):
+              scan_tune: int = 0, fuse_conv_xproj: bool = False, frame_len: int = 0):
     """Whole Mamba mixer on token-major ``hidden (B, L, D)``.
     Returns ``(out, new_conv_state | None, last_ssm_state | None)``."""
     _require_cuda(hidden)
@@ -514,6 +520,7 @@ def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = No
     a.dtype, a.reverse, a.path = dt, 1 if reverse else 0, path
     a.a_geometric, a.scan_tune = 1 if w.a_geometric else 0, int(scan_tune)
     a.fuse_conv_xproj = 1 if fuse_conv_xproj else 0
+    a.frame_len = int(frame_len) if reverse else 0
     with _on_device(hidden):
         rc = lib.vmb_mixer_fwd(C.byref(a), _stream(hidden))
     _lib.check(rc, "vmb_mixer_fwd")

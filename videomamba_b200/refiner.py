@@ -4,8 +4,9 @@ Drop-in for the reference's models/refiner_backbone.py:13-135.  The reference ma
 reversed sequence with ``torch.flip`` before and after the backward block; here the backward
 block's conv and scan WALK the tokens back to front (``reverse`` flag of ``vmb_mixer_fwd``), so a
 3-D input needs no flip copies at all.  A 4-D ``(B, T, N, C)`` input flips the frame axis only
-(intra-frame order is kept, refiner_backbone.py:61-68); that permutation is not a plain
-reversal, so it still goes through one gather each way.
+(intra-frame order is kept, refiner_backbone.py:61-68): the same kernels walk the frames back to
+front and the tokens of a frame front to back (``frame_len`` of ``vmb_mixer_fwd``), again without
+a copy.
 """
 from __future__ import annotations
 
@@ -74,11 +75,13 @@ class BiMambaRefinerBlock(nn.Module):
         """block_bwd on the time-reversed sequence, result in ORIGINAL token order."""
         blk = self.block_bwd
         mixer = blk.mixer
-        if packed is None and hasattr(mixer, "_kernel_weights"):
-            # norm is per token, so only the mixer needs the reversed walk
+        if hasattr(mixer, "_kernel_weights"):
+            # norm is per token, so only the mixer needs the reversed walk (3-D input: token axis;
+            # 4-D input: frame axis, frames of packed[2] tokens)
             normed, _ = blk._add_norm(x_seq, None)
             out, _, _ = ops.mixer_fwd(mixer._kernel_weights(), normed, state[0], state[1],
-                                      want_conv_state=False, want_ssm_state=False, reverse=True)
+                                      want_conv_state=False, want_ssm_state=False, reverse=True,
+                                      frame_len=0 if packed is None else packed[2])
             return out
         out_rev, _, _ = blk(self._flip_time(x_seq, packed), state=state, return_state=True)
         return self._flip_time(out_rev, packed)
