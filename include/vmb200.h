@@ -221,6 +221,33 @@ VMB_API int vmb_selective_state_update(void* state, int state_dtype,
                                int B, int Di, int N, int dtype, vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused single-token decode step: everything between in_proj and out_proj of Mamba.step
+ * (models/videomamba/mamba_simple.py:466-494) in one kernel -- causal_conv1d_update (:468-474),
+ * x_proj (:476), split + dt_proj without bias (:477-479), selective_state_update with dt_bias,
+ * softplus, D skip and the SiLU(z) gate (:483-494).  conv_state (B, Di, W) and ssm_state (B, Di, N)
+ * are updated IN PLACE, as the reference's step does.  xz (B, 2Di) is the in_proj output
+ * (x = [:, :Di], z = [:, Di:]); y (B, Di) is the gated output that goes into out_proj.  The conv
+ * output, x_dbl and delta_raw are rounded to `dtype` between the stages like the reference's
+ * separate calls; the state update runs in fp32.  Any Di / N / R / W; one CTA per batch row.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vmb_step_args {
+  const void* xz;      int64_t xz_bstride;               /* (B, 2Di) */
+  void* conv_state;    int32_t cs_dtype;                 /* (B, Di, W) contiguous, in place */
+  void* ssm_state;     int32_t ss_dtype;                 /* (B, Di, N) contiguous, in place */
+  const void* w_conv;  /* (Di, W) */
+  const void* b_conv;  /* (Di) nullable */
+  const void* w_x;     /* (R+2N, Di) contiguous */
+  const void* w_dt;    /* (Di, R) contiguous */
+  const float* A2;     /* (Di, N) fp32, A*log2(e) */
+  const float* Dskip;  /* (Di) fp32, nullable */
+  const float* dt_bias;/* (Di) fp32, nullable */
+  void* y;             int64_t y_bstride;                /* (B, Di) */
+  int32_t B, Di, N, R, W;
+  int32_t dtype;       /* element type of xz / weights / y */
+} vmb_step_args;
+VMB_API int vmb_mixer_step_fwd(const vmb_step_args* args, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Whole mixer block: in_proj -> conv(+SiLU) -> x_proj -> dt_proj -> scan(+gate) -> out_proj.
  * Replaces the body of Mamba.forward, models/videomamba/mamba_simple.py:332-446, for the
  * stateless, (conv_state, ssm_state)-streaming and ssm-only cases, and stands where

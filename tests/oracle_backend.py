@@ -45,15 +45,19 @@ def gate_blend(g1, g2, fwd, bwd):
     return (s * fwd.float() + (1.0 - s) * bwd.float()).to(fwd.dtype)
 
 
-def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None):
-    return orc.causal_conv1d_update_ref(x, conv_state, weight.reshape(x.shape[1], -1), bias,
-                                        activation)
-
-
-def state_update(ssm_state, x, dt, w, B, C, z):
+def mixer_step(w, xz, conv_state, ssm_state):
+    # reference mamba_simple.py:466-494 between in_proj and out_proj; states in place
     p = _params(w)
+    d_inner, _, d_conv = p["conv1d.weight"].shape
+    d_state, dt_rank = p["A_log"].shape[1], p["dt_proj.weight"].shape[1]
+    x, z = xz[:, :d_inner], xz[:, d_inner:]
+    x = orc.causal_conv1d_update_ref(x, conv_state, p["conv1d.weight"].reshape(d_inner, d_conv),
+                                     p.get("conv1d.bias"), "silu")
+    x_db = orc._linear(x, p["x_proj.weight"])
+    dt_low, Bm, Cm = torch.split(x_db, [dt_rank, d_state, d_state], dim=-1)
+    dt = orc._linear(dt_low, p["dt_proj.weight"])
     A = -torch.exp(p["A_log"].float())
-    return orc.selective_state_update_ref(ssm_state, x, dt, A, B, C, p["D"], z=z,
+    return orc.selective_state_update_ref(ssm_state, x, dt, A, Bm, Cm, p["D"], z=z,
                                           dt_bias=p["dt_proj.bias"], dt_softplus=True)
 
 
@@ -87,6 +91,5 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "gate_blend", gate_blend)
     monkeypatch.setattr(ops, "patchify", patchify)
     monkeypatch.setattr(ops, "embed_tokens", embed_tokens)
-    monkeypatch.setattr(ops, "causal_conv1d_update", causal_conv1d_update)
-    monkeypatch.setattr(mixer_mod, "_state_update", state_update)
+    monkeypatch.setattr(ops, "mixer_step", mixer_step)
     monkeypatch.setattr(mixer_mod.Mamba, "_require_cuda", staticmethod(lambda t: None))

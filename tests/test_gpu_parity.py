@@ -280,6 +280,44 @@ def test_oracle_parity_at_baseline_sizes(case):
     _close(got_pool, want_pool, _tol(dtype))
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("geom", [(384, 16, 4, 1), (384, 16, 4, 32), (576, 16, 4, 5), (40, 8, 3, 3)])
+def test_fused_decode_step_matches_oracle(dtype, tol, geom):
+    """Mamba.step (reference mamba_simple.py:453-497): in_proj, ONE fused kernel for conv update + x_proj +
+    dt_proj + state update + gate (vmb_mixer_step_fwd), out_proj.  Five consecutive tokens after a
+    prefill through the inference cache, against the oracle: outputs and both in-place states."""
+    d_model, d_state, d_conv, batch = geom
+    torch.manual_seed(d_model + batch)
+    mx = Mamba(d_model=d_model, d_state=d_state, d_conv=d_conv, use_fast_path=False, layer_idx=0).eval()
+    with torch.no_grad():
+        mx.A_log.add_(0.1 * torch.randn_like(mx.A_log))
+    mx = mx.to(dtype)
+    p = {k: v.detach().clone() for k, v in mx.state_dict().items()}
+    x = torch.randn(batch, 9, d_model).to(dtype)
+    # oracle: prefill 4 tokens, then 5 single-token steps
+    di = 2 * d_model
+    o_conv = torch.zeros(batch, di, d_conv, dtype=dtype)
+    o_ssm = torch.zeros(batch, di, d_state, dtype=dtype)
+    want = [orc.mixer_prefill_cache_ref(p, x[:, :4], o_conv, o_ssm)]
+    for t in range(4, 9):
+        want.append(orc.mixer_step_ref(p, x[:, t:t + 1], o_conv, o_ssm))
+    mx.to(DEV)
+    cache = SimpleNamespace(seqlen_offset=0, key_value_memory_dict={})
+    launches0 = _lib.load().vmb_launch_count()
+    with torch.no_grad():
+        got = [mx(x[:, :4].to(DEV), inference_params=cache)]
+        before = _lib.load().vmb_launch_count()
+        for t in range(4, 9):
+            cache.seqlen_offset = t
+            got.append(mx(x[:, t:t + 1].to(DEV), inference_params=cache))
+    assert _lib.load().vmb_launch_count() - before == 5 * 3      # in_proj, fused step, out_proj per token
+    for g, w_ in zip(got, want):
+        _close(g, w_, tol)
+    g_conv, g_ssm = cache.key_value_memory_dict[0]
+    _close(g_conv, o_conv, tol)
+    _close(g_ssm, o_ssm, tol)
+
+
 def test_mixer_fused_conv_xproj_is_bit_identical():
     """Mamba.fuse_conv_xproj routes stateless forward walks through the one-kernel conv + x_proj
     (vmb_conv_xproj_fwd inside vmb_mixer_fwd): same bits as the two-kernel path, at the bench width."""

@@ -74,6 +74,20 @@ class MixerArgs(C.Structure):
     ]
 
 
+class StepArgs(C.Structure):
+    """struct vmb_step_args"""
+    _fields_ = [
+        ("xz", c_void_p), ("xz_bstride", c_int64),
+        ("conv_state", c_void_p), ("cs_dtype", c_int32),
+        ("ssm_state", c_void_p), ("ss_dtype", c_int32),
+        ("w_conv", c_void_p), ("b_conv", c_void_p), ("w_x", c_void_p), ("w_dt", c_void_p),
+        ("A2", c_void_p), ("Dskip", c_void_p), ("dt_bias", c_void_p),
+        ("y", c_void_p), ("y_bstride", c_int64),
+        ("B", c_int32), ("Di", c_int32), ("N", c_int32), ("R", c_int32), ("W", c_int32),
+        ("dtype", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/vmb200.h declares
 SIGNATURES = {
     "vmb_abi_version": (c_int, []),
@@ -101,6 +115,7 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                            c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                            c_int, c_int, c_int, c_int, c_void_p]),
+    "vmb_mixer_step_fwd": (c_int, [C.POINTER(StepArgs), c_void_p]),
     "vmb_mixer_workspace_bytes": (c_int64, [c_int] * 7),
     "vmb_mixer_fwd": (c_int, [C.POINTER(MixerArgs), c_void_p]),
     "vmb_patchify": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

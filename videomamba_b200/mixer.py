@@ -215,14 +215,10 @@ class Mamba(nn.Module):
         self._require_cuda(hidden_states)
         assert hidden_states.shape[1] == 1, "Only support decoding with 1 token at a time for now"
         w = self._kernel_weights()
+        # three launches: in_proj, the fused step kernel (conv update + x_proj + dt_proj + state update +
+        # gate, csrc/step.cu), out_proj
         xz = ops.linear(hidden_states[:, 0], w.w_in, w.b_in)
-        x, z = xz[:, : self.d_inner], xz[:, self.d_inner:]
-        x = ops.causal_conv1d_update(x, conv_state, w.w_conv, w.b_conv, self.activation)
-        x_db = ops.linear(x, w.w_x)
-        dt = ops.linear(x_db[:, : self.dt_rank], w.w_dt)           # bias is added in the update
-        B = x_db[:, self.dt_rank: self.dt_rank + self.d_state]
-        C = x_db[:, self.dt_rank + self.d_state:]
-        y = _state_update(ssm_state, x, dt, w, B, C, z)
+        y = ops.mixer_step(w, xz, conv_state, ssm_state)
         out = ops.linear(y, w.w_out, w.b_out)
         return out.unsqueeze(1), conv_state, ssm_state
 
@@ -258,24 +254,3 @@ class Mamba(nn.Module):
             entry[0].zero_()
             entry[1].zero_()
         return entry
-
-
-def _state_update(ssm_state, x, dt, w: ops.MixerWeights, B, C, z):
-    """selective_state_update with the prepared A2 / D / dt_bias (avoids re-deriving them)."""
-    import ctypes as C_
-
-    from . import _lib
-    lib = _lib.load()
-    if not ssm_state.is_contiguous():
-        raise ValueError("ssm_state must be contiguous (it is updated in place)")
-    row = lambda t: t if t.stride(-1) == 1 else t.contiguous()
-    x, dt, B, C, z = row(x), row(dt), row(B), row(C), row(z)
-    y = torch.empty_like(x, memory_format=torch.contiguous_format)
-    p = lambda t: C_.c_void_p(t.data_ptr())
-    with ops._on_device(x):
-        rc = lib.vmb_selective_state_update(
-            p(ssm_state), ops._dt(ssm_state), p(x), x.stride(0), p(dt), dt.stride(0), p(w.A2),
-            p(B), B.stride(0), p(C), C.stride(0), p(w.Dskip), p(z), z.stride(0), p(w.dt_bias), 1,
-            p(y), y.stride(0), x.shape[0], x.shape[1], w.N, ops._dt(x), ops._stream(x))
-    _lib.check(rc, "vmb_selective_state_update")
-    return y

@@ -21,7 +21,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import VMB_BF16, VMB_F32, FusedScanArgs, MixerArgs, ScanArgs
+from ._lib import VMB_BF16, VMB_F32, FusedScanArgs, MixerArgs, ScanArgs, StepArgs
 
 LOG2E = 1.4426950408889634
 
@@ -525,6 +525,37 @@ def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = No
         rc = lib.vmb_mixer_fwd(C.byref(a), _stream(hidden))
     _lib.check(rc, "vmb_mixer_fwd")
     return forward_only((out, cs_out, ss_out), hidden, conv_state, ssm_state, *w.raw.values())
+
+
+def mixer_step(w: MixerWeights, xz: Tensor, conv_state: Tensor, ssm_state: Tensor) -> Tensor:
+    """Single-token decode between in_proj and out_proj (reference mamba_simple.py:466-494) as ONE
+    kernel: conv update, x_proj, dt_proj, state update, D skip, gate.  ``xz (B, 2Di)``; both states are
+    updated in place.  Returns the gated ``y (B, Di)``."""
+    _require_cuda(xz)
+    lib = _lib.load()
+    B = xz.shape[0]
+    if xz.shape[1] != 2 * w.Di or xz.dtype != w.dtype:
+        raise ValueError("mixer_step: xz must be (B, 2 * d_inner) in the weights' dtype")
+    if tuple(conv_state.shape) != (B, w.Di, w.W) or tuple(ssm_state.shape) != (B, w.Di, w.N):
+        raise ValueError("mixer_step: state shapes do not match the batch / mixer")
+    if not conv_state.is_contiguous() or not ssm_state.is_contiguous():
+        raise ValueError("conv_state / ssm_state must be contiguous (they are updated in place)")
+    if xz.stride(-1) != 1:
+        xz = xz.contiguous()
+    y = torch.empty((B, w.Di), dtype=w.dtype, device=xz.device)
+    a = StepArgs()
+    a.xz, a.xz_bstride = xz.data_ptr(), xz.stride(0)
+    a.conv_state, a.cs_dtype = conv_state.data_ptr(), _dt(conv_state)
+    a.ssm_state, a.ss_dtype = ssm_state.data_ptr(), _dt(ssm_state)
+    a.w_conv, a.b_conv = w.w_conv.data_ptr(), None if w.b_conv is None else w.b_conv.data_ptr()
+    a.w_x, a.w_dt = w.w_x.data_ptr(), w.w_dt.data_ptr()
+    a.A2, a.Dskip, a.dt_bias = w.A2.data_ptr(), w.Dskip.data_ptr(), w.dt_bias.data_ptr()
+    a.y, a.y_bstride = y.data_ptr(), y.stride(0)
+    a.B, a.Di, a.N, a.R, a.W, a.dtype = B, w.Di, w.N, w.R, w.W, _dt(xz)
+    with _on_device(xz):
+        rc = lib.vmb_mixer_step_fwd(C.byref(a), _stream(xz))
+    _lib.check(rc, "vmb_mixer_step_fwd")
+    return forward_only(y, xz, conv_state, ssm_state, *w.raw.values())
 
 
 def state_gather(pool: Tensor, index: Tensor) -> Tensor:
