@@ -320,6 +320,26 @@ VMB_API int vmb_embed_tokens(const void* patches, const void* spatial, const voi
                      void* out, int64_t B, int t, int hw, int D, int dtype, vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Back glue of the token path.
+ * vmb_pool_norm_fwd: the pooling block of PretrainVideoMamba.forward
+ * (models/videomamba/videomamba.py:983-1063).  x (B, has_cls + G*per, C) are the tokens after the final
+ * norm (token 0 = CLS when has_cls); group g = patch tokens [g*per, (g+1)*per) (G = 1: all patch tokens;
+ * G = temporal tokens, per = tokens per frame: keep_temporal).  mode 0 `cls`: LN(cls) -> out (B, 1, C);
+ * 1 `cls+avg`: LN(cls + mean_g) -> (B, G, C); 2 `cls_cat_avg`: LN(cat[cls, mean_g]) -> (B, 1 + G, C);
+ * 3 `avg`: LN(mean_g) -> (B, G, C).  LN = nn.LayerNorm(C) (pool_norm: weight / bias nullable, eps).  The mean
+ * and the sum with CLS are rounded to `dtype` like the reference's torch ops.  workspace: device scratch of
+ * vmb_pool_norm_workspace_bytes(B, G, per, C) bytes (unused in mode 0).
+ * vmb_gather_rows: dst (B, n, C) = src[b, index[b, i], :] -- the visible-token gather of the masked path
+ * (videomamba.py:826-836); index (B, n) int64 on the device.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int64_t vmb_pool_norm_workspace_bytes(int B, int G, int per, int C);
+VMB_API int vmb_pool_norm_fwd(const void* x, int64_t x_bstride, int64_t x_tstride, int B, int G, int per, int C,
+                      int has_cls, int mode, const void* ln_weight, const void* ln_bias, float eps,
+                      void* out, void* workspace, int64_t workspace_bytes, int dtype, vmb_stream_t stream);
+VMB_API int vmb_gather_rows(const void* src, int64_t src_bstride, int64_t src_tstride, const int64_t* index,
+                    int B, int n_per_batch, int C, void* dst, int dtype, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Per-stage device timing (measurement aid, off by default; nothing like it exists in the
  * reference).  While enabled, every entry point above brackets the kernels it enqueues with
  * cudaEvents on `stream`, tagged with the stage they belong to.  vmb_prof_read synchronises

@@ -81,6 +81,27 @@ def embed_tokens(patches, spatial, temporal, cls_row=None):
     return tokens
 
 
+def pool_norm(x_vis, has_cls, groups, per, pool_type, ln_weight, ln_bias, eps):
+    # reference videomamba.py:983-1063 with torch ops in the model dtype
+    F = torch.nn.functional
+    C = x_vis.shape[-1]
+    ln = lambda t: F.layer_norm(t, (C,), ln_weight, ln_bias, eps)
+    cls = x_vis[:, :1] if has_cls else None
+    patches = x_vis[:, 1:] if has_cls else x_vis
+    if pool_type == "cls":
+        return ln(cls)
+    avg = patches.reshape(x_vis.shape[0], groups, per, C).mean(2)
+    if pool_type == "cls+avg":
+        return ln(cls + avg)
+    if pool_type == "cls_cat_avg":
+        return ln(torch.cat([cls, avg], dim=1))
+    return ln(avg)
+
+
+def gather_rows(src, index):
+    return src.gather(1, index.unsqueeze(-1).expand(-1, -1, src.shape[-1]))
+
+
 def install(monkeypatch):
     import videomamba_b200.mixer as mixer_mod
     import videomamba_b200.ops as ops
@@ -92,4 +113,6 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "patchify", patchify)
     monkeypatch.setattr(ops, "embed_tokens", embed_tokens)
     monkeypatch.setattr(ops, "mixer_step", mixer_step)
+    monkeypatch.setattr(ops, "pool_norm", pool_norm)
+    monkeypatch.setattr(ops, "gather_rows", gather_rows)
     monkeypatch.setattr(mixer_mod.Mamba, "_require_cuda", staticmethod(lambda t: None))

@@ -722,3 +722,45 @@ def test_frame_axis_reversal_equals_flip_copies(geom):
     assert rel_err(got, _flip_frames(want, n)) <= 1e-2 and torch.equal(got_cs, want_cs)
     with pytest.raises(RuntimeError, match="whole number of frames"):
         ops.causal_conv1d_tokens(u, w, b, reverse=True, frame_len=n + 1 if L % (n + 1) else n + 2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("pool_type", ["cls", "cls+avg", "cls_cat_avg", "avg"])
+@pytest.mark.parametrize("geom", [(3, 1, 196, 384), (2, 4, 49, 192), (5, 8, 196, 576), (1, 1, 3136, 384), (2, 3, 7, 20)])
+def test_pool_norm_against_torch(dtype, pool_type, geom):
+    """Pooling over the patch tokens + pool_norm (reference videomamba.py:983-1063): all four pool types,
+    whole-clip mean (groups = 1) and keep_temporal (per-frame mean), with and without a CLS row."""
+    Bsz, G, per, Cdim = geom
+    gen = torch.Generator().manual_seed(G * per + Cdim)
+    F = torch.nn.functional
+    for has_cls in ((True,) if pool_type != "avg" else (True, False)):
+        x = _rand(gen, Bsz, (1 if has_cls else 0) + G * per, Cdim, dtype=dtype).to(DEV)
+        w = (1 + 0.1 * torch.randn(Cdim, generator=gen)).to(dtype).to(DEV)
+        b = (0.1 * torch.randn(Cdim, generator=gen)).to(dtype).to(DEV)
+        groups = 1 if pool_type == "cls" else G
+        per_g = (G * per) // groups
+        got = ops.pool_norm(x, has_cls, groups, per_g, pool_type, w, b, 1e-5)
+        cls = x[:, :1]
+        patches = x[:, 1:] if has_cls else x
+        ln = lambda t: F.layer_norm(t, (Cdim,), w, b, 1e-5)
+        avg = patches.reshape(Bsz, groups, per_g, Cdim).mean(2)
+        want = {"cls": lambda: ln(cls), "cls+avg": lambda: ln(cls + avg),
+                "cls_cat_avg": lambda: ln(torch.cat([cls, avg], dim=1)), "avg": lambda: ln(avg)}[pool_type]()
+        assert got.shape == want.shape and got.dtype == dtype
+        # LayerNorm of a mean amplifies the last-bit differences of the bf16 mean by 1 / std(mean)
+        assert rel_err(got, want) <= (2e-2 if dtype == torch.bfloat16 else 2e-5), rel_err(got, want)
+    with pytest.raises(RuntimeError, match="CLS"):
+        ops.pool_norm(x[:, : G * per] if not has_cls else x[:, 1:], False, G, per, "cls+avg", w, b, 1e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gather_rows_equals_torch_gather(dtype):
+    gen = torch.Generator().manual_seed(1)
+    for Bsz, L, n, Cdim in ((4, 197, 50, 384), (2, 65, 65, 20), (3, 33, 1, 7)):
+        src = _rand(gen, Bsz, L, Cdim, dtype=dtype).to(DEV)
+        idx = torch.stack([torch.randperm(L, generator=gen)[:n].sort().values for _ in range(Bsz)]).to(DEV)
+        got = ops.gather_rows(src, idx)
+        assert torch.equal(got, src.gather(1, idx.unsqueeze(-1).expand(-1, -1, Cdim)))
+        view = src[..., : Cdim // 2 * 2][:, :, : max(1, Cdim // 2)]     # strided source rows
+        got = ops.gather_rows(view, idx)
+        assert torch.equal(got, view.gather(1, idx.unsqueeze(-1).expand(-1, -1, view.shape[-1])))

@@ -122,6 +122,11 @@ SIGNATURES = {
                              c_int, c_void_p]),
     "vmb_embed_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                  c_int, c_int, c_void_p]),
+    "vmb_pool_norm_workspace_bytes": (c_int64, [c_int] * 4),
+    "vmb_pool_norm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vmb_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                c_void_p]),
     "vmb_state_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "vmb_state_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "vmb_launch_count": (c_int64, []),

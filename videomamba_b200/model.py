@@ -401,7 +401,7 @@ class PretrainVideoMamba(nn.Module):
         _, visible = self._visible_token_positions(mask, B, tokens.shape[1], tokens.device,
                                                    require_cls_visible=has_cls)
         if visible is not None:
-            tokens = tokens.gather(1, visible.unsqueeze(-1).expand(-1, -1, C))
+            tokens = ops.gather_rows(tokens, visible)          # visible-token gather (csrc/pool.cu)
 
         hidden, residual = tokens, None
         new_states: Optional[Union[Dict[int, LayerState], List[Optional[LayerState]]]] = None
@@ -469,22 +469,20 @@ class PretrainVideoMamba(nn.Module):
         if self.pool_type != "cls" and patches.shape[1] == 0:
             raise ValueError("mask must keep at least one patch token visible when using "
                              f"pool_type='{self.pool_type}'.")
-        if self.pool_type == "cls":
-            pooled = self.pool_norm(cls_token)
+        if self.pool_type not in ops.POOL_MODES:
+            raise ValueError(f"Unsupported pool_type: {self.pool_type}")
+        if self.pool_type == "cls" or not (keep_temporal and mask is not None):
+            # mean over the patch tokens (all, or per frame) + CLS combine + pool_norm: csrc/pool.cu
+            groups = temporal_tokens if (keep_temporal and self.pool_type != "cls") else 1
+            pooled = ops.pool_norm(x_vis, has_cls, groups, patches.shape[1] // groups, self.pool_type,
+                                   self.pool_norm.weight, self.pool_norm.bias, self.pool_norm.eps)
         else:
-            if self.pool_type not in {"cls+avg", "cls_cat_avg", "avg"}:
-                raise ValueError(f"Unsupported pool_type: {self.pool_type}")
-            if not keep_temporal:
-                avg = patches.mean(1, keepdim=True)
-            elif mask is None:
-                avg = patches.view(patches.shape[0], temporal_tokens, per_frame,
-                                   patches.shape[2]).mean(2)
-            else:
-                total = (1 if has_cls else 0) + temporal_tokens * per_frame
-                _, visible = self._visible_token_positions(mask, patches.shape[0], total,
-                                                           x.device, require_cls_visible=has_cls)
-                avg = self._masked_temporal_average(patches, visible, temporal_tokens, per_frame,
-                                                    has_cls)
+            # keep_temporal under a mask: per-frame mean over the VISIBLE patch tokens (host-checked like
+            # the reference, videomamba.py:702-751), then the reference's own combine + pool_norm
+            total = (1 if has_cls else 0) + temporal_tokens * per_frame
+            _, visible = self._visible_token_positions(mask, patches.shape[0], total,
+                                                       x.device, require_cls_visible=has_cls)
+            avg = self._masked_temporal_average(patches, visible, temporal_tokens, per_frame, has_cls)
             if self.pool_type == "cls+avg":
                 pooled = self.pool_norm(cls_token + avg)
             elif self.pool_type == "cls_cat_avg":

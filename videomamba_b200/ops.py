@@ -258,6 +258,52 @@ def embed_tokens(patches: Tensor, spatial: Tensor, temporal: Tensor,
     return forward_only(out, patches, spatial, temporal, cls_row)
 
 
+POOL_MODES = {"cls": 0, "cls+avg": 1, "cls_cat_avg": 2, "avg": 3}
+
+
+def pool_norm(x_vis: Tensor, has_cls: bool, groups: int, per: int, pool_type: str,
+              ln_weight: Optional[Tensor], ln_bias: Optional[Tensor], eps: float) -> Tensor:
+    """Pooling over the patch tokens + ``pool_norm`` (reference videomamba.py:983-1063) in two launches.
+    ``x_vis (B, has_cls + groups * per, C)``: tokens after the final norm.  ``groups = 1`` averages all
+    patch tokens, ``groups = T`` with ``per`` tokens per frame is ``keep_temporal``."""
+    _require_cuda(x_vis)
+    lib = _lib.load()
+    mode = POOL_MODES[pool_type]
+    x_vis = _token_major(x_vis)
+    B, L, Cdim = x_vis.shape
+    if L != (1 if has_cls else 0) + groups * per:
+        raise ValueError("pool_norm: token count does not match has_cls + groups * per")
+    cast = lambda t: None if t is None else t.to(x_vis.dtype).contiguous()
+    ln_weight, ln_bias = cast(ln_weight), cast(ln_bias)
+    rows = 1 if mode == 0 else (groups + 1 if mode == 2 else groups)
+    out = torch.empty((B, rows, Cdim), dtype=x_vis.dtype, device=x_vis.device)
+    nbytes = lib.vmb_pool_norm_workspace_bytes(B, groups, per, Cdim) if mode != 0 else 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x_vis.device) if nbytes else None
+    with _on_device(x_vis):
+        rc = lib.vmb_pool_norm_fwd(_p(x_vis), x_vis.stride(0), x_vis.stride(1), B, groups, per, Cdim,
+                                   1 if has_cls else 0, mode, _p(ln_weight), _p(ln_bias), float(eps), _p(out),
+                                   _p(ws), nbytes, _dt(x_vis), _stream(x_vis))
+    _lib.check(rc, "vmb_pool_norm_fwd")
+    return forward_only(out, x_vis, ln_weight, ln_bias)
+
+
+def gather_rows(src: Tensor, index: Tensor) -> Tensor:
+    """``src (B, L, C)``, ``index (B, n)`` -> ``(B, n, C)`` rows ``src[b, index[b, i]]`` (the visible-token
+    gather of the masked path, reference videomamba.py:826-836)."""
+    _require_cuda(src)
+    lib = _lib.load()
+    src = _token_major(src)
+    B, L, Cdim = src.shape
+    index = index.to(device=src.device, dtype=torch.int64).contiguous()
+    n = index.shape[1]
+    out = torch.empty((B, n, Cdim), dtype=src.dtype, device=src.device)
+    with _on_device(src):
+        rc = lib.vmb_gather_rows(_p(src), src.stride(0), src.stride(1), _p(index), B, n, Cdim, _p(out),
+                                 _dt(src), _stream(src))
+    _lib.check(rc, "vmb_gather_rows")
+    return forward_only(out, src)
+
+
 def _token_major(t: Tensor) -> Tensor:
     """(B, L, C) tensor with channel stride 1 (copy only when needed)."""
     if t.stride(-1) != 1:
