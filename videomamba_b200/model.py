@@ -231,8 +231,16 @@ class PretrainVideoMamba(nn.Module):
 
     @torch.jit.ignore()
     def load_pretrained(self, checkpoint_path, prefix=""):
-        raise NotImplementedError(
-            "timm .npz checkpoints are not supported; use load_state_dict(path, model, ...)")
+        """The reference hands the model to timm's ViT ``.npz`` loader (videomamba.py:587-589); do the
+        same when timm is installed.  Plain state_dict checkpoints go through ``load_state_dict(path,
+        model, ckpt_num_frame, num_frames)`` below."""
+        try:
+            from timm.models.vision_transformer import _load_weights
+        except ImportError as e:        # timm is an optional dependency of this package
+            raise ImportError("load_pretrained needs timm (the reference delegates to "
+                              "timm.models.vision_transformer._load_weights); for plain state_dict "
+                              "checkpoints use load_state_dict(path, model, ckpt_num_frame, num_frames)") from e
+        _load_weights(self, checkpoint_path, prefix)
 
     # ---- helpers ------------------------------------------------------------------------------
     def _get_layer_state(self, state: Optional[StateCollection], idx: int) -> Optional[LayerState]:
