@@ -587,6 +587,20 @@ def test_graphed_stream_equals_eager_chunks():
         assert torch.equal(pool, eager[i][1]), i
     for (c, s), (ec, es) in zip(runner.state, st):
         assert torch.equal(c, ec) and torch.equal(s, es)
+    # the streams restart: the first chunk (CLS included, zero state) is a graph replay of its own, and the
+    # continuation graph keeps working on the same carried buffers
+    for _ in range(2):
+        vis, pool = runner.first(chunks[0])
+        assert runner.offset == T and runner._first_graph is not None
+        assert torch.equal(vis, eager[0][0]) and torch.equal(pool, eager[0][1])
+        for i in range(1, 3):
+            vis, pool = runner.step(chunks[i])
+            assert torch.equal(vis, eager[i][0]) and torch.equal(pool, eager[i][1]), i
+    # an explicit initial state runs the first chunk eagerly
+    with torch.no_grad():
+        st0 = m.allocate_state(B, dtype=bf, device=DEV)
+    vis, pool = runner.first(chunks[0], state=st0)
+    assert torch.equal(vis, eager[0][0]) and torch.equal(runner.step(chunks[1])[0], eager[1][0])
     with pytest.raises(ValueError, match="pool_type='avg'"):
         GraphedStream(video_mamba.PretrainVideoMamba(img_size=32, patch_size=16, depth=1, embed_dim=32,
                                                      channels=3, num_frames=4, pool_type="cls+avg"))

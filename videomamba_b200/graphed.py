@@ -9,9 +9,10 @@ videomamba.py:655-675, computed eagerly per chunk so the interpolation rule is u
 into a fixed buffer before each replay.
 
 Semantics are those of ``model(x, ssm_state=state, temporal_pos_offset=offset)`` with the state of
-the previous call (streaming contract 1.0.0): the first chunk runs eagerly (it carries the CLS
-token, so its shapes differ), every later chunk is one graph launch.  Results are bit-identical to
-the eager calls (same kernels, same order).
+the previous call (streaming contract 1.0.0).  The first chunk carries the CLS token, so its shapes
+differ: it has a graph of its own (zero state in, captured on its first use; an explicit initial state
+runs eagerly), every later chunk replays the continuation graph.  Results are bit-identical to the
+eager calls (same kernels, same order).
 """
 from __future__ import annotations
 
@@ -42,6 +43,13 @@ class GraphedStream:
         # and recapture when any of them was rebuilt (parameter update, refresh_weights())
         self._captured_keys: Optional[list] = None
         self._captured_weights: Optional[list] = None
+        # first-chunk graph (offset 0, CLS included, zero state in)
+        self._first_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._first_x: Optional[Tensor] = None
+        self._first_out = None
+        self._first_keys: Optional[list] = None
+        self._first_weights: Optional[list] = None
+        self._zero_state: Optional[List[LayerState]] = None
 
     # ---- public -------------------------------------------------------------------------
     @property
@@ -50,17 +58,24 @@ class GraphedStream:
         return self._state
 
     def first(self, x: Tensor, state=None):
-        """First chunk of the streams (offset 0, CLS included): eager.  Returns what
-        ``model(x, ssm_state=state, temporal_pos_offset=0)`` returns, minus the state."""
+        """First chunk of the streams (offset 0, CLS included).  Returns what
+        ``model(x, ssm_state=state, temporal_pos_offset=0)`` returns, minus the state.  With the default
+        zero state the chunk is one graph launch (the returned tensors are then the graph's output
+        buffers, overwritten by the next ``first``); an explicit ``state`` runs eagerly."""
         m = self.model
-        if state is None:
-            p = next(m.parameters())
-            state = m.allocate_state(x.shape[0], dtype=p.dtype, device=x.device)
-        with torch.no_grad():
-            out = m(x, ssm_state=state, temporal_pos_offset=0)
-        self._state = [(c.clone(), s.clone()) for c, s in self._as_list(out[-1])]
         self.offset = m._validate_temporal_length(x.shape[2])
-        self._graph = None
+        if state is not None:
+            with torch.no_grad():
+                out = m(x, ssm_state=state, temporal_pos_offset=0)
+            self._adopt_state(out[-1])
+            return out[:-1] if len(out) > 2 else out[0]
+        if self._first_graph is None or self._first_x.shape != x.shape or self._first_x.dtype != x.dtype \
+                or self._first_keys != self._mixer_keys():
+            self._capture_first(x)
+        else:
+            self._first_x.copy_(x)
+            self._first_graph.replay()
+        out = self._first_out
         return out[:-1] if len(out) > 2 else out[0]
 
     def step(self, x: Tensor):
@@ -83,6 +98,44 @@ class GraphedStream:
         return out[:-1] if len(out) > 2 else out[0]
 
     # ---- internals ----------------------------------------------------------------------
+    def _adopt_state(self, new_state) -> None:
+        """Copy a freshly returned state into the carried buffers (allocating them on first use; the
+        continuation graph keeps reading the SAME buffers)."""
+        new = self._as_list(new_state)
+        if self._state is None or any(c.shape != nc.shape or c.dtype != nc.dtype or s.dtype != ns.dtype
+                                      for (c, s), (nc, ns) in zip(self._state, new)):
+            self._state = [(c.clone(), s.clone()) for c, s in new]
+            self._graph = None
+        else:
+            for (c, s), (nc, ns) in zip(self._state, new):
+                c.copy_(nc)
+                s.copy_(ns)
+
+    def _run_first(self):
+        out = self.model(self._first_x, ssm_state=self._zero_state, temporal_pos_offset=0)
+        self._adopt_state(out[-1])
+        return out
+
+    def _capture_first(self, x: Tensor) -> None:
+        m = self.model
+        p = next(m.parameters())
+        self._first_x = x.clone()
+        self._zero_state = m.allocate_state(x.shape[0], dtype=p.dtype, device=x.device)   # never written
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, self.warmup)):    # also allocates the carried state buffers
+                    self._run_first()
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._first_out = self._run_first()
+            graph.replay()
+        self._first_graph = graph
+        self._first_keys = self._mixer_keys()
+        self._first_weights = [mod._kernel_weights() for mod in self._mixers()]
+
     @staticmethod
     def _as_list(state) -> List[LayerState]:
         if isinstance(state, dict):
