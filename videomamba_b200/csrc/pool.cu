@@ -19,19 +19,58 @@ namespace {
 constexpr int kPoolRows = 64;      // rows per partial-sum CTA
 constexpr int kPoolThreads = 128;
 
-// ws[(b * G + g) * chunks + chunk][C] = sum of rows [chunk * kPoolRows, ...) of group g
-template <typename T>
+// ws[(b * G + g) * chunks + chunk][C] = sum of rows [chunk * kPoolRows, ...) of group g.
+// Thread (cx, ry) sums rows ry, ry + kPoolRy, ... of VEC consecutive channels (one 16-byte load per row);
+// the kPoolRy row slices are added through shared memory in a fixed order (deterministic).
+constexpr int kPoolRy = 4;
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_partial_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, int first_row, int per, int C,
                     int chunks, float* __restrict__ ws) {
+  __shared__ float part[kPoolRy][kPoolThreads / kPoolRy][VEC];
   const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
   const int r0 = chunk * kPoolRows, r1 = min(per, r0 + kPoolRows);
   const T* base = x + (int64_t)b * x_bs + (int64_t)(first_row + g * per) * x_ts;
   float* out = ws + ((int64_t)(b * gridDim.y + g) * chunks + chunk) * C;
-  for (int c = threadIdx.x; c < C; c += kPoolThreads) {
-    float acc = 0.f;
-    for (int r = r0; r < r1; ++r) acc += to_f32<T>(base[(int64_t)r * x_ts + c]);
-    out[c] = acc;
+  constexpr int kCx = kPoolThreads / kPoolRy;            // channel groups per pass
+  const int cx = threadIdx.x % kCx, ry = threadIdx.x / kCx;
+  for (int c0 = 0; c0 < C; c0 += kCx * VEC) {
+    const int c = c0 + cx * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    if (c < C) {
+      for (int r = r0 + ry; r < r1; r += kPoolRy) {
+        const T* p = base + (int64_t)r * x_ts + c;
+        if constexpr (VEC == 8) {                          // bf16: one 16-byte load
+          const uint4 q = *reinterpret_cast<const uint4*>(p);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[2 * k] += __uint_as_float(w[k] << 16);
+            acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+          }
+        } else if constexpr (VEC == 4) {                   // fp32: one 16-byte load
+          const float4 q = *reinterpret_cast<const float4*>(p);
+          acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+        } else {
+          acc[0] += to_f32<T>(*p);
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) part[ry][cx][v] = acc[v];
+    __syncthreads();
+    if (ry == 0 && c < C) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float t = part[0][cx][v];
+#pragma unroll
+        for (int k = 1; k < kPoolRy; ++k) t += part[k][cx][v];
+        out[c + v] = t;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -107,8 +146,15 @@ int pool_launch(const void* x, int64_t x_bs, int64_t x_ts, int B, int G, int per
   const int out_rows = mode == 0 ? 1 : (mode == 2 ? G + 1 : G);
   if (mode != 0) {
     dim3 grid(chunks, G, B);
-    pool_partial_kernel<T><<<grid, kPoolThreads, 0, st>>>((const T*)x, x_bs, x_ts, has_cls ? 1 : 0, per, C,
-                                                          chunks, ws);
+    constexpr int kVec = 16 / (int)sizeof(T);
+    const bool vec = C % kVec == 0 && x_bs % kVec == 0 && x_ts % kVec == 0 &&
+                     reinterpret_cast<uintptr_t>(x) % 16 == 0;
+    if (vec)
+      pool_partial_kernel<T, kVec><<<grid, kPoolThreads, 0, st>>>((const T*)x, x_bs, x_ts, has_cls ? 1 : 0, per,
+                                                                  C, chunks, ws);
+    else
+      pool_partial_kernel<T, 1><<<grid, kPoolThreads, 0, st>>>((const T*)x, x_bs, x_ts, has_cls ? 1 : 0, per, C,
+                                                               chunks, ws);
     VMB_LAUNCH_CHECK("pool_partial_kernel");
   }
   dim3 grid(out_rows, B);
