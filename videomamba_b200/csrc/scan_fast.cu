@@ -790,8 +790,11 @@ void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
   const int64_t want = 12ll * sm_count();       // 3 warps per scheduler
   *nseg = 1;
   *seg_len = (a.L + kTT - 1) / kTT * kTT;
-  if (warps >= want || a.L < 768) return;       // a lone warp needs ~230 clk per token, 3 per scheduler ~120 each
-  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 256);
+  // Segments of >= 128 tokens: a lone warp needs ~230 clk per token, three per scheduler ~120 each; below
+  // ~128 tokens the two extra dependent launches cost what the split saves (B = 1, graph replay, us per
+  // layer: L 392 unsplit 33 / split 34, L 1568 50 -> 35 at 128-token segments, 45 at 256, 37 at 64).
+  if (warps >= want || a.L < 3 * 128) return;
+  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 128);
   if (n < 3) return;                           // two segments cost 1.26x the work for less than that in occupancy
   const int len = ((a.L + n - 1) / n + kTT - 1) / kTT * kTT;
   *nseg = (a.L + len - 1) / len;
