@@ -391,7 +391,7 @@ def test_fused_scan_layouts_agree_bitwise():
     same order: identical bits; the sequence split re-associates the carry and is merely close."""
     run = lambda args, **kw: ops.selective_scan_fused_tokens(*args[:4], args[4], 24, 16, args[5], args[6],
                                                              want_last=True, **kw)
-    short = _scan_inputs(6, 700)                     # below the split threshold (768 tokens)
+    short = _scan_inputs(6, 350)                     # below the split threshold (3 x 128 tokens)
     auto, h_auto = run(short)
     for tune in (10, 20, 30):
         got, h = run(short, tune=tune)

@@ -355,6 +355,25 @@ def test_oracle_parity_middle_32f_full_size():
     _close(got_pool, want_pool, 2e-2)
 
 
+def test_oracle_parity_long_clip_128_frames_full_size():
+    """BASELINE.json configs[4] at full size: VideoMamba-Small, 128 frames @224 (25 089 tokens in one
+    sequence: the scan runs split into segments with the exact two-pass carry), bf16, batch 1, general-A
+    weights, against the CPU oracle."""
+    dtype, dim, frames = torch.bfloat16, 384, 128
+    cfg = dict(img_size=224, patch_size=16, depth=24, embed_dim=dim, kernel_size=1, num_frames=frames,
+               norm_epsilon=1e-5, rms_norm=True, fused_add_norm=True, residual_in_fp32=True,
+               pool_type="cls+avg", add_pool_norm=True)
+    sd = _synthetic(cfg, dtype, True, seed=23)
+    x = torch.rand(1, 3, frames, 224, 224, generator=torch.Generator().manual_seed(6)).to(dtype)
+    m = _model_from(cfg, sd, dtype)
+    with torch.no_grad():
+        want_vis, want_pool = orc.OracleVideoMamba(cfg, sd).forward(x)
+        got_vis, got_pool = m(x.to(DEV))
+    assert got_vis.shape == (1, frames * 196, dim)
+    _close(got_vis, want_vis, 2e-2)
+    _close(got_pool, want_pool, 2e-2)
+
+
 def test_oracle_parity_streaming_64_frame_chunks_full_size():
     """BASELINE.json configs[3] at full chunk size: VideoMamba-Small, two 64-frame chunks @224
     (12 545 tokens with CLS, then 12 544) with (conv_state, ssm_state) carry and temporal_pos_offset,
