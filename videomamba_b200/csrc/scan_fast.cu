@@ -27,14 +27,16 @@
 //     fragment registers -- and ONE HMMA multiplies them with C_t (replicated over the 8 columns of
 //     the B operand), so every lane of a channel receives <C_t, h_t>: no shuffle.
 //   * the decay factors exp2(delta * A2[n]) come from one of three evaluators (template kExp):
-//       general, MUFU:  one MUFU.EX2 per factor (8 per lane-token);
+//       general, MUFU:  one MUFU.EX2 per factor (8 per lane-token) -- shipped for general A;
 //       general, split: kExp of the lane's four state pairs use a Cody-Waite range reduction +
-//                       degree-3 polynomial on the FMA pipe (packed), the rest MUFU -- same issue
-//                       slots, fewer XU cycles, which is what the recurrence phase queues on;
+//                       degree-3 polynomial on the FMA pipe (packed), the rest MUFU.  Measured (B200,
+//                       profiles/r02_scan_evaluators.jsonl): one pair is a wash, two or more lose 8-40 %
+//                       (10 issue slots per pair for the 2 MUFU it replaces) -- measurement builds only
+//                       (-DVMB_SCAN_LAB);
 //       geometric A:    A[d][n] = (n+1) * A[d][0] (exact S4D-real structure, reference
 //                       mamba_simple.py:265-272): two MUFU per channel (r = e^(delta*A0) and
-//                       r^(2*tig+1)), the other factors by packed multiplies.  Selected by the caller
-//                       (weights are checked when they are loaded), never guessed in the kernel.
+//                       r^(2*tig+1)), the other factors by packed multiplies: -13 %.  Selected by the
+//                       caller (weights are checked when they are loaded), never guessed in the kernel.
 //   * two kernels share that code: scan1w (one warp per unit: tile staging, phase A, recurrence and
 //     finalisation in one instruction stream; small footprint, two launches can share an SM) and
 //     scan2w (helper warp: TMA, gathers, phase A, finalisation; consumer warp: recurrence only --
@@ -43,7 +45,8 @@
 //     state from a zero start (recurrence only) and sum(delta); a tiny kernel chains the carries;
 //     the second pass runs all segments concurrently from their true initial states.  Exact.
 //   * reverse = 1 walks the sequence back to front (the flipped branch of BiMambaRefinerBlock,
-//     models/refiner_backbone.py:61-68, :92-135, without flip copies).
+//     models/refiner_backbone.py:61-68, :92-135, without flip copies); with frame_len > 0 only the
+//     frame axis is reversed (4-D input): every frame is cut into its own tiles (tile_geom).
 #include <algorithm>
 
 #include "internal.h"
