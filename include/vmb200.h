@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VMB_ABI_VERSION 2
+#define VMB_ABI_VERSION 3
 
 /* element types */
 #define VMB_F32 0
@@ -338,6 +338,80 @@ VMB_API int vmb_pool_norm_fwd(const void* x, int64_t x_bstride, int64_t x_tstrid
                       void* out, void* workspace, int64_t workspace_bytes, int dtype, vmb_stream_t stream);
 VMB_API int vmb_gather_rows(const void* src, int64_t src_bstride, int64_t src_tstride, const int64_t* index,
                     int B, int n_per_batch, int C, void* dst, int dtype, vmb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward passes (training).  The reference gets its gradients from
+ * autograd through the third-party operators: the streaming-training check differentiates through
+ * the carried (conv_state, ssm_state) (scripts/check_streaming_state.py:47-60) and Block.forward wraps
+ * the mixer in activation checkpointing (models/videomamba/videomamba.py:168-206).  These entry points
+ * are the backward halves of the forward operators above, for the FORWARD token order (the reversed
+ * walk of BiMambaRefinerBlock is differentiated through flip copies).  fp32 math; every reduction over
+ * rows / batch is two-stage through the caller's workspace (no atomics: deterministic).  Parameter
+ * gradients (dweight, dbias, dA, dD, ddt_bias) are written, not accumulated, as fp32.
+ *
+ * vmb_add_norm_bwd: backward of vmb_add_norm_fwd.  x / residual / weight are the forward inputs, dy the
+ *   gradient of y (x's dtype), dresidual_out the gradient of residual_out (nullable).  dx (rows, dim,
+ *   x's dtype); dresidual (residual's dtype, nullable) receives the same values; dweight / dbias (dim)
+ *   fp32, nullable.
+ * vmb_causal_conv1d_bwd: backward of vmb_causal_conv1d_fwd (reverse = 0).  dy (B, L, Di) contiguous;
+ *   dconv_state_out = gradient of the returned state (nullable); dx (B, L, Di) contiguous;
+ *   dconv_state_in (conv_state_in's dtype, nullable); dweight (Di, W), dbias (Di) fp32, nullable.
+ * vmb_selective_scan_bwd: backward of vmb_selective_scan_fwd (reverse = 0, d_state <= 16).
+ *   dout (B, L, Di) view; dh_last (B, Di, N) fp32 nullable.  du / ddelta / dz (B, L, Di) contiguous in
+ *   `dtype` (ddelta is the gradient of delta_raw, i.e. through the softplus); dbc has bc's layout: the
+ *   kernel writes columns [b_off, b_off+N) and [c_off, c_off+N) of every row and leaves the rest alone;
+ *   dA is the gradient with respect to A (= A2 / log2(e)), (Di, N) fp32; dD, ddt_bias (Di) fp32; dh0
+ *   (B, Di, N) fp32; all four nullable.
+ * vmb_transpose_2d / vmb_colsum: out (cols, rows; row stride ldo) = in^T; out (N) = column sums of x (M, N).  The
+ *   projection backward is two vmb_linear_fwd calls on transposed operands (dX = dY W, dW = dY^T X)
+ *   plus a column sum for the bias.
+ * ---------------------------------------------------------------------------------------- */
+VMB_API int64_t vmb_add_norm_bwd_workspace_bytes(int64_t rows, int dim);
+VMB_API int vmb_add_norm_bwd(const void* x, int x_dtype, int64_t ldx,
+                     const void* residual, int residual_dtype,       /* nullable */
+                     const void* weight, int w_dtype,
+                     const void* dy,                                 /* x_dtype */
+                     const void* dresidual_out, int dresidual_out_dtype, /* nullable */
+                     void* dx, void* dresidual /* nullable */,
+                     float* dweight, float* dbias,                   /* nullable */
+                     int64_t rows, int dim, float eps, int is_rms,
+                     void* workspace, int64_t workspace_bytes, vmb_stream_t stream);
+VMB_API int64_t vmb_causal_conv1d_bwd_workspace_bytes(int B, int L, int Di, int W);
+VMB_API int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x_tstride,
+                          const void* weight, const void* bias /* nullable */,
+                          const void* conv_state_in, int cs_in_dtype,     /* nullable */
+                          const void* dy,
+                          const void* dconv_state_out, int dcs_out_dtype, /* nullable */
+                          void* dx, void* dconv_state_in /* nullable */,
+                          float* dweight, float* dbias,                   /* nullable */
+                          int B, int L, int Di, int W, int silu, int dtype,
+                          void* workspace, int64_t workspace_bytes, vmb_stream_t stream);
+typedef struct vmb_scan_bwd_args {
+  const void* u;      int64_t u_bstride, u_tstride;
+  const void* delta;  int64_t d_bstride, d_tstride;
+  const void* z;      int64_t z_bstride, z_tstride;      /* nullable */
+  const void* bc;     int64_t bc_bstride, bc_tstride;    int32_t b_off, c_off;
+  const float* A2;        /* (Di, N) fp32, A*log2(e) */
+  const float* D;         /* (Di) fp32, nullable */
+  const float* dt_bias;   /* (Di) fp32, nullable */
+  const void* h0;     int32_t h0_dtype;                  /* (B,Di,N), nullable */
+  const void* dout;   int64_t dout_bstride, dout_tstride;
+  const float* dh_last;                                  /* (B,Di,N) fp32, nullable */
+  void* du;  void* ddelta;  void* dz;                    /* (B,L,Di) contiguous; dz nullable iff z is */
+  void* dbc;          int64_t dbc_tstride;               /* rows (B*L), same columns as bc */
+  float* dA;  float* dD;  float* ddt_bias;  float* dh0;  /* nullable */
+  void* workspace;    int64_t workspace_bytes;
+  int32_t B, L, Di, N;
+  int32_t dtype;
+  int32_t softplus;
+} vmb_scan_bwd_args;
+VMB_API int64_t vmb_selective_scan_bwd_workspace_bytes(int B, int L, int Di, int N);
+VMB_API int vmb_selective_scan_bwd(const vmb_scan_bwd_args* args, vmb_stream_t stream);
+VMB_API int vmb_transpose_2d(const void* in, int64_t ld, void* out, int64_t ldo, int64_t rows, int cols,
+                     int dtype, vmb_stream_t stream);
+VMB_API int64_t vmb_colsum_workspace_bytes(int64_t M, int N);
+VMB_API int vmb_colsum(const void* x, int64_t ld, int64_t M, int N, int dtype, void* out, int out_dtype,
+               void* workspace, int64_t workspace_bytes, vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-stage device timing (measurement aid, off by default; nothing like it exists in the

@@ -32,6 +32,18 @@ def mixer_fwd(w, hidden, conv_state=None, ssm_state=None, want_conv_state=False,
     return out, (new_conv if want_conv_state else None), (last if want_ssm_state else None)
 
 
+def mixer_train(in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dp, out_w, out_b, hidden,
+                conv_state=None, ssm_state=None, want_conv_state=False, want_ssm_state=False):
+    # the training-mode mixer (videomamba_b200.autograd.mixer_train) on the oracle: live parameters,
+    # so torch autograd differentiates it on the CPU
+    p = {"in_proj.weight": in_w, "in_proj.bias": in_b, "conv1d.weight": conv_w, "conv1d.bias": conv_b,
+         "x_proj.weight": x_w, "dt_proj.weight": dt_w, "dt_proj.bias": dt_b, "A_log": A_log, "D": Dp,
+         "out_proj.weight": out_w, "out_proj.bias": out_b}
+    p = {k: v for k, v in p.items() if v is not None}
+    out, (new_conv, last) = orc.mixer_ref(p, hidden, conv_state, ssm_state, want_state=True)
+    return out, (new_conv if want_conv_state else None), (last if want_ssm_state else None)
+
+
 def add_norm(x, weight, bias, residual, eps, is_rms, prenorm, residual_in_fp32):
     return orc.add_norm_ref(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms)
 
@@ -103,9 +115,11 @@ def gather_rows(src, index):
 
 
 def install(monkeypatch):
+    import videomamba_b200.autograd as autograd_mod
     import videomamba_b200.mixer as mixer_mod
     import videomamba_b200.ops as ops
 
+    monkeypatch.setattr(autograd_mod, "mixer_train", mixer_train)
     monkeypatch.setattr(ops, "mixer_fwd", mixer_fwd)
     monkeypatch.setattr(ops, "add_norm", add_norm)
     monkeypatch.setattr(ops, "linear", linear)

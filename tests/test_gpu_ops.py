@@ -648,17 +648,23 @@ def test_add_norm_and_gate_accept_misaligned_views():
     torch.cuda.synchronize()
 
 
-def test_mixer_refuses_silent_training_and_detects_stale_weights():
-    """backward through the kernels raises; writes through .data are caught by
-    verify_weights and cured by refresh_weights()."""
+def test_forward_only_entry_points_refuse_backward_and_stale_weights_are_detected():
+    """entry points without a backward kernel (the fused inference mixer) raise in backward
+    instead of dropping gradients -- the modules themselves train through autograd.py
+    (tests/test_gpu_backward.py); writes through .data are caught by verify_weights and cured by
+    refresh_weights()."""
     from video_mamba.mamba_simple import Mamba
     torch.manual_seed(2)
     mx = Mamba(d_model=64, use_fast_path=False).to(DEV)
     x = torch.randn(2, 20, 64, device=DEV)
-    out = mx(x)                                   # grad enabled, parameters require grad
+    out = mx(x)                                   # grad enabled, parameters require grad: differentiable
     assert out.requires_grad
+    out.sum().backward()
+    assert mx.in_proj.weight.grad is not None and mx.A_log.grad is not None
+    fused, _, _ = ops.mixer_fwd(mx._kernel_weights(), x)    # the fused inference entry point is not
+    assert fused.requires_grad
     with pytest.raises(NotImplementedError, match="forward-only"):
-        out.sum().backward()
+        fused.sum().backward()
     with torch.no_grad():
         base = mx(x)
         assert not base.requires_grad

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvmb200.so")
 
 VMB_F32, VMB_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 
@@ -88,6 +88,27 @@ class StepArgs(C.Structure):
     ]
 
 
+class ScanBwdArgs(C.Structure):
+    """struct vmb_scan_bwd_args"""
+    _fields_ = [
+        ("u", c_void_p), ("u_bstride", c_int64), ("u_tstride", c_int64),
+        ("delta", c_void_p), ("d_bstride", c_int64), ("d_tstride", c_int64),
+        ("z", c_void_p), ("z_bstride", c_int64), ("z_tstride", c_int64),
+        ("bc", c_void_p), ("bc_bstride", c_int64), ("bc_tstride", c_int64),
+        ("b_off", c_int32), ("c_off", c_int32),
+        ("A2", c_void_p), ("D", c_void_p), ("dt_bias", c_void_p),
+        ("h0", c_void_p), ("h0_dtype", c_int32),
+        ("dout", c_void_p), ("dout_bstride", c_int64), ("dout_tstride", c_int64),
+        ("dh_last", c_void_p),
+        ("du", c_void_p), ("ddelta", c_void_p), ("dz", c_void_p),
+        ("dbc", c_void_p), ("dbc_tstride", c_int64),
+        ("dA", c_void_p), ("dD", c_void_p), ("ddt_bias", c_void_p), ("dh0", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32),
+        ("dtype", c_int32), ("softplus", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/vmb200.h declares
 SIGNATURES = {
     "vmb_abi_version": (c_int, []),
@@ -129,6 +150,21 @@ SIGNATURES = {
                                 c_void_p]),
     "vmb_state_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "vmb_state_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "vmb_add_norm_bwd_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "vmb_add_norm_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                 c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "vmb_causal_conv1d_bwd_workspace_bytes": (c_int64, [c_int] * 4),
+    "vmb_causal_conv1d_bwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                                      c_void_p]),
+    "vmb_selective_scan_bwd_workspace_bytes": (c_int64, [c_int] * 4),
+    "vmb_selective_scan_bwd": (c_int, [C.POINTER(ScanBwdArgs), c_void_p]),
+    "vmb_transpose_2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "vmb_colsum_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "vmb_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int64,
+                           c_void_p]),
     "vmb_launch_count": (c_int64, []),
     "vmb_prof_enable": (c_int, [c_int]),
     "vmb_prof_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_int64), c_int]),

@@ -1,0 +1,303 @@
+"""Differentiable operators: autograd nodes over the libvmb200 forward AND backward kernels.
+
+The reference trains through the third-party operators' own autograd (streaming-training check
+``scripts/check_streaming_state.py:47-60``: gradients flow through the carried
+``(conv_state, ssm_state)``; ``Block.forward`` wraps the mixer in activation checkpointing,
+``models/videomamba/videomamba.py:168-206``).  Here every operator of the block has an
+``autograd.Function`` whose backward is a library kernel (``csrc/backward.cu``, ``csrc/scan_bwd.cu``)
+or, for the projections, two calls of the forward GEMM on transposed operands.  The training-mode
+mixer (``mixer_train``) is the reference's slow path op for op (mamba_simple.py:333-446), so the
+rounding points are the reference's and torch's checkpoint wrapper can recompute it.
+
+Not differentiable: the fused inference entry points (``vmb_mixer_fwd``, the fused scan, the decode
+step) and the reversed token walks -- they stay tagged forward-only (``ops.forward_only``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+from ._lib import VMB_F32, ScanBwdArgs
+from .ops import LOG2E, _dt, _on_device, _p, _stream
+
+
+def wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, Tensor) and t.requires_grad for t in tensors)
+
+
+def _ws(nbytes: int, like: Tensor) -> Optional[Tensor]:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=like.device)
+
+
+def transpose2d(x2: Tensor, pad_to: int = 8) -> Tensor:
+    """``x2 (rows, cols)`` (row stride >= cols) -> its transpose ``(cols, rows)`` as a view of a buffer
+    whose row pitch is a multiple of ``pad_to`` elements (zero tail), the pitch the GEMM's TMA needs."""
+    lib = _lib.load()
+    rows, cols = x2.shape
+    pitch = (rows + pad_to - 1) // pad_to * pad_to
+    out = torch.zeros((cols, pitch), dtype=x2.dtype, device=x2.device) if pitch != rows else \
+        torch.empty((cols, pitch), dtype=x2.dtype, device=x2.device)
+    with _on_device(x2):
+        rc = lib.vmb_transpose_2d(_p(x2), x2.stride(0) if rows > 1 else cols, _p(out), pitch, rows, cols,
+                                  _dt(x2), _stream(x2))
+    _lib.check(rc, "vmb_transpose_2d")
+    return out            # (cols, pitch): columns >= rows are zero
+
+
+def colsum(x2: Tensor, out_dtype: torch.dtype) -> Tensor:
+    lib = _lib.load()
+    M, N = x2.shape
+    out = torch.empty(N, dtype=torch.float32, device=x2.device)
+    nbytes = lib.vmb_colsum_workspace_bytes(M, N)
+    ws = _ws(nbytes, x2)
+    with _on_device(x2):
+        rc = lib.vmb_colsum(_p(x2), x2.stride(0) if M > 1 else N, M, N, _dt(x2), _p(out), VMB_F32, _p(ws),
+                            nbytes, _stream(x2))
+    _lib.check(rc, "vmb_colsum")
+    return out.to(out_dtype)
+
+
+def _rows(t: Tensor, width: int) -> Tensor:
+    t2 = t.reshape(-1, width)
+    if t2.stride(-1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < width):
+        t2 = t2.contiguous()
+    return t2
+
+
+class LinearFn(torch.autograd.Function):
+    """``x @ weight.T (+ bias)``; backward: dX = dY W, dW = dY^T X (both on the forward GEMM), db = colsum(dY)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return ops.linear_raw(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = _rows(dy.to(x.dtype), N)
+        x2 = _rows(x, K)
+        M = x2.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            w_t = transpose2d(_rows(weight.to(x.dtype), K))[:, :N]             # (K, N)
+            dx = ops.linear_raw(dy2, w_t).reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            if M == 0:
+                dw = torch.zeros_like(weight)
+            else:
+                dy_t = transpose2d(dy2)                                        # (N, Mp), zero tail
+                x_t = transpose2d(x2)                                          # (K, Mp)
+                dw = ops.linear_raw(dy_t, x_t).to(weight.dtype)                # (N, K): sum over the M rows
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2, ctx.bias_dtype)
+        return dx, dw, db
+
+
+class AddNormFn(torch.autograd.Function):
+    """Fused residual add + RMSNorm / LayerNorm (``vmb_add_norm_fwd`` / ``vmb_add_norm_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, eps, is_rms, prenorm, residual_in_fp32):
+        ctx.set_materialize_grads(False)
+        y, res_out, x2, res2 = ops.add_norm_raw(x, weight, bias, residual, eps, is_rms, prenorm,
+                                                residual_in_fp32)
+        ctx.save_for_backward(x2, res2, weight)
+        ctx.meta = (eps, is_rms, x.shape, None if residual is None else residual.dtype,
+                    None if bias is None else bias.dtype)
+        if not prenorm:
+            return y
+        if res_out is None:
+            # no incoming residual and the same dtype: the residual stream IS x (a new node-owned alias)
+            res_out = x.view_as(x)
+            ctx.alias_x = True
+        else:
+            ctx.alias_x = False
+        return y, res_out
+
+    @staticmethod
+    def backward(ctx, dy, dres_out=None):
+        lib = _lib.load()
+        x2, res2, weight = ctx.saved_tensors
+        eps, is_rms, shape, res_dtype, bias_dtype = ctx.meta
+        rows, dim = x2.shape
+        if dy is None:
+            dy2 = torch.zeros_like(x2)
+        else:
+            dy2 = dy.reshape(rows, dim).to(x2.dtype).contiguous()
+        dro = None
+        if dres_out is not None:
+            dro = dres_out.reshape(rows, dim).contiguous()
+            if dro.dtype not in (torch.float32, torch.bfloat16):
+                dro = dro.float()
+        dx = torch.empty((rows, dim), dtype=x2.dtype, device=x2.device)
+        dres = torch.empty((rows, dim), dtype=res2.dtype, device=x2.device) if res2 is not None else None
+        dw = torch.empty(dim, dtype=torch.float32, device=x2.device)
+        db = torch.empty(dim, dtype=torch.float32, device=x2.device) if bias_dtype is not None else None
+        nbytes = lib.vmb_add_norm_bwd_workspace_bytes(rows, dim)
+        ws = _ws(nbytes, x2)
+        w = weight.contiguous()
+        with _on_device(x2):
+            rc = lib.vmb_add_norm_bwd(
+                _p(x2), _dt(x2), x2.stride(0) if rows > 1 else dim,
+                _p(res2), _dt(res2) if res2 is not None else VMB_F32,
+                _p(w), _dt(w), _p(dy2), _p(dro), _dt(dro) if dro is not None else VMB_F32,
+                _p(dx), _p(dres), _p(dw), _p(db), rows, dim, float(eps), 1 if is_rms else 0,
+                _p(ws), nbytes, _stream(x2))
+        _lib.check(rc, "vmb_add_norm_bwd")
+        return (dx.reshape(shape), dw.to(weight.dtype), None if db is None else db.to(bias_dtype),
+                None if dres is None else dres.reshape(shape), None, None, None, None)
+
+
+class ConvFn(torch.autograd.Function):
+    """Depthwise causal conv + SiLU with streaming history, token-major (``vmb_causal_conv1d_fwd`` /
+    ``_bwd``).  Gradients flow into ``conv_state`` and arrive through the returned state."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, conv_state, want_state, silu):
+        ctx.set_materialize_grads(False)
+        out = ops.causal_conv1d_tokens_raw(x, weight, bias, conv_state, want_state, silu)
+        ctx.save_for_backward(x, weight, bias, conv_state)
+        ctx.silu = silu
+        if want_state:
+            return out
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dy, dcs_out=None):
+        lib = _lib.load()
+        x, weight, bias, conv_state = ctx.saved_tensors
+        x = ops._token_major(x)
+        B, L, Di = x.shape
+        W = weight.shape[-1]
+        w2 = weight.reshape(Di, W).to(x.dtype).contiguous()
+        b2 = None if bias is None else bias.to(x.dtype).contiguous()
+        cs = None if conv_state is None else conv_state.contiguous()
+        dy = torch.zeros_like(x, memory_format=torch.contiguous_format) if dy is None \
+            else dy.to(x.dtype).contiguous()
+        if dcs_out is not None:
+            dcs_out = dcs_out.contiguous()
+            if dcs_out.dtype not in (torch.float32, torch.bfloat16):
+                dcs_out = dcs_out.float()
+        dx = torch.empty((B, L, Di), dtype=x.dtype, device=x.device)
+        dcs_in = torch.empty_like(cs) if cs is not None and ctx.needs_input_grad[3] else None
+        dw = torch.empty((Di, W), dtype=torch.float32, device=x.device)
+        db = torch.empty(Di, dtype=torch.float32, device=x.device) if bias is not None else None
+        nbytes = lib.vmb_causal_conv1d_bwd_workspace_bytes(B, L, Di, W)
+        ws = _ws(nbytes, x)
+        with _on_device(x):
+            rc = lib.vmb_causal_conv1d_bwd(
+                _p(x), x.stride(0), x.stride(1), _p(w2), _p(b2), _p(cs),
+                _dt(cs) if cs is not None else VMB_F32, _p(dy), _p(dcs_out),
+                _dt(dcs_out) if dcs_out is not None else VMB_F32, _p(dx), _p(dcs_in), _p(dw), _p(db),
+                B, L, Di, W, 1 if ctx.silu else 0, _dt(x), _p(ws), nbytes, _stream(x))
+        _lib.check(rc, "vmb_causal_conv1d_bwd")
+        return (dx, dw.reshape(weight.shape).to(weight.dtype),
+                None if db is None else db.to(bias.dtype), dcs_in, None, None)
+
+
+class ScanFn(torch.autograd.Function):
+    """Selective scan, token-major, explicit ``delta_raw`` (``vmb_selective_scan_fwd`` / ``_bwd``).
+    ``A`` is the natural ``A = -exp(A_log)`` (fp32); B_t / C_t are columns of ``bc``."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, bc, b_off, c_off, d_state, D, z, dt_bias, softplus, h0, want_last):
+        ctx.set_materialize_grads(False)
+        A2 = (A.float() * LOG2E).contiguous()
+        Df = None if D is None else D.float().contiguous()
+        bias = None if dt_bias is None else dt_bias.float().contiguous()
+        u, delta, bc = ops._token_major(u), ops._token_major(delta), ops._token_major(bc)
+        z = None if z is None else ops._token_major(z)
+        out = ops.selective_scan_tokens_raw(u, delta, A2, bc, b_off, c_off, d_state, Df, z, bias,
+                                            softplus, h0, want_last)
+        ctx.save_for_backward(u, delta, A2, bc, Df, z, bias, h0)
+        ctx.meta = (b_off, c_off, d_state, softplus, A.dtype, None if D is None else D.dtype,
+                    None if dt_bias is None else dt_bias.dtype)
+        if want_last:
+            return out
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, dh_last=None):
+        lib = _lib.load()
+        u, delta, A2, bc, Df, z, bias, h0 = ctx.saved_tensors
+        b_off, c_off, N, softplus, A_dtype, D_dtype, bias_dtype = ctx.meta
+        B, L, Di = u.shape
+        dev = u.device
+        dout = torch.zeros_like(u, memory_format=torch.contiguous_format) if dout is None \
+            else ops._token_major(dout.to(u.dtype))
+        du = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
+        dd = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
+        dz = torch.empty((B, L, Di), dtype=u.dtype, device=dev) if z is not None else None
+        dbc = torch.zeros(bc.shape, dtype=bc.dtype, device=dev)
+        dA = torch.empty((Di, N), dtype=torch.float32, device=dev)
+        dD = torch.empty(Di, dtype=torch.float32, device=dev) if Df is not None else None
+        dbias = torch.empty(Di, dtype=torch.float32, device=dev) if bias is not None else None
+        dh0 = torch.empty((B, Di, N), dtype=torch.float32, device=dev) \
+            if h0 is not None and ctx.needs_input_grad[11] else None
+        if dh_last is not None:
+            dh_last = dh_last.float().contiguous()
+        h0c = None if h0 is None else h0.contiguous()
+        nbytes = lib.vmb_selective_scan_bwd_workspace_bytes(B, L, Di, N)
+        ws = _ws(nbytes, u)
+        a = ScanBwdArgs()
+        a.u, a.u_bstride, a.u_tstride = u.data_ptr(), u.stride(0), u.stride(1)
+        a.delta, a.d_bstride, a.d_tstride = delta.data_ptr(), delta.stride(0), delta.stride(1)
+        if z is not None:
+            a.z, a.z_bstride, a.z_tstride = z.data_ptr(), z.stride(0), z.stride(1)
+        a.bc, a.bc_bstride, a.bc_tstride = bc.data_ptr(), bc.stride(0), bc.stride(1)
+        a.b_off, a.c_off = b_off, c_off
+        a.A2 = A2.data_ptr()
+        a.D = None if Df is None else Df.data_ptr()
+        a.dt_bias = None if bias is None else bias.data_ptr()
+        if h0c is not None:
+            a.h0, a.h0_dtype = h0c.data_ptr(), _dt(h0c)
+        a.dout, a.dout_bstride, a.dout_tstride = dout.data_ptr(), dout.stride(0), dout.stride(1)
+        a.dh_last = None if dh_last is None else dh_last.data_ptr()
+        a.du, a.ddelta = du.data_ptr(), dd.data_ptr()
+        a.dz = None if dz is None else dz.data_ptr()
+        a.dbc, a.dbc_tstride = dbc.data_ptr(), dbc.stride(1)
+        a.dA = dA.data_ptr()
+        a.dD = None if dD is None else dD.data_ptr()
+        a.ddt_bias = None if dbias is None else dbias.data_ptr()
+        a.dh0 = None if dh0 is None else dh0.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        a.B, a.L, a.Di, a.N = B, L, Di, N
+        a.dtype, a.softplus = _dt(u), 1 if softplus else 0
+        with _on_device(u):
+            rc = lib.vmb_selective_scan_bwd(C.byref(a), _stream(u))
+        _lib.check(rc, "vmb_selective_scan_bwd")
+        if dh0 is not None and h0.dtype != torch.float32:
+            dh0 = dh0.to(h0.dtype)
+        return (du, dd, dA.to(A_dtype), dbc, None, None, None,
+                None if dD is None else dD.to(D_dtype), dz,
+                None if dbias is None else dbias.to(bias_dtype), None, dh0, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# training-mode mixer: the reference's slow path, op for op (mamba_simple.py:333-446)
+# ----------------------------------------------------------------------------------------------
+def mixer_train(in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dp, out_w, out_b,
+                hidden: Tensor, conv_state: Optional[Tensor] = None, ssm_state: Optional[Tensor] = None,
+                want_conv_state: bool = False, want_ssm_state: bool = False):
+    """Returns ``(out, new_conv_state | None, last_ssm_state | None)``; every step is differentiable,
+    including the two state inputs and the two state outputs."""
+    Di = conv_w.shape[0]
+    N, R = A_log.shape[1], dt_w.shape[1]
+    xz = ops.linear(hidden, in_w, in_b)                                  # :333-339
+    x_in, z = xz[..., :Di], xz[..., Di:]                                 # :369
+    xc, new_conv = ConvFn.apply(x_in, conv_w, conv_b, conv_state, want_conv_state, True)   # :381-404
+    x_dbl = ops.linear(xc, x_w)                                          # :409
+    delta = ops.linear(x_dbl[..., :R], dt_w)                             # :413-414 (rounded to the model dtype)
+    A = -torch.exp(A_log.float())                                        # :341
+    y, last = ScanFn.apply(xc, delta, A, x_dbl, R, R + N, N, Dp.float(), z,
+                           None if dt_b is None else dt_b.float(), True, ssm_state, want_ssm_state)
+    out = ops.linear(y, out_w, out_b)                                    # :445-446
+    return out, new_conv, last

@@ -33,6 +33,9 @@ int conv_xproj_tc(const void* x, int64_t x_ld, const void* cw, const void* cb, c
                   int64_t ldw, void* xc, int64_t xc_ld, void* C, int64_t ldc, int64_t M, int N, int K,
                   int L, int silu, cudaStream_t st);
 
+// backward.cu -- out[n] = sum over P rows of partial[P][n] (fp32 partials)
+int reduce_partials(const float* partial, int P, int64_t n, void* out, int out_dtype, cudaStream_t st);
+
 // scan_generic.cu
 int scan_generic(const vmb_scan_args& a, cudaStream_t st);
 

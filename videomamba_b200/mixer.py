@@ -153,6 +153,12 @@ class Mamba(nn.Module):
                         "was written through .data; call refresh_weights() after such writes.")
         return self._weights
 
+    def _wants_grad(self, *tensors) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return any(isinstance(t, Tensor) and t.requires_grad for t in tensors) or \
+            any(p is not None and p.requires_grad for p in self._params())
+
     @staticmethod
     def _require_cuda(t: Tensor) -> None:
         if not t.is_cuda:
@@ -200,11 +206,19 @@ class Mamba(nn.Module):
 
         inplace_ssm = ssm_state is not None and state is None and not return_state
         want = return_state or inplace_ssm
-        out, new_conv, last = ops.mixer_fwd(w, hidden_states, conv_state, ssm_state,
-                                            want_conv_state=return_state, want_ssm_state=want,
-                                            fuse_conv_xproj=self.fuse_conv_xproj)
+        if self._wants_grad(hidden_states, conv_state, ssm_state):
+            # training: the reference's slow path op for op, every operator with a backward kernel
+            # (autograd.py); the fused inference entry point below has none
+            from .autograd import mixer_train
+            out, new_conv, last = mixer_train(*self._params(), hidden_states, conv_state, ssm_state,
+                                              want_conv_state=return_state, want_ssm_state=want)
+        else:
+            out, new_conv, last = ops.mixer_fwd(w, hidden_states, conv_state, ssm_state,
+                                                want_conv_state=return_state, want_ssm_state=want,
+                                                fuse_conv_xproj=self.fuse_conv_xproj)
         if inplace_ssm:
-            ssm_state.copy_(last)
+            with torch.no_grad():
+                ssm_state.copy_(last)
         if return_state:
             return out, (new_conv, last)
         return out

@@ -71,9 +71,10 @@ class _on_device:
 
 
 class _ForwardOnly(torch.autograd.Function):
-    """libvmb200 has no backward kernels.  Outputs computed from tensors that require grad get this
-    node, so ``loss.backward()`` fails HERE with a clear message instead of silently training only
-    the parameters that happen to live in torch glue."""
+    """Entry points WITHOUT a backward kernel (the fused inference mixer / scan / decode step, the
+    reversed token walks).  Outputs computed from tensors that require grad get this node, so
+    ``loss.backward()`` fails HERE with a clear message instead of silently dropping gradients.
+    The differentiable operators live in ``autograd.py``."""
 
     @staticmethod
     def forward(ctx, out, *deps):
@@ -82,8 +83,9 @@ class _ForwardOnly(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(
-            "videomamba_b200 (libvmb200) is forward-only: its kernels have no backward pass. "
-            "Run inference under torch.no_grad() / torch.inference_mode(), or train with the reference.")
+            "this libvmb200 entry point is forward-only (fused inference kernel or reversed token walk). "
+            "Call it under torch.no_grad(), or go through the differentiable operators "
+            "(videomamba_b200.autograd / the modules in training mode).")
 
 
 def forward_only(out, *deps):
@@ -99,6 +101,10 @@ def forward_only(out, *deps):
     return _ForwardOnly.apply(out, *deps)
 
 
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, Tensor) and t.requires_grad for t in tensors)
+
+
 def aligned_rows(t: Tensor, elems: int = 4) -> Tensor:
     """A view whose base address is a multiple of ``elems`` elements, or a contiguous copy."""
     return t if t.data_ptr() % (elems * t.element_size()) == 0 else t.clone(memory_format=torch.contiguous_format)
@@ -112,9 +118,11 @@ def xdbl_pitch(dt_rank: int, d_state: int) -> int:
 # ----------------------------------------------------------------------------------------------
 # token-major primitives
 # ----------------------------------------------------------------------------------------------
-def add_norm(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
-             eps: float, is_rms: bool, prenorm: bool, residual_in_fp32: bool):
-    """Fused residual add + norm over the last dim.  Returns ``y`` or ``(y, residual_out)``."""
+def add_norm_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
+                 eps: float, is_rms: bool, prenorm: bool, residual_in_fp32: bool):
+    """One ``vmb_add_norm_fwd`` launch.  Returns ``(y, residual_out | None, x2, res2)``: ``y`` in x's
+    shape, ``residual_out`` in x's shape (None when the sum is x itself), and the 2-D operands the
+    kernel read (what the backward needs)."""
     _require_cuda(x)
     lib = _lib.load()
     dim = x.shape[-1]
@@ -147,16 +155,37 @@ def add_norm(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Option
             _p(res_out), _dt(res_out) if res_out is not None else VMB_F32,
             rows, dim, float(eps), 1 if is_rms else 0, _stream(x))
     _lib.check(rc, "vmb_add_norm_fwd")
-    y = forward_only(y.reshape(x.shape), x, residual, weight, bias)
+    return y.reshape(x.shape), None if res_out is None else res_out.reshape(x.shape), x2, res2
+
+
+def add_norm(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
+             eps: float, is_rms: bool, prenorm: bool, residual_in_fp32: bool):
+    """Fused residual add + norm over the last dim.  Returns ``y`` or ``(y, residual_out)``.
+    Differentiable (``autograd.AddNormFn``) when an input requires grad."""
+    res_dtype = residual.dtype if residual is not None else (torch.float32 if residual_in_fp32 else x.dtype)
+    alias = prenorm and residual is None and res_dtype == x.dtype   # the residual stream IS x
+    if _wants_grad(x, weight, bias, residual):
+        from . import autograd as ag
+        if alias or not prenorm:
+            y = ag.AddNormFn.apply(x, weight, bias, residual, eps, is_rms, False, residual_in_fp32)
+            return (y, x) if prenorm else y
+        return ag.AddNormFn.apply(x, weight, bias, residual, eps, is_rms, True, residual_in_fp32)
+    y, res_out, _, _ = add_norm_raw(x, weight, bias, residual, eps, is_rms, prenorm, residual_in_fp32)
     if not prenorm:
         return y
-    if res_out is None:       # no incoming residual and same dtype: the sum IS x
-        return y, x
-    return y, res_out.reshape(x.shape)
+    return y, (x if res_out is None else res_out)
 
 
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
-    """``x @ weight.T (+ bias)`` over the last dim (fp32 accumulate, one rounding)."""
+    """``x @ weight.T (+ bias)`` over the last dim (fp32 accumulate, one rounding).  Differentiable
+    (``autograd.LinearFn``) when an input requires grad."""
+    if _wants_grad(x, weight, bias):
+        from . import autograd as ag
+        return ag.LinearFn.apply(x, weight, bias)
+    return linear_raw(x, weight, bias)
+
+
+def linear_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     _require_cuda(x)
     lib = _lib.load()
     K = x.shape[-1]
@@ -177,7 +206,7 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
         rc = lib.vmb_linear_fwd(_p(x2), x2.stride(0) if M > 1 else K, _p(weight), weight.stride(0),
                                 _p(bias), _p(out), N, M, N, K, _dt(x2), _stream(x))
     _lib.check(rc, "vmb_linear_fwd")
-    return forward_only(out.reshape(*x.shape[:-1], N), x, weight, bias)
+    return out.reshape(*x.shape[:-1], N)
 
 
 def conv_xproj_tokens(x: Tensor, conv_weight: Tensor, conv_bias: Optional[Tensor], w_x_pad: Tensor):
@@ -210,6 +239,9 @@ def gate_blend(g1: Tensor, g2: Optional[Tensor], fwd: Tensor, bwd: Tensor) -> Te
     lib = _lib.load()
     if not (g1.shape == fwd.shape == bwd.shape) or (g2 is not None and g2.shape != fwd.shape):
         raise ValueError("gate_blend: shape mismatch")
+    if _wants_grad(g1, g2, fwd, bwd):      # autograd glue (element-wise, not on the mixer path)
+        s = torch.sigmoid((g1.float() + g2.float()) if g2 is not None else g1.float())
+        return (s * fwd.float() + (1.0 - s) * bwd.float()).to(fwd.dtype)
     g1, fwd, bwd = aligned_rows(g1.contiguous()), aligned_rows(fwd.contiguous()), aligned_rows(bwd.contiguous())
     if g2 is not None:
         g2 = aligned_rows(g2.contiguous())
@@ -229,6 +261,9 @@ def patchify(x: Tensor, tubelet: int, ph: int, pw: int) -> Tensor:
     x = x.contiguous()
     B, C, T, H, W = x.shape
     t, h, w = T // tubelet, H // ph, W // pw
+    if _wants_grad(x):        # autograd glue (gradient with respect to the clip): a permuting view + copy
+        v = x[:, :, :t * tubelet, :h * ph, :w * pw].reshape(B, C, t, tubelet, h, ph, w, pw)
+        return v.permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * t * h * w, C * tubelet * ph * pw)
     cols = torch.empty((B * t * h * w, C * tubelet * ph * pw), dtype=x.dtype, device=x.device)
     with _on_device(x):
         rc = lib.vmb_patchify(_p(x), _p(cols), B, C, T, H, W, tubelet, ph, pw, _dt(x), _stream(x))
@@ -245,6 +280,12 @@ def embed_tokens(patches: Tensor, spatial: Tensor, temporal: Tensor,
     lib = _lib.load()
     B, t, hw, D = patches.shape
     dt = patches.dtype
+    if _wants_grad(patches, spatial, temporal, cls_row):   # autograd glue: the same two rounded adds + cat
+        tok = patches + spatial.to(dt).reshape(1, 1, hw, D)
+        tok = (tok + temporal.to(dt).reshape(1, t, 1, D)).reshape(B, t * hw, D)
+        if cls_row is not None:
+            tok = torch.cat([cls_row.to(dt).reshape(1, 1, D).expand(B, -1, -1), tok], dim=1)
+        return tok
     patches = patches.contiguous()
     spatial = spatial.to(dt).reshape(hw, D).contiguous()
     temporal = temporal.to(dt).reshape(t, D).contiguous()
@@ -273,6 +314,15 @@ def pool_norm(x_vis: Tensor, has_cls: bool, groups: int, per: int, pool_type: st
     B, L, Cdim = x_vis.shape
     if L != (1 if has_cls else 0) + groups * per:
         raise ValueError("pool_norm: token count does not match has_cls + groups * per")
+    if _wants_grad(x_vis, ln_weight, ln_bias):     # autograd glue: the reference's own torch ops
+        cls = x_vis[:, :1] if has_cls else None
+        pat = x_vis[:, 1:] if has_cls else x_vis
+        if mode == 0:
+            pooled = cls
+        else:
+            avg = pat.reshape(B, groups, per, Cdim).mean(dim=2)
+            pooled = cls + avg if mode == 1 else (torch.cat([cls, avg], dim=1) if mode == 2 else avg)
+        return torch.nn.functional.layer_norm(pooled, (Cdim,), ln_weight, ln_bias, eps)
     cast = lambda t: None if t is None else t.to(x_vis.dtype).contiguous()
     ln_weight, ln_bias = cast(ln_weight), cast(ln_bias)
     rows = 1 if mode == 0 else (groups + 1 if mode == 2 else groups)
@@ -295,6 +345,8 @@ def gather_rows(src: Tensor, index: Tensor) -> Tensor:
     src = _token_major(src)
     B, L, Cdim = src.shape
     index = index.to(device=src.device, dtype=torch.int64).contiguous()
+    if _wants_grad(src):                           # autograd glue
+        return torch.gather(src, 1, index.unsqueeze(-1).expand(-1, -1, Cdim))
     n = index.shape[1]
     out = torch.empty((B, n, Cdim), dtype=src.dtype, device=src.device)
     with _on_device(src):
@@ -317,7 +369,19 @@ def causal_conv1d_tokens(x: Tensor, weight: Tensor, bias: Optional[Tensor],
     """Depthwise causal conv on token-major ``x (B, L, Di)``; ``weight (Di, W)``.
     ``reverse``: walk the tokens back to front; with ``frame_len > 0`` only the FRAME axis is reversed
     (frames of ``frame_len`` tokens back to front, tokens inside a frame front to back).
-    Returns ``y`` or ``(y, new_conv_state (B, Di, W))``."""
+    Returns ``y`` or ``(y, new_conv_state (B, Di, W))``.  The forward walk is differentiable
+    (``autograd.ConvFn``); the reversed walks are forward-only."""
+    if not reverse and _wants_grad(x, weight, bias, conv_state):
+        from . import autograd as ag
+        y, cs = ag.ConvFn.apply(x, weight, bias, conv_state, want_state, silu)
+        return (y, cs) if want_state else y
+    out = causal_conv1d_tokens_raw(x, weight, bias, conv_state, want_state, silu, reverse, frame_len)
+    return forward_only(out, x, weight, bias, conv_state)
+
+
+def causal_conv1d_tokens_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor],
+                             conv_state: Optional[Tensor] = None, want_state: bool = False,
+                             silu: bool = True, reverse: bool = False, frame_len: int = 0):
     _require_cuda(x)
     lib = _lib.load()
     x = _token_major(x)
@@ -345,7 +409,7 @@ def causal_conv1d_tokens(x: Tensor, weight: Tensor, bias: Optional[Tensor],
             B, L, Di, W, 1 if silu else 0, 1 if reverse else 0, int(frame_len) if reverse else 0,
             _dt(x), _stream(x))
     _lib.check(rc, "vmb_causal_conv1d_fwd")
-    return forward_only((y, cs_out) if want_state else y, x, weight, bias, conv_state)
+    return (y, cs_out) if want_state else y
 
 
 def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_off: int, c_off: int,
@@ -354,7 +418,19 @@ def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_of
                           h0: Optional[Tensor] = None, want_last: bool = False,
                           reverse: bool = False, frame_len: int = 0):
     """Token-major selective scan.  ``u, delta, z: (B, L, Di)``; ``bc: (B, L, >=c_off+N)`` holds
-    B_t at ``[b_off, b_off+N)`` and C_t at ``[c_off, c_off+N)``; ``A2 = A*log2(e)`` fp32 (Di, N)."""
+    B_t at ``[b_off, b_off+N)`` and C_t at ``[c_off, c_off+N)``; ``A2 = A*log2(e)`` fp32 (Di, N).
+    Forward-only in this form (``A2`` is a derived operand); the differentiable operator is
+    ``autograd.ScanFn`` (natural ``A``), used by ``selective_scan_fn`` and the training-mode mixer."""
+    out = selective_scan_tokens_raw(u, delta, A2, bc, b_off, c_off, d_state, D, z, dt_bias, softplus, h0,
+                                    want_last, reverse, frame_len)
+    return forward_only(out, u, delta, A2, bc, D, z, dt_bias, h0)
+
+
+def selective_scan_tokens_raw(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_off: int, c_off: int,
+                              d_state: int, D: Optional[Tensor] = None, z: Optional[Tensor] = None,
+                              dt_bias: Optional[Tensor] = None, softplus: bool = True,
+                              h0: Optional[Tensor] = None, want_last: bool = False,
+                              reverse: bool = False, frame_len: int = 0):
     _require_cuda(u)
     lib = _lib.load()
     u, delta, bc = _token_major(u), _token_major(delta), _token_major(bc)
@@ -385,7 +461,7 @@ def selective_scan_tokens(u: Tensor, delta: Tensor, A2: Tensor, bc: Tensor, b_of
     with _on_device(u):
         rc = lib.vmb_selective_scan_fwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_fwd")
-    return forward_only((y, h_last) if want_last else y, u, delta, A2, bc, D, z, dt_bias, h0)
+    return (y, h_last) if want_last else y
 
 
 def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor, A2: Tensor,
@@ -684,6 +760,12 @@ def selective_scan_fn(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, C_: Tensor
         raise NotImplementedError("only real A and (B, N, L) input-dependent B / C are supported")
     N = A.shape[1]
     bc = torch.cat([B.transpose(1, 2), C_.transpose(1, 2)], dim=-1).to(u.dtype).contiguous()
+    if _wants_grad(u, delta, A, B, C_, D, z, delta_bias, initial_state):
+        from . import autograd as ag
+        y, last = ag.ScanFn.apply(u.transpose(1, 2), delta.to(u.dtype).transpose(1, 2), A, bc, 0, N, N, D,
+                                  None if z is None else z.to(u.dtype).transpose(1, 2), delta_bias,
+                                  delta_softplus, initial_state, return_last_state)
+        return (y.transpose(1, 2), last) if return_last_state else y.transpose(1, 2)
     A2 = (A.float() * LOG2E).contiguous()
     out = selective_scan_tokens(
         u.transpose(1, 2), delta.to(u.dtype).transpose(1, 2), A2, bc, 0, N, N,
@@ -751,6 +833,15 @@ def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_wei
     Di = xz.shape[1] // 2
     N, R = A.shape[1], delta_proj_weight.shape[1]
     xz_t = xz.transpose(1, 2)
+    if _wants_grad(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                   out_proj_bias, A, D, delta_bias):
+        from . import autograd as ag
+        xc, _ = ag.ConvFn.apply(xz_t[..., :Di], conv1d_weight, conv1d_bias, None, False, True)
+        x_dbl = linear(xc, x_proj_weight)
+        delta = linear(x_dbl[..., :R], delta_proj_weight)
+        y, _ = ag.ScanFn.apply(xc, delta, A, x_dbl, R, R + N, N, D, xz_t[..., Di:], delta_bias, True,
+                               None, False)
+        return linear(y, out_proj_weight, out_proj_bias)
     xc = causal_conv1d_tokens(xz_t[..., :Di], conv1d_weight, conv1d_bias)
     x_dbl = linear(xc, x_proj_weight)
     delta = linear(x_dbl[..., :R], delta_proj_weight)

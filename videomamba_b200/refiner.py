@@ -75,7 +75,9 @@ class BiMambaRefinerBlock(nn.Module):
         """block_bwd on the time-reversed sequence, result in ORIGINAL token order."""
         blk = self.block_bwd
         mixer = blk.mixer
-        if hasattr(mixer, "_kernel_weights"):
+        grad = torch.is_grad_enabled() and (x_seq.requires_grad or any(
+            t.requires_grad for t in state) or any(q.requires_grad for q in blk.parameters()))
+        if hasattr(mixer, "_kernel_weights") and not grad:
             # norm is per token, so only the mixer needs the reversed walk (3-D input: token axis;
             # 4-D input: frame axis, frames of packed[2] tokens)
             normed, _ = blk._add_norm(x_seq, None)
@@ -83,6 +85,8 @@ class BiMambaRefinerBlock(nn.Module):
                                       want_conv_state=False, want_ssm_state=False, reverse=True,
                                       frame_len=0 if packed is None else packed[2])
             return out
+        # training (the reversed walks have no backward kernel): flip copies, as the reference does
+        # (refiner_backbone.py:61-68, :112-121)
         out_rev, _, _ = blk(self._flip_time(x_seq, packed), state=state, return_state=True)
         return self._flip_time(out_rev, packed)
 
