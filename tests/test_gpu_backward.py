@@ -274,16 +274,21 @@ def test_mixer_backward_streaming_state(dtype, d_model, d_state):
         _check(got[n], p[n].grad, tol, n)
 
 
-def test_mixer_training_forward_matches_inference_path():
-    """The training-mode mixer (op by op, differentiable) and the fused inference entry point agree."""
+@pytest.mark.parametrize("dtype,d_model", [(torch.float32, 128), (torch.bfloat16, 384), (torch.bfloat16, 576)])
+def test_mixer_training_forward_matches_inference_path(dtype, d_model):
+    """The training-mode mixer (op by op, differentiable; bf16 production widths run the fused scan in the
+    forward) and the fused inference entry point agree -- bit for bit where both run the fused scan."""
     torch.manual_seed(1)
-    mx = Mamba(d_model=128, use_fast_path=False).to(DEV)
-    x = torch.randn(2, 70, 128, device=DEV)
-    a = mx(x)
+    mx = Mamba(d_model=d_model, use_fast_path=False).to(dtype).to(DEV)
+    x = torch.randn(2, 70, d_model, device=DEV).to(dtype)
+    a, (ca, sa) = mx(x, return_state=True)
     with torch.no_grad():
-        b = mx(x)
+        b, (cb, sb) = mx(x, return_state=True)
     assert a.requires_grad and not b.requires_grad
-    assert rel_err(a, b) <= 1e-5
+    if dtype == torch.bfloat16:
+        assert torch.equal(a, b) and torch.equal(ca, cb) and torch.equal(sa, sb)
+    else:
+        assert rel_err(a, b) <= 1e-5 and rel_err(sa, sb) <= 1e-5
 
 
 # ---- whole model -----------------------------------------------------------------------------------------

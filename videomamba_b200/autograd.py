@@ -114,12 +114,7 @@ class AddNormFn(torch.autograd.Function):
                     None if bias is None else bias.dtype)
         if not prenorm:
             return y
-        if res_out is None:
-            # no incoming residual and the same dtype: the residual stream IS x (a new node-owned alias)
-            res_out = x.view_as(x)
-            ctx.alias_x = True
-        else:
-            ctx.alias_x = False
+        # (ops.add_norm never asks for prenorm when the residual stream would be x itself)
         return y, res_out
 
     @staticmethod
@@ -226,59 +221,112 @@ class ScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, dh_last=None):
-        lib = _lib.load()
         u, delta, A2, bc, Df, z, bias, h0 = ctx.saved_tensors
         b_off, c_off, N, softplus, A_dtype, D_dtype, bias_dtype = ctx.meta
-        B, L, Di = u.shape
-        dev = u.device
-        dout = torch.zeros_like(u, memory_format=torch.contiguous_format) if dout is None \
-            else ops._token_major(dout.to(u.dtype))
-        du = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
-        dd = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
-        dz = torch.empty((B, L, Di), dtype=u.dtype, device=dev) if z is not None else None
-        dbc = torch.zeros(bc.shape, dtype=bc.dtype, device=dev)
-        dA = torch.empty((Di, N), dtype=torch.float32, device=dev)
-        dD = torch.empty(Di, dtype=torch.float32, device=dev) if Df is not None else None
-        dbias = torch.empty(Di, dtype=torch.float32, device=dev) if bias is not None else None
-        dh0 = torch.empty((B, Di, N), dtype=torch.float32, device=dev) \
-            if h0 is not None and ctx.needs_input_grad[11] else None
-        if dh_last is not None:
-            dh_last = dh_last.float().contiguous()
-        h0c = None if h0 is None else h0.contiguous()
-        nbytes = lib.vmb_selective_scan_bwd_workspace_bytes(B, L, Di, N)
-        ws = _ws(nbytes, u)
-        a = ScanBwdArgs()
-        a.u, a.u_bstride, a.u_tstride = u.data_ptr(), u.stride(0), u.stride(1)
-        a.delta, a.d_bstride, a.d_tstride = delta.data_ptr(), delta.stride(0), delta.stride(1)
-        if z is not None:
-            a.z, a.z_bstride, a.z_tstride = z.data_ptr(), z.stride(0), z.stride(1)
-        a.bc, a.bc_bstride, a.bc_tstride = bc.data_ptr(), bc.stride(0), bc.stride(1)
-        a.b_off, a.c_off = b_off, c_off
-        a.A2 = A2.data_ptr()
-        a.D = None if Df is None else Df.data_ptr()
-        a.dt_bias = None if bias is None else bias.data_ptr()
-        if h0c is not None:
-            a.h0, a.h0_dtype = h0c.data_ptr(), _dt(h0c)
-        a.dout, a.dout_bstride, a.dout_tstride = dout.data_ptr(), dout.stride(0), dout.stride(1)
-        a.dh_last = None if dh_last is None else dh_last.data_ptr()
-        a.du, a.ddelta = du.data_ptr(), dd.data_ptr()
-        a.dz = None if dz is None else dz.data_ptr()
-        a.dbc, a.dbc_tstride = dbc.data_ptr(), dbc.stride(1)
-        a.dA = dA.data_ptr()
-        a.dD = None if dD is None else dD.data_ptr()
-        a.ddt_bias = None if dbias is None else dbias.data_ptr()
-        a.dh0 = None if dh0 is None else dh0.data_ptr()
-        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
-        a.B, a.L, a.Di, a.N = B, L, Di, N
-        a.dtype, a.softplus = _dt(u), 1 if softplus else 0
-        with _on_device(u):
-            rc = lib.vmb_selective_scan_bwd(C.byref(a), _stream(u))
-        _lib.check(rc, "vmb_selective_scan_bwd")
-        if dh0 is not None and h0.dtype != torch.float32:
-            dh0 = dh0.to(h0.dtype)
+        du, dd, dz, dbc, dA, dD, dbias, dh0 = _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias,
+                                                         softplus, h0, dout, dh_last,
+                                                         ctx.needs_input_grad[11])
         return (du, dd, dA.to(A_dtype), dbc, None, None, None,
                 None if dD is None else dD.to(D_dtype), dz,
                 None if dbias is None else dbias.to(bias_dtype), None, dh0, None)
+
+
+def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout, dh_last, want_dh0):
+    """One ``vmb_selective_scan_bwd`` call.  Returns (du, ddelta_raw, dz, dbc, dA, dD, dbias, dh0);
+    ``dbc`` is zero outside the B / C columns."""
+    lib = _lib.load()
+    B, L, Di = u.shape
+    dev = u.device
+    dout = torch.zeros_like(u, memory_format=torch.contiguous_format) if dout is None \
+        else ops._token_major(dout.to(u.dtype))
+    du = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
+    dd = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
+    dz = torch.empty((B, L, Di), dtype=u.dtype, device=dev) if z is not None else None
+    dbc = torch.zeros(bc.shape, dtype=bc.dtype, device=dev)
+    dA = torch.empty((Di, N), dtype=torch.float32, device=dev)
+    dD = torch.empty(Di, dtype=torch.float32, device=dev) if Df is not None else None
+    dbias = torch.empty(Di, dtype=torch.float32, device=dev) if bias is not None else None
+    dh0 = torch.empty((B, Di, N), dtype=torch.float32, device=dev) if h0 is not None and want_dh0 else None
+    if dh_last is not None:
+        dh_last = dh_last.float().contiguous()
+    h0c = None if h0 is None else h0.contiguous()
+    nbytes = lib.vmb_selective_scan_bwd_workspace_bytes(B, L, Di, N)
+    ws = _ws(nbytes, u)
+    a = ScanBwdArgs()
+    a.u, a.u_bstride, a.u_tstride = u.data_ptr(), u.stride(0), u.stride(1)
+    a.delta, a.d_bstride, a.d_tstride = delta.data_ptr(), delta.stride(0), delta.stride(1)
+    if z is not None:
+        a.z, a.z_bstride, a.z_tstride = z.data_ptr(), z.stride(0), z.stride(1)
+    a.bc, a.bc_bstride, a.bc_tstride = bc.data_ptr(), bc.stride(0), bc.stride(1)
+    a.b_off, a.c_off = b_off, c_off
+    a.A2 = A2.data_ptr()
+    a.D = None if Df is None else Df.data_ptr()
+    a.dt_bias = None if bias is None else bias.data_ptr()
+    if h0c is not None:
+        a.h0, a.h0_dtype = h0c.data_ptr(), _dt(h0c)
+    a.dout, a.dout_bstride, a.dout_tstride = dout.data_ptr(), dout.stride(0), dout.stride(1)
+    a.dh_last = None if dh_last is None else dh_last.data_ptr()
+    a.du, a.ddelta = du.data_ptr(), dd.data_ptr()
+    a.dz = None if dz is None else dz.data_ptr()
+    a.dbc, a.dbc_tstride = dbc.data_ptr(), dbc.stride(1)
+    a.dA = dA.data_ptr()
+    a.dD = None if dD is None else dD.data_ptr()
+    a.ddt_bias = None if dbias is None else dbias.data_ptr()
+    a.dh0 = None if dh0 is None else dh0.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    a.B, a.L, a.Di, a.N = B, L, Di, N
+    a.dtype, a.softplus = _dt(u), 1 if softplus else 0
+    with _on_device(u):
+        rc = lib.vmb_selective_scan_bwd(C.byref(a), _stream(u))
+    _lib.check(rc, "vmb_selective_scan_bwd")
+    if dh0 is not None and h0.dtype != torch.float32:
+        dh0 = dh0.to(h0.dtype)
+    return du, dd, dz, dbc, dA, dD, dbias, dh0
+
+
+class FusedScanFn(torch.autograd.Function):
+    """dt_proj + softplus + scan + D skip + SiLU(z) gate on the FUSED inference kernel (bf16, d_state 16:
+    delta is never materialised in the forward).  The backward recomputes ``delta_raw`` with one projection
+    (rounded to bf16 where the reference rounds it, mamba_simple.py:413-414), runs the scan backward kernel
+    and folds the dt_proj backward in (``d dt_low = d delta W_dt``, ``d W_dt = d delta^T dt_low``)."""
+
+    @staticmethod
+    def forward(ctx, u, z, xdbl, w_dt, A, D, dt_bias, h0, want_last, R, N):
+        ctx.set_materialize_grads(False)
+        A2 = (A.float() * LOG2E).contiguous()
+        Df = None if D is None else D.float().contiguous()
+        bias = None if dt_bias is None else dt_bias.float().contiguous()
+        u, z, xdbl = ops._token_major(u), ops._token_major(z), ops._token_major(xdbl)
+        w_dt = w_dt.contiguous()
+        out = ops.selective_scan_fused_tokens_raw(u, z, xdbl, w_dt, A2, R, N, Df, bias, h0, want_last)
+        ctx.save_for_backward(u, z, xdbl, w_dt, A2, Df, bias, h0)
+        ctx.meta = (R, N, A.dtype, None if D is None else D.dtype, None if dt_bias is None else dt_bias.dtype)
+        if want_last:
+            return out
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, dh_last=None):
+        u, z, xdbl, w_dt, A2, Df, bias, h0 = ctx.saved_tensors
+        R, N, A_dtype, D_dtype, bias_dtype = ctx.meta
+        B, L, Di = u.shape
+        dt_low = xdbl[..., :R]
+        delta = ops.linear_raw(dt_low, w_dt)                                  # (B, L, Di), bf16
+        du, dd, dz, dbc, dA, dD, dbias, dh0 = _scan_bwd(u, delta, A2, xdbl, R, R + N, N, Df, z, bias, True, h0,
+                                                         dout, dh_last, ctx.needs_input_grad[7])
+        dd2 = dd.reshape(B * L, Di)
+        w_t = transpose2d(w_dt)[:, :Di]                                       # (R, Di)
+        dbc[..., :R] = ops.linear_raw(dd2, w_t).reshape(B, L, R)              # d dt_low
+        dw_dt = None
+        if ctx.needs_input_grad[3]:
+            dw_dt = ops.linear_raw(transpose2d(dd2), transpose2d(_rows(dt_low, R))).to(w_dt.dtype)   # (Di, R)
+        return (du, dz, dbc, dw_dt, dA.to(A_dtype), None if dD is None else dD.to(D_dtype),
+                None if dbias is None else dbias.to(bias_dtype), dh0, None, None, None)
+
+
+def fused_scan_covers(dtype, Di: int, N: int, R: int) -> bool:
+    """Shapes of the fused bf16 scan kernel (csrc/scan_fast.cu: scan_fast_supported)."""
+    return dtype == torch.bfloat16 and N == 16 and R in (12, 24, 36) and Di % 16 == 0
 
 
 # ----------------------------------------------------------------------------------------------
@@ -294,10 +342,16 @@ def mixer_train(in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dp, out_w, o
     xz = ops.linear(hidden, in_w, in_b)                                  # :333-339
     x_in, z = xz[..., :Di], xz[..., Di:]                                 # :369
     xc, new_conv = ConvFn.apply(x_in, conv_w, conv_b, conv_state, want_conv_state, True)   # :381-404
-    x_dbl = ops.linear(xc, x_w)                                          # :409
-    delta = ops.linear(x_dbl[..., :R], dt_w)                             # :413-414 (rounded to the model dtype)
     A = -torch.exp(A_log.float())                                        # :341
-    y, last = ScanFn.apply(xc, delta, A, x_dbl, R, R + N, N, Dp.float(), z,
-                           None if dt_b is None else dt_b.float(), True, ssm_state, want_ssm_state)
+    if fused_scan_covers(hidden.dtype, Di, N, R) and x_w.dtype == hidden.dtype and dt_w.dtype == hidden.dtype:
+        # production bf16 shapes: the forward runs the fused inference scan (dt_proj inside, delta never in HBM)
+        Xp = ops.xdbl_pitch(R, N)
+        x_dbl = ops.linear(xc, torch.nn.functional.pad(x_w, (0, 0, 0, Xp - x_w.shape[0])))   # rows [dt_low | B | C | 0]
+        y, last = FusedScanFn.apply(xc, z, x_dbl, dt_w, A, Dp, dt_b, ssm_state, want_ssm_state, R, N)
+    else:
+        x_dbl = ops.linear(xc, x_w)                                      # :409
+        delta = ops.linear(x_dbl[..., :R], dt_w)                         # :413-414 (rounded to the model dtype)
+        y, last = ScanFn.apply(xc, delta, A, x_dbl, R, R + N, N, Dp.float(), z,
+                               None if dt_b is None else dt_b.float(), True, ssm_state, want_ssm_state)
     out = ops.linear(y, out_w, out_b)                                    # :445-446
     return out, new_conv, last

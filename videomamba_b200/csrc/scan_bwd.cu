@@ -10,12 +10,18 @@
 //
 // h_{t-1} is needed in reverse order.  Pass 1 (scan_ckpt_kernel) walks the sequence forward and stores
 // the state at the start of every 8-token chunk; pass 2 (scan_bwd_kernel) walks the chunks back to
-// front, recomputes the 8 states of a chunk from its checkpoint into shared memory and runs the
-// reverse recurrence on them.  One thread owns one (batch, channel) chain with all N <= 16 states in
-// registers, so the reductions over n are in-thread; dB_t / dC_t need a sum over channels: a warp
-// reduces its 32 channels with a transposing butterfly (31 shuffles for the 32 values of a token) and
-// writes one 128-byte row per token into a per-warp slab, a last kernel sums the Di / 32 slabs.  dA, dD
-// and d(dt_bias) are summed over the batch the same way.  No atomics: results are deterministic.
+// front, recomputes the 8 states of a chunk from its checkpoint and runs the reverse recurrence on them.
+//
+// Thread layout: ONE LANE PER (channel, state) -- a half-warp is a channel, a warp two channels, a CTA
+// of 8 warps 16 adjacent channels of one sequence -- so a batch of 8 already gives 3072 warps and the
+// per-token dependent chain is one exp2 + one FMA.  Per-channel scalars of a chunk (delta, its
+// derivative, u; the gate terms of dout / z) are computed once by the lanes of the half-warp (lane n < 8:
+// token n; lane n >= 8: token n - 8) and handed round by shuffles.  Sums over the 16 states (ypre, du,
+// ddelta) are transposing butterflies over the chunk's 8 tokens (8 / 15 shuffles per chunk instead of
+// 4 per token and value).  dB_t / dC_t need a sum over channels: one shuffle adds the two channels of
+// a warp, the 8 warps of a CTA meet in shared memory once per chunk, every CTA writes one slab row
+// {dB_t[0..15], dC_t[0..15]} per token and a last kernel sums the Di / 16 slabs.  dA, dD and d(dt_bias)
+// are summed over the batch the same way.  No atomics: results are deterministic.
 #include <algorithm>
 
 #include "internal.h"
@@ -24,197 +30,228 @@ namespace vmb {
 namespace {
 
 constexpr int kT = 8;          // tokens per chunk
-constexpr int kThr = 128;      // channels per CTA
+constexpr int kWarps = 8;      // warps per CTA
+constexpr int kChan = 2 * kWarps;   // channels per CTA
 constexpr int kNMax = 16;
 
+// sum over the 16 lanes of a half-warp of 8 per-lane values: afterwards every lane holds the total of
+// value (lane >> 1) & 7  (8 shuffles)
+__device__ __forceinline__ float halfwarp_sum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int s = 8, w = 4; w >= 1; s >>= 1, w >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = up ? v[k + w] : v[k];
+      const float send = up ? v[k] : v[k + w];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+// sum over the 16 lanes of a half-warp of 16 per-lane values: lane n ends with the total of value n & 15
+__device__ __forceinline__ float halfwarp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float keep = up ? v[k + s] : v[k];
+      const float send = up ? v[k] : v[k + s];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 template <typename T, bool kAccurate>
-__global__ void __launch_bounds__(kThr)
+__global__ void __launch_bounds__(kWarps * 32)
 scan_ckpt_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int nchunks) {
   __shared__ float sB[kT][kNMax];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = lane & 15, half = lane & 16;       // half = first lane of this channel's half-warp
   const int b = blockIdx.y;
-  const int d = blockIdx.x * kThr + tid;
-  const bool valid = d < a.Di;
+  const int d = (blockIdx.x * kWarps + warp) * 2 + (lane >> 4);
   const int N = a.N, L = a.L;
-  float A2[kNMax], h[kNMax];
-#pragma unroll
-  for (int n = 0; n < kNMax; ++n) {
-    A2[n] = (valid && n < N) ? a.A2[(int64_t)d * N + n] : 0.f;
-    h[n] = (valid && n < N && a.h0) ? load_as_f32(a.h0, ((int64_t)b * a.Di + d) * N + n, a.h0_dtype) : 0.f;
-  }
-  const float bias = (valid && a.dt_bias) ? a.dt_bias[d] : 0.f;
-  const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + d;
-  const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + d;
+  const bool valid = d < a.Di && n < N;
+  const int dc = min(d, a.Di - 1);                  // clamped channel for loads (results of invalid lanes are unused)
+  const float A2 = valid ? a.A2[(int64_t)d * N + n] : 0.f;
+  float h = (valid && a.h0) ? load_as_f32(a.h0, ((int64_t)b * a.Di + d) * N + n, a.h0_dtype) : 0.f;
+  const float bias = a.dt_bias ? a.dt_bias[dc] : 0.f;
+  const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc;
+  const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc;
   const T* bc = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride;
   for (int c = 0; c < nchunks; ++c) {
     const int t0 = c * kT, nt = min(kT, L - t0);
-    for (int e = tid; e < nt * N; e += kThr) sB[e / N][e % N] = to_f32<T>(bc[(int64_t)(t0 + e / N) * a.bc_tstride + a.b_off + e % N]);
+    if (tid < kT * kNMax) {
+      const int t = tid >> 4, k = tid & 15;
+      sB[t][k] = (t < nt && k < N) ? to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]) : 0.f;
+    }
+    // lane n < 8 prepares token n of its channel
+    float dv = 0.f, uv = 0.f;
+    if (n < nt && n < kT) {
+      uv = to_f32<T>(u[(int64_t)(t0 + n) * a.u_tstride]);
+      dv = to_f32<T>(dl[(int64_t)(t0 + n) * a.d_tstride]) + bias;
+      if (a.softplus) dv = softplus_f<kAccurate>(dv);
+    }
     __syncthreads();
-    if (valid) {
+    if (valid) ckpt[(((int64_t)b * nchunks + c) * N + n) * a.Di + d] = h;
 #pragma unroll
-      for (int n = 0; n < kNMax; ++n)
-        if (n < N) ckpt[(((int64_t)b * nchunks + c) * N + n) * a.Di + d] = h[n];
-      for (int t = 0; t < nt; ++t) {
-        const float uv = to_f32<T>(u[(int64_t)(t0 + t) * a.u_tstride]);
-        float dv = to_f32<T>(dl[(int64_t)(t0 + t) * a.d_tstride]) + bias;
-        if (a.softplus) dv = softplus_f<kAccurate>(dv);
-        const float du = dv * uv;
-#pragma unroll
-        for (int n = 0; n < kNMax; ++n)
-          if (n < N) h[n] = fmaf(exp2_f<kAccurate>(dv * A2[n]), h[n], du * sB[t][n]);
-      }
+    for (int t = 0; t < kT; ++t) {
+      const float dt = __shfl_sync(0xffffffffu, dv, half + t);
+      const float ut = __shfl_sync(0xffffffffu, uv, half + t);
+      h = fmaf(exp2_f<kAccurate>(dt * A2), h, dt * ut * sB[t][n]);
     }
     __syncthreads();
   }
 }
 
 template <typename T, bool kAccurate>
-__global__ void __launch_bounds__(kThr)
+__global__ void __launch_bounds__(kWarps * 32)
 scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int nchunks,
                 float* __restrict__ bc_slabs, float* __restrict__ pA, float* __restrict__ pD,
                 float* __restrict__ pBias) {
-  extern __shared__ float hist[];                 // [kT][kNMax][kThr]: h_{t-1} of the chunk's tokens
   __shared__ float sB[kT][kNMax];
   __shared__ float sC[kT][kNMax];
+  __shared__ float wbuf[kWarps][kT][32];           // per warp: {dB_t[n], dC_t[n]} summed over its two channels
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = lane & 15, half = lane & 16;
   const int b = blockIdx.y;
-  const int d = blockIdx.x * kThr + tid;
-  const bool valid = d < a.Di;
+  const int d = (blockIdx.x * kWarps + warp) * 2 + (lane >> 4);
   const int N = a.N, L = a.L;
   const int64_t Di = a.Di;
+  const bool chan_ok = d < a.Di;
+  const bool valid = chan_ok && n < N;
+  const int dc = min(d, a.Di - 1);
+  const bool lo = n < kT;                           // lanes 0..7 of a channel: delta / u of token n
+  const int tk = n & 7;                             // token this lane prepares and finalises
 
-  float A2[kNMax], g[kNMax], dA[kNMax];
-#pragma unroll
-  for (int n = 0; n < kNMax; ++n) {
-    A2[n] = (valid && n < N) ? a.A2[(int64_t)d * N + n] : 0.f;
-    g[n] = (valid && n < N && a.dh_last) ? a.dh_last[((int64_t)b * Di + d) * N + n] : 0.f;
-    dA[n] = 0.f;
-  }
-  const float Dv = (valid && a.D) ? a.D[d] : 0.f;
-  const float bias = (valid && a.dt_bias) ? a.dt_bias[d] : 0.f;
-  float dD = 0.f, dBias = 0.f;
-  const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + d;
-  const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + d;
-  const T* z = a.z ? reinterpret_cast<const T*>(a.z) + (int64_t)b * a.z_bstride + d : nullptr;
-  const T* go = reinterpret_cast<const T*>(a.dout) + (int64_t)b * a.dout_bstride + d;
+  const float A2 = valid ? a.A2[(int64_t)d * N + n] : 0.f;
+  const float An = A2 * kLn2;
+  float g = (valid && a.dh_last) ? a.dh_last[((int64_t)b * Di + d) * N + n] : 0.f;
+  float dA = 0.f, dD = 0.f, dBias = 0.f;
+  const float Dv = a.D ? a.D[dc] : 0.f;
+  const float bias = a.dt_bias ? a.dt_bias[dc] : 0.f;
+  const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc;
+  const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc;
+  const T* z = a.z ? reinterpret_cast<const T*>(a.z) + (int64_t)b * a.z_bstride + dc : nullptr;
+  const T* go = reinterpret_cast<const T*>(a.dout) + (int64_t)b * a.dout_bstride + dc;
   const T* bc = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride;
-  T* du_out = reinterpret_cast<T*>(a.du) + (int64_t)b * L * Di + d;
-  T* dd_out = reinterpret_cast<T*>(a.ddelta) + (int64_t)b * L * Di + d;
-  T* dz_out = a.dz ? reinterpret_cast<T*>(a.dz) + (int64_t)b * L * Di + d : nullptr;
-  // slab of this warp: [(slab * B + b) * L + t][32] = {dB_t[0..15], dC_t[0..15]} summed over its 32 channels
-  float* slab = bc_slabs + (((int64_t)(blockIdx.x * (kThr / 32) + warp) * a.B + b) * L) * 32;
+  T* du_out = reinterpret_cast<T*>(a.du) + (int64_t)b * L * Di + dc;
+  T* dd_out = reinterpret_cast<T*>(a.ddelta) + (int64_t)b * L * Di + dc;
+  T* dz_out = a.dz ? reinterpret_cast<T*>(a.dz) + (int64_t)b * L * Di + dc : nullptr;
+  // slab of this CTA: [(slab * B + b) * L + t][32] = {dB_t[0..15], dC_t[0..15]} summed over its 16 channels
+  float* slab = bc_slabs + (((int64_t)blockIdx.x * a.B + b) * L) * 32;
 
   for (int c = nchunks - 1; c >= 0; --c) {
     const int t0 = c * kT, nt = min(kT, L - t0);
-    for (int e = tid; e < nt * N; e += kThr) {
-      const int t = e / N, n = e % N;
-      sB[t][n] = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + n]);
-      sC[t][n] = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.c_off + n]);
+    if (tid < kT * kNMax) {
+      const int t = tid >> 4, k = tid & 15;
+      const bool ok = t < nt && k < N;
+      sB[t][k] = ok ? to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]) : 0.f;
+      sC[t][k] = ok ? to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.c_off + k]) : 0.f;
     }
-    __syncthreads();
-    float dlt[kT], sg[kT], ypre[kT];
-    // ---- recompute the chunk forward from its checkpoint -------------------------------------------
-    {
-      float h[kNMax];
-#pragma unroll
-      for (int n = 0; n < kNMax; ++n)
-        h[n] = (valid && n < N) ? ckpt[(((int64_t)b * nchunks + c) * N + n) * Di + d] : 0.f;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) {
-        dlt[t] = sg[t] = ypre[t] = 0.f;
-        if (t < nt && valid) {
-          const float uv = to_f32<T>(u[(int64_t)(t0 + t) * a.u_tstride]);
-          const float raw = to_f32<T>(dl[(int64_t)(t0 + t) * a.d_tstride]) + bias;
-          float dv = raw;
-          sg[t] = 1.f;
-          if (a.softplus) {
-            dv = softplus_f<kAccurate>(raw);
-            // d softplus = sigmoid; torch's softplus is the identity above its threshold (20)
-            sg[t] = raw > 20.f ? 1.f : 1.f / (1.f + (kAccurate ? expf(-raw) : ex2_approx(-raw * kLog2e)));
-          }
-          dlt[t] = dv;
-          const float duv = dv * uv;
-          float acc = 0.f;
-#pragma unroll
-          for (int n = 0; n < kNMax; ++n) {
-            if (n < N) {
-              hist[(t * kNMax + n) * kThr + tid] = h[n];
-              h[n] = fmaf(exp2_f<kAccurate>(dv * A2[n]), h[n], duv * sB[t][n]);
-              acc = fmaf(h[n], sC[t][n], acc);
-            }
-          }
-          ypre[t] = fmaf(Dv, uv, acc);
+    // ---- per-channel scalars of the chunk: lanes 0..7 {delta, softplus', u}, lanes 8..15 {dy, dz factor, -}
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    if (tk < nt && chan_ok) {                        // lanes of a channel beyond Di contribute zeros everywhere
+      const int64_t row = t0 + tk;
+      if (lo) {
+        const float raw = to_f32<T>(dl[row * a.d_tstride]) + bias;
+        p0 = raw;
+        p1 = 1.f;
+        if (a.softplus) {
+          p0 = softplus_f<kAccurate>(raw);
+          // d softplus = sigmoid; torch's softplus is the identity above its threshold (20)
+          p1 = raw > 20.f ? 1.f : 1.f / (1.f + (kAccurate ? expf(-raw) : ex2_approx(-raw * kLog2e)));
+        }
+        p2 = to_f32<T>(u[row * a.u_tstride]);
+      } else {
+        const float gout = to_f32<T>(go[row * a.dout_tstride]);
+        p0 = gout;
+        if (z != nullptr) {
+          const float zv = to_f32<T>(z[row * a.z_tstride]);
+          const float s = 1.f / (1.f + (kAccurate ? expf(-zv) : ex2_approx(-zv * kLog2e)));
+          p0 = gout * zv * s;                        // dy
+          p1 = gout * s * (1.f + zv * (1.f - s));    // dz = p1 * ypre
         }
       }
     }
+    __syncthreads();                                 // tiles staged (and last chunk's wbuf consumed)
+    // ---- recompute the chunk forward from its checkpoint -------------------------------------------
+    float h = valid ? ckpt[(((int64_t)b * nchunks + c) * N + n) * Di + d] : 0.f;
+    float hp[kT], an[kT], yc[kT];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      const float dt = __shfl_sync(0xffffffffu, p0, half + t);
+      const float ut = __shfl_sync(0xffffffffu, p2, half + t);
+      hp[t] = h;
+      an[t] = exp2_f<kAccurate>(dt * A2);
+      h = fmaf(an[t], h, dt * ut * sB[t][n]);
+      yc[t] = h * sC[t][n];
+    }
+    // ypre of token (lane >> 1) & 7 of this channel (without the D skip), then to the lane that owns dz
+    const float ysum = halfwarp_sum8(yc, lane);
+    const float ypre_tk = __shfl_sync(0xffffffffu, ysum, half + 2 * tk);
     // ---- reverse recurrence over the chunk -----------------------------------------------------------
+    float red[16];                                   // [0..7] du contributions, [8..15] ddelta contributions
+    float hn = h;                                    // h_t of the token being processed
 #pragma unroll
     for (int t = kT - 1; t >= 0; --t) {
-      if (t < nt) {                                 // uniform over the CTA
-        float v[32];                                // {dB contributions, dC contributions} of this thread
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        if (valid) {
-          const int64_t row = t0 + t;
-          const float uv = to_f32<T>(u[row * a.u_tstride]);
-          const float gout = to_f32<T>(go[row * a.dout_tstride]);
-          float dy = gout;
-          if (z != nullptr) {
-            const float zv = to_f32<T>(z[row * a.z_tstride]);
-            const float s = 1.f / (1.f + (kAccurate ? expf(-zv) : ex2_approx(-zv * kLog2e)));
-            dy = gout * zv * s;
-            if (dz_out) dz_out[row * Di] = from_f32<T>(gout * ypre[t] * s * (1.f + zv * (1.f - s)));
-          }
-          const float dv = dlt[t];
-          const float duv = dv * uv;
-          float dut = dy * Dv, ddel = 0.f;
-          dD = fmaf(dy, uv, dD);
-#pragma unroll
-          for (int n = 0; n < kNMax; ++n) {
-            if (n < N) {
-              const float hp = hist[(t * kNMax + n) * kThr + tid];
-              const float an = exp2_f<kAccurate>(dv * A2[n]);
-              const float bt = sB[t][n], ct = sC[t][n];
-              const float hn = fmaf(an, hp, duv * bt);
-              g[n] = fmaf(dy, ct, g[n]);
-              v[16 + n] = dy * hn;
-              v[n] = g[n] * duv;
-              dut = fmaf(g[n] * dv, bt, dut);
-              const float ahp = an * hp;
-              ddel = fmaf(g[n], fmaf(ahp, A2[n] * kLn2, uv * bt), ddel);
-              dA[n] = fmaf(g[n] * ahp, dv, dA[n]);
-              g[n] *= an;
-            }
-          }
-          const float draw = ddel * sg[t];
-          dBias += draw;
-          du_out[row * Di] = from_f32<T>(dut);
-          dd_out[row * Di] = from_f32<T>(draw);
-        }
-        // transposing butterfly: afterwards lane i holds the warp's sum of v[i]
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-          const bool up = (lane & s) != 0;
-#pragma unroll
-          for (int k = 0; k < s; ++k) {
-            const float keep = up ? v[k + s] : v[k];
-            const float send = up ? v[k] : v[k + s];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-          }
-        }
-        slab[(int64_t)(t0 + t) * 32 + lane] = v[0];
+      const float dt = __shfl_sync(0xffffffffu, p0, half + t);
+      const float ut = __shfl_sync(0xffffffffu, p2, half + t);
+      const float dy = __shfl_sync(0xffffffffu, p0, half + 8 + t);
+      const float bt = sB[t][n], ct = sC[t][n];
+      g = fmaf(dy, ct, g);                           // dLoss / dh_t
+      const float vC = dy * hn;                      // -> dC_t[n]
+      const float vB = g * dt * ut;                  // -> dB_t[n]
+      const float ahp = an[t] * hp[t];
+      red[t] = g * dt * bt;
+      red[8 + t] = g * fmaf(ahp, An, ut * bt);
+      dA = fmaf(g * ahp, dt, dA);
+      g *= an[t];
+      hn = hp[t];
+      // the two channels of the warp: lanes 0..15 collect dB, lanes 16..31 collect dC
+      const float mine = half ? vC : vB, other = half ? vB : vC;
+      wbuf[warp][t][lane] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+    }
+    // lane n < 8: du of token n; lane n >= 8: ddelta of token n - 8
+    const float tot = halfwarp_sum16(red, lane);
+    const float dy_tk = __shfl_sync(0xffffffffu, p0, half + 8 + tk);     // for the lanes 0..7
+    const float sg_tk = __shfl_sync(0xffffffffu, p1, half + tk);         // for the lanes 8..15
+    const float u_tk = __shfl_sync(0xffffffffu, p2, half + tk);
+    if (chan_ok && tk < nt) {
+      const int64_t row = t0 + tk;
+      if (lo) {
+        du_out[row * Di] = from_f32<T>(fmaf(dy_tk, Dv, tot));
+      } else {
+        const float draw = tot * sg_tk;
+        dd_out[row * Di] = from_f32<T>(draw);
+        dBias += draw;
+        dD = fmaf(p0, u_tk, dD);
+        if (dz_out) dz_out[row * Di] = from_f32<T>(p1 * fmaf(Dv, u_tk, ypre_tk));
       }
     }
-    __syncthreads();
+    __syncthreads();                                 // wbuf complete
+    {
+      const int t = tid >> 5, k = tid & 31;          // 8 tokens x 32 values
+      if (t < nt) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += wbuf[w][t][k];
+        slab[(int64_t)(t0 + t) * 32 + k] = s;
+      }
+    }
+    // the next iteration's first __syncthreads orders these wbuf reads before its writes
   }
   if (valid) {
-#pragma unroll
-    for (int n = 0; n < kNMax; ++n) {
-      if (n < N) {
-        if (a.dh0) a.dh0[((int64_t)b * Di + d) * N + n] = g[n];
-        pA[((int64_t)b * Di + d) * N + n] = dA[n];
-      }
-    }
+    if (a.dh0) a.dh0[((int64_t)b * Di + d) * N + n] = g;
+    pA[((int64_t)b * Di + d) * N + n] = dA;
+  }
+  // dD / d(dt_bias): lanes 8..15 of a channel hold per-token partial sums
+  dD += __shfl_xor_sync(0xffffffffu, dD, 1);  dBias += __shfl_xor_sync(0xffffffffu, dBias, 1);
+  dD += __shfl_xor_sync(0xffffffffu, dD, 2);  dBias += __shfl_xor_sync(0xffffffffu, dBias, 2);
+  dD += __shfl_xor_sync(0xffffffffu, dD, 4);  dBias += __shfl_xor_sync(0xffffffffu, dBias, 4);
+  if (chan_ok && n == 8) {
     pD[(int64_t)b * Di + d] = dD;
     pBias[(int64_t)b * Di + d] = dBias;
   }
@@ -241,7 +278,7 @@ struct Plan {
 Plan plan(int B, int L, int Di, int N) {
   Plan p{};
   p.nchunks = (L + kT - 1) / kT;
-  p.nslabs = (Di + kThr - 1) / kThr * (kThr / 32);
+  p.nslabs = (Di + kChan - 1) / kChan;
   auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
   int64_t off = 0;
   p.ckpt = off; off += up((int64_t)B * p.nchunks * N * Di * 4);
@@ -264,16 +301,10 @@ int run(const vmb_scan_bwd_args& a, cudaStream_t st) {
   float* pA = reinterpret_cast<float*>(base + p.pA);
   float* pD = reinterpret_cast<float*>(base + p.pD);
   float* pBias = reinterpret_cast<float*>(base + p.pBias);
-  dim3 grid((a.Di + kThr - 1) / kThr, a.B);
-  scan_ckpt_kernel<T, kAccurate><<<grid, kThr, 0, st>>>(a, ckpt, p.nchunks);
+  dim3 grid((a.Di + kChan - 1) / kChan, a.B);
+  scan_ckpt_kernel<T, kAccurate><<<grid, kWarps * 32, 0, st>>>(a, ckpt, p.nchunks);
   VMB_LAUNCH_CHECK("scan_ckpt_kernel");
-  constexpr int smem = kT * kNMax * kThr * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VMB_CUDA(cudaFuncSetAttribute(scan_bwd_kernel<T, kAccurate>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  scan_bwd_kernel<T, kAccurate><<<grid, kThr, smem, st>>>(a, ckpt, p.nchunks, slabs, pA, pD, pBias);
+  scan_bwd_kernel<T, kAccurate><<<grid, kWarps * 32, 0, st>>>(a, ckpt, p.nchunks, slabs, pA, pD, pBias);
   VMB_LAUNCH_CHECK("scan_bwd_kernel");
   const int64_t rows = (int64_t)a.B * a.L;
   scan_bwd_bc_kernel<T><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(

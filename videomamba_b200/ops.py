@@ -474,7 +474,19 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
     ``u, z: (B, L, Di)``; ``xdbl: (B, L, Xp)`` rows ``[dt_low (R) | B (N) | C (N) | pad]`` with
     ``Xp = xdbl_pitch(R, N)``; ``w_dt: (Di, R)`` bf16, or already zero-padded to ``(Di, Rp)`` with
     ``Rp = round_up(R, 16)``; ``A2 = A*log2(e)`` fp32.  ``a_geometric``: the caller's promise that
-    ``A2[d, n] == (n+1) * A2[d, 0]`` (see ``is_geometric``).  Raises when the shape is not covered."""
+    ``A2[d, n] == (n+1) * A2[d, 0]`` (see ``is_geometric``).  Raises when the shape is not covered.
+    Forward-only in this form; ``autograd.FusedScanFn`` is the differentiable operator over it."""
+    out = selective_scan_fused_tokens_raw(u, z, xdbl, w_dt, A2, dt_rank, d_state, D, dt_bias, h0, want_last,
+                                          reverse, allow_split, a_geometric, tune, frame_len)
+    return forward_only(out, u, z, xdbl, w_dt, A2, D, dt_bias, h0)
+
+
+def selective_scan_fused_tokens_raw(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor, A2: Tensor,
+                                    dt_rank: int, d_state: int, D: Optional[Tensor] = None,
+                                    dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
+                                    want_last: bool = False, reverse: bool = False,
+                                    allow_split: bool = True, a_geometric: bool = False, tune: int = 0,
+                                    frame_len: int = 0):
     _require_cuda(u)
     lib = _lib.load()
     u, z, xdbl = _token_major(u), _token_major(z), _token_major(xdbl)
@@ -513,7 +525,7 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
         rc = lib.vmb_selective_scan_fused_fwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_fused_fwd")
-    return forward_only((y, h_last) if want_last else y, u, z, xdbl, w_dt, A2, D, dt_bias, h0)
+    return (y, h_last) if want_last else y
 
 
 def is_geometric(A2: Tensor, rtol: float = 1e-6) -> bool:
