@@ -407,6 +407,14 @@ typedef struct vmb_scan_bwd_args {
 } vmb_scan_bwd_args;
 VMB_API int64_t vmb_selective_scan_bwd_workspace_bytes(int B, int L, int Di, int N);
 VMB_API int vmb_selective_scan_bwd(const vmb_scan_bwd_args* args, vmb_stream_t stream);
+/* Weight gradient of a projection without transposed copies: dw (N, K) = dy^T x, dy (M, N) row stride
+ * ldy, x (M, K) row stride ldx, both bf16 with 16-byte aligned rows (N, K, ldy, ldx multiples of 8); dw in
+ * dw_dtype.  Tensor-core kernel with the token axis split over the grid (csrc/wgrad.cu).  Returns
+ * VMB_ERR_UNSUPPORTED for other layouts (callers then use vmb_transpose_2d + vmb_linear_fwd). */
+VMB_API int64_t vmb_linear_wgrad_workspace_bytes(int64_t M, int N, int K);
+VMB_API int vmb_linear_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, void* dw, int dw_dtype,
+                     int64_t M, int N, int K, void* workspace, int64_t workspace_bytes,
+                     vmb_stream_t stream);
 VMB_API int vmb_transpose_2d(const void* in, int64_t ld, void* out, int64_t ldo, int64_t rows, int cols,
                      int dtype, vmb_stream_t stream);
 VMB_API int64_t vmb_colsum_workspace_bytes(int64_t M, int N);

@@ -407,3 +407,20 @@ def test_refiner_backward():
     for name, prm in blk.named_parameters():
         if p[name].grad is not None:
             _check(prm.grad, p[name].grad, 5e-4, name)
+
+
+@pytest.mark.parametrize("shape", [(3137 * 2, 768, 384), (1000, 64, 768), (777, 768, 24), (40, 1536, 384), (5000, 56, 768)])
+def test_linear_wgrad_kernel(shape):
+    """vmb_linear_wgrad (split-token tensor-core kernel, operands read in place) against fp32 matmul,
+    including strided operand views and ragged token / tile edges."""
+    M, N, K = shape
+    g = _gen(M + N)
+    dy = torch.randn(M, N + 8, generator=g).to(torch.bfloat16).to(DEV)[:, :N]      # row pitch N + 8
+    x = torch.randn(M, 2 * K, generator=g).to(torch.bfloat16).to(DEV)[:, K:]      # the upper half of a wider buffer
+    want = dy.float().t() @ x.float()
+    for out_dtype in (torch.float32, torch.bfloat16):
+        got = ag.linear_wgrad(dy, x, out_dtype)
+        assert got.dtype == out_dtype and got.shape == (N, K)
+        assert rel_err(got, want) <= (1e-5 if out_dtype == torch.float32 else 5e-3)
+    again = ag.linear_wgrad(dy, x, torch.float32)
+    assert torch.equal(again, ag.linear_wgrad(dy, x, torch.float32))               # deterministic

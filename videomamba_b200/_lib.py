@@ -161,6 +161,9 @@ SIGNATURES = {
                                       c_void_p]),
     "vmb_selective_scan_bwd_workspace_bytes": (c_int64, [c_int] * 4),
     "vmb_selective_scan_bwd": (c_int, [C.POINTER(ScanBwdArgs), c_void_p]),
+    "vmb_linear_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "vmb_linear_wgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_int,
+                                 c_void_p, c_int64, c_void_p]),
     "vmb_transpose_2d": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "vmb_colsum_workspace_bytes": (c_int64, [c_int64, c_int]),
     "vmb_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_int64,

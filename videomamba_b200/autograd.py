@@ -61,6 +61,32 @@ def colsum(x2: Tensor, out_dtype: torch.dtype) -> Tensor:
     return out.to(out_dtype)
 
 
+def linear_wgrad(dy2: Tensor, x2: Tensor, out_dtype: torch.dtype) -> Tensor:
+    """``dy2^T @ x2`` -> ``(N, K)``: the weight gradient of ``y = x W^T`` summed over the M rows.  bf16
+    operands with aligned rows run the split-token tensor-core kernel (``vmb_linear_wgrad``, no transposed
+    copies); everything else goes through two transposes and the forward projection."""
+    lib = _lib.load()
+    M, N = dy2.shape
+    K = x2.shape[1]
+    lds = (dy2.stride(0) if M > 1 else N, x2.stride(0) if M > 1 else K)
+    direct = (dy2.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16 and M > 0
+              and N % 8 == 0 and K % 8 == 0 and lds[0] % 8 == 0 and lds[1] % 8 == 0
+              and dy2.data_ptr() % 16 == 0 and x2.data_ptr() % 16 == 0
+              and out_dtype in (torch.bfloat16, torch.float32))
+    if direct:
+        dw = torch.empty((N, K), dtype=out_dtype, device=dy2.device)
+        nbytes = lib.vmb_linear_wgrad_workspace_bytes(M, N, K)
+        ws = _ws(nbytes, dy2)
+        with _on_device(dy2):
+            rc = lib.vmb_linear_wgrad(_p(dy2), lds[0], _p(x2), lds[1], _p(dw), _dt(dw), M, N, K, _p(ws), nbytes,
+                                      _stream(dy2))
+        _lib.check(rc, "vmb_linear_wgrad")
+        return dw
+    if M == 0:
+        return torch.zeros((N, K), dtype=out_dtype, device=dy2.device)
+    return ops.linear_raw(transpose2d(dy2), transpose2d(x2)).to(out_dtype)   # zero tails: exact
+
+
 def _rows(t: Tensor, width: int) -> Tensor:
     t2 = t.reshape(-1, width)
     if t2.stride(-1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < width):
@@ -90,12 +116,7 @@ class LinearFn(torch.autograd.Function):
             w_t = transpose2d(_rows(weight.to(x.dtype), K))[:, :N]             # (K, N)
             dx = ops.linear_raw(dy2, w_t).reshape(x.shape)
         if ctx.needs_input_grad[1]:
-            if M == 0:
-                dw = torch.zeros_like(weight)
-            else:
-                dy_t = transpose2d(dy2)                                        # (N, Mp), zero tail
-                x_t = transpose2d(x2)                                          # (K, Mp)
-                dw = ops.linear_raw(dy_t, x_t).to(weight.dtype)                # (N, K): sum over the M rows
+            dw = linear_wgrad(dy2, x2, weight.dtype)                           # (N, K): sum over the M rows
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2, ctx.bias_dtype)
         return dx, dw, db
@@ -319,7 +340,7 @@ class FusedScanFn(torch.autograd.Function):
         dbc[..., :R] = ops.linear_raw(dd2, w_t).reshape(B, L, R)              # d dt_low
         dw_dt = None
         if ctx.needs_input_grad[3]:
-            dw_dt = ops.linear_raw(transpose2d(dd2), transpose2d(_rows(dt_low, R))).to(w_dt.dtype)   # (Di, R)
+            dw_dt = linear_wgrad(dd2, _rows(dt_low, R), w_dt.dtype)           # (Di, R)
         return (du, dz, dbc, dw_dt, dA.to(A_dtype), None if dD is None else dD.to(D_dtype),
                 None if dbias is None else dbias.to(bias_dtype), dh0, None, None, None)
 

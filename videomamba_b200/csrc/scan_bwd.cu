@@ -9,7 +9,8 @@
 //   dA[n] += g a h_{t-1} delta;  g *= a  (-> t-1);   ddraw = ddelta sigmoid(draw + bias);  dh0 = g after t = 0
 //
 // h_{t-1} is needed in reverse order.  Pass 1 (scan_ckpt_kernel) walks the sequence forward and stores
-// the state at the start of every 8-token chunk; pass 2 (scan_bwd_kernel) walks the chunks back to
+// the state at the start of every 8-token chunk ([batch][chunk][channel][state]: a warp's two channels are
+// one 128-byte line); pass 2 (scan_bwd_kernel) walks the chunks back to
 // front, recomputes the 8 states of a chunk from its checkpoint and runs the reverse recurrence on them.
 //
 // Thread layout: ONE LANE PER (channel, state) -- a half-warp is a channel, a warp two channels, a CTA
@@ -81,21 +82,34 @@ scan_ckpt_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int nchunk
   const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc;
   const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc;
   const T* bc = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride;
-  for (int c = 0; c < nchunks; ++c) {
+  struct Pre { float dv, uv, tb; };
+  auto prefetch = [&](int c) {                      // the next chunk's loads, one chunk ahead (see scan_bwd_kernel)
+    Pre q{0.f, 0.f, 0.f};
     const int t0 = c * kT, nt = min(kT, L - t0);
+    if (n < nt && n < kT) {                         // lane n < 8 prepares token n of its channel
+      q.uv = to_f32<T>(u[(int64_t)(t0 + n) * a.u_tstride]);
+      q.dv = to_f32<T>(dl[(int64_t)(t0 + n) * a.d_tstride]);
+    }
     if (tid < kT * kNMax) {
       const int t = tid >> 4, k = tid & 15;
-      sB[t][k] = (t < nt && k < N) ? to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]) : 0.f;
+      if (t < nt && k < N) q.tb = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]);
     }
-    // lane n < 8 prepares token n of its channel
-    float dv = 0.f, uv = 0.f;
+    return q;
+  };
+  Pre nxt = prefetch(0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int t0 = c * kT, nt = min(kT, L - t0);
+    const Pre cur = nxt;
+    if (tid < kT * kNMax) sB[tid >> 4][tid & 15] = cur.tb;
+    if (c + 1 < nchunks) nxt = prefetch(c + 1);
+    float dv = 0.f;
+    const float uv = cur.uv;
     if (n < nt && n < kT) {
-      uv = to_f32<T>(u[(int64_t)(t0 + n) * a.u_tstride]);
-      dv = to_f32<T>(dl[(int64_t)(t0 + n) * a.d_tstride]) + bias;
+      dv = cur.dv + bias;
       if (a.softplus) dv = softplus_f<kAccurate>(dv);
     }
     __syncthreads();
-    if (valid) ckpt[(((int64_t)b * nchunks + c) * N + n) * a.Di + d] = h;
+    if (valid) ckpt[(((int64_t)b * nchunks + c) * a.Di + d) * N + n] = h;
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       const float dt = __shfl_sync(0xffffffffu, dv, half + t);
@@ -143,20 +157,47 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
   // slab of this CTA: [(slab * B + b) * L + t][32] = {dB_t[0..15], dC_t[0..15]} summed over its 16 channels
   float* slab = bc_slabs + (((int64_t)blockIdx.x * a.B + b) * L) * 32;
 
-  for (int c = nchunks - 1; c >= 0; --c) {
+  // Global loads of a chunk (two per-channel scalars per lane, the checkpointed state, the B / C tile
+  // elements) are issued one chunk AHEAD into registers: with 8 tokens of work per chunk and CTA-wide
+  // barriers, a load issued where it is needed would expose its full latency three times per chunk.
+  struct Pre { float r0, r1, hck, tb, tc; };
+  auto prefetch = [&](int c) {
+    Pre q{0.f, 0.f, 0.f, 0.f, 0.f};
     const int t0 = c * kT, nt = min(kT, L - t0);
+    if (tk < nt && chan_ok) {
+      const int64_t row = t0 + tk;
+      if (lo) {
+        q.r0 = to_f32<T>(dl[row * a.d_tstride]);
+        q.r1 = to_f32<T>(u[row * a.u_tstride]);
+      } else {
+        q.r0 = to_f32<T>(go[row * a.dout_tstride]);
+        if (z != nullptr) q.r1 = to_f32<T>(z[row * a.z_tstride]);
+      }
+    }
+    if (valid) q.hck = ckpt[(((int64_t)b * nchunks + c) * Di + d) * N + n];
     if (tid < kT * kNMax) {
       const int t = tid >> 4, k = tid & 15;
-      const bool ok = t < nt && k < N;
-      sB[t][k] = ok ? to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]) : 0.f;
-      sC[t][k] = ok ? to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.c_off + k]) : 0.f;
+      if (t < nt && k < N) {
+        q.tb = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]);
+        q.tc = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.c_off + k]);
+      }
     }
+    return q;
+  };
+  Pre nxt = prefetch(nchunks - 1);
+  for (int c = nchunks - 1; c >= 0; --c) {
+    const int t0 = c * kT, nt = min(kT, L - t0);
+    const Pre cur = nxt;
+    if (tid < kT * kNMax) {
+      sB[tid >> 4][tid & 15] = cur.tb;
+      sC[tid >> 4][tid & 15] = cur.tc;
+    }
+    if (c > 0) nxt = prefetch(c - 1);
     // ---- per-channel scalars of the chunk: lanes 0..7 {delta, softplus', u}, lanes 8..15 {dy, dz factor, -}
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
     if (tk < nt && chan_ok) {                        // lanes of a channel beyond Di contribute zeros everywhere
-      const int64_t row = t0 + tk;
       if (lo) {
-        const float raw = to_f32<T>(dl[row * a.d_tstride]) + bias;
+        const float raw = cur.r0 + bias;
         p0 = raw;
         p1 = 1.f;
         if (a.softplus) {
@@ -164,12 +205,12 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
           // d softplus = sigmoid; torch's softplus is the identity above its threshold (20)
           p1 = raw > 20.f ? 1.f : 1.f / (1.f + (kAccurate ? expf(-raw) : ex2_approx(-raw * kLog2e)));
         }
-        p2 = to_f32<T>(u[row * a.u_tstride]);
+        p2 = cur.r1;
       } else {
-        const float gout = to_f32<T>(go[row * a.dout_tstride]);
+        const float gout = cur.r0;
         p0 = gout;
         if (z != nullptr) {
-          const float zv = to_f32<T>(z[row * a.z_tstride]);
+          const float zv = cur.r1;
           const float s = 1.f / (1.f + (kAccurate ? expf(-zv) : ex2_approx(-zv * kLog2e)));
           p0 = gout * zv * s;                        // dy
           p1 = gout * s * (1.f + zv * (1.f - s));    // dz = p1 * ypre
@@ -178,7 +219,7 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
     }
     __syncthreads();                                 // tiles staged (and last chunk's wbuf consumed)
     // ---- recompute the chunk forward from its checkpoint -------------------------------------------
-    float h = valid ? ckpt[(((int64_t)b * nchunks + c) * N + n) * Di + d] : 0.f;
+    float h = cur.hck;
     float hp[kT], an[kT], yc[kT];
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
