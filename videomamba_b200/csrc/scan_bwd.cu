@@ -68,7 +68,7 @@ __device__ __forceinline__ float halfwarp_sum16(float (&v)[16], int lane) {
 template <typename T, bool kAccurate>
 __global__ void __launch_bounds__(kWarps * 32)
 scan_ckpt_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int nchunks) {
-  __shared__ float sB[kT][kNMax];
+  __shared__ float sB[2][kT][kNMax];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = lane & 15, half = lane & 16;       // half = first lane of this channel's half-warp
   const int b = blockIdx.y;
@@ -79,44 +79,50 @@ scan_ckpt_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int nchunk
   const float A2 = valid ? a.A2[(int64_t)d * N + n] : 0.f;
   float h = (valid && a.h0) ? load_as_f32(a.h0, ((int64_t)b * a.Di + d) * N + n, a.h0_dtype) : 0.f;
   const float bias = a.dt_bias ? a.dt_bias[dc] : 0.f;
-  const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc;
-  const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc;
-  const T* bc = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride;
+  // per-lane walking pointers (advanced by one chunk per iteration: no 64-bit index arithmetic in the loop)
+  const bool prep = n < kT;                         // lane n < 8 prepares token n of its channel
+  const T* pu = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc + (int64_t)n * a.u_tstride;
+  const T* pd = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc + (int64_t)n * a.d_tstride;
+  const int64_t su = (int64_t)kT * a.u_tstride, sd = (int64_t)kT * a.d_tstride;
+  const bool tile_lane = tid < kT * kNMax && (tid & 15) < N;
+  const T* pb = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride + (int64_t)(tid >> 4) * a.bc_tstride +
+                a.b_off + (tid & 15);
+  const int64_t sbc = (int64_t)kT * a.bc_tstride;
+  float* pc = ckpt + (((int64_t)b * nchunks) * a.Di + d) * N + n;
+  const int64_t sc = (int64_t)a.Di * N;
   struct Pre { float dv, uv, tb; };
-  auto prefetch = [&](int c) {                      // the next chunk's loads, one chunk ahead (see scan_bwd_kernel)
+  auto prefetch = [&](int nt) {                     // the next chunk's loads, one chunk ahead (see scan_bwd_kernel)
     Pre q{0.f, 0.f, 0.f};
-    const int t0 = c * kT, nt = min(kT, L - t0);
-    if (n < nt && n < kT) {                         // lane n < 8 prepares token n of its channel
-      q.uv = to_f32<T>(u[(int64_t)(t0 + n) * a.u_tstride]);
-      q.dv = to_f32<T>(dl[(int64_t)(t0 + n) * a.d_tstride]);
+    if (prep && n < nt) {
+      q.uv = to_f32<T>(*pu);
+      q.dv = to_f32<T>(*pd);
     }
-    if (tid < kT * kNMax) {
-      const int t = tid >> 4, k = tid & 15;
-      if (t < nt && k < N) q.tb = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]);
-    }
+    if (tile_lane && (tid >> 4) < nt) q.tb = to_f32<T>(*pb);
+    pu += su; pd += sd; pb += sbc;
     return q;
   };
-  Pre nxt = prefetch(0);
+  Pre nxt = prefetch(min(kT, L));
   for (int c = 0; c < nchunks; ++c) {
-    const int t0 = c * kT, nt = min(kT, L - t0);
+    const int nt = min(kT, L - c * kT);
     const Pre cur = nxt;
-    if (tid < kT * kNMax) sB[tid >> 4][tid & 15] = cur.tb;
-    if (c + 1 < nchunks) nxt = prefetch(c + 1);
+    float (*tile)[kNMax] = sB[c & 1];               // double buffered: one barrier per chunk
+    if (tid < kT * kNMax) tile[tid >> 4][tid & 15] = cur.tb;
+    if (c + 1 < nchunks) nxt = prefetch(min(kT, L - (c + 1) * kT));
     float dv = 0.f;
     const float uv = cur.uv;
-    if (n < nt && n < kT) {
+    if (prep && n < nt) {
       dv = cur.dv + bias;
       if (a.softplus) dv = softplus_f<kAccurate>(dv);
     }
     __syncthreads();
-    if (valid) ckpt[(((int64_t)b * nchunks + c) * a.Di + d) * N + n] = h;
+    if (valid) *pc = h;
+    pc += sc;
 #pragma unroll
     for (int t = 0; t < kT; ++t) {
       const float dt = __shfl_sync(0xffffffffu, dv, half + t);
       const float ut = __shfl_sync(0xffffffffu, uv, half + t);
-      h = fmaf(exp2_f<kAccurate>(dt * A2), h, dt * ut * sB[t][n]);
+      h = fmaf(exp2_f<kAccurate>(dt * A2), h, dt * ut * tile[t][n]);
     }
-    __syncthreads();
   }
 }
 
@@ -146,53 +152,63 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
   float dA = 0.f, dD = 0.f, dBias = 0.f;
   const float Dv = a.D ? a.D[dc] : 0.f;
   const float bias = a.dt_bias ? a.dt_bias[dc] : 0.f;
-  const T* u = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc;
-  const T* dl = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc;
-  const T* z = a.z ? reinterpret_cast<const T*>(a.z) + (int64_t)b * a.z_bstride + dc : nullptr;
-  const T* go = reinterpret_cast<const T*>(a.dout) + (int64_t)b * a.dout_bstride + dc;
-  const T* bc = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride;
-  T* du_out = reinterpret_cast<T*>(a.du) + (int64_t)b * L * Di + dc;
-  T* dd_out = reinterpret_cast<T*>(a.ddelta) + (int64_t)b * L * Di + dc;
-  T* dz_out = a.dz ? reinterpret_cast<T*>(a.dz) + (int64_t)b * L * Di + dc : nullptr;
+  // Per-lane walking pointers, stepped back one chunk per iteration (no 64-bit index arithmetic in the loop).
+  // Lane roles within a channel: lanes 0..7 read delta / u and write du of token n; lanes 8..15 read
+  // dout / z and write ddelta / dz of token n - 8.
+  const int64_t last0 = (int64_t)(nchunks - 1) * kT;                 // first token of the last chunk
+  const T* pa;  const T* pb2;  int64_t sa, sb2;                     // the lane's two scalar streams
+  if (lo) {
+    pa = reinterpret_cast<const T*>(a.delta) + (int64_t)b * a.d_bstride + dc + (last0 + tk) * a.d_tstride;
+    pb2 = reinterpret_cast<const T*>(a.u) + (int64_t)b * a.u_bstride + dc + (last0 + tk) * a.u_tstride;
+    sa = (int64_t)kT * a.d_tstride;  sb2 = (int64_t)kT * a.u_tstride;
+  } else {
+    pa = reinterpret_cast<const T*>(a.dout) + (int64_t)b * a.dout_bstride + dc + (last0 + tk) * a.dout_tstride;
+    pb2 = a.z ? reinterpret_cast<const T*>(a.z) + (int64_t)b * a.z_bstride + dc + (last0 + tk) * a.z_tstride : nullptr;
+    sa = (int64_t)kT * a.dout_tstride;  sb2 = (int64_t)kT * a.z_tstride;
+  }
+  const bool has_z = a.z != nullptr;
+  const bool load_b = lo || has_z;
+  const float* pck = ckpt + (((int64_t)b * nchunks + (nchunks - 1)) * Di + d) * N + n;
+  const int64_t sck = Di * N;
+  const bool tile_lane = tid < kT * kNMax && (tid & 15) < N;
+  const T* ptb = reinterpret_cast<const T*>(a.bc) + (int64_t)b * a.bc_bstride + (last0 + (tid >> 4)) * a.bc_tstride +
+                 (tid & 15);
+  const int64_t stb = (int64_t)kT * a.bc_tstride;
+  const int b_off = a.b_off, c_off = a.c_off;
+  // outputs: lanes 0..7 -> du, lanes 8..15 -> ddelta (and dz)
+  T* po = (lo ? reinterpret_cast<T*>(a.du) : reinterpret_cast<T*>(a.ddelta)) + ((int64_t)b * L + last0 + tk) * Di + dc;
+  T* pz = a.dz ? reinterpret_cast<T*>(a.dz) + ((int64_t)b * L + last0 + tk) * Di + dc : nullptr;
+  const int64_t so = (int64_t)kT * Di;
   // slab of this CTA: [(slab * B + b) * L + t][32] = {dB_t[0..15], dC_t[0..15]} summed over its 16 channels
-  float* slab = bc_slabs + (((int64_t)blockIdx.x * a.B + b) * L) * 32;
+  float* pslab = bc_slabs + (((int64_t)blockIdx.x * a.B + b) * L + last0 + (tid >> 5)) * 32 + (tid & 31);
 
   // Global loads of a chunk (two per-channel scalars per lane, the checkpointed state, the B / C tile
   // elements) are issued one chunk AHEAD into registers: with 8 tokens of work per chunk and CTA-wide
-  // barriers, a load issued where it is needed would expose its full latency three times per chunk.
+  // barriers, a load issued where it is needed would expose its full latency every chunk.
   struct Pre { float r0, r1, hck, tb, tc; };
-  auto prefetch = [&](int c) {
+  auto prefetch = [&](int nt) {
     Pre q{0.f, 0.f, 0.f, 0.f, 0.f};
-    const int t0 = c * kT, nt = min(kT, L - t0);
     if (tk < nt && chan_ok) {
-      const int64_t row = t0 + tk;
-      if (lo) {
-        q.r0 = to_f32<T>(dl[row * a.d_tstride]);
-        q.r1 = to_f32<T>(u[row * a.u_tstride]);
-      } else {
-        q.r0 = to_f32<T>(go[row * a.dout_tstride]);
-        if (z != nullptr) q.r1 = to_f32<T>(z[row * a.z_tstride]);
-      }
+      q.r0 = to_f32<T>(*pa);
+      if (load_b) q.r1 = to_f32<T>(*pb2);
     }
-    if (valid) q.hck = ckpt[(((int64_t)b * nchunks + c) * Di + d) * N + n];
-    if (tid < kT * kNMax) {
-      const int t = tid >> 4, k = tid & 15;
-      if (t < nt && k < N) {
-        q.tb = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.b_off + k]);
-        q.tc = to_f32<T>(bc[(int64_t)(t0 + t) * a.bc_tstride + a.c_off + k]);
-      }
+    if (valid) q.hck = *pck;
+    if (tile_lane && (tid >> 4) < nt) {
+      q.tb = to_f32<T>(ptb[b_off]);
+      q.tc = to_f32<T>(ptb[c_off]);
     }
+    pa -= sa; pb2 -= sb2; pck -= sck; ptb -= stb;
     return q;
   };
-  Pre nxt = prefetch(nchunks - 1);
+  Pre nxt = prefetch(min(kT, L - (int)last0));
   for (int c = nchunks - 1; c >= 0; --c) {
-    const int t0 = c * kT, nt = min(kT, L - t0);
+    const int nt = min(kT, L - c * kT);
     const Pre cur = nxt;
     if (tid < kT * kNMax) {
       sB[tid >> 4][tid & 15] = cur.tb;
       sC[tid >> 4][tid & 15] = cur.tc;
     }
-    if (c > 0) nxt = prefetch(c - 1);
+    if (c > 0) nxt = prefetch(kT);
     // ---- per-channel scalars of the chunk: lanes 0..7 {delta, softplus', u}, lanes 8..15 {dy, dz factor, -}
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
     if (tk < nt && chan_ok) {                        // lanes of a channel beyond Di contribute zeros everywhere
@@ -209,7 +225,7 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
       } else {
         const float gout = cur.r0;
         p0 = gout;
-        if (z != nullptr) {
+        if (has_z) {
           const float zv = cur.r1;
           const float s = 1.f / (1.f + (kAccurate ? expf(-zv) : ex2_approx(-zv * kLog2e)));
           p0 = gout * zv * s;                        // dy
@@ -261,17 +277,18 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
     const float sg_tk = __shfl_sync(0xffffffffu, p1, half + tk);         // for the lanes 8..15
     const float u_tk = __shfl_sync(0xffffffffu, p2, half + tk);
     if (chan_ok && tk < nt) {
-      const int64_t row = t0 + tk;
       if (lo) {
-        du_out[row * Di] = from_f32<T>(fmaf(dy_tk, Dv, tot));
+        *po = from_f32<T>(fmaf(dy_tk, Dv, tot));
       } else {
         const float draw = tot * sg_tk;
-        dd_out[row * Di] = from_f32<T>(draw);
+        *po = from_f32<T>(draw);
         dBias += draw;
         dD = fmaf(p0, u_tk, dD);
-        if (dz_out) dz_out[row * Di] = from_f32<T>(p1 * fmaf(Dv, u_tk, ypre_tk));
+        if (pz) *pz = from_f32<T>(p1 * fmaf(Dv, u_tk, ypre_tk));
       }
     }
+    po -= so;
+    if (pz) pz -= so;
     __syncthreads();                                 // wbuf complete
     {
       const int t = tid >> 5, k = tid & 31;          // 8 tokens x 32 values
@@ -279,8 +296,9 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += wbuf[w][t][k];
-        slab[(int64_t)(t0 + t) * 32 + k] = s;
+        *pslab = s;
       }
+      pslab -= kT * 32;
     }
     // the next iteration's first __syncthreads orders these wbuf reads before its writes
   }
