@@ -172,6 +172,31 @@ class AddNormFn(torch.autograd.Function):
                 None if dres is None else dres.reshape(shape), None, None, None, None)
 
 
+class SplitXZ(torch.autograd.Function):
+    """``xz (.., 2 Di) -> (x, z)`` as two strided views (mamba_simple.py:369).  torch's own slice backward
+    materialises one zero-filled (.., 2 Di) tensor per half and adds them (five passes over the largest
+    activation of the block); here the two incoming gradients are written side by side into one buffer."""
+
+    @staticmethod
+    def forward(ctx, xz, di):
+        ctx.set_materialize_grads(False)
+        ctx.di = di
+        ctx.meta = (xz.shape, xz.dtype, xz.device)
+        return xz[..., :di], xz[..., di:]
+
+    @staticmethod
+    def backward(ctx, dx, dz):
+        shape, dtype, dev = ctx.meta
+        di = ctx.di
+        out = torch.empty(shape, dtype=dtype, device=dev)
+        for part, grad in ((out[..., :di], dx), (out[..., di:], dz)):
+            if grad is None:
+                part.zero_()
+            else:
+                part.copy_(grad)
+        return out, None
+
+
 class ConvFn(torch.autograd.Function):
     """Depthwise causal conv + SiLU with streaming history, token-major (``vmb_causal_conv1d_fwd`` /
     ``_bwd``).  Gradients flow into ``conv_state`` and arrive through the returned state."""
@@ -361,7 +386,7 @@ def mixer_train(in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dp, out_w, o
     Di = conv_w.shape[0]
     N, R = A_log.shape[1], dt_w.shape[1]
     xz = ops.linear(hidden, in_w, in_b)                                  # :333-339
-    x_in, z = xz[..., :Di], xz[..., Di:]                                 # :369
+    x_in, z = SplitXZ.apply(xz, Di)                                      # :369
     xc, new_conv = ConvFn.apply(x_in, conv_w, conv_b, conv_state, want_conv_state, True)   # :381-404
     A = -torch.exp(A_log.float())                                        # :341
     if fused_scan_covers(hidden.dtype, Di, N, R) and x_w.dtype == hidden.dtype and dt_w.dtype == hidden.dtype:

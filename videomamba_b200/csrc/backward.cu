@@ -168,6 +168,164 @@ add_norm_bwd_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx, const 
   }
 }
 
+// Vectorised variant for the production type combinations (x / dy / dx / weight of type T, residual stream
+// and its gradients fp32): a lane owns 4 consecutive columns per step, 8-byte (bf16) / 16-byte (fp32) accesses.
+template <typename T> struct V4;
+template <> struct V4<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct V4<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&f)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+template <typename T, int kIters, bool kRms>        // kIters * 128 >= dim, dim % 4 == 0
+__global__ void __launch_bounds__(kBwdWarps * 32)
+add_norm_bwd_vec_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ residual,
+                        const T* __restrict__ weight, const T* __restrict__ dy,
+                        const float* __restrict__ dres_out, T* __restrict__ dx, float* __restrict__ dres,
+                        float* __restrict__ partial_w, float* __restrict__ partial_b, int64_t rows, int dim,
+                        float eps) {
+  __shared__ float red[kBwdWarps][kIters * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = dim >> 2;
+  float w[kIters][4], dw[kIters][4], db[kIters][4];
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    const int c = it * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[it][j] = dw[it][j] = db[it][j] = 0.f;
+    if (c < nvec) V4<T>::ld(weight + 4 * c, w[it]);
+  }
+  const float inv_dim = 1.f / (float)dim;
+  for (int64_t row = (int64_t)blockIdx.x * kBwdWarps + warp; row < rows; row += (int64_t)gridDim.x * kBwdWarps) {
+    float v[kIters][4], g[kIters][4];
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = it * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[it][j] = g[it][j] = 0.f;
+      if (c < nvec) {
+        V4<T>::ld(x + row * ldx + 4 * c, v[it]);
+        if (residual != nullptr) {
+          float r[4];
+          V4<float>::ld(residual + row * (int64_t)dim + 4 * c, r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[it][j] += r[j];
+        }
+        V4<T>::ld(dy + row * (int64_t)dim + 4 * c, g[it]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sum += v[it][j]; sumsq += v[it][j] * v[it][j]; }
+      }
+    }
+    float mean = 0.f, rstd;
+    if constexpr (kRms) {
+      rstd = rsqrtf(warp_sum(sumsq) * inv_dim + eps);
+    } else {
+      mean = warp_sum(sum) * inv_dim;
+      float var = 0.f;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it)
+        if (it * 32 + lane < nvec)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) var += (v[it][j] - mean) * (v[it][j] - mean);
+      rstd = rsqrtf(warp_sum(var) * inv_dim + eps);
+    }
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it)
+      if (it * 32 + lane < nvec)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xhat = (v[it][j] - mean) * rstd;
+          dw[it][j] += g[it][j] * xhat;
+          db[it][j] += g[it][j];
+          const float wg = w[it][j] * g[it][j];
+          c1 += wg * xhat;
+          c2 += wg;
+          v[it][j] = xhat;
+          g[it][j] = wg;
+        }
+    c1 = warp_sum(c1) * inv_dim;
+    c2 = kRms ? 0.f : warp_sum(c2) * inv_dim;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = it * 32 + lane;
+      if (c < nvec) {
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = rstd * (g[it][j] - v[it][j] * c1 - c2);
+        if (dres_out != nullptr) {
+          float r[4];
+          V4<float>::ld(dres_out + row * (int64_t)dim + 4 * c, r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] += r[j];
+        }
+        V4<T>::st(dx + row * (int64_t)dim + 4 * c, d);
+        if (dres != nullptr) V4<float>::st(dres + row * (int64_t)dim + 4 * c, d);
+      }
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kIters; ++it)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[warp][(it * 32 + lane) * 4 + j] = pass ? db[it][j] : dw[it][j];
+    __syncthreads();
+    float* dst = pass ? partial_b : partial_w;
+    if (dst != nullptr)
+      for (int c = threadIdx.x; c < dim; c += kBwdWarps * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kBwdWarps; ++j) s += red[j][c];
+        dst[(int64_t)blockIdx.x * dim + c] = s;
+      }
+  }
+}
+
+template <typename T>
+bool launch_add_norm_bwd_vec(const void* x, int64_t ldx, const void* residual, const void* weight, const void* dy,
+                             const void* dres_out, void* dx, void* dres, float* pw, float* pb, int64_t rows,
+                             int dim, float eps, bool rms, int ctas, cudaStream_t st) {
+#define VMB_ANV(IT)                                                                                         \
+  do {                                                                                                      \
+    if (rms)                                                                                                \
+      add_norm_bwd_vec_kernel<T, IT, true><<<ctas, kBwdWarps * 32, 0, st>>>(                                \
+          (const T*)x, ldx, (const float*)residual, (const T*)weight, (const T*)dy, (const float*)dres_out, \
+          (T*)dx, (float*)dres, pw, pb, rows, dim, eps);                                                    \
+    else                                                                                                    \
+      add_norm_bwd_vec_kernel<T, IT, false><<<ctas, kBwdWarps * 32, 0, st>>>(                               \
+          (const T*)x, ldx, (const float*)residual, (const T*)weight, (const T*)dy, (const float*)dres_out, \
+          (T*)dx, (float*)dres, pw, pb, rows, dim, eps);                                                    \
+  } while (0)
+  if (dim <= 128 * 2) VMB_ANV(2);
+  else if (dim <= 128 * 3) VMB_ANV(3);
+  else if (dim <= 128 * 5) VMB_ANV(5);
+  else if (dim <= 128 * 9) VMB_ANV(9);
+  else return false;
+#undef VMB_ANV
+  return true;
+}
+
 // ---- causal conv + SiLU backward -------------------------------------------------------------------
 // Thread = channel; a CTA walks one chunk of kConvChunk tokens of one sequence in order, carrying the last
 // W inputs and the last W pre-activation gradients in registers.  hist[j], j in [-(W-1), L): x[j] for
@@ -253,6 +411,125 @@ conv1d_bwd_kernel(const void* __restrict__ x, int64_t x_bs, int64_t x_ts, const 
   float* p = partial + (((int64_t)b * gridDim.z + chunk) * Di + d) * (W + 1);
   for (int k = 0; k < W; ++k) p[k] = dwa[k];
   p[W] = dba;
+}
+
+// Fast variant: compile-time W (windows stay in registers), a thread owns TWO adjacent channels (4-byte bf16 /
+// 8-byte fp32 accesses), fast exp.  Same walk and the same partial layout as conv1d_bwd_kernel.
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct Pair<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 v) {
+    __nv_bfloat162 r = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&r);
+  }
+};
+
+template <typename T, int W>
+__global__ void __launch_bounds__(128)
+conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* __restrict__ weight,
+                       const T* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
+                       const T* __restrict__ dy, const void* __restrict__ dcs_out, int dcs_out_dtype,
+                       T* __restrict__ dx, void* __restrict__ dcs_in, float* __restrict__ partial,
+                       int L, int Di, int silu) {
+  const int d = (blockIdx.x * 128 + threadIdx.x) * 2;
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.z;
+  if (d >= Di) return;
+  const int c0 = chunk * kConvChunk;
+  const int c1 = min(L, c0 + kConvChunk);
+  float2 w[W], hist[W], dpre[W], dwa[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    w[k] = make_float2(to_f32<T>(weight[(int64_t)d * W + k]), to_f32<T>(weight[(int64_t)(d + 1) * W + k]));
+    hist[k] = dpre[k] = dwa[k] = make_float2(0.f, 0.f);
+  }
+  const float2 bv = bias ? Pair<T>::ld(bias + d) : make_float2(0.f, 0.f);
+  float2 dba = make_float2(0.f, 0.f);
+  const T* xp = x + (int64_t)b * x_bs + d;
+  const T* gp = dy + (int64_t)b * L * Di + d;
+  T* op = dx + (int64_t)b * L * Di + d;
+  auto hist_at = [&](int j) -> float2 {
+    if (j >= 0) return Pair<T>::ld(xp + (int64_t)j * x_ts);
+    if (!cs_in) return make_float2(0.f, 0.f);
+    const int64_t o = ((int64_t)b * Di + d) * W + (W + j);
+    return make_float2(load_as_f32(cs_in, o, cs_in_dtype), load_as_f32(cs_in, o + W, cs_in_dtype));
+  };
+  auto dcs_out_at = [&](int i) -> float2 {
+    if (!dcs_out) return make_float2(0.f, 0.f);
+    const int64_t o = ((int64_t)b * Di + d) * W + i;
+    return make_float2(load_as_f32(dcs_out, o, dcs_out_dtype), load_as_f32(dcs_out, o + W, dcs_out_dtype));
+  };
+#pragma unroll
+  for (int k = 1; k < W; ++k) hist[k] = hist_at(c0 - W + k);
+  const int lend = min(L, c1 + W - 1);
+  for (int l = c0; l < c1 + W - 1; ++l) {
+#pragma unroll
+    for (int k = 0; k + 1 < W; ++k) { hist[k] = hist[k + 1]; dpre[k] = dpre[k + 1]; }
+    float2 g = make_float2(0.f, 0.f);
+    if (l < lend) {
+      hist[W - 1] = hist_at(l);
+      float2 pre = bv;
+#pragma unroll
+      for (int k = 0; k < W; ++k) { pre.x = fmaf(w[k].x, hist[k].x, pre.x); pre.y = fmaf(w[k].y, hist[k].y, pre.y); }
+      g = Pair<T>::ld(gp + (int64_t)l * Di);
+      if (silu) {
+        const float sx = 1.f / (1.f + __expf(-pre.x)), sy = 1.f / (1.f + __expf(-pre.y));
+        g.x *= sx * (1.f + pre.x * (1.f - sx));
+        g.y *= sy * (1.f + pre.y * (1.f - sy));
+      }
+      if (l < c1) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) { dwa[k].x = fmaf(g.x, hist[k].x, dwa[k].x); dwa[k].y = fmaf(g.y, hist[k].y, dwa[k].y); }
+        dba.x += g.x; dba.y += g.y;
+      }
+    }
+    dpre[W - 1] = g;
+    const int j = l - (W - 1);
+    if (j >= c0 || (chunk == 0 && j >= -(W - 1))) {
+      float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < W; ++i) { s.x = fmaf(w[W - 1 - i].x, dpre[i].x, s.x); s.y = fmaf(w[W - 1 - i].y, dpre[i].y, s.y); }
+      if (j >= 0) {
+        if (j < c1) {
+          if (j >= L - W) { const float2 e = dcs_out_at(j - (L - W)); s.x += e.x; s.y += e.y; }
+          Pair<T>::st(op + (int64_t)j * Di, s);
+        }
+      } else if (dcs_in != nullptr) {
+        const int si = W + j;
+        if (si >= L) { const float2 e = dcs_out_at(si - L); s.x += e.x; s.y += e.y; }
+        const int64_t o = ((int64_t)b * Di + d) * W + si;
+        store_from_f32(dcs_in, o, cs_in_dtype, s.x);
+        store_from_f32(dcs_in, o + W, cs_in_dtype, s.y);
+      }
+    }
+  }
+  if (chunk == 0 && dcs_in != nullptr) {              // slot 0 never reaches the conv (L >= 1 here)
+    const int64_t o = ((int64_t)b * Di + d) * W;
+    store_from_f32(dcs_in, o, cs_in_dtype, 0.f);
+    store_from_f32(dcs_in, o + W, cs_in_dtype, 0.f);
+  }
+  float* p = partial + (((int64_t)b * gridDim.z + chunk) * Di + d) * (W + 1);
+#pragma unroll
+  for (int k = 0; k < W; ++k) { p[k] = dwa[k].x; p[W + 1 + k] = dwa[k].y; }
+  p[W] = dba.x;
+  p[2 * W + 1] = dba.y;
+}
+
+template <typename T, int W>
+void launch_conv_bwd_pair(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, const void* bias,
+                          const void* cs_in, int cs_in_dtype, const void* dy, const void* dcs_out, int dcs_out_dtype,
+                          void* dx, void* dcs_in, float* partial, int B, int L, int Di, int silu, int chunks,
+                          cudaStream_t st) {
+  conv1d_bwd_pair_kernel<T, W><<<dim3((Di / 2 + 127) / 128, B, chunks), 128, 0, st>>>(
+      (const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias, cs_in, cs_in_dtype, (const T*)dy, dcs_out,
+      dcs_out_dtype, (T*)dx, dcs_in, partial, L, Di, silu);
 }
 
 }  // namespace
@@ -351,6 +628,26 @@ extern "C" int vmb_add_norm_bwd(const void* x, int x_dtype, int64_t ldx, const v
                 "add_norm_bwd: workspace too small");
   float* pw = reinterpret_cast<float*>(workspace);
   float* pb = pw + (int64_t)ctas * dim;
+  {
+    auto al = [](const void* p, int bytes) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % bytes == 0; };
+    const int vb = x_dtype == VMB_F32 ? 16 : 8;
+    const bool vec = w_dtype == x_dtype && residual_dtype == VMB_F32 && dresidual_out_dtype == VMB_F32 &&
+                     dim % 4 == 0 && ldx % 4 == 0 && al(x, vb) && al(dy, vb) && al(dx, vb) && al(weight, vb) &&
+                     al(residual, 16) && al(dresidual_out, 16) && al(dresidual, 16);
+    if (vec) {
+      const bool ok = x_dtype == VMB_F32
+          ? launch_add_norm_bwd_vec<float>(x, ldx, residual, weight, dy, dresidual_out, dx, dresidual, pw, pb,
+                                           rows, dim, eps, is_rms != 0, ctas, st)
+          : launch_add_norm_bwd_vec<__nv_bfloat16>(x, ldx, residual, weight, dy, dresidual_out, dx, dresidual,
+                                                   pw, pb, rows, dim, eps, is_rms != 0, ctas, st);
+      if (ok) {
+        VMB_LAUNCH_CHECK("add_norm_bwd_vec_kernel");
+        if (dweight) { int rc = reduce_partials(pw, ctas, dim, dweight, VMB_F32, st); if (rc) return rc; }
+        if (dbias) { int rc = reduce_partials(pb, ctas, dim, dbias, VMB_F32, st); if (rc) return rc; }
+        return VMB_OK;
+      }
+    }
+  }
 #define VMB_ANB(IT)                                                                                      \
   do {                                                                                                   \
     if (is_rms)                                                                                          \
@@ -421,10 +718,25 @@ extern "C" int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x
   const int64_t need = (int64_t)B * chunks * Di * (W + 1) * (int64_t)sizeof(float);
   VMB_CHECK_ARG(workspace && workspace_bytes >= need, "conv1d_bwd: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
-  conv1d_bwd_kernel<<<dim3((Di + 127) / 128, B, chunks), 128, 0, st>>>(
-      x, x_bstride, x_tstride, weight, bias, conv_state_in, cs_in_dtype, dy, dconv_state_out, dcs_out_dtype,
-      dx, dconv_state_in, partial, B, L, Di, W, silu, dtype);
-  VMB_LAUNCH_CHECK("conv1d_bwd_kernel");
+  // fast path: even channel count, pair-aligned rows, d_conv 2..4
+  const int esz = dtype_size(dtype);
+  auto al = [&](const void* p) { return reinterpret_cast<uintptr_t>(p) % (2 * esz) == 0; };
+  const bool pair_ok = Di % 2 == 0 && x_bstride % 2 == 0 && x_tstride % 2 == 0 && al(x) && al(dy) && al(dx) &&
+                       (bias == nullptr || al(bias)) && W >= 2 && W <= 4;
+  if (pair_ok) {
+#define VMB_CBP(T, WW)                                                                                          \
+  launch_conv_bwd_pair<T, WW>(x, x_bstride, x_tstride, weight, bias, conv_state_in, cs_in_dtype, dy,            \
+                              dconv_state_out, dcs_out_dtype, dx, dconv_state_in, partial, B, L, Di, silu, chunks, st)
+    if (dtype == VMB_F32) { if (W == 4) VMB_CBP(float, 4); else if (W == 3) VMB_CBP(float, 3); else VMB_CBP(float, 2); }
+    else { if (W == 4) VMB_CBP(__nv_bfloat16, 4); else if (W == 3) VMB_CBP(__nv_bfloat16, 3); else VMB_CBP(__nv_bfloat16, 2); }
+#undef VMB_CBP
+    VMB_LAUNCH_CHECK("conv1d_bwd_pair_kernel");
+  } else {
+    conv1d_bwd_kernel<<<dim3((Di + 127) / 128, B, chunks), 128, 0, st>>>(
+        x, x_bstride, x_tstride, weight, bias, conv_state_in, cs_in_dtype, dy, dconv_state_out, dcs_out_dtype,
+        dx, dconv_state_in, partial, B, L, Di, W, silu, dtype);
+    VMB_LAUNCH_CHECK("conv1d_bwd_kernel");
+  }
   // partial rows are [dw_0 .. dw_{W-1}, db] per channel: reduce into one (Di, W + 1) fp32 table, then split
   const int64_t n = (int64_t)Di * (W + 1);
   float* table = partial;   // in place: row 0 of the partials becomes the sum
