@@ -160,6 +160,13 @@ def test_conv_backward(geom, dtype):
     (3, 8, 32, 16, False, False, True, True),
     (2, 1, 16, 16, True, True, True, True),
     (1, 65, 24, 4, False, True, False, True),
+    # d_state 16, Di % 16 == 0: in bf16 these run scan_bwd_fast.cu (ragged tiles / sub-chunks, every option)
+    (2, 37, 48, 16, True, True, True, True),
+    (1, 100, 32, 16, True, False, False, False),
+    (2, 16, 16, 16, True, True, False, True),
+    (1, 3, 16, 16, True, True, True, True),
+    (2, 65, 64, 16, False, True, True, False),
+    (1, 131, 32, 16, True, True, True, True),
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_scan_backward(geom, dtype):

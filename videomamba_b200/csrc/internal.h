@@ -36,6 +36,14 @@ int conv_xproj_tc(const void* x, int64_t x_ld, const void* cw, const void* cb, c
 // backward.cu -- out[n] = sum over P rows of partial[P][n] (fp32 partials)
 int reduce_partials(const float* partial, int P, int64_t n, void* out, int out_dtype, cudaStream_t st);
 
+// scan_bwd_fast.cu -- selective-scan backward for bf16, d_state 16, Di % 16 == 0, 16-byte aligned rows:
+// the checkpoint pass + the reverse pass; slabs / pA / pD / pBias laid out as in scan_bwd.cu, which
+// runs the final reductions.
+bool scan_bwd_fast_supported(const vmb_scan_bwd_args& a);
+int64_t scan_bwd_fast_ckpt_bytes(int B, int L, int Di);
+int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* pA, float* pD, float* pBias,
+                  cudaStream_t st);
+
 // scan_generic.cu
 int scan_generic(const vmb_scan_args& a, cudaStream_t st);
 

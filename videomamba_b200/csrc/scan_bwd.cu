@@ -340,7 +340,8 @@ Plan plan(int B, int L, int Di, int N) {
   p.nslabs = (Di + kChan - 1) / kChan;
   auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
   int64_t off = 0;
-  p.ckpt = off; off += up((int64_t)B * p.nchunks * N * Di * 4);
+  // the larger of the two checkpoint layouts (every 8 tokens here, every 4 in scan_bwd_fast.cu)
+  p.ckpt = off; off += up(std::max((int64_t)B * p.nchunks * N * Di * 4, scan_bwd_fast_ckpt_bytes(B, L, Di)));
   p.slabs = off; off += up((int64_t)p.nslabs * B * L * 32 * 4);
   p.pA = off; off += up((int64_t)B * Di * N * 4);
   p.pD = off; off += up((int64_t)B * Di * 4);
@@ -360,11 +361,16 @@ int run(const vmb_scan_bwd_args& a, cudaStream_t st) {
   float* pA = reinterpret_cast<float*>(base + p.pA);
   float* pD = reinterpret_cast<float*>(base + p.pD);
   float* pBias = reinterpret_cast<float*>(base + p.pBias);
-  dim3 grid((a.Di + kChan - 1) / kChan, a.B);
-  scan_ckpt_kernel<T, kAccurate><<<grid, kWarps * 32, 0, st>>>(a, ckpt, p.nchunks);
-  VMB_LAUNCH_CHECK("scan_ckpt_kernel");
-  scan_bwd_kernel<T, kAccurate><<<grid, kWarps * 32, 0, st>>>(a, ckpt, p.nchunks, slabs, pA, pD, pBias);
-  VMB_LAUNCH_CHECK("scan_bwd_kernel");
+  if (scan_bwd_fast_supported(a)) {
+    const int rc = scan_bwd_fast(a, ckpt, slabs, pA, pD, pBias, st);
+    if (rc != VMB_OK) return rc;
+  } else {
+    dim3 grid((a.Di + kChan - 1) / kChan, a.B);
+    scan_ckpt_kernel<T, kAccurate><<<grid, kWarps * 32, 0, st>>>(a, ckpt, p.nchunks);
+    VMB_LAUNCH_CHECK("scan_ckpt_kernel");
+    scan_bwd_kernel<T, kAccurate><<<grid, kWarps * 32, 0, st>>>(a, ckpt, p.nchunks, slabs, pA, pD, pBias);
+    VMB_LAUNCH_CHECK("scan_bwd_kernel");
+  }
   const int64_t rows = (int64_t)a.B * a.L;
   scan_bwd_bc_kernel<T><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(
       slabs, p.nslabs, rows, a.N, reinterpret_cast<T*>(a.dbc), a.dbc_tstride, a.b_off, a.c_off);
