@@ -33,17 +33,22 @@ constexpr int kTT = 16;                   // tokens per tile
 constexpr int kN = 16;
 using bf16 = __nv_bfloat16;
 
-// shared memory of a warp (bytes)
+// shared memory of a warp (bytes).  Pass 2 stage: the six staged arrays, then the two bf16 vectors phase A
+// derives; [B | C | Yh | Uh] are adjacent and the zero region sits behind both stages, so ONE per-lane
+// displacement turns the address of any of the four into an address of zeros (operand masking).
 constexpr int kRaw = kTT * 32;            // one staged array: 16 rows x 16 channels / states bf16
-constexpr int kStage = 6 * kRaw;          // u, delta_raw, z, dout, B, C
 constexpr int oU = 0, oDl = kRaw, oZ = 2 * kRaw, oGo = 3 * kRaw, oB = 4 * kRaw, oC = 5 * kRaw;
-constexpr int oDD = 2 * kStage;           // [t][pair ^ ((t & 3) << 1)] {delta_a, delta_b, du_a, du_b}
+constexpr int oYh = 6 * kRaw;             // [t][16 channels] bf16 dy        (written by phase A)
+constexpr int oUh = 7 * kRaw;             // [t][16 channels] bf16 delta * u (written by phase A)
+constexpr int kStage = 8 * kRaw;
+constexpr int oZero = 2 * kStage;         // 4 * kRaw (+ 64: masked lanes read 16 banks away from the real rows) bytes of zeros
+constexpr int kZeroBytes = 4 * kRaw + 64;
+constexpr int oDD = oZero + kZeroBytes + 64;    // [t][pair ^ ((t & 3) << 1)] {delta_a, delta_b, du_a, du_b}
 constexpr int oDY = oDD + kTT * 128;      // same indexing: {dy_a, dy_b, u_a, u_b}
-constexpr int oFin = oDY + kTT * 128;     // [j][lane] {sig_a, sig_b, dzf_a, dzf_b} (private to the lane)
-constexpr int oDyh = oFin + 4 * 32 * 16;  // [t][16 channels] bf16 dy
-constexpr int oDuh = oDyh + kRaw;         // [t][16 channels] bf16 delta * u
-constexpr int kSmemBwd = oDuh + kRaw;     // 13312 + 6144 = 19456? (see static_assert)
-static_assert(kSmemBwd == 2 * kStage + 3 * 2048 + 2 * kRaw, "smem plan");
+constexpr int oFin = oDY + kTT * 128;     // [j][lane] bf16 {sig_a, sig_b, dzf_a, dzf_b} (private to the lane)
+constexpr int oRing = oFin + 4 * 32 * 8;  // three 1 KB checkpoint records in flight (cp.async ring)
+constexpr int kSmemBwd = oRing + 3 * 1024;
+static_assert(kSmemBwd == 8192 + 2112 + 64 + 4096 + 1024 + 3072 && oDD % 128 == 0 && oRing % 128 == 0, "smem plan");
 constexpr int kStage1 = 3 * kRaw;         // pass 1 stages u, delta_raw, B only
 constexpr int kSmemCkpt = 2 * kStage1 + kTT * 128;
 
@@ -197,7 +202,9 @@ scan_ckpt_fast_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int n
 // ---------------------------------------------------------------------------------------------------
 // pass 2: reverse walk
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 11)
+// 168 registers: the register file is split per scheduler (16 K each), so 3 one-warp CTAs per scheduler = 12
+// per SM need <= 170 (1536 units at batch 32 are 10.4 per SM); 184 would leave 2 per scheduler
+__global__ void __launch_bounds__(32, 12)
 scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int nck,
                      float* __restrict__ bc_slabs, float* __restrict__ pA, float* __restrict__ pD,
                      float* __restrict__ pBias) {
@@ -224,9 +231,9 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
   const float Da = a.D ? a.D[cw + g] : 0.f, Db = a.D ? a.D[cw + g + 8] : 0.f;
   float dD_a = 0.f, dD_b = 0.f, dBias_a = 0.f, dBias_b = 0.f;
   // operand masks: the vector of token i of a sub-chunk lives in columns {2i, 2i+1} of the B operand
-  uint32_t cmask[4];
+  uint32_t onesm[4];                                // the all-ones vector (bf16 pairs), masked the same way
 #pragma unroll
-  for (int i = 0; i < 4; ++i) cmask[i] = (g >> 1) == i ? 0xffffffffu : 0u;
+  for (int i = 0; i < 4; ++i) onesm[i] = (g >> 1) == i ? 0x3f803f80u : 0u;
   int posoff[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) posoff[i] = (g ^ (i << 1)) << 4;
@@ -246,33 +253,47 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
   };
   stage(ntiles - 1, (ntiles - 1) & 1);
 
-  // checkpoint records, one sub-chunk ahead
-  const float4* pck = reinterpret_cast<const float4*>(ckpt + ((int64_t)(b * gridDim.x + unit) * nck) * 256) +
-                      (int64_t)(nck - 1) * 64 + lane;
-  Rec nxt{pck[0], pck[32]};
-  pck -= 64;
-  int kleft = nck - 1;                              // records still to prefetch
+  // zero region (never written again)
+  for (int i = lane; i < kZeroBytes / 16; i += 32) reinterpret_cast<uint4*>(smem + oZero)[i] = make_uint4(0u, 0u, 0u, 0u);
 
-  // output pointers of token 0, this lane's two channels
-  bf16* const du_p = reinterpret_cast<bf16*>(a.du) + (int64_t)b * L * Di + cw + g;
-  bf16* const dd_p = reinterpret_cast<bf16*>(a.ddelta) + (int64_t)b * L * Di + cw + g;
-  bf16* const dz_p = a.dz ? reinterpret_cast<bf16*>(a.dz) + (int64_t)b * L * Di + cw + g : nullptr;
-  float* const slab_p = bc_slabs + ((int64_t)unit * a.B + b) * L * 32 + g;
+  // checkpoint records: 16-byte cp.async into a ring of three, two sub-chunks ahead.  cp.async groups in
+  // commit order: every tile top commits one group (the next tile's rows), every sub-chunk top one (a
+  // record; possibly empty), so "all but the newest N" is exact bookkeeping (see the waits).
+  const float* rec_g = ckpt + ((int64_t)(b * gridDim.x + unit) * nck) * 256 + lane * 4;
+  auto fetch_rec = [&](int k, uint32_t slot_off) {  // record k -> ring slot (empty group when k < 0)
+    if (k >= 0) {
+      const float* src = rec_g + (int64_t)k * 256;
+      cp_async16(sbase + slot_off + lane * 16, src, 16);
+      cp_async16(sbase + slot_off + 512 + lane * 16, src + 128, 16);
+    }
+    cp_commit();
+  };
+  uint32_t ring_cur = oRing, ring_n1 = oRing + 1024, ring_n2 = oRing + 2048;
+  fetch_rec(nck - 1, ring_cur);
+  fetch_rec(nck - 2, ring_n1);
+  int krec = nck - 3;                               // next record to fetch
+
+  // output rows of the token this lane finalises in the current sub-chunk (4 k + tig), stepped back 4 tokens
+  // per sub-chunk; channels g / g + 8 of the unit
+  int tok = 4 * (nck - 1) + tig;
+  const int64_t row_last = (int64_t)b * L + tok;
+  bf16* du_p = reinterpret_cast<bf16*>(a.du) + row_last * Di + cw + g;
+  bf16* dd_p = reinterpret_cast<bf16*>(a.ddelta) + row_last * Di + cw + g;
+  bf16* dz_p = a.dz ? reinterpret_cast<bf16*>(a.dz) + row_last * Di + cw + g : nullptr;
+  float* slab_p = bc_slabs + (((int64_t)unit * a.B + b) * L + tok) * 32 + g;
+  const int64_t step_o = 4 * (int64_t)Di;
 
   uint8_t* const sdd = smem + oDD;
   uint8_t* const sdy = smem + oDY;
-  float4* const sfin = reinterpret_cast<float4*>(smem + oFin) + lane;
-  uint8_t* const sdyh = smem + oDyh;
-  uint8_t* const sduh = smem + oDuh;
-  const uint32_t kOnes = 0x3f803f80u;
+  uint2* const sfin = reinterpret_cast<uint2*>(smem + oFin) + lane;
 
   for (int tile = ntiles - 1; tile >= 0; --tile) {
     const int stg = tile & 1;
-    if (tile > 0) { stage(tile - 1, stg ^ 1); cp_wait<1>(); } else { cp_wait<0>(); }
+    if (tile > 0) stage(tile - 1, stg ^ 1); else cp_commit();
+    cp_wait<3>();                                   // newer: that group and at most two records
     __syncwarp();
     const uint8_t* raw = smem + stg * kStage;
-    const int t0 = tile * kTT;
-    const int nvalid = min(kTT, L - t0);
+    const int nvalid = min(kTT, L - tile * kTT);
 
     // ---- phase A: per-(token, channel) scalars of the tile ------------------------------------------
 #pragma unroll
@@ -299,11 +320,12 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
       const float dua = da * ua, dub = db * ub;
       *reinterpret_cast<float4*>(sdd + t * 128 + pos_own) = make_float4(da, db, dua, dub);
       *reinterpret_cast<float4*>(sdy + t * 128 + pos_own) = make_float4(dya, dyb, ua, ub);
-      sfin[j * 32] = make_float4(sa, sb, dzfa, dzfb);
-      *reinterpret_cast<bf16*>(sdyh + t * 32 + g * 2) = __float2bfloat16_rn(dya);
-      *reinterpret_cast<bf16*>(sdyh + t * 32 + g * 2 + 16) = __float2bfloat16_rn(dyb);
-      *reinterpret_cast<bf16*>(sduh + t * 32 + g * 2) = __float2bfloat16_rn(dua);
-      *reinterpret_cast<bf16*>(sduh + t * 32 + g * 2 + 16) = __float2bfloat16_rn(dub);
+      sfin[j * 32] = make_uint2(pack_bf16x2(sa, sb), pack_bf16x2(dzfa, dzfb));
+      uint8_t* w = smem + stg * kStage + t * 32 + g * 2;
+      *reinterpret_cast<bf16*>(w + oYh) = __float2bfloat16_rn(dya);
+      *reinterpret_cast<bf16*>(w + oYh + 16) = __float2bfloat16_rn(dyb);
+      *reinterpret_cast<bf16*>(w + oUh) = __float2bfloat16_rn(dua);
+      *reinterpret_cast<bf16*>(w + oUh + 16) = __float2bfloat16_rn(dub);
     }
     __syncwarp();
 
@@ -311,21 +333,28 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
     const int nsub = (nvalid + 3) >> 2;
     const uint8_t* sB = raw + oB + 4 * tig + (nsub - 1) * (4 * 32);
     const uint8_t* sC = raw + oC + 4 * tig + (nsub - 1) * (4 * 32);
-    const uint8_t* sYh = sdyh + 4 * tig + (nsub - 1) * (4 * 32);
-    const uint8_t* sUh = sduh + 4 * tig + (nsub - 1) * (4 * 32);
     const uint8_t* sD = sdd + (nsub - 1) * (4 * 128);
     const uint8_t* sY = sdy + (nsub - 1) * (4 * 128);
+    // token i of a sub-chunk: lanes of columns {2i, 2i+1} read the real [B | C | Yh | Uh] rows, the others zeros
+    const int zdisp = oZero + 64 - (stg * kStage + oB);
+    const uint8_t* sM[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sM[i] = sB + ((g >> 1) == i ? 0 : zdisp);
 #pragma unroll 1
-    for (int c = nsub - 1; c >= 0; --c, sB -= 4 * 32, sC -= 4 * 32, sYh -= 4 * 32, sUh -= 4 * 32, sD -= 4 * 128, sY -= 4 * 128) {
-      float2 h[4], hp[4][4], an[4][4];
-      rec_to(nxt, h);
-      if (kleft > 0) {                              // next record (the sub-chunk before this one) in flight
-        nxt.lo = pck[0];
-        nxt.hi = pck[32];
-        pck -= 64;
-        --kleft;
+    for (int c = nsub - 1; c >= 0; --c, sB -= 4 * 32, sC -= 4 * 32, sD -= 4 * 128, sY -= 4 * 128) {
+      float2 h[4], q[4][4], an[4][4];
+      fetch_rec(krec--, ring_n2);                   // the record two sub-chunks before this one
+      cp_wait<2>();                                 // this sub-chunk's record has landed
+      {
+        const Rec r{*reinterpret_cast<const float4*>(smem + ring_cur + lane * 16),
+                    *reinterpret_cast<const float4*>(smem + ring_cur + 512 + lane * 16)};
+        rec_to(r, h);
+        const uint32_t t = ring_cur; ring_cur = ring_n1; ring_n1 = ring_n2; ring_n2 = t;
       }
-      // forward recompute of the sub-chunk
+      float acc_y[4] = {0.f, 0.f, 0.f, 0.f}, acc_s[4] = {0.f, 0.f, 0.f, 0.f}, acc_w[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc_c[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
+      // forward recompute of the sub-chunk (keeps a_t and a_t h_{t-1}); everything that needs h_t only --
+      // <C_t, h_t> and dC_t -- runs here, beside the exponentials
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 dd = *reinterpret_cast<const float4*>(sD + i * 128 + posoff[i]);
@@ -335,17 +364,24 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
         const float2 dab = make_float2(dd.x, dd.y), du = make_float2(dd.z, dd.w);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          hp[i][s] = h[s];
           an[i][s] = ex2_pair(__fmul2_rn(dab, A2[s]));
-          h[s] = __ffma2_rn(an[i][s], h[s], __fmul2_rn(du, bc2(Bv[s])));
+          q[i][s] = __fmul2_rn(an[i][s], h[s]);
+          h[s] = __ffma2_rn(du, bc2(Bv[s]), q[i][s]);
         }
+        const uint32_t hf[4] = {pack_bf16x2(h[0].x, h[1].x), pack_bf16x2(h[0].y, h[1].y),
+                                pack_bf16x2(h[2].x, h[3].x), pack_bf16x2(h[2].y, h[3].y)};
+        const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oC - oB));
+        const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oC - oB) + 16);
+        mma_acc(acc_y, hf, c0, c1);
+        uint32_t tf[4];
+        transpose_frag(hf, tf);
+        const uint32_t v0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oYh - oB));
+        const uint32_t v1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oYh - oB) + 16);
+        mma_acc(acc_c, tf, v0, v1);
       }
       // reverse recurrence
-      float acc_y[4] = {0.f, 0.f, 0.f, 0.f}, acc_s[4] = {0.f, 0.f, 0.f, 0.f}, acc_w[4] = {0.f, 0.f, 0.f, 0.f};
-      float acc_c[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 3; i >= 0; --i) {
-        const uint32_t m = cmask[i];
         const float4 yu = *reinterpret_cast<const float4*>(sY + i * 128 + posoff[i]);
         const float2 dlt = *reinterpret_cast<const float2*>(sD + i * 128 + posoff[i]);
         const float2 dy = make_float2(yu.x, yu.y);
@@ -354,75 +390,68 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
         const float Cv[4] = {bf16lo(cr0), bf16hi(cr0), bf16lo(cr1), bf16hi(cr1)};
 #pragma unroll
         for (int s = 0; s < 4; ++s) gg[s] = __ffma2_rn(dy, bc2(Cv[s]), gg[s]);       // dLoss / dh_t
-        // h_t: <C_t, h_t> and dC_t
-        {
-          const float2* ht = (i == 3) ? h : hp[(i + 1) & 3];
-          const uint32_t hf[4] = {pack_bf16x2(ht[0].x, ht[1].x), pack_bf16x2(ht[0].y, ht[1].y),
-                                  pack_bf16x2(ht[2].x, ht[3].x), pack_bf16x2(ht[2].y, ht[3].y)};
-          mma_acc(acc_y, hf, cr0 & m, cr1 & m);
-          uint32_t tf[4];
-          transpose_frag(hf, tf);
-          const uint32_t v0 = *reinterpret_cast<const uint32_t*>(sYh + i * 32);
-          const uint32_t v1 = *reinterpret_cast<const uint32_t*>(sYh + i * 32 + 16);
-          mma_acc(acc_c, tf, v0 & m, v1 & m);
-        }
         // g a h_{t-1}: dA and the state part of ddelta
         {
           float2 w[4];
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
-            const float2 gq = __fmul2_rn(gg[s], __fmul2_rn(an[i][s], hp[i][s]));
+            const float2 gq = __fmul2_rn(gg[s], q[i][s]);
             dA[s] = __ffma2_rn(gq, dlt, dA[s]);
             w[s] = __fmul2_rn(gq, A2[s]);
           }
           const uint32_t wf[4] = {pack_bf16x2(w[0].x, w[1].x), pack_bf16x2(w[0].y, w[1].y),
                                   pack_bf16x2(w[2].x, w[3].x), pack_bf16x2(w[2].y, w[3].y)};
-          mma_acc(acc_w, wf, kOnes & m, kOnes & m);
+          mma_acc(acc_w, wf, onesm[i], onesm[i]);
         }
         // g: <B_t, g> and dB_t
         {
           const uint32_t gf[4] = {pack_bf16x2(gg[0].x, gg[1].x), pack_bf16x2(gg[0].y, gg[1].y),
                                   pack_bf16x2(gg[2].x, gg[3].x), pack_bf16x2(gg[2].y, gg[3].y)};
-          const uint32_t br0 = *reinterpret_cast<const uint32_t*>(sB + i * 32);
-          const uint32_t br1 = *reinterpret_cast<const uint32_t*>(sB + i * 32 + 16);
-          mma_acc(acc_s, gf, br0 & m, br1 & m);
+          const uint32_t br0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32);
+          const uint32_t br1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + 16);
+          mma_acc(acc_s, gf, br0, br1);
           uint32_t tf[4];
           transpose_frag(gf, tf);
-          const uint32_t v0 = *reinterpret_cast<const uint32_t*>(sUh + i * 32);
-          const uint32_t v1 = *reinterpret_cast<const uint32_t*>(sUh + i * 32 + 16);
-          mma_acc(acc_b, tf, v0 & m, v1 & m);
+          const uint32_t v0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oUh - oB));
+          const uint32_t v1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oUh - oB) + 16);
+          mma_acc(acc_b, tf, v0, v1);
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) gg[s] = __fmul2_rn(gg[s], an[i][s]);              // -> dLoss / dh_{t-1} (partial)
       }
       // lane tig finalises token 4c + tig of channels g, g + 8 (states g, g + 8 for dB / dC)
       {
-        const int tl = 4 * c + tig;
         const float4 dd = *reinterpret_cast<const float4*>(sD + tig * 128 + pos_own);
         const float4 yu = *reinterpret_cast<const float4*>(sY + tig * 128 + pos_own);
-        const float4 fin = sfin[c * 32];
-        if (tl < nvalid) {
-          const int64_t row = (int64_t)(t0 + tl);
+        const uint2 finp = sfin[c * 32];
+        const float4 fin = make_float4(bf16lo(finp.x), bf16hi(finp.x), bf16lo(finp.y), bf16hi(finp.y));
+        if (tok < L) {
           const float du_a = fmaf(dd.x, acc_s[0], yu.x * Da), du_b = fmaf(dd.y, acc_s[2], yu.y * Db);
           const float dr_a = fmaf(kLn2, acc_w[0], yu.z * acc_s[0]) * fin.x;
           const float dr_b = fmaf(kLn2, acc_w[2], yu.w * acc_s[2]) * fin.y;
-          du_p[row * Di] = __float2bfloat16_rn(du_a);
-          du_p[row * Di + 8] = __float2bfloat16_rn(du_b);
-          dd_p[row * Di] = __float2bfloat16_rn(dr_a);
-          dd_p[row * Di + 8] = __float2bfloat16_rn(dr_b);
+          du_p[0] = __float2bfloat16_rn(du_a);
+          du_p[8] = __float2bfloat16_rn(du_b);
+          dd_p[0] = __float2bfloat16_rn(dr_a);
+          dd_p[8] = __float2bfloat16_rn(dr_b);
           dBias_a += dr_a;
           dBias_b += dr_b;
           if (dz_p) {
-            dz_p[row * Di] = __float2bfloat16_rn(fin.z * fmaf(Da, yu.z, acc_y[0]));
-            dz_p[row * Di + 8] = __float2bfloat16_rn(fin.w * fmaf(Db, yu.w, acc_y[2]));
+            dz_p[0] = __float2bfloat16_rn(fin.z * fmaf(Da, yu.z, acc_y[0]));
+            dz_p[8] = __float2bfloat16_rn(fin.w * fmaf(Db, yu.w, acc_y[2]));
           }
-          float* sl = slab_p + row * 32;
-          sl[0] = acc_b[0];
-          sl[8] = acc_b[2];
-          sl[16] = acc_c[0];
-          sl[24] = acc_c[2];
+          slab_p[0] = acc_b[0];
+          slab_p[8] = acc_b[2];
+          slab_p[16] = acc_c[0];
+          slab_p[24] = acc_c[2];
         }
+        tok -= 4;
+        du_p -= step_o;
+        dd_p -= step_o;
+        if (dz_p) dz_p -= step_o;
+        slab_p -= 4 * 32;
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sM[i] -= 4 * 32;
     }
     __syncwarp();                                  // the tile's shared memory is rewritten by the next iteration
   }
@@ -471,6 +500,12 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
                   cudaStream_t st) {
   const int nck = (a.L + 3) / 4;
   dim3 grid(a.Di / 16, a.B);
+  static const bool carve = [] {                    // 11 CTAs x 18.1 KB per SM need the largest shared-memory split
+    cudaFuncSetAttribute(scan_bwd_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(scan_ckpt_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)carve;
   scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
   VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
   scan_bwd_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck, slabs, pA, pD, pBias);
