@@ -24,6 +24,8 @@
 // recurrence on them.  Tiles of 16 tokens are staged by 16-byte cp.async, double buffered.
 // Per-channel scalars (softplus, its derivative, the gate terms) are computed once per tile (phase A:
 // lane (g, tig) prepares tokens tig + 4j of channels g, g + 8).  No atomics: deterministic.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace vmb {
@@ -33,22 +35,27 @@ constexpr int kTT = 16;                   // tokens per tile
 constexpr int kN = 16;
 using bf16 = __nv_bfloat16;
 
-// shared memory of a warp (bytes).  Pass 2 stage: the six staged arrays, then the two bf16 vectors phase A
-// derives; [B | C | Yh | Uh] are adjacent and the zero region sits behind both stages, so ONE per-lane
-// displacement turns the address of any of the four into an address of zeros (operand masking).
-constexpr int kRaw = kTT * 32;            // one staged array: 16 rows x 16 channels / states bf16
+// shared memory of a warp (bytes).  Pass 2: two TMA stages of six raw arrays (16 rows x 32 B each); once
+// phase A has consumed a stage its u / delta / z arrays become the staging rows of du / ddelta / dz (TMA
+// stores).  Phase A also writes the operand rows the HMMAs read, permuted so a lane's two words are one
+// 64-bit load: [t][tig]{(2tig, 2tig+1), (2tig+8, 2tig+9)} for B_t, C_t (states) and dy, delta*u (channels).
+// [Bp | Cp | Yh | Uh] are adjacent and a zero region follows: ONE per-lane displacement turns the address
+// of any of the four into an address of zeros (operand masking), 16 banks away from the real rows.
+constexpr int kRaw = kTT * 32;
 constexpr int oU = 0, oDl = kRaw, oZ = 2 * kRaw, oGo = 3 * kRaw, oB = 4 * kRaw, oC = 5 * kRaw;
-constexpr int oYh = 6 * kRaw;             // [t][16 channels] bf16 dy        (written by phase A)
-constexpr int oUh = 7 * kRaw;             // [t][16 channels] bf16 delta * u (written by phase A)
-constexpr int kStage = 8 * kRaw;
-constexpr int oZero = 2 * kStage;         // 4 * kRaw (+ 64: masked lanes read 16 banks away from the real rows) bytes of zeros
-constexpr int kZeroBytes = 4 * kRaw + 64;
-constexpr int oDD = oZero + kZeroBytes + 64;    // [t][pair ^ ((t & 3) << 1)] {delta_a, delta_b, du_a, du_b}
-constexpr int oDY = oDD + kTT * 128;      // same indexing: {dy_a, dy_b, u_a, u_b}
-constexpr int oFin = oDY + kTT * 128;     // [j][lane] bf16 {sig_a, sig_b, dzf_a, dzf_b} (private to the lane)
-constexpr int oRing = oFin + 4 * 32 * 8;  // three 1 KB checkpoint records in flight (cp.async ring)
-constexpr int kSmemBwd = oRing + 3 * 1024;
-static_assert(kSmemBwd == 8192 + 2112 + 64 + 4096 + 1024 + 3072 && oDD % 128 == 0 && oRing % 128 == 0, "smem plan");
+constexpr int kStage = 6 * kRaw;
+constexpr int oBp = 2 * kStage, oCp = oBp + kRaw, oYh = oCp + kRaw, oUh = oYh + kRaw;
+constexpr int oZero = oUh + kRaw;
+constexpr int kZeroBytes = 4 * kRaw + 128;
+constexpr int kZDisp = oZero + 64 - oBp;  // real row address -> zeros
+constexpr int oDD = oZero + kZeroBytes;   // [t][pair ^ ((t & 3) << 1)] {delta_a, delta_b, du_a, du_b}
+constexpr int oDY = oDD + kTT * 128;      // same indexing: {dy_a, dy_b, delta_a, delta_b}
+constexpr int oFin = oDY + kTT * 128;     // [j][lane] bf16 pairs {sig_a, sig_b | dzf_a, dzf_b | u_a, u_b | -} (private to the lane)
+constexpr int oRing = oFin + 4 * 32 * 16; // three 1 KB checkpoint records in flight (bulk copies)
+constexpr int oBar = oRing + 3 * 1024;    // mbarriers: two stages, three ring slots
+constexpr int kSmemBwd = oBar + 64;
+static_assert(oDD % 128 == 0 && oRing % 128 == 0 && oZero % 128 == 0, "smem plan");
+static_assert(11 * (kSmemBwd + 1024) <= 227 * 1024, "11 one-warp CTAs per SM");
 constexpr int kStage1 = 3 * kRaw;         // pass 1 stages u, delta_raw, B only
 constexpr int kSmemCkpt = 2 * kStage1 + kTT * 128;
 
@@ -107,6 +114,45 @@ __device__ __forceinline__ void stage_rows(uint32_t dst, const void* base, int64
   const bf16* src = reinterpret_cast<const bf16*>(base) + (int64_t)b * bs + (int64_t)min(t, L - 1) * ts + col + half * 8;
   cp_async16(dst + row * 32 + half * 16, src, t < L ? 16 : 0);
 }
+
+// ---- mbarrier / TMA (async proxy) ----------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // the lane's state registers <-> the checkpoint record of a (unit, sub-chunk): 256 floats, lane l owns
 // floats [4l, 4l+4) and [128 + 4l, 128 + 4l + 4)
@@ -202,13 +248,15 @@ scan_ckpt_fast_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int n
 // ---------------------------------------------------------------------------------------------------
 // pass 2: reverse walk
 // ---------------------------------------------------------------------------------------------------
+struct BwdMaps { CUtensorMap u, dl, z, go, bc, du, dd, dz; };
+
 // 168 registers: the register file is split per scheduler (16 K each), so 3 one-warp CTAs per scheduler = 12
 // per SM need <= 170 (1536 units at batch 32 are 10.4 per SM); 184 would leave 2 per scheduler
 __global__ void __launch_bounds__(32, 12)
-scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int nck,
-                     float* __restrict__ bc_slabs, float* __restrict__ pA, float* __restrict__ pD,
+scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps maps, const float* __restrict__ ckpt,
+                     int nck, float* __restrict__ bc_slabs, float* __restrict__ pA, float* __restrict__ pD,
                      float* __restrict__ pBias) {
-  __shared__ __align__(128) uint8_t smem[kSmemBwd];
+  __shared__ __align__(1024) uint8_t smem[kSmemBwd];
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
   const int unit = blockIdx.x, cw = unit * 16, b = blockIdx.y;
@@ -232,67 +280,69 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
   float dD_a = 0.f, dD_b = 0.f, dBias_a = 0.f, dBias_b = 0.f;
   // operand masks: the vector of token i of a sub-chunk lives in columns {2i, 2i+1} of the B operand
   uint32_t onesm[4];                                // the all-ones vector (bf16 pairs), masked the same way
+  int mdisp[4];                                     // displacement of this lane's operand reads for token i
 #pragma unroll
-  for (int i = 0; i < 4; ++i) onesm[i] = (g >> 1) == i ? 0x3f803f80u : 0u;
+  for (int i = 0; i < 4; ++i) {
+    onesm[i] = (g >> 1) == i ? 0x3f803f80u : 0u;
+    mdisp[i] = (g >> 1) == i ? 0 : kZDisp;
+  }
   int posoff[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) posoff[i] = (g ^ (i << 1)) << 4;
   const int pos_own = (g ^ (tig << 1)) << 4;        // entry of the tokens this lane prepares / finalises (t & 3 == tig)
 
   const int ntiles = (L + kTT - 1) / kTT;
-  auto stage = [&](int tile, int stg) {
-    const uint32_t d = sbase + stg * kStage;
-    const int t0 = tile * kTT;
-    stage_rows(d + oU, a.u, a.u_bstride, a.u_tstride, b, cw, t0, L, lane);
-    stage_rows(d + oDl, a.delta, a.d_bstride, a.d_tstride, b, cw, t0, L, lane);
-    if (has_z) stage_rows(d + oZ, a.z, a.z_bstride, a.z_tstride, b, cw, t0, L, lane);
-    stage_rows(d + oGo, a.dout, a.dout_bstride, a.dout_tstride, b, cw, t0, L, lane);
-    stage_rows(d + oB, a.bc, a.bc_bstride, a.bc_tstride, b, a.b_off, t0, L, lane);
-    stage_rows(d + oC, a.bc, a.bc_bstride, a.bc_tstride, b, a.c_off, t0, L, lane);
-    cp_commit();
-  };
-  stage(ntiles - 1, (ntiles - 1) & 1);
-
+  const uint32_t bar0 = sbase + oBar;               // +8 s: stage s; +16 + 8 r: ring slot r
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // zero region (never written again)
   for (int i = lane; i < kZeroBytes / 16; i += 32) reinterpret_cast<uint4*>(smem + oZero)[i] = make_uint4(0u, 0u, 0u, 0u);
-
-  // checkpoint records: 16-byte cp.async into a ring of three, two sub-chunks ahead.  cp.async groups in
-  // commit order: every tile top commits one group (the next tile's rows), every sub-chunk top one (a
-  // record; possibly empty), so "all but the newest N" is exact bookkeeping (see the waits).
-  const float* rec_g = ckpt + ((int64_t)(b * gridDim.x + unit) * nck) * 256 + lane * 4;
-  auto fetch_rec = [&](int k, uint32_t slot_off) {  // record k -> ring slot (empty group when k < 0)
-    if (k >= 0) {
-      const float* src = rec_g + (int64_t)k * 256;
-      cp_async16(sbase + slot_off + lane * 16, src, 16);
-      cp_async16(sbase + slot_off + 512 + lane * 16, src + 128, 16);
-    }
-    cp_commit();
+  __syncwarp();
+  const uint32_t kTileBytes = (has_z ? 6 : 5) * kRaw;
+  auto issue_tile = [&](int tile, int stg) {        // lane 0
+    const uint32_t d = sbase + stg * kStage, bar = bar0 + 8 * stg;
+    const int t0 = tile * kTT;
+    mbar_expect_tx(bar, kTileBytes);
+    tma_load_3d(d + oU, &maps.u, bar, cw, t0, b);
+    tma_load_3d(d + oDl, &maps.dl, bar, cw, t0, b);
+    if (has_z) tma_load_3d(d + oZ, &maps.z, bar, cw, t0, b);
+    tma_load_3d(d + oGo, &maps.go, bar, cw, t0, b);
+    tma_load_3d(d + oB, &maps.bc, bar, a.b_off, t0, b);
+    tma_load_3d(d + oC, &maps.bc, bar, a.c_off, t0, b);
   };
-  uint32_t ring_cur = oRing, ring_n1 = oRing + 1024, ring_n2 = oRing + 2048;
-  fetch_rec(nck - 1, ring_cur);
-  fetch_rec(nck - 2, ring_n1);
+  // checkpoint records: 1 KB bulk copies into a ring of three, two sub-chunks ahead
+  const float* rec_g = ckpt + ((int64_t)(b * gridDim.x + unit) * nck) * 256;
+  auto issue_rec = [&](int k, int slot) {           // lane 0; record k -> ring slot
+    mbar_expect_tx(bar0 + 16 + 8 * slot, 1024);
+    bulk_load(sbase + oRing + slot * 1024, rec_g + (int64_t)k * 256, 1024, bar0 + 16 + 8 * slot);
+  };
+  if (lane == 0) {
+    issue_tile(ntiles - 1, (ntiles - 1) & 1);
+    issue_rec(nck - 1, 0);
+    if (nck > 1) issue_rec(nck - 2, 1);
+  }
   int krec = nck - 3;                               // next record to fetch
+  int slot_cur = 0, slot_nxt = 2;                   // slot of this sub-chunk's record / of the record fetched now
+  uint32_t ring_par = 0;                            // bit r: parity to wait for on slot r
 
   // output rows of the token this lane finalises in the current sub-chunk (4 k + tig), stepped back 4 tokens
-  // per sub-chunk; channels g / g + 8 of the unit
+  // per sub-chunk: dB / dC slab row (states g, g + 8)
   int tok = 4 * (nck - 1) + tig;
-  const int64_t row_last = (int64_t)b * L + tok;
-  bf16* du_p = reinterpret_cast<bf16*>(a.du) + row_last * Di + cw + g;
-  bf16* dd_p = reinterpret_cast<bf16*>(a.ddelta) + row_last * Di + cw + g;
-  bf16* dz_p = a.dz ? reinterpret_cast<bf16*>(a.dz) + row_last * Di + cw + g : nullptr;
   float* slab_p = bc_slabs + (((int64_t)unit * a.B + b) * L + tok) * 32 + g;
-  const int64_t step_o = 4 * (int64_t)Di;
 
   uint8_t* const sdd = smem + oDD;
   uint8_t* const sdy = smem + oDY;
-  uint2* const sfin = reinterpret_cast<uint2*>(smem + oFin) + lane;
+  uint4* const sfin = reinterpret_cast<uint4*>(smem + oFin) + lane;
+  uint32_t par_stage = 0;                           // bit s: parity to wait for on stage s
 
   for (int tile = ntiles - 1; tile >= 0; --tile) {
     const int stg = tile & 1;
-    if (tile > 0) stage(tile - 1, stg ^ 1); else cp_commit();
-    cp_wait<3>();                                   // newer: that group and at most two records
-    __syncwarp();
-    const uint8_t* raw = smem + stg * kStage;
+    mbar_wait(bar0 + 8 * stg, (par_stage >> stg) & 1u);
+    par_stage ^= 1u << stg;
+    uint8_t* const raw = smem + stg * kStage;
     const int nvalid = min(kTT, L - tile * kTT);
 
     // ---- phase A: per-(token, channel) scalars of the tile ------------------------------------------
@@ -319,37 +369,56 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
       dD_b = fmaf(dyb, ub, dD_b);
       const float dua = da * ua, dub = db * ub;
       *reinterpret_cast<float4*>(sdd + t * 128 + pos_own) = make_float4(da, db, dua, dub);
-      *reinterpret_cast<float4*>(sdy + t * 128 + pos_own) = make_float4(dya, dyb, ua, ub);
-      sfin[j * 32] = make_uint2(pack_bf16x2(sa, sb), pack_bf16x2(dzfa, dzfb));
-      uint8_t* w = smem + stg * kStage + t * 32 + g * 2;
+      *reinterpret_cast<float4*>(sdy + t * 128 + pos_own) = make_float4(dya, dyb, da, db);
+      sfin[j * 32] = make_uint4(pack_bf16x2(sa, sb), pack_bf16x2(dzfa, dzfb), pack_bf16x2(ua, ub), 0u);
+      // channel c of the unit -> word (c & 7) >> 1 of half c >> 3, element c & 1: permuted position
+      // [t][tig' = (c & 7) >> 1]{half 0 word, half 1 word}
+      uint8_t* w = smem + t * 32 + (g >> 1) * 8 + (g & 1) * 2;
       *reinterpret_cast<bf16*>(w + oYh) = __float2bfloat16_rn(dya);
-      *reinterpret_cast<bf16*>(w + oYh + 16) = __float2bfloat16_rn(dyb);
+      *reinterpret_cast<bf16*>(w + oYh + 4) = __float2bfloat16_rn(dyb);
       *reinterpret_cast<bf16*>(w + oUh) = __float2bfloat16_rn(dua);
-      *reinterpret_cast<bf16*>(w + oUh + 16) = __float2bfloat16_rn(dub);
+      *reinterpret_cast<bf16*>(w + oUh + 4) = __float2bfloat16_rn(dub);
+    }
+    {                                               // B_t / C_t rows -> permuted rows
+      const int row = lane >> 1, half = lane & 1;
+      const uint4 vb = *reinterpret_cast<const uint4*>(raw + oB + row * 32 + half * 16);
+      const uint4 vc = *reinterpret_cast<const uint4*>(raw + oC + row * 32 + half * 16);
+      uint32_t* pb = reinterpret_cast<uint32_t*>(smem + oBp + row * 32 + half * 4);
+      uint32_t* pc = reinterpret_cast<uint32_t*>(smem + oCp + row * 32 + half * 4);
+      pb[0] = vb.x; pb[2] = vb.y; pb[4] = vb.z; pb[6] = vb.w;
+      pc[0] = vc.x; pc[2] = vc.y; pc[4] = vc.z; pc[6] = vc.w;
     }
     __syncwarp();
+    // the stage's raw rows are consumed: its u / delta / z arrays now stage du / ddelta / dz.  The other
+    // stage is free for the next tile once the stores of the previous tile have read their rows.
+    if (lane == 0 && tile > 0) {
+      bulk_wait_read_all();
+      fence_async_smem();
+      issue_tile(tile - 1, stg ^ 1);
+    }
 
     // ---- phase B: sub-chunks back to front -------------------------------------------------------------
     const int nsub = (nvalid + 3) >> 2;
-    const uint8_t* sB = raw + oB + 4 * tig + (nsub - 1) * (4 * 32);
-    const uint8_t* sC = raw + oC + 4 * tig + (nsub - 1) * (4 * 32);
+    const uint8_t* sP = smem + oBp + 8 * tig + (nsub - 1) * (4 * 32);     // permuted operand rows of the sub-chunk
     const uint8_t* sD = sdd + (nsub - 1) * (4 * 128);
     const uint8_t* sY = sdy + (nsub - 1) * (4 * 128);
-    // token i of a sub-chunk: lanes of columns {2i, 2i+1} read the real [B | C | Yh | Uh] rows, the others zeros
-    const int zdisp = oZero + 64 - (stg * kStage + oB);
-    const uint8_t* sM[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sM[i] = sB + ((g >> 1) == i ? 0 : zdisp);
+    bf16* so = reinterpret_cast<bf16*>(raw + (4 * (nsub - 1) + tig) * 32) + g;    // output staging row of the lane's token
 #pragma unroll 1
-    for (int c = nsub - 1; c >= 0; --c, sB -= 4 * 32, sC -= 4 * 32, sD -= 4 * 128, sY -= 4 * 128) {
+    for (int c = nsub - 1; c >= 0; --c, sP -= 4 * 32, sD -= 4 * 128, sY -= 4 * 128, so -= 4 * 16) {
       float2 h[4], q[4][4], an[4][4];
-      fetch_rec(krec--, ring_n2);                   // the record two sub-chunks before this one
-      cp_wait<2>();                                 // this sub-chunk's record has landed
+      if (lane == 0 && krec >= 0) {                 // the record two sub-chunks before this one (its slot was read last sub-chunk)
+        fence_async_smem();
+        issue_rec(krec, slot_nxt);
+      }
+      --krec;
+      mbar_wait(bar0 + 16 + 8 * slot_cur, (ring_par >> slot_cur) & 1u);
+      ring_par ^= 1u << slot_cur;
       {
-        const Rec r{*reinterpret_cast<const float4*>(smem + ring_cur + lane * 16),
-                    *reinterpret_cast<const float4*>(smem + ring_cur + 512 + lane * 16)};
+        const uint8_t* rp = smem + oRing + slot_cur * 1024 + lane * 16;
+        const Rec r{*reinterpret_cast<const float4*>(rp), *reinterpret_cast<const float4*>(rp + 512)};
         rec_to(r, h);
-        const uint32_t t = ring_cur; ring_cur = ring_n1; ring_n1 = ring_n2; ring_n2 = t;
+        slot_nxt = slot_cur;
+        slot_cur = slot_cur == 2 ? 0 : slot_cur + 1;
       }
       float acc_y[4] = {0.f, 0.f, 0.f, 0.f}, acc_s[4] = {0.f, 0.f, 0.f, 0.f}, acc_w[4] = {0.f, 0.f, 0.f, 0.f};
       float acc_c[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
@@ -358,9 +427,8 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 dd = *reinterpret_cast<const float4*>(sD + i * 128 + posoff[i]);
-        const uint32_t br0 = *reinterpret_cast<const uint32_t*>(sB + i * 32);
-        const uint32_t br1 = *reinterpret_cast<const uint32_t*>(sB + i * 32 + 16);
-        const float Bv[4] = {bf16lo(br0), bf16hi(br0), bf16lo(br1), bf16hi(br1)};
+        const uint2 br = *reinterpret_cast<const uint2*>(sP + i * 32);
+        const float Bv[4] = {bf16lo(br.x), bf16hi(br.x), bf16lo(br.y), bf16hi(br.y)};
         const float2 dab = make_float2(dd.x, dd.y), du = make_float2(dd.z, dd.w);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -370,24 +438,20 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
         }
         const uint32_t hf[4] = {pack_bf16x2(h[0].x, h[1].x), pack_bf16x2(h[0].y, h[1].y),
                                 pack_bf16x2(h[2].x, h[3].x), pack_bf16x2(h[2].y, h[3].y)};
-        const uint32_t c0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oC - oB));
-        const uint32_t c1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oC - oB) + 16);
-        mma_acc(acc_y, hf, c0, c1);
+        const uint2 cm = *reinterpret_cast<const uint2*>(sP + mdisp[i] + i * 32 + (oCp - oBp));
+        mma_acc(acc_y, hf, cm.x, cm.y);
         uint32_t tf[4];
         transpose_frag(hf, tf);
-        const uint32_t v0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oYh - oB));
-        const uint32_t v1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oYh - oB) + 16);
-        mma_acc(acc_c, tf, v0, v1);
+        const uint2 ym = *reinterpret_cast<const uint2*>(sP + mdisp[i] + i * 32 + (oYh - oBp));
+        mma_acc(acc_c, tf, ym.x, ym.y);
       }
       // reverse recurrence
 #pragma unroll
       for (int i = 3; i >= 0; --i) {
-        const float4 yu = *reinterpret_cast<const float4*>(sY + i * 128 + posoff[i]);
-        const float2 dlt = *reinterpret_cast<const float2*>(sD + i * 128 + posoff[i]);
-        const float2 dy = make_float2(yu.x, yu.y);
-        const uint32_t cr0 = *reinterpret_cast<const uint32_t*>(sC + i * 32);
-        const uint32_t cr1 = *reinterpret_cast<const uint32_t*>(sC + i * 32 + 16);
-        const float Cv[4] = {bf16lo(cr0), bf16hi(cr0), bf16lo(cr1), bf16hi(cr1)};
+        const float4 yd = *reinterpret_cast<const float4*>(sY + i * 128 + posoff[i]);     // dy_a, dy_b, delta_a, delta_b
+        const float2 dy = make_float2(yd.x, yd.y), dlt = make_float2(yd.z, yd.w);
+        const uint2 cr = *reinterpret_cast<const uint2*>(sP + i * 32 + (oCp - oBp));
+        const float Cv[4] = {bf16lo(cr.x), bf16hi(cr.x), bf16lo(cr.y), bf16hi(cr.y)};
 #pragma unroll
         for (int s = 0; s < 4; ++s) gg[s] = __ffma2_rn(dy, bc2(Cv[s]), gg[s]);       // dLoss / dh_t
         // g a h_{t-1}: dA and the state part of ddelta
@@ -407,54 +471,54 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, 
         {
           const uint32_t gf[4] = {pack_bf16x2(gg[0].x, gg[1].x), pack_bf16x2(gg[0].y, gg[1].y),
                                   pack_bf16x2(gg[2].x, gg[3].x), pack_bf16x2(gg[2].y, gg[3].y)};
-          const uint32_t br0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32);
-          const uint32_t br1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + 16);
-          mma_acc(acc_s, gf, br0, br1);
+          const uint2 bm = *reinterpret_cast<const uint2*>(sP + mdisp[i] + i * 32);
+          mma_acc(acc_s, gf, bm.x, bm.y);
           uint32_t tf[4];
           transpose_frag(gf, tf);
-          const uint32_t v0 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oUh - oB));
-          const uint32_t v1 = *reinterpret_cast<const uint32_t*>(sM[i] + i * 32 + (oUh - oB) + 16);
-          mma_acc(acc_b, tf, v0, v1);
+          const uint2 um = *reinterpret_cast<const uint2*>(sP + mdisp[i] + i * 32 + (oUh - oBp));
+          mma_acc(acc_b, tf, um.x, um.y);
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) gg[s] = __fmul2_rn(gg[s], an[i][s]);              // -> dLoss / dh_{t-1} (partial)
       }
-      // lane tig finalises token 4c + tig of channels g, g + 8 (states g, g + 8 for dB / dC)
+      // lane tig finalises token 4c + tig of channels g, g + 8 (states g, g + 8 for dB / dC); rows beyond
+      // the sequence are clipped by the TMA stores
       {
-        const float4 dd = *reinterpret_cast<const float4*>(sD + tig * 128 + pos_own);
-        const float4 yu = *reinterpret_cast<const float4*>(sY + tig * 128 + pos_own);
-        const uint2 finp = sfin[c * 32];
-        const float4 fin = make_float4(bf16lo(finp.x), bf16hi(finp.x), bf16lo(finp.y), bf16hi(finp.y));
+        const float4 yd = *reinterpret_cast<const float4*>(sY + tig * 128 + pos_own);
+        const uint4 finp = sfin[c * 32];
+        const float sg_a = bf16lo(finp.x), sg_b = bf16hi(finp.x), dzf_a = bf16lo(finp.y), dzf_b = bf16hi(finp.y);
+        const float ua = bf16lo(finp.z), ub = bf16hi(finp.z);
+        const float dr_a = fmaf(kLn2, acc_w[0], ua * acc_s[0]) * sg_a;
+        const float dr_b = fmaf(kLn2, acc_w[2], ub * acc_s[2]) * sg_b;
+        so[oU / 2] = __float2bfloat16_rn(fmaf(yd.z, acc_s[0], yd.x * Da));            // du
+        so[oU / 2 + 8] = __float2bfloat16_rn(fmaf(yd.w, acc_s[2], yd.y * Db));
+        so[oDl / 2] = __float2bfloat16_rn(dr_a);                                      // ddelta_raw
+        so[oDl / 2 + 8] = __float2bfloat16_rn(dr_b);
+        so[oZ / 2] = __float2bfloat16_rn(dzf_a * fmaf(Da, ua, acc_y[0]));             // dz
+        so[oZ / 2 + 8] = __float2bfloat16_rn(dzf_b * fmaf(Db, ub, acc_y[2]));
         if (tok < L) {
-          const float du_a = fmaf(dd.x, acc_s[0], yu.x * Da), du_b = fmaf(dd.y, acc_s[2], yu.y * Db);
-          const float dr_a = fmaf(kLn2, acc_w[0], yu.z * acc_s[0]) * fin.x;
-          const float dr_b = fmaf(kLn2, acc_w[2], yu.w * acc_s[2]) * fin.y;
-          du_p[0] = __float2bfloat16_rn(du_a);
-          du_p[8] = __float2bfloat16_rn(du_b);
-          dd_p[0] = __float2bfloat16_rn(dr_a);
-          dd_p[8] = __float2bfloat16_rn(dr_b);
           dBias_a += dr_a;
           dBias_b += dr_b;
-          if (dz_p) {
-            dz_p[0] = __float2bfloat16_rn(fin.z * fmaf(Da, yu.z, acc_y[0]));
-            dz_p[8] = __float2bfloat16_rn(fin.w * fmaf(Db, yu.w, acc_y[2]));
-          }
           slab_p[0] = acc_b[0];
           slab_p[8] = acc_b[2];
           slab_p[16] = acc_c[0];
           slab_p[24] = acc_c[2];
         }
         tok -= 4;
-        du_p -= step_o;
-        dd_p -= step_o;
-        if (dz_p) dz_p -= step_o;
         slab_p -= 4 * 32;
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sM[i] -= 4 * 32;
     }
-    __syncwarp();                                  // the tile's shared memory is rewritten by the next iteration
+    __syncwarp();                                   // staging rows complete; the tile's shared memory is rewritten next
+    if (lane == 0) {
+      fence_async_smem();
+      const uint32_t d = sbase + stg * kStage;
+      tma_store_3d(&maps.du, d + oU, cw, tile * kTT, b);
+      tma_store_3d(&maps.dd, d + oDl, cw, tile * kTT, b);
+      if (a.dz) tma_store_3d(&maps.dz, d + oZ, cw, tile * kTT, b);
+      bulk_commit();
+    }
   }
+  if (lane == 0) bulk_wait_read_all();
 
   // ---- per-unit results ----------------------------------------------------------------------------------
 #pragma unroll
@@ -500,15 +564,30 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
                   cudaStream_t st) {
   const int nck = (a.L + 3) / 4;
   dim3 grid(a.Di / 16, a.B);
-  static const bool carve = [] {                    // 11 CTAs x 18.1 KB per SM need the largest shared-memory split
+  static const bool carve = [] {                    // 11 CTAs x 20 KB per SM need the largest shared-memory split
     cudaFuncSetAttribute(scan_bwd_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(scan_ckpt_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return true;
   }();
   (void)carve;
+  // 3-D maps (channel x token x batch), 16 x 16 boxes; a batch of one still needs a valid outer stride
+  BwdMaps m;
+  const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B, Di = (uint64_t)a.Di;
+  auto map_of = [&](CUtensorMap* out, const void* p, uint64_t d0, int64_t ts, int64_t bs) {
+    return make_tensor_map_3d_bf16(out, p, d0, L, B, (uint64_t)ts * 2, (uint64_t)(a.B > 1 ? bs : ts * a.L) * 2, 16, kTT, false);
+  };
+  int rc;
+  if ((rc = map_of(&m.u, a.u, Di, a.u_tstride, a.u_bstride))) return rc;
+  if ((rc = map_of(&m.dl, a.delta, Di, a.d_tstride, a.d_bstride))) return rc;
+  if (a.z) { if ((rc = map_of(&m.z, a.z, Di, a.z_tstride, a.z_bstride))) return rc; } else m.z = m.u;
+  if ((rc = map_of(&m.go, a.dout, Di, a.dout_tstride, a.dout_bstride))) return rc;
+  if ((rc = map_of(&m.bc, a.bc, (uint64_t)std::max(a.b_off, a.c_off) + 16, a.bc_tstride, a.bc_bstride))) return rc;
+  if ((rc = map_of(&m.du, a.du, Di, a.Di, (int64_t)a.L * a.Di))) return rc;
+  if ((rc = map_of(&m.dd, a.ddelta, Di, a.Di, (int64_t)a.L * a.Di))) return rc;
+  if (a.dz) { if ((rc = map_of(&m.dz, a.dz, Di, a.Di, (int64_t)a.L * a.Di))) return rc; } else m.dz = m.du;
   scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
   VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
-  scan_bwd_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck, slabs, pA, pD, pBias);
+  scan_bwd_fast_kernel<<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
   VMB_LAUNCH_CHECK("scan_bwd_fast_kernel");
   return VMB_OK;
 }
