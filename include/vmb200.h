@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VMB_ABI_VERSION 3
+#define VMB_ABI_VERSION 4
 
 /* element types */
 #define VMB_F32 0
@@ -354,7 +354,8 @@ VMB_API int vmb_gather_rows(const void* src, int64_t src_bstride, int64_t src_ts
  *   x's dtype); dresidual (residual's dtype, nullable) receives the same values; dweight / dbias (dim)
  *   fp32, nullable.
  * vmb_causal_conv1d_bwd: backward of vmb_causal_conv1d_fwd (reverse = 0).  dy (B, L, Di) contiguous;
- *   dconv_state_out = gradient of the returned state (nullable); dx (B, L, Di) contiguous;
+ *   dconv_state_out = gradient of the returned state (nullable); dx a (B, L, Di) view with element strides
+ *   dx_bstride / dx_tstride (channel stride 1; 0, 0 = contiguous), e.g. the x half of a d(xz) buffer;
  *   dconv_state_in (conv_state_in's dtype, nullable); dweight (Di, W), dbias (Di) fp32, nullable.
  * vmb_selective_scan_bwd: backward of vmb_selective_scan_fwd (reverse = 0, d_state <= 16).
  *   dout (B, L, Di) view; dh_last (B, Di, N) fp32 nullable.  du / ddelta / dz (B, L, Di) contiguous in
@@ -382,7 +383,8 @@ VMB_API int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x_ts
                           const void* conv_state_in, int cs_in_dtype,     /* nullable */
                           const void* dy,
                           const void* dconv_state_out, int dcs_out_dtype, /* nullable */
-                          void* dx, void* dconv_state_in /* nullable */,
+                          void* dx, int64_t dx_bstride, int64_t dx_tstride, /* 0, 0 = contiguous (B, L, Di) */
+                          void* dconv_state_in /* nullable */,
                           float* dweight, float* dbias,                   /* nullable */
                           int B, int L, int Di, int W, int silu, int dtype,
                           void* workspace, int64_t workspace_bytes, vmb_stream_t stream);
@@ -398,6 +400,8 @@ typedef struct vmb_scan_bwd_args {
   const void* dout;   int64_t dout_bstride, dout_tstride;
   const float* dh_last;                                  /* (B,Di,N) fp32, nullable */
   void* du;  void* ddelta;  void* dz;                    /* (B,L,Di) contiguous; dz nullable iff z is */
+  int64_t dz_bstride, dz_tstride;                        /* dz only: element strides of a (B,L,Di) VIEW (e.g. the z half
+                                                            of a d(xz) buffer); 0, 0 = contiguous */
   void* dbc;          int64_t dbc_tstride;               /* rows (B*L), same columns as bc */
   float* dA;  float* dD;  float* ddt_bias;  float* dh0;  /* nullable */
   void* workspace;    int64_t workspace_bytes;

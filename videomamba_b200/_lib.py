@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvmb200.so")
 
 VMB_F32, VMB_BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 
@@ -101,6 +101,7 @@ class ScanBwdArgs(C.Structure):
         ("dout", c_void_p), ("dout_bstride", c_int64), ("dout_tstride", c_int64),
         ("dh_last", c_void_p),
         ("du", c_void_p), ("ddelta", c_void_p), ("dz", c_void_p),
+        ("dz_bstride", c_int64), ("dz_tstride", c_int64),
         ("dbc", c_void_p), ("dbc_tstride", c_int64),
         ("dA", c_void_p), ("dD", c_void_p), ("ddt_bias", c_void_p), ("dh0", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
@@ -156,8 +157,8 @@ SIGNATURES = {
                                  c_float, c_int, c_void_p, c_int64, c_void_p]),
     "vmb_causal_conv1d_bwd_workspace_bytes": (c_int64, [c_int] * 4),
     "vmb_causal_conv1d_bwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
-                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64,
                                       c_void_p]),
     "vmb_selective_scan_bwd_workspace_bytes": (c_int64, [c_int] * 4),
     "vmb_selective_scan_bwd": (c_int, [C.POINTER(ScanBwdArgs), c_void_p]),

@@ -172,15 +172,39 @@ class AddNormFn(torch.autograd.Function):
                 None if dres is None else dres.reshape(shape), None, None, None, None)
 
 
+class XZGrad:
+    """The d(xz) buffer of one mixer call, shared by the backward nodes of its two halves: the conv backward
+    writes dx into ``[..., :Di]`` and the scan backward dz into ``[..., Di:]`` (both kernels take strided
+    outputs), so ``SplitXZ.backward`` returns the buffer as it is instead of copying two (B, L, Di) tensors
+    side by side.  Anything else that arrives (a gradient torch accumulated, a missing half) is copied."""
+
+    __slots__ = ("buf", "di")
+
+    def __init__(self, di: int):
+        self.buf, self.di = None, di
+
+    def half(self, which: int, B: int, L: int, dtype, device) -> Tensor:
+        if self.buf is None or self.buf.shape != (B, L, 2 * self.di) or self.buf.dtype != dtype:
+            self.buf = torch.empty((B, L, 2 * self.di), dtype=dtype, device=device)
+        return self.buf[..., :self.di] if which == 0 else self.buf[..., self.di:]
+
+    def owns(self, which: int, grad: Tensor) -> bool:
+        b = self.buf
+        return (b is not None and grad is not None and grad.dtype == b.dtype and grad.shape == (*b.shape[:2], self.di)
+                and grad.stride() == b.stride()
+                and grad.data_ptr() == b.data_ptr() + which * self.di * b.element_size())
+
+
 class SplitXZ(torch.autograd.Function):
     """``xz (.., 2 Di) -> (x, z)`` as two strided views (mamba_simple.py:369).  torch's own slice backward
     materialises one zero-filled (.., 2 Di) tensor per half and adds them (five passes over the largest
     activation of the block); here the two incoming gradients are written side by side into one buffer."""
 
     @staticmethod
-    def forward(ctx, xz, di):
+    def forward(ctx, xz, di, arena=None):
         ctx.set_materialize_grads(False)
         ctx.di = di
+        ctx.arena = arena
         ctx.meta = (xz.shape, xz.dtype, xz.device)
         return xz[..., :di], xz[..., di:]
 
@@ -188,13 +212,23 @@ class SplitXZ(torch.autograd.Function):
     def backward(ctx, dx, dz):
         shape, dtype, dev = ctx.meta
         di = ctx.di
+        arena = ctx.arena
+        if arena is not None:
+            buf = arena.buf
+            arena.buf = None                                  # one backward pass owns it
+            if buf is not None and buf.shape == shape:
+                arena.buf = buf
+                ok = arena.owns(0, dx) and arena.owns(1, dz)
+                arena.buf = None
+                if ok:
+                    return buf, None, None
         out = torch.empty(shape, dtype=dtype, device=dev)
         for part, grad in ((out[..., :di], dx), (out[..., di:], dz)):
             if grad is None:
                 part.zero_()
             else:
                 part.copy_(grad)
-        return out, None
+        return out, None, None
 
 
 class ConvFn(torch.autograd.Function):
@@ -202,11 +236,12 @@ class ConvFn(torch.autograd.Function):
     ``_bwd``).  Gradients flow into ``conv_state`` and arrive through the returned state."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, conv_state, want_state, silu):
+    def forward(ctx, x, weight, bias, conv_state, want_state, silu, arena=None):
         ctx.set_materialize_grads(False)
         out = ops.causal_conv1d_tokens_raw(x, weight, bias, conv_state, want_state, silu)
         ctx.save_for_backward(x, weight, bias, conv_state)
         ctx.silu = silu
+        ctx.arena = arena
         if want_state:
             return out
         return out, None
@@ -227,7 +262,10 @@ class ConvFn(torch.autograd.Function):
             dcs_out = dcs_out.contiguous()
             if dcs_out.dtype not in (torch.float32, torch.bfloat16):
                 dcs_out = dcs_out.float()
-        dx = torch.empty((B, L, Di), dtype=x.dtype, device=x.device)
+        if ctx.arena is not None and ctx.arena.di == Di:
+            dx = ctx.arena.half(0, B, L, x.dtype, x.device)   # the x half of d(xz), written in place
+        else:
+            dx = torch.empty((B, L, Di), dtype=x.dtype, device=x.device)
         dcs_in = torch.empty_like(cs) if cs is not None and ctx.needs_input_grad[3] else None
         dw = torch.empty((Di, W), dtype=torch.float32, device=x.device)
         db = torch.empty(Di, dtype=torch.float32, device=x.device) if bias is not None else None
@@ -237,11 +275,12 @@ class ConvFn(torch.autograd.Function):
             rc = lib.vmb_causal_conv1d_bwd(
                 _p(x), x.stride(0), x.stride(1), _p(w2), _p(b2), _p(cs),
                 _dt(cs) if cs is not None else VMB_F32, _p(dy), _p(dcs_out),
-                _dt(dcs_out) if dcs_out is not None else VMB_F32, _p(dx), _p(dcs_in), _p(dw), _p(db),
+                _dt(dcs_out) if dcs_out is not None else VMB_F32, _p(dx), dx.stride(0), dx.stride(1), _p(dcs_in),
+                _p(dw), _p(db),
                 B, L, Di, W, 1 if ctx.silu else 0, _dt(x), _p(ws), nbytes, _stream(x))
         _lib.check(rc, "vmb_causal_conv1d_bwd")
         return (dx, dw.reshape(weight.shape).to(weight.dtype),
-                None if db is None else db.to(bias.dtype), dcs_in, None, None)
+                None if db is None else db.to(bias.dtype), dcs_in, None, None, None)
 
 
 class ScanFn(torch.autograd.Function):
@@ -249,8 +288,9 @@ class ScanFn(torch.autograd.Function):
     ``A`` is the natural ``A = -exp(A_log)`` (fp32); B_t / C_t are columns of ``bc``."""
 
     @staticmethod
-    def forward(ctx, u, delta, A, bc, b_off, c_off, d_state, D, z, dt_bias, softplus, h0, want_last):
+    def forward(ctx, u, delta, A, bc, b_off, c_off, d_state, D, z, dt_bias, softplus, h0, want_last, arena=None):
         ctx.set_materialize_grads(False)
+        ctx.arena = arena
         A2 = (A.float() * LOG2E).contiguous()
         Df = None if D is None else D.float().contiguous()
         bias = None if dt_bias is None else dt_bias.float().contiguous()
@@ -271,15 +311,15 @@ class ScanFn(torch.autograd.Function):
         b_off, c_off, N, softplus, A_dtype, D_dtype, bias_dtype = ctx.meta
         du, dd, dz, dbc, dA, dD, dbias, dh0 = _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias,
                                                          softplus, h0, dout, dh_last,
-                                                         ctx.needs_input_grad[11])
+                                                         ctx.needs_input_grad[11], ctx.arena)
         return (du, dd, dA.to(A_dtype), dbc, None, None, None,
                 None if dD is None else dD.to(D_dtype), dz,
-                None if dbias is None else dbias.to(bias_dtype), None, dh0, None)
+                None if dbias is None else dbias.to(bias_dtype), None, dh0, None, None)
 
 
-def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout, dh_last, want_dh0):
+def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout, dh_last, want_dh0, arena=None):
     """One ``vmb_selective_scan_bwd`` call.  Returns (du, ddelta_raw, dz, dbc, dA, dD, dbias, dh0);
-    ``dbc`` is zero outside the B / C columns."""
+    ``dbc`` is zero outside the B / C columns.  With an ``XZGrad`` arena dz is its z half (written in place)."""
     lib = _lib.load()
     B, L, Di = u.shape
     dev = u.device
@@ -287,7 +327,12 @@ def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout
         else ops._token_major(dout.to(u.dtype))
     du = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
     dd = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
-    dz = torch.empty((B, L, Di), dtype=u.dtype, device=dev) if z is not None else None
+    if z is None:
+        dz = None
+    elif arena is not None and arena.di == Di:
+        dz = arena.half(1, B, L, u.dtype, dev)
+    else:
+        dz = torch.empty((B, L, Di), dtype=u.dtype, device=dev)
     dbc = torch.zeros(bc.shape, dtype=bc.dtype, device=dev)
     dA = torch.empty((Di, N), dtype=torch.float32, device=dev)
     dD = torch.empty(Di, dtype=torch.float32, device=dev) if Df is not None else None
@@ -313,7 +358,8 @@ def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout
     a.dout, a.dout_bstride, a.dout_tstride = dout.data_ptr(), dout.stride(0), dout.stride(1)
     a.dh_last = None if dh_last is None else dh_last.data_ptr()
     a.du, a.ddelta = du.data_ptr(), dd.data_ptr()
-    a.dz = None if dz is None else dz.data_ptr()
+    if dz is not None:
+        a.dz, a.dz_bstride, a.dz_tstride = dz.data_ptr(), dz.stride(0), dz.stride(1)
     a.dbc, a.dbc_tstride = dbc.data_ptr(), dbc.stride(1)
     a.dA = dA.data_ptr()
     a.dD = None if dD is None else dD.data_ptr()
@@ -337,8 +383,9 @@ class FusedScanFn(torch.autograd.Function):
     and folds the dt_proj backward in (``d dt_low = d delta W_dt``, ``d W_dt = d delta^T dt_low``)."""
 
     @staticmethod
-    def forward(ctx, u, z, xdbl, w_dt, A, D, dt_bias, h0, want_last, R, N):
+    def forward(ctx, u, z, xdbl, w_dt, A, D, dt_bias, h0, want_last, R, N, arena=None):
         ctx.set_materialize_grads(False)
+        ctx.arena = arena
         A2 = (A.float() * LOG2E).contiguous()
         Df = None if D is None else D.float().contiguous()
         bias = None if dt_bias is None else dt_bias.float().contiguous()
@@ -359,7 +406,7 @@ class FusedScanFn(torch.autograd.Function):
         dt_low = xdbl[..., :R]
         delta = ops.linear_raw(dt_low, w_dt)                                  # (B, L, Di), bf16
         du, dd, dz, dbc, dA, dD, dbias, dh0 = _scan_bwd(u, delta, A2, xdbl, R, R + N, N, Df, z, bias, True, h0,
-                                                         dout, dh_last, ctx.needs_input_grad[7])
+                                                         dout, dh_last, ctx.needs_input_grad[7], ctx.arena)
         dd2 = dd.reshape(B * L, Di)
         w_t = transpose2d(w_dt)[:, :Di]                                       # (R, Di)
         dbc[..., :R] = ops.linear_raw(dd2, w_t).reshape(B, L, R)              # d dt_low
@@ -367,7 +414,7 @@ class FusedScanFn(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             dw_dt = linear_wgrad(dd2, _rows(dt_low, R), w_dt.dtype)           # (Di, R)
         return (du, dz, dbc, dw_dt, dA.to(A_dtype), None if dD is None else dD.to(D_dtype),
-                None if dbias is None else dbias.to(bias_dtype), dh0, None, None, None)
+                None if dbias is None else dbias.to(bias_dtype), dh0, None, None, None, None)
 
 
 def fused_scan_covers(dtype, Di: int, N: int, R: int) -> bool:
@@ -386,18 +433,19 @@ def mixer_train(in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dp, out_w, o
     Di = conv_w.shape[0]
     N, R = A_log.shape[1], dt_w.shape[1]
     xz = ops.linear(hidden, in_w, in_b)                                  # :333-339
-    x_in, z = SplitXZ.apply(xz, Di)                                      # :369
-    xc, new_conv = ConvFn.apply(x_in, conv_w, conv_b, conv_state, want_conv_state, True)   # :381-404
+    arena = XZGrad(Di)                                                   # dx / dz are written into one d(xz) buffer
+    x_in, z = SplitXZ.apply(xz, Di, arena)                               # :369
+    xc, new_conv = ConvFn.apply(x_in, conv_w, conv_b, conv_state, want_conv_state, True, arena)   # :381-404
     A = -torch.exp(A_log.float())                                        # :341
     if fused_scan_covers(hidden.dtype, Di, N, R) and x_w.dtype == hidden.dtype and dt_w.dtype == hidden.dtype:
         # production bf16 shapes: the forward runs the fused inference scan (dt_proj inside, delta never in HBM)
         Xp = ops.xdbl_pitch(R, N)
         x_dbl = ops.linear(xc, torch.nn.functional.pad(x_w, (0, 0, 0, Xp - x_w.shape[0])))   # rows [dt_low | B | C | 0]
-        y, last = FusedScanFn.apply(xc, z, x_dbl, dt_w, A, Dp, dt_b, ssm_state, want_ssm_state, R, N)
+        y, last = FusedScanFn.apply(xc, z, x_dbl, dt_w, A, Dp, dt_b, ssm_state, want_ssm_state, R, N, arena)
     else:
         x_dbl = ops.linear(xc, x_w)                                      # :409
         delta = ops.linear(x_dbl[..., :R], dt_w)                         # :413-414 (rounded to the model dtype)
         y, last = ScanFn.apply(xc, delta, A, x_dbl, R, R + N, N, Dp.float(), z,
-                               None if dt_b is None else dt_b.float(), True, ssm_state, want_ssm_state)
+                               None if dt_b is None else dt_b.float(), True, ssm_state, want_ssm_state, arena)
     out = ops.linear(y, out_w, out_b)                                    # :445-446
     return out, new_conv, last

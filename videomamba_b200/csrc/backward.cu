@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(128)
 conv1d_bwd_kernel(const void* __restrict__ x, int64_t x_bs, int64_t x_ts, const void* __restrict__ weight,
                   const void* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
                   const void* __restrict__ dy, const void* __restrict__ dcs_out, int dcs_out_dtype,
-                  void* __restrict__ dx, void* __restrict__ dcs_in, float* __restrict__ partial,
-                  int B, int L, int Di, int W, int silu, int dtype) {
+                  void* __restrict__ dx, int64_t dx_bs, int64_t dx_ts, void* __restrict__ dcs_in,
+                  float* __restrict__ partial, int B, int L, int Di, int W, int silu, int dtype) {
   const int d = blockIdx.x * 128 + threadIdx.x;
   const int b = blockIdx.y;
   const int chunk = blockIdx.z;
@@ -393,7 +393,7 @@ conv1d_bwd_kernel(const void* __restrict__ x, int64_t x_bs, int64_t x_ts, const 
       if (j >= 0) {
         if (j < c1) {
           if (j >= L - W) s += dcs_out_at(j - (L - W));
-          store_from_f32(dx, ((int64_t)b * L + j) * Di + d, dtype, s);
+          store_from_f32(dx, (int64_t)b * dx_bs + (int64_t)j * dx_ts + d, dtype, s);
         }
       } else if (dcs_in != nullptr) {
         const int si = W + j;                         // history slot
@@ -436,8 +436,8 @@ __global__ void __launch_bounds__(128)
 conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* __restrict__ weight,
                        const T* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
                        const T* __restrict__ dy, const void* __restrict__ dcs_out, int dcs_out_dtype,
-                       T* __restrict__ dx, void* __restrict__ dcs_in, float* __restrict__ partial,
-                       int L, int Di, int silu) {
+                       T* __restrict__ dx, int64_t dx_bs, int64_t dx_ts, void* __restrict__ dcs_in,
+                       float* __restrict__ partial, int L, int Di, int silu) {
   const int d = (blockIdx.x * 128 + threadIdx.x) * 2;
   const int b = blockIdx.y;
   const int chunk = blockIdx.z;
@@ -454,7 +454,7 @@ conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, cons
   float2 dba = make_float2(0.f, 0.f);
   const T* xp = x + (int64_t)b * x_bs + d;
   const T* gp = dy + (int64_t)b * L * Di + d;
-  T* op = dx + (int64_t)b * L * Di + d;
+  T* op = dx + (int64_t)b * dx_bs + d;
   auto hist_at = [&](int j) -> float2 {
     if (j >= 0) return Pair<T>::ld(xp + (int64_t)j * x_ts);
     if (!cs_in) return make_float2(0.f, 0.f);
@@ -499,7 +499,7 @@ conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, cons
       if (j >= 0) {
         if (j < c1) {
           if (j >= L - W) { const float2 e = dcs_out_at(j - (L - W)); s.x += e.x; s.y += e.y; }
-          Pair<T>::st(op + (int64_t)j * Di, s);
+          Pair<T>::st(op + (int64_t)j * dx_ts, s);
         }
       } else if (dcs_in != nullptr) {
         const int si = W + j;
@@ -525,11 +525,11 @@ conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, cons
 template <typename T, int W>
 void launch_conv_bwd_pair(const void* x, int64_t x_bs, int64_t x_ts, const void* weight, const void* bias,
                           const void* cs_in, int cs_in_dtype, const void* dy, const void* dcs_out, int dcs_out_dtype,
-                          void* dx, void* dcs_in, float* partial, int B, int L, int Di, int silu, int chunks,
-                          cudaStream_t st) {
+                          void* dx, int64_t dx_bs, int64_t dx_ts, void* dcs_in, float* partial, int B, int L, int Di,
+                          int silu, int chunks, cudaStream_t st) {
   conv1d_bwd_pair_kernel<T, W><<<dim3((Di / 2 + 127) / 128, B, chunks), 128, 0, st>>>(
       (const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias, cs_in, cs_in_dtype, (const T*)dy, dcs_out,
-      dcs_out_dtype, (T*)dx, dcs_in, partial, L, Di, silu);
+      dcs_out_dtype, (T*)dx, dx_bs, dx_ts, dcs_in, partial, L, Di, silu);
 }
 
 }  // namespace
@@ -686,9 +686,10 @@ extern "C" int64_t vmb_causal_conv1d_bwd_workspace_bytes(int B, int L, int Di, i
 extern "C" int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x_tstride, const void* weight,
                                      const void* bias, const void* conv_state_in, int cs_in_dtype,
                                      const void* dy, const void* dconv_state_out, int dcs_out_dtype,
-                                     void* dx, void* dconv_state_in, float* dweight, float* dbias, int B,
-                                     int L, int Di, int W, int silu, int dtype, void* workspace,
-                                     int64_t workspace_bytes, vmb_stream_t stream) {
+                                     void* dx, int64_t dx_bstride, int64_t dx_tstride, void* dconv_state_in,
+                                     float* dweight, float* dbias, int B, int L, int Di, int W, int silu,
+                                     int dtype, void* workspace, int64_t workspace_bytes, vmb_stream_t stream) {
+  if (dx_bstride == 0 && dx_tstride == 0) { dx_tstride = Di; dx_bstride = (int64_t)L * Di; }
   VMB_CHECK_ARG(dtype_ok(dtype), "conv1d_bwd: bad dtype %d", dtype);
   VMB_CHECK_ARG(B >= 0 && L >= 0 && Di > 0 && W > 0, "conv1d_bwd: bad sizes");
   if (W > kConvWMax) VMB_UNSUPPORTED("conv1d_bwd: d_conv %d > %d not supported", W, kConvWMax);
@@ -721,12 +722,15 @@ extern "C" int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x
   // fast path: even channel count, pair-aligned rows, d_conv 2..4
   const int esz = dtype_size(dtype);
   auto al = [&](const void* p) { return reinterpret_cast<uintptr_t>(p) % (2 * esz) == 0; };
-  const bool pair_ok = Di % 2 == 0 && x_bstride % 2 == 0 && x_tstride % 2 == 0 && al(x) && al(dy) && al(dx) &&
+  VMB_CHECK_ARG(dx_tstride >= Di, "conv1d_bwd: dx token stride %lld < Di", (long long)dx_tstride);
+  const bool pair_ok = Di % 2 == 0 && x_bstride % 2 == 0 && x_tstride % 2 == 0 && dx_bstride % 2 == 0 &&
+                       dx_tstride % 2 == 0 && al(x) && al(dy) && al(dx) &&
                        (bias == nullptr || al(bias)) && W >= 2 && W <= 4;
   if (pair_ok) {
 #define VMB_CBP(T, WW)                                                                                          \
   launch_conv_bwd_pair<T, WW>(x, x_bstride, x_tstride, weight, bias, conv_state_in, cs_in_dtype, dy,            \
-                              dconv_state_out, dcs_out_dtype, dx, dconv_state_in, partial, B, L, Di, silu, chunks, st)
+                              dconv_state_out, dcs_out_dtype, dx, dx_bstride, dx_tstride, dconv_state_in, partial, B, L, \
+                              Di, silu, chunks, st)
     if (dtype == VMB_F32) { if (W == 4) VMB_CBP(float, 4); else if (W == 3) VMB_CBP(float, 3); else VMB_CBP(float, 2); }
     else { if (W == 4) VMB_CBP(__nv_bfloat16, 4); else if (W == 3) VMB_CBP(__nv_bfloat16, 3); else VMB_CBP(__nv_bfloat16, 2); }
 #undef VMB_CBP
@@ -734,7 +738,7 @@ extern "C" int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x
   } else {
     conv1d_bwd_kernel<<<dim3((Di + 127) / 128, B, chunks), 128, 0, st>>>(
         x, x_bstride, x_tstride, weight, bias, conv_state_in, cs_in_dtype, dy, dconv_state_out, dcs_out_dtype,
-        dx, dconv_state_in, partial, B, L, Di, W, silu, dtype);
+        dx, dx_bstride, dx_tstride, dconv_state_in, partial, B, L, Di, W, silu, dtype);
     VMB_LAUNCH_CHECK("conv1d_bwd_kernel");
   }
   // partial rows are [dw_0 .. dw_{W-1}, db] per channel: reduce into one (Di, W + 1) fp32 table, then split

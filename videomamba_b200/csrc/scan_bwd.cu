@@ -177,8 +177,9 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
   const int b_off = a.b_off, c_off = a.c_off;
   // outputs: lanes 0..7 -> du, lanes 8..15 -> ddelta (and dz)
   T* po = (lo ? reinterpret_cast<T*>(a.du) : reinterpret_cast<T*>(a.ddelta)) + ((int64_t)b * L + last0 + tk) * Di + dc;
-  T* pz = a.dz ? reinterpret_cast<T*>(a.dz) + ((int64_t)b * L + last0 + tk) * Di + dc : nullptr;
-  const int64_t so = (int64_t)kT * Di;
+  const int64_t dz_ts = a.dz_tstride ? a.dz_tstride : Di, dz_bs = a.dz_tstride ? a.dz_bstride : (int64_t)L * Di;
+  T* pz = a.dz ? reinterpret_cast<T*>(a.dz) + (int64_t)b * dz_bs + (last0 + tk) * dz_ts + dc : nullptr;
+  const int64_t so = (int64_t)kT * Di, sz = (int64_t)kT * dz_ts;
   // slab of this CTA: [(slab * B + b) * L + t][32] = {dB_t[0..15], dC_t[0..15]} summed over its 16 channels
   float* pslab = bc_slabs + (((int64_t)blockIdx.x * a.B + b) * L + last0 + (tid >> 5)) * 32 + (tid & 31);
 
@@ -288,7 +289,7 @@ scan_bwd_kernel(const vmb_scan_bwd_args a, const float* __restrict__ ckpt, int n
       }
     }
     po -= so;
-    if (pz) pz -= so;
+    if (pz) pz -= sz;
     __syncthreads();                                 // wbuf complete
     {
       const int t = tid >> 5, k = tid & 31;          // 8 tokens x 32 values
@@ -413,6 +414,7 @@ extern "C" int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, vmb_stream_t s
   VMB_CHECK_ARG(a->u && a->delta && a->bc && a->A2 && a->dout && a->du && a->ddelta && a->dbc,
                 "selective_scan_bwd: null tensor");
   VMB_CHECK_ARG(a->z == nullptr || a->dz != nullptr, "selective_scan_bwd: z without dz");
+  VMB_CHECK_ARG(a->dz_tstride == 0 || a->dz_tstride >= a->Di, "selective_scan_bwd: dz token stride < Di");
   if (a->dtype == VMB_F32) return run<float, true>(*a, st);
   return run<__nv_bfloat16, false>(*a, st);
 }

@@ -553,6 +553,7 @@ bool scan_bwd_fast_supported(const vmb_scan_bwd_args& a) {
       !s8(a.dout_tstride) || !s8(a.bc_bstride) || !s8(a.bc_tstride) || !s8(a.b_off) || !s8(a.c_off))
     return false;
   if (a.z && (!s8(a.z_bstride) || !s8(a.z_tstride))) return false;
+  if (!al16(a.du) || !al16(a.ddelta) || (a.dz && (!al16(a.dz) || !s8(a.dz_bstride) || !s8(a.dz_tstride)))) return false;
   return true;
 }
 
@@ -584,7 +585,12 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
   if ((rc = map_of(&m.bc, a.bc, (uint64_t)std::max(a.b_off, a.c_off) + 16, a.bc_tstride, a.bc_bstride))) return rc;
   if ((rc = map_of(&m.du, a.du, Di, a.Di, (int64_t)a.L * a.Di))) return rc;
   if ((rc = map_of(&m.dd, a.ddelta, Di, a.Di, (int64_t)a.L * a.Di))) return rc;
-  if (a.dz) { if ((rc = map_of(&m.dz, a.dz, Di, a.Di, (int64_t)a.L * a.Di))) return rc; } else m.dz = m.du;
+  if (a.dz) {
+    const bool dense = a.dz_tstride == 0;
+    if ((rc = map_of(&m.dz, a.dz, Di, dense ? a.Di : a.dz_tstride, dense ? (int64_t)a.L * a.Di : a.dz_bstride))) return rc;
+  } else {
+    m.dz = m.du;
+  }
   scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
   VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
   scan_bwd_fast_kernel<<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
