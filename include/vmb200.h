@@ -203,6 +203,10 @@ typedef struct vmb_fused_scan_args {
    * measurement builds (-DVMB_SCAN_LAB) and return VMB_ERR_UNSUPPORTED otherwise. */
   int32_t tune;
   int32_t frame_len;      /* with reverse != 0: frame-axis reversal (see vmb_causal_conv1d_fwd); else 0 */
+  /* training forward (reverse == 0 only), nullable: vmb_scan_bwd_ckpt_bytes(B, L, Di) bytes (device, 16-byte
+   * aligned) that receive the state before every 4-token group -- handed to vmb_selective_scan_bwd as
+   * vmb_scan_bwd_args.fwd_ckpt, the backward then skips its own forward pass over the sequence. */
+  float* bwd_ckpt;
 } vmb_fused_scan_args;
 VMB_API int64_t vmb_fused_scan_workspace_bytes(int B, int L, int Di, int N);
 VMB_API int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* args, vmb_stream_t stream);
@@ -408,8 +412,13 @@ typedef struct vmb_scan_bwd_args {
   int32_t B, L, Di, N;
   int32_t dtype;
   int32_t softplus;
+  /* nullable: the records vmb_selective_scan_fused_fwd wrote through bwd_ckpt for the SAME u / delta / B / h0
+   * (bf16, d_state 16, Di % 16 == 0 only; ignored by the generic kernels, which always recompute) */
+  const float* fwd_ckpt;
 } vmb_scan_bwd_args;
 VMB_API int64_t vmb_selective_scan_bwd_workspace_bytes(int B, int L, int Di, int N);
+/* bytes of the state records of one (B, L, Di) scan with d_state 16: 1 KB per (batch, 16 channels, 4 tokens) */
+VMB_API int64_t vmb_scan_bwd_ckpt_bytes(int B, int L, int Di);
 VMB_API int vmb_selective_scan_bwd(const vmb_scan_bwd_args* args, vmb_stream_t stream);
 /* Weight gradient of a projection without transposed copies: dw (N, K) = dy^T x, dy (M, N) row stride
  * ldy, x (M, K) row stride ldx, both bf16 with 16-byte aligned rows (N, K, ldy, ldx multiples of 8); dw in

@@ -298,6 +298,33 @@ def test_mixer_training_forward_matches_inference_path(dtype, d_model):
         assert rel_err(a, b) <= 1e-5 and rel_err(sa, sb) <= 1e-5
 
 
+@pytest.mark.parametrize("geom", [(2, 70, 384), (1, 700, 128), (40, 50, 768), (3, 131, 576)])
+def test_scan_states_saved_by_the_forward_equal_a_recomputing_backward(geom, monkeypatch):
+    """The fused training forward writes the state before every 4-token group (one-warp kernel, two-warp
+    kernel, sequence split); the backward that reads those records and the backward that recomputes them with
+    its own pass agree (the records differ only by delta being rounded to bf16 in the recomputation)."""
+    B, L, d_model = geom
+    torch.manual_seed(4)
+    mx = Mamba(d_model=d_model, use_fast_path=False).to(torch.bfloat16).to(DEV)
+    x0 = torch.randn(B, L, d_model, device=DEV).to(torch.bfloat16)
+    gy = torch.randn(B, L, d_model, device=DEV)
+    gs = torch.randn(B, mx.d_inner, mx.d_state, device=DEV)
+
+    def run(save):
+        monkeypatch.setattr(ag, "SAVE_SCAN_STATES", save)
+        mx.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        out, (_, ss) = mx(x, return_state=True)
+        ((out.float() * gy).sum() + (ss * gs).sum()).backward()
+        return out.detach(), {"x": x.grad, **{n: p.grad.clone() for n, p in mx.named_parameters()}}
+
+    out_a, ga = run(True)
+    out_b, gb = run(False)
+    assert torch.equal(out_a, out_b)
+    for n in ga:
+        assert rel_err(ga[n], gb[n]) <= 1e-2, (n, rel_err(ga[n], gb[n]))
+
+
 # ---- whole model -----------------------------------------------------------------------------------------
 def _cfg(**over):
     cfg = dict(img_size=32, patch_size=16, depth=2, embed_dim=64, kernel_size=1, num_frames=2,

@@ -49,6 +49,7 @@ class FusedScanArgs(C.Structure):
         ("Rp", c_int32), ("Xp", c_int32), ("reverse", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("a_geometric", c_int32), ("tune", c_int32), ("frame_len", c_int32),
+        ("bwd_ckpt", c_void_p),
     ]
 
 
@@ -107,6 +108,7 @@ class ScanBwdArgs(C.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("B", c_int32), ("L", c_int32), ("Di", c_int32), ("N", c_int32),
         ("dtype", c_int32), ("softplus", c_int32),
+        ("fwd_ckpt", c_void_p),
     ]
 
 
@@ -162,6 +164,7 @@ SIGNATURES = {
                                       c_void_p]),
     "vmb_selective_scan_bwd_workspace_bytes": (c_int64, [c_int] * 4),
     "vmb_selective_scan_bwd": (c_int, [C.POINTER(ScanBwdArgs), c_void_p]),
+    "vmb_scan_bwd_ckpt_bytes": (c_int64, [c_int] * 3),
     "vmb_linear_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "vmb_linear_wgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_int,
                                  c_void_p, c_int64, c_void_p]),

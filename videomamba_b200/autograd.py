@@ -172,6 +172,12 @@ class AddNormFn(torch.autograd.Function):
                 None if dres is None else dres.reshape(shape), None, None, None, None)
 
 
+# The fused training forward stores the scan state before every 4-token group for the backward (12 KB per
+# token and layer at Di 768: 1.2 GB per layer at batch 32 x 3137 tokens).  False: the backward recomputes them
+# with a forward pass of its own (+0.45 ms per layer at that size, no extra memory between the passes).
+SAVE_SCAN_STATES = True
+
+
 class XZGrad:
     """The d(xz) buffer of one mixer call, shared by the backward nodes of its two halves: the conv backward
     writes dx into ``[..., :Di]`` and the scan backward dz into ``[..., Di:]`` (both kernels take strided
@@ -317,7 +323,8 @@ class ScanFn(torch.autograd.Function):
                 None if dbias is None else dbias.to(bias_dtype), None, dh0, None, None)
 
 
-def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout, dh_last, want_dh0, arena=None):
+def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout, dh_last, want_dh0, arena=None,
+              fwd_ckpt=None):
     """One ``vmb_selective_scan_bwd`` call.  Returns (du, ddelta_raw, dz, dbc, dA, dD, dbias, dh0);
     ``dbc`` is zero outside the B / C columns.  With an ``XZGrad`` arena dz is its z half (written in place)."""
     lib = _lib.load()
@@ -368,6 +375,8 @@ def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
     a.B, a.L, a.Di, a.N = B, L, Di, N
     a.dtype, a.softplus = _dt(u), 1 if softplus else 0
+    if fwd_ckpt is not None:
+        a.fwd_ckpt = fwd_ckpt.data_ptr()
     with _on_device(u):
         rc = lib.vmb_selective_scan_bwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_bwd")
@@ -391,8 +400,14 @@ class FusedScanFn(torch.autograd.Function):
         bias = None if dt_bias is None else dt_bias.float().contiguous()
         u, z, xdbl = ops._token_major(u), ops._token_major(z), ops._token_major(xdbl)
         w_dt = w_dt.contiguous()
-        out = ops.selective_scan_fused_tokens_raw(u, z, xdbl, w_dt, A2, R, N, Df, bias, h0, want_last)
-        ctx.save_for_backward(u, z, xdbl, w_dt, A2, Df, bias, h0)
+        # the forward also writes the state before every 4-token group (1 KB per 16 channels): the backward
+        # then needs no forward pass of its own over the sequence
+        ckpt = None
+        if SAVE_SCAN_STATES:
+            B, L, Di = u.shape
+            ckpt = torch.empty(ops.scan_bwd_ckpt_bytes(B, L, Di), dtype=torch.uint8, device=u.device)
+        out = ops.selective_scan_fused_tokens_raw(u, z, xdbl, w_dt, A2, R, N, Df, bias, h0, want_last, bwd_ckpt=ckpt)
+        ctx.save_for_backward(u, z, xdbl, w_dt, A2, Df, bias, h0, ckpt)
         ctx.meta = (R, N, A.dtype, None if D is None else D.dtype, None if dt_bias is None else dt_bias.dtype)
         if want_last:
             return out
@@ -400,13 +415,13 @@ class FusedScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, dh_last=None):
-        u, z, xdbl, w_dt, A2, Df, bias, h0 = ctx.saved_tensors
+        u, z, xdbl, w_dt, A2, Df, bias, h0, ckpt = ctx.saved_tensors
         R, N, A_dtype, D_dtype, bias_dtype = ctx.meta
         B, L, Di = u.shape
         dt_low = xdbl[..., :R]
         delta = ops.linear_raw(dt_low, w_dt)                                  # (B, L, Di), bf16
         du, dd, dz, dbc, dA, dD, dbias, dh0 = _scan_bwd(u, delta, A2, xdbl, R, R + N, N, Df, z, bias, True, h0,
-                                                         dout, dh_last, ctx.needs_input_grad[7], ctx.arena)
+                                                         dout, dh_last, ctx.needs_input_grad[7], ctx.arena, ckpt)
         dd2 = dd.reshape(B * L, Di)
         w_t = transpose2d(w_dt)[:, :Di]                                       # (R, Di)
         dbc[..., :R] = ops.linear_raw(dd2, w_t).reshape(B, L, R)              # d dt_low

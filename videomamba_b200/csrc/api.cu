@@ -205,6 +205,9 @@ extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_st
   f.frame_len = a->reverse ? a->frame_len : 0;
   VMB_CHECK_ARG(f.frame_len >= 0 && (f.frame_len == 0 || a->L % f.frame_len == 0),
                 "fused_scan: L=%d is not a whole number of frames of %d tokens", a->L, f.frame_len);
+  VMB_CHECK_ARG(a->bwd_ckpt == nullptr || (!a->reverse && reinterpret_cast<uintptr_t>(a->bwd_ckpt) % 16 == 0),
+                "fused_scan: bwd_ckpt needs the forward walk and 16-byte alignment");
+  f.ckpt = a->bwd_ckpt;
   f.seg_ws = reinterpret_cast<float*>(a->workspace);
   f.seg_ws_bytes = a->workspace ? a->workspace_bytes : 0;
   VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->workspace) % 16 == 0, "fused_scan: workspace not 16-byte aligned");

@@ -62,6 +62,7 @@ struct FastScanArgs {
   int frame_len = 0;     // with reverse: frame-axis reversal, frames of frame_len tokens (0 = whole-sequence reversal)
   int a_geometric = 0;   // caller's promise: A2[d][n] == (n+1) * A2[d][0] (checked when the weights are loaded)
   int tune = 0;          // measurement aid: 10 * layout + evaluator, 0 = automatic (see scan_fast())
+  float* ckpt = nullptr; // forward walk only: records of the state before every 4-token group (scan_bwd_fast.cu layout)
   // sequence split for small batches (filled by scan_fast itself): nseg segments of seg_len tokens,
   // carried through seg_ws = [H (nseg,B,Di,N) | S (nseg,B,Di) | Hin (nseg,B,Di,N)] fp32
   float* seg_ws = nullptr;

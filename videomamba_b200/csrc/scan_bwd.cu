@@ -388,6 +388,11 @@ int run(const vmb_scan_bwd_args& a, cudaStream_t st) {
 
 using namespace vmb;
 
+extern "C" int64_t vmb_scan_bwd_ckpt_bytes(int B, int L, int Di) {
+  if (B <= 0 || L <= 0 || Di <= 0) return 0;
+  return scan_bwd_fast_ckpt_bytes(B, L, Di);
+}
+
 extern "C" int64_t vmb_selective_scan_bwd_workspace_bytes(int B, int L, int Di, int N) {
   if (B <= 0 || L <= 0 || Di <= 0 || N <= 0) return 0;
   return plan(B, L, Di, N).total + 256;

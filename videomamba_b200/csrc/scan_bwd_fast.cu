@@ -591,8 +591,13 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
   } else {
     m.dz = m.du;
   }
-  scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
-  VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
+  if (a.fwd_ckpt) {                                 // the fused forward already wrote the records
+    VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a.fwd_ckpt) % 16 == 0, "selective_scan_bwd: fwd_ckpt not 16-byte aligned");
+    ckpt = const_cast<float*>(a.fwd_ckpt);
+  } else {
+    scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
+    VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
+  }
   scan_bwd_fast_kernel<<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
   VMB_LAUNCH_CHECK("scan_bwd_fast_kernel");
   return VMB_OK;

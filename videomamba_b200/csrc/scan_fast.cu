@@ -196,6 +196,13 @@ struct Lane {
     *reinterpret_cast<float2*>(dst + hoff_b + 8) = make_float2(h[2].y, h[3].y);
   }
 
+  // record of the state for the backward (scan_bwd_fast.cu): 256 floats per (unit, 4-token group), lane l
+  // owns floats [4l, 4l + 4) and [128 + 4l, 128 + 4l + 4)
+  __device__ __forceinline__ void checkpoint(float4* rec) const {
+    rec[0] = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+    rec[32] = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
+  }
+
   // dd = {delta_a, delta_b, du_a, du_b}; Bv = B_t of the lane's four states; c0 / c1 = the lane's
   // bf16 pairs of C_t (mma B fragment).  d[0] / d[2] return <C_t, h_t> of channels a / b.
   __device__ __forceinline__ void token(const float4 dd, const float4 Bv, uint32_t c0, uint32_t c1,
@@ -337,7 +344,7 @@ __host__ __device__ constexpr Plan plan(int Xp) {
   return p;
 }
 
-template <int R, bool kStateOnly, bool kRev, int kExp>
+template <int R, bool kStateOnly, bool kRev, int kExp, bool kCkpt = false>
 __global__ void __launch_bounds__(32, 18)
 scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
@@ -372,6 +379,10 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
 
   bf16* yg = reinterpret_cast<bf16*>(a.y) + (int64_t)b * a.y_bs + cw;
   const int y_ts = (int)a.y_ts;
+  // training forward: the state before every 4-token group, for the backward pass
+  float4* const ckrec = kCkpt ? reinterpret_cast<float4*>(a.ckpt) +
+                                    ((int64_t)(b * gridDim.x + blockIdx.x) * ((a.L + 3) / 4)) * 64 + lane
+                              : nullptr;
 
   // shared-memory row of logical tile row r: the reversed direction holds the box in memory order
   auto srow = [](int r) { return kRev ? kTT - 1 - r : r; };
@@ -464,6 +475,9 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
 #pragma unroll
     for (int tg = 0; tg < kTT; tg += 4) {
       float ya = 0.f, yb = 0.f;
+      if constexpr (kCkpt) {
+        if (row0 + tg < a.L) st.checkpoint(ckrec + (int64_t)((row0 + tg) >> 2) * 64);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = tg + i;
@@ -556,7 +570,7 @@ __host__ __device__ constexpr Plan plan(int Xp) {
   return p;
 }
 
-template <int R, bool kStateOnly, bool kRev, int kExp>
+template <int R, bool kStateOnly, bool kRev, int kExp, bool kCkpt = false>
 __global__ void __launch_bounds__(64, 11)
 scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
@@ -719,8 +733,12 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     Lane<kExp, kStateOnly> st;
     const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
     st.init(a, cw + g, tig, hoff_a, seg > 0 ? wsHin + seg * seg_stride : nullptr);
+    float4* const ckrec = kCkpt ? reinterpret_cast<float4*>(a.ckpt) +
+                                      ((int64_t)(b * gridDim.x + blockIdx.x) * ((a.L + 3) / 4)) * 64 + lane
+                                : nullptr;
     for (int it = 0; it < nit; ++it) {
       const int pb = it & 1;
+      const int tok0 = (tile_lo + it) * kTT;           // kCkpt: forward walk without frames, tile = 16 consecutive tokens
       mbar_wait(full_bar(pb), (uint32_t)(it >> 1) & 1u);
       const uint8_t* sdd0 = smem + sp.D(pb) + (g << 4);
       const uint8_t* sdd1 = smem + sp.D(pb) + ((g ^ 1) << 4);
@@ -730,6 +748,9 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
 #pragma unroll
       for (int tg = 0; tg < kTT; tg += 4) {
         float ya = 0.f, yb = 0.f;
+        if constexpr (kCkpt) {
+          if (tok0 + tg < a.L) st.checkpoint(ckrec + (int64_t)((tok0 + tg) >> 2) * 64);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int t = tg + i;
@@ -836,9 +857,11 @@ int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
     constexpr bool kSO = decltype(state_only)::value;
     if constexpr (kTwoWarp) {
       if (a.reverse && a.frame_len == 0) two_warp::scan2w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      else if (!kSO && a.ckpt) two_warp::scan2w_kernel<R, false, false, kExp, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else two_warp::scan2w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
     } else {
       if (a.reverse && a.frame_len == 0) one_warp::scan1w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      else if (!kSO && a.ckpt) one_warp::scan1w_kernel<R, false, false, kExp, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else one_warp::scan1w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
     }
   };

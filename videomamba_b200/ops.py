@@ -486,7 +486,9 @@ def selective_scan_fused_tokens_raw(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Te
                                     dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
                                     want_last: bool = False, reverse: bool = False,
                                     allow_split: bool = True, a_geometric: bool = False, tune: int = 0,
-                                    frame_len: int = 0):
+                                    frame_len: int = 0, bwd_ckpt: Optional[Tensor] = None):
+    """``bwd_ckpt``: a ``scan_bwd_ckpt_bytes(B, L, Di)`` byte buffer that receives the state records the
+    backward kernel needs (training forward; forward walk only)."""
     _require_cuda(u)
     lib = _lib.load()
     u, z, xdbl = _token_major(u), _token_major(z), _token_major(xdbl)
@@ -515,6 +517,8 @@ def selective_scan_fused_tokens_raw(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Te
     a.Rp, a.Xp, a.reverse = w_dt.stride(0), xdbl.shape[-1], 1 if reverse else 0
     a.a_geometric, a.tune = 1 if a_geometric else 0, int(tune)
     a.frame_len = int(frame_len) if reverse else 0
+    if bwd_ckpt is not None:
+        a.bwd_ckpt = bwd_ckpt.data_ptr()
     if u.dtype != torch.bfloat16 or z.dtype != u.dtype or xdbl.dtype != u.dtype \
             or w_dt.dtype != u.dtype:
         raise TypeError("the fused scan is a bf16 kernel")
@@ -526,6 +530,10 @@ def selective_scan_fused_tokens_raw(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Te
         rc = lib.vmb_selective_scan_fused_fwd(C.byref(a), _stream(u))
     _lib.check(rc, "vmb_selective_scan_fused_fwd")
     return (y, h_last) if want_last else y
+
+
+def scan_bwd_ckpt_bytes(B: int, L: int, Di: int) -> int:
+    return int(_lib.load().vmb_scan_bwd_ckpt_bytes(B, L, Di))
 
 
 def is_geometric(A2: Tensor, rtol: float = 1e-6) -> bool:
