@@ -443,10 +443,13 @@ def test_refiner_backward():
             _check(prm.grad, p[name].grad, 5e-4, name)
 
 
-@pytest.mark.parametrize("shape", [(3137 * 2, 768, 384), (1000, 64, 768), (777, 768, 24), (40, 1536, 384), (5000, 56, 768)])
+@pytest.mark.parametrize("shape", [(3137 * 2, 768, 384), (1000, 64, 768), (777, 768, 24), (40, 1536, 384), (5000, 56, 768),
+                                   (20001, 1536, 384), (9000, 384, 768), (4097, 576, 1152), (6000, 2304, 576),
+                                   (300, 128, 512), (8191, 1152, 40)])
 def test_linear_wgrad_kernel(shape):
-    """vmb_linear_wgrad (split-token tensor-core kernel, operands read in place) against fp32 matmul,
-    including strided operand views and ragged token / tile edges."""
+    """vmb_linear_wgrad against fp32 matmul, including strided operand views and ragged token / tile edges:
+    the tcgen05 kernel (csrc/wgrad_tc.cu: N >= 128, M >= 256; MN-major operands read in place) and the mma.sync
+    kernel (csrc/wgrad.cu) for the rest."""
     M, N, K = shape
     g = _gen(M + N)
     dy = torch.randn(M, N + 8, generator=g).to(torch.bfloat16).to(DEV)[:, :N]      # row pitch N + 8

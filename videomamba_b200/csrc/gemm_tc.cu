@@ -972,6 +972,12 @@ int make_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int6
 
 }  // namespace
 
+// 2-D bf16 row-major map with 64-column (128-byte, 128B-swizzled) boxes of box_rows rows (wgrad_tc.cu).
+int make_tensor_map_2d_bf16_sw128(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                                  int box_rows) {
+  return make_map(out, ptr, rows, cols, ld, box_rows);
+}
+
 // 3-D bf16 tensor map (innermost dimension contiguous), box = box0 x box1 x 1, used by the scan's
 // TMA staging (scan_fast.cu).  Cached like the 2-D maps.
 int make_tensor_map_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,

@@ -23,6 +23,16 @@ int make_tensor_map_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint
                             uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                             uint32_t box1, bool swizzle128);
 
+int make_tensor_map_2d_bf16_sw128(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                                  int box_rows);
+
+// wgrad_tc.cu -- weight gradient dW (N, K) = dY^T X on tcgen05 (both operands MN-major: the token axis is the
+// contraction).  partial: [splits][N][K] fp32 (summed by the caller); supported() decides, splits() sizes.
+bool wgrad_tc_supported(const void* dy, int64_t ldy, const void* x, int64_t ldx, int64_t M, int N, int K);
+int wgrad_tc_splits(int64_t M, int N, int K);
+int wgrad_tc(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* partial, int64_t M, int N, int K,
+             int splits, cudaStream_t st);
+
 // gemm_tc.cu -- causal conv (d_conv 4, bf16) + SiLU fused into the x_proj projection: x (M rows of K
 // channels, row pitch x_ld; rows are (batch, token) flattened, L tokens per sequence), conv taps cw
 // (K, 4) / bias cb (K), W (N = 64, K) -> xc (M, K) and C = xc * W^T (M, N).  Stateless forward walk only.

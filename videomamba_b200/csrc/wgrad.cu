@@ -152,7 +152,8 @@ using namespace vmb;
 
 extern "C" int64_t vmb_linear_wgrad_workspace_bytes(int64_t M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  return (int64_t)wgrad_splits(M, N, K) * N * K * (int64_t)sizeof(float);
+  const int splits = std::max(wgrad_splits(M, N, K), (N >= 128 || K >= 128) ? wgrad_tc_splits(M, N, K) : 1);
+  return (int64_t)splits * N * K * (int64_t)sizeof(float);
 }
 
 extern "C" int vmb_linear_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, void* dw, int dw_dtype,
@@ -170,6 +171,14 @@ extern "C" int vmb_linear_wgrad(const void* dy, int64_t ldy, const void* x, int6
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (!al16(dy) || !al16(x) || ldy % 8 != 0 || ldx % 8 != 0 || N % 8 != 0 || K % 8 != 0)
     VMB_UNSUPPORTED("linear_wgrad: operands must be bf16 with 16-byte aligned rows and N, K multiples of 8");
+  if (wgrad_tc_supported(dy, ldy, x, ldx, M, N, K)) {   // tcgen05: both operands MN-major, read in place
+    const int sp = wgrad_tc_splits(M, N, K);
+    VMB_CHECK_ARG(workspace && workspace_bytes >= (int64_t)sp * N * K * (int64_t)sizeof(float),
+                  "linear_wgrad: workspace too small");
+    const int rc = wgrad_tc(dy, ldy, x, ldx, reinterpret_cast<float*>(workspace), M, N, K, sp, st);
+    if (rc != VMB_OK) return rc;
+    return reduce_partials(reinterpret_cast<const float*>(workspace), sp, (int64_t)N * K, dw, dw_dtype, st);
+  }
   const int splits = wgrad_splits(M, N, K);
   VMB_CHECK_ARG(workspace && workspace_bytes >= (int64_t)splits * N * K * (int64_t)sizeof(float),
                 "linear_wgrad: workspace too small");
