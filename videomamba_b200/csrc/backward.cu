@@ -15,6 +15,7 @@
 // then one reduce launch -- no atomics, results are run-to-run deterministic.  All math is fp32;
 // element types are resolved at run time (these kernels are not on the forward hot path).
 #include <algorithm>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -52,6 +53,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int P,
   float s = 0.f;
   for (int p = 0; p < P; ++p) s += partial[(int64_t)p * n + i];
   store_from_f32(out, i, out_dtype, s);
+}
+
+// Many partial rows, few columns (per-CTA partials of the conv / add-norm backward: P in the hundreds, n a few
+// thousand): CTA = 32 columns x 8 row lanes, fixed summation order (deterministic).  In-place use (out == row 0
+// of partial) is safe: a column is read and written by one CTA only, the write follows the barrier.
+__global__ void __launch_bounds__(256)
+reduce_partials_tall_kernel(const float* __restrict__ partial, int P, int64_t n, void* __restrict__ out,
+                            int out_dtype) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < n)
+    for (int p = ty; p < P; p += 8) s += partial[(int64_t)p * n + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    store_from_f32(out, c, out_dtype, t);
+  }
 }
 
 // ---- column sums of x (M, N) with row stride ld: CTA = 32 columns x 8 row lanes over a row chunk --
@@ -215,22 +238,31 @@ add_norm_bwd_vec_kernel(const T* __restrict__ x, int64_t ldx, const float* __res
   }
   const float inv_dim = 1.f / (float)dim;
   for (int64_t row = (int64_t)blockIdx.x * kBwdWarps + warp; row < rows; row += (int64_t)gridDim.x * kBwdWarps) {
-    float v[kIters][4], g[kIters][4];
+    float v[kIters][4], g[kIters][4], ro[kIters][4];
     float sum = 0.f, sumsq = 0.f;
+    // every load of the row is issued up front (the incoming residual gradient too: loading it after the two
+    // reductions would give the row a second, dependent trip to memory)
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       const int c = it * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[it][j] = g[it][j] = 0.f;
+      for (int j = 0; j < 4; ++j) v[it][j] = g[it][j] = ro[it][j] = 0.f;
       if (c < nvec) {
         V4<T>::ld(x + row * ldx + 4 * c, v[it]);
+        V4<T>::ld(dy + row * (int64_t)dim + 4 * c, g[it]);
+        if (dres_out != nullptr) V4<float>::ld(dres_out + row * (int64_t)dim + 4 * c, ro[it]);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int c = it * 32 + lane;
+      if (c < nvec) {
         if (residual != nullptr) {
           float r[4];
           V4<float>::ld(residual + row * (int64_t)dim + 4 * c, r);
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[it][j] += r[j];
         }
-        V4<T>::ld(dy + row * (int64_t)dim + 4 * c, g[it]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { sum += v[it][j]; sumsq += v[it][j] * v[it][j]; }
       }
@@ -271,13 +303,7 @@ add_norm_bwd_vec_kernel(const T* __restrict__ x, int64_t ldx, const float* __res
       if (c < nvec) {
         float d[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = rstd * (g[it][j] - v[it][j] * c1 - c2);
-        if (dres_out != nullptr) {
-          float r[4];
-          V4<float>::ld(dres_out + row * (int64_t)dim + 4 * c, r);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d[j] += r[j];
-        }
+        for (int j = 0; j < 4; ++j) d[j] = rstd * (g[it][j] - v[it][j] * c1 - c2) + ro[it][j];
         V4<T>::st(dx + row * (int64_t)dim + 4 * c, d);
         if (dres != nullptr) V4<float>::st(dres + row * (int64_t)dim + 4 * c, d);
       }
@@ -330,7 +356,7 @@ bool launch_add_norm_bwd_vec(const void* x, int64_t ldx, const void* residual, c
 // Thread = channel; a CTA walks one chunk of kConvChunk tokens of one sequence in order, carrying the last
 // W inputs and the last W pre-activation gradients in registers.  hist[j], j in [-(W-1), L): x[j] for
 // j >= 0, conv_state_in[W + j] for j < 0 (zeros without a state).
-constexpr int kConvChunk = 64;
+constexpr int kConvChunk = 32;
 constexpr int kConvWMax = 8;
 
 __global__ void __launch_bounds__(128)
@@ -431,7 +457,11 @@ template <> struct Pair<__nv_bfloat16> {
   }
 };
 
-template <typename T, int W>
+// kStaged (bf16, 16-byte aligned rows): the x and dy rows of the chunk are brought into shared memory with
+// 16-byte cp.async first (38 + 35 rows x 512 B: ~37 KB per CTA, six CTAs per SM), the walk then reads
+// shared memory.  Without it every token of the dependent walk exposes a global-load latency and 28 resident
+// warps x two 128-byte requests keep only ~7 KB in flight per SM (1.5 TB/s).
+template <typename T, int W, bool kStaged>
 __global__ void __launch_bounds__(128)
 conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, const T* __restrict__ weight,
                        const T* __restrict__ bias, const void* __restrict__ cs_in, int cs_in_dtype,
@@ -441,21 +471,52 @@ conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, cons
   const int d = (blockIdx.x * 128 + threadIdx.x) * 2;
   const int b = blockIdx.y;
   const int chunk = blockIdx.z;
-  if (d >= Di) return;
+  if (!kStaged && d >= Di) return;
+  const int dw_ = min(d, Di - 2);                     // (staged: every thread helps with the copies first)
   const int c0 = chunk * kConvChunk;
   const int c1 = min(L, c0 + kConvChunk);
   float2 w[W], hist[W], dpre[W], dwa[W];
 #pragma unroll
   for (int k = 0; k < W; ++k) {
-    w[k] = make_float2(to_f32<T>(weight[(int64_t)d * W + k]), to_f32<T>(weight[(int64_t)(d + 1) * W + k]));
+    w[k] = make_float2(to_f32<T>(weight[(int64_t)dw_ * W + k]), to_f32<T>(weight[(int64_t)(dw_ + 1) * W + k]));
     hist[k] = dpre[k] = dwa[k] = make_float2(0.f, 0.f);
   }
-  const float2 bv = bias ? Pair<T>::ld(bias + d) : make_float2(0.f, 0.f);
+  const float2 bv = bias ? Pair<T>::ld(bias + dw_) : make_float2(0.f, 0.f);
   float2 dba = make_float2(0.f, 0.f);
   const T* xp = x + (int64_t)b * x_bs + d;
   const T* gp = dy + (int64_t)b * L * Di + d;
   T* op = dx + (int64_t)b * dx_bs + d;
+  // staged rows: sx[r] = x row max(c0 - (W-1), 0) + r, sg[r] = dy row c0 + r, 256 channels (512 B) per row
+  extern __shared__ __align__(16) uint8_t conv_smem[];
+  constexpr int kRowsMax = kConvChunk + 2 * (W - 1);  // x rows [c0 - (W-1), c1 + W - 1); dy rows [c0, c1 + W - 1)
+  const int xr0 = max(c0 - (W - 1), 0);
+  const T* sx = reinterpret_cast<const T*>(conv_smem) + 2 * threadIdx.x;
+  const T* sg = sx + kRowsMax * 256;
+  if constexpr (kStaged) {
+    const int d0 = blockIdx.x * 256;
+    const int xrows = min(L, c1 + W - 1) - xr0, grows = min(L, c1 + W - 1) - c0;
+    const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(conv_smem));
+    for (int i = threadIdx.x; i < xrows * 32; i += 128) {
+      const int r = i >> 5, ch = (i & 31) * 8;
+      if (d0 + ch < Di) {
+        const T* src = x + (int64_t)b * x_bs + (int64_t)(xr0 + r) * x_ts + d0 + ch;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + (r * 256 + ch) * 2), "l"(src) : "memory");
+      }
+    }
+    for (int i = threadIdx.x; i < grows * 32; i += 128) {
+      const int r = i >> 5, ch = (i & 31) * 8;
+      if (d0 + ch < Di) {
+        const T* src = dy + ((int64_t)b * L + c0 + r) * Di + d0 + ch;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + ((kRowsMax + r) * 256 + ch) * 2), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (d >= Di) return;
+  }
   auto hist_at = [&](int j) -> float2 {
+    if (kStaged && j >= 0) return Pair<T>::ld(sx + (j - xr0) * 256);
     if (j >= 0) return Pair<T>::ld(xp + (int64_t)j * x_ts);
     if (!cs_in) return make_float2(0.f, 0.f);
     const int64_t o = ((int64_t)b * Di + d) * W + (W + j);
@@ -478,11 +539,11 @@ conv1d_bwd_pair_kernel(const T* __restrict__ x, int64_t x_bs, int64_t x_ts, cons
       float2 pre = bv;
 #pragma unroll
       for (int k = 0; k < W; ++k) { pre.x = fmaf(w[k].x, hist[k].x, pre.x); pre.y = fmaf(w[k].y, hist[k].y, pre.y); }
-      g = Pair<T>::ld(gp + (int64_t)l * Di);
+      g = kStaged ? Pair<T>::ld(sg + (l - c0) * 256) : Pair<T>::ld(gp + (int64_t)l * Di);
       if (silu) {
-        const float sx = 1.f / (1.f + __expf(-pre.x)), sy = 1.f / (1.f + __expf(-pre.y));
-        g.x *= sx * (1.f + pre.x * (1.f - sx));
-        g.y *= sy * (1.f + pre.y * (1.f - sy));
+        const float sgx = 1.f / (1.f + __expf(-pre.x)), sgy = 1.f / (1.f + __expf(-pre.y));
+        g.x *= sgx * (1.f + pre.x * (1.f - sgx));
+        g.y *= sgy * (1.f + pre.y * (1.f - sgy));
       }
       if (l < c1) {
 #pragma unroll
@@ -527,7 +588,20 @@ void launch_conv_bwd_pair(const void* x, int64_t x_bs, int64_t x_ts, const void*
                           const void* cs_in, int cs_in_dtype, const void* dy, const void* dcs_out, int dcs_out_dtype,
                           void* dx, int64_t dx_bs, int64_t dx_ts, void* dcs_in, float* partial, int B, int L, int Di,
                           int silu, int chunks, cudaStream_t st) {
-  conv1d_bwd_pair_kernel<T, W><<<dim3((Di / 2 + 127) / 128, B, chunks), 128, 0, st>>>(
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (std::is_same<T, __nv_bfloat16>::value && Di % 8 == 0 && x_bs % 8 == 0 && x_ts % 8 == 0 && al16(x) && al16(dy)) {
+    constexpr int smem = 2 * (kConvChunk + 2 * (W - 1)) * 256 * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(conv1d_bwd_pair_kernel<T, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    conv1d_bwd_pair_kernel<T, W, true><<<dim3((Di / 2 + 127) / 128, B, chunks), 128, smem, st>>>(
+        (const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias, cs_in, cs_in_dtype, (const T*)dy, dcs_out,
+        dcs_out_dtype, (T*)dx, dx_bs, dx_ts, dcs_in, partial, L, Di, silu);
+    return;
+  }
+  conv1d_bwd_pair_kernel<T, W, false><<<dim3((Di / 2 + 127) / 128, B, chunks), 128, 0, st>>>(
       (const T*)x, x_bs, x_ts, (const T*)weight, (const T*)bias, cs_in, cs_in_dtype, (const T*)dy, dcs_out,
       dcs_out_dtype, (T*)dx, dx_bs, dx_ts, dcs_in, partial, L, Di, silu);
 }
@@ -536,6 +610,11 @@ void launch_conv_bwd_pair(const void* x, int64_t x_bs, int64_t x_ts, const void*
 
 int reduce_partials(const float* partial, int P, int64_t n, void* out, int out_dtype, cudaStream_t st) {
   if (n <= 0) return VMB_OK;
+  if (P >= 32 && n <= (int64_t)P * 4096) {        // tall and narrow: one thread per column would walk P rows alone
+    reduce_partials_tall_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(partial, P, n, out, out_dtype);
+    VMB_LAUNCH_CHECK("reduce_partials_tall_kernel");
+    return VMB_OK;
+  }
   reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, P, n, out, out_dtype);
   VMB_LAUNCH_CHECK("reduce_partials_kernel");
   return VMB_OK;
@@ -588,8 +667,7 @@ extern "C" int vmb_colsum(const void* x, int64_t ld, int64_t M, int N, int dtype
   float* partial = reinterpret_cast<float*>(workspace);
   colsum_partial_kernel<<<dim3((N + 31) / 32, (unsigned)P), 256, 0, st>>>(x, dtype, ld, M, N, per, partial);
   VMB_LAUNCH_CHECK("colsum_partial_kernel");
-  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, (int)P, N, out, out_dtype);
-  VMB_LAUNCH_CHECK("reduce_partials_kernel");
+  { const int rc = reduce_partials(partial, (int)P, N, out, out_dtype, st); if (rc != VMB_OK) return rc; }
   return VMB_OK;
 }
 
@@ -666,14 +744,8 @@ extern "C" int vmb_add_norm_bwd(const void* x, int x_dtype, int64_t ldx, const v
   else VMB_UNSUPPORTED("add_norm_bwd: dim %d > 1152 not supported", dim);
 #undef VMB_ANB
   VMB_LAUNCH_CHECK("add_norm_bwd_kernel");
-  if (dweight) {
-    reduce_partials_kernel<<<(dim + 255) / 256, 256, 0, st>>>(pw, ctas, dim, dweight, VMB_F32);
-    VMB_LAUNCH_CHECK("reduce_partials_kernel");
-  }
-  if (dbias) {
-    reduce_partials_kernel<<<(dim + 255) / 256, 256, 0, st>>>(pb, ctas, dim, dbias, VMB_F32);
-    VMB_LAUNCH_CHECK("reduce_partials_kernel");
-  }
+  if (dweight) { const int rc = reduce_partials(pw, ctas, dim, dweight, VMB_F32, st); if (rc) return rc; }
+  if (dbias) { const int rc = reduce_partials(pb, ctas, dim, dbias, VMB_F32, st); if (rc) return rc; }
   return VMB_OK;
 }
 
@@ -745,8 +817,8 @@ extern "C" int vmb_causal_conv1d_bwd(const void* x, int64_t x_bstride, int64_t x
   const int64_t n = (int64_t)Di * (W + 1);
   float* table = partial;   // in place: row 0 of the partials becomes the sum
   if (B * chunks > 1) {
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, B * chunks, n, table, VMB_F32);
-    VMB_LAUNCH_CHECK("reduce_partials_kernel");
+    const int rc = reduce_partials(partial, B * chunks, n, table, VMB_F32, st);
+    if (rc != VMB_OK) return rc;
   }
   if (dweight) VMB_CUDA(cudaMemcpy2DAsync(dweight, (size_t)W * sizeof(float), table, (size_t)(W + 1) * sizeof(float),
                                           (size_t)W * sizeof(float), Di, cudaMemcpyDeviceToDevice, st));
