@@ -565,12 +565,16 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
                   cudaStream_t st) {
   const int nck = (a.L + 3) / 4;
   dim3 grid(a.Di / 16, a.B);
-  static const bool carve = [] {                    // 11 CTAs x 20 KB per SM need the largest shared-memory split
-    cudaFuncSetAttribute(scan_bwd_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(scan_ckpt_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return true;
-  }();
-  (void)carve;
+  {                                                 // 11 CTAs x 20 KB per SM need the largest shared-memory split
+    static bool carved[64] = {false};
+    int dev = 0;
+    VMB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !carved[dev]) {
+      cudaFuncSetAttribute(scan_bwd_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(scan_ckpt_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (dev >= 0 && dev < 64) carved[dev] = true;
+    }
+  }
   // 3-D maps (channel x token x batch), 16 x 16 boxes; a batch of one still needs a valid outer stride
   BwdMaps m;
   const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B, Di = (uint64_t)a.Di;
