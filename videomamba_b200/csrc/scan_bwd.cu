@@ -1,4 +1,6 @@
-// Backward of the selective scan.
+// Backward of the selective scan: the C entry point, the final reductions, and
+// the any-shape kernels (true fp32, d_state <= 16, any Di / strides).  The bf16 production shapes run the
+// kernels of scan_bwd_fast.cu (dispatched in run() below); both write the same slab / partial layouts.
 //
 // Forward (reference _selective_scan_ref, models/videomamba/mamba_simple.py:30-106):
 //   delta = softplus(draw + bias);  a_t[n] = exp(delta_t A[n]);  h_t = a_t h_{t-1} + delta_t u_t B_t

@@ -16,14 +16,23 @@
 // The vector operand of token i of a 4-token sub-chunk is masked to columns {2i, 2i+1} of the B operand
 // and the four tokens accumulate into one accumulator: afterwards lane tig holds the sums of token
 // t0 + tig of its two channels (its two states for dB / dC) -- no shuffle, no select -- and finalises
-// that token (du, ddelta_raw, dz stores; dB / dC into its slab row).
+// that token.  The mask is an ADDRESS: the operand rows [B | C | dy | delta*u] (bf16, permuted so a lane's
+// two words are one 64-bit load) are adjacent in shared memory with a zero region behind them, and one
+// per-lane displacement (0 for the lanes of columns {2i, 2i+1}, a constant for the others) turns the address
+// of any of them into an address of zeros, 16 banks away from the real row.
 //
-// h_{t-1} in reverse order: pass 1 (ckpt kernel) walks forward and stores the state before every
-// 4-token sub-chunk (1 KB per warp and sub-chunk, coalesced 128-bit stores); pass 2 reloads it one
-// sub-chunk ahead, recomputes the 4 states (keeping h_{t-1} and a_t in registers) and runs the reverse
-// recurrence on them.  Tiles of 16 tokens are staged by 16-byte cp.async, double buffered.
-// Per-channel scalars (softplus, its derivative, the gate terms) are computed once per tile (phase A:
-// lane (g, tig) prepares tokens tig + 4j of channels g, g + 8).  No atomics: deterministic.
+// h_{t-1} in reverse order: state records, 1 KB per (unit, 4 tokens) = the lane registers of the state before
+// every 4-token sub-chunk.  The fused training forward writes them (scan_fast.cu, kCkpt instantiations;
+// vmb_scan_bwd_args.fwd_ckpt); without them pass 1 here (scan_ckpt_fast_kernel) walks the sequence forward
+// first.  Pass 2 streams the records through a ring of three 1 KB cp.async.bulk copies two sub-chunks ahead,
+// recomputes the 4 states of the sub-chunk (a_t and a_t h_{t-1} stay in registers; the h_t-only products --
+// <C_t, h_t>, dC_t -- run there, beside the exponentials) and runs the reverse recurrence on them.
+// Tiles of 16 tokens arrive by TMA (six 16 x 16 boxes on an mbarrier, double buffered; pass 1 uses 16-byte
+// cp.async); per-channel scalars (softplus and its derivative from one exponential, the gate terms) are computed
+// once per tile (phase A: lane (g, tig) prepares tokens tig + 4j of channels g, g + 8); the stage's consumed
+// u / delta / z arrays then stage du / ddelta_raw / dz, written back by TMA stores that clip at L.
+// dB / dC go to one slab row per (unit, token) (summed over the units by scan_bwd.cu), dA / dD / d(dt_bias)
+// to per-batch partials.  No atomics: deterministic.  Measurements: profiles/r02_scan_bwd_fast_ncu.txt.
 #include <algorithm>
 
 #include "internal.h"

@@ -2,6 +2,8 @@
 // tokens (backward of the nn.Linear calls of the mixer, reference mamba_simple.py:333-339, :409,
 // :413-414, :445-446, which the reference differentiates through torch autograd).
 //
+// The production shapes (N or K >= 128, M >= 256) run on tcgen05 (wgrad_tc.cu, dispatched by the entry point
+// below); this mma.sync kernel keeps the rest.
 // The contraction runs over the TOKEN axis, which is the slow axis of both operands, and the output is
 // small (at most 1536 x 384): the forward GEMM (gemm_tc.cu) would need transposed copies of two
 // activation tensors and would run on a handful of CTAs.  Here both operands are read in place,
