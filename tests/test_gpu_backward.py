@@ -120,7 +120,9 @@ def _conv_ref(x, w, b, cs, want_state):
 
 
 @pytest.mark.parametrize("geom", [(2, 150, 40, 4, True, True), (2, 3, 40, 4, True, True), (1, 64, 130, 4, False, False),
-                                  (2, 70, 40, 3, False, True), (3, 1, 24, 4, True, True), (1, 129, 768, 4, True, False)])
+                                  (2, 70, 40, 3, False, True), (3, 1, 24, 4, True, True), (1, 129, 768, 4, True, False),
+                                  # >= 32 per-CTA partial rows (the tall reduction), channel tail of a 256-wide CTA
+                                  (5, 300, 264, 4, True, True)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_backward(geom, dtype):
     B, L, Di, W, with_state, want_state = geom
@@ -445,7 +447,7 @@ def test_refiner_backward():
 
 @pytest.mark.parametrize("shape", [(3137 * 2, 768, 384), (1000, 64, 768), (777, 768, 24), (40, 1536, 384), (5000, 56, 768),
                                    (20001, 1536, 384), (9000, 384, 768), (4097, 576, 1152), (6000, 2304, 576),
-                                   (300, 128, 512), (8191, 1152, 40)])
+                                   (300, 128, 512), (8191, 1152, 40), (2000, 256, 128), (1500, 48, 136)])
 def test_linear_wgrad_kernel(shape):
     """vmb_linear_wgrad against fp32 matmul, including strided operand views and ragged token / tile edges:
     the tcgen05 kernel (csrc/wgrad_tc.cu: N >= 128, M >= 256; MN-major operands read in place) and the mma.sync
