@@ -246,7 +246,8 @@ def test_scan_backward_is_deterministic_and_chunk_invariant():
 
 # ---- mixer with the state carried between chunks (reference scripts/check_streaming_state.py) ----------
 @pytest.mark.parametrize("dtype,d_model,d_state", [(torch.float32, 64, 8), (torch.float32, 96, 16),
-                                                   (torch.bfloat16, 384, 16)])
+                                                   (torch.bfloat16, 384, 16), (torch.bfloat16, 192, 16),
+                                                   (torch.bfloat16, 576, 16)])
 def test_mixer_backward_streaming_state(dtype, d_model, d_state):
     torch.manual_seed(0)
     mx = Mamba(d_model=d_model, d_state=d_state, d_conv=4, expand=2, use_fast_path=False).to(dtype).to(DEV)

@@ -63,6 +63,12 @@ constexpr int oFin = oDY + kTT * 128;     // [j][lane] bf16 pairs {sig_a, sig_b 
 constexpr int oRing = oFin + 4 * 32 * 16; // three 1 KB checkpoint records in flight (bulk copies)
 constexpr int oBar = oRing + 3 * 1024;    // mbarriers: two stages, three ring slots
 constexpr int kSmemBwd = oBar + 64;
+// B / C columns that do not start on a 16-byte boundary (x_dbl behind a dt_rank of 12 or 36: TMA boxes must):
+// ONE box of 40 columns from the aligned column below B_t covers [B | C]; it lands in two extra 1280-byte slots
+// (80-byte rows) behind the plan above and the repack step reads it at the 4-byte granular offset
+constexpr int kWideCols = 40;
+constexpr int kWideBytes = kTT * kWideCols * 2;
+constexpr int oWide = oBar + 128;
 static_assert(oDD % 128 == 0 && oRing % 128 == 0 && oZero % 128 == 0, "smem plan");
 static_assert(11 * (kSmemBwd + 1024) <= 227 * 1024, "11 one-warp CTAs per SM");
 constexpr int kStage1 = 3 * kRaw;         // pass 1 stages u, delta_raw, B only
@@ -163,6 +169,20 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// the same for a column offset that is only 4-byte aligned (B_t rows of x_dbl behind a dt_rank of 12 or 36):
+// 16 rows x 8 words, four 4-byte copies per lane
+__device__ __forceinline__ void stage_rows_w(uint32_t dst, const void* base, int64_t bs, int64_t ts, int b, int col,
+                                             int t0, int L, int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int w = lane + 32 * k, row = w >> 3, cw = w & 7;
+    const int t = t0 + row;
+    const bf16* src = reinterpret_cast<const bf16*>(base) + (int64_t)b * bs + (int64_t)min(t, L - 1) * ts + col + cw * 2;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + row * 32 + cw * 4), "l"(src), "r"(t < L ? 4 : 0)
+                 : "memory");
+  }
+}
+
 // the lane's state registers <-> the checkpoint record of a (unit, sub-chunk): 256 floats, lane l owns
 // floats [4l, 4l+4) and [128 + 4l, 128 + 4l + 4)
 struct Rec { float4 lo, hi; };
@@ -202,7 +222,8 @@ scan_ckpt_fast_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int n
     const uint32_t d = sbase + stg * kStage1;
     stage_rows(d, a.u, a.u_bstride, a.u_tstride, b, cw, tile * kTT, L, lane);
     stage_rows(d + kRaw, a.delta, a.d_bstride, a.d_tstride, b, cw, tile * kTT, L, lane);
-    stage_rows(d + 2 * kRaw, a.bc, a.bc_bstride, a.bc_tstride, b, a.b_off, tile * kTT, L, lane);
+    if (a.b_off & 7) stage_rows_w(d + 2 * kRaw, a.bc, a.bc_bstride, a.bc_tstride, b, a.b_off, tile * kTT, L, lane);
+    else stage_rows(d + 2 * kRaw, a.bc, a.bc_bstride, a.bc_tstride, b, a.b_off, tile * kTT, L, lane);
     cp_commit();
   };
   stage(0, 0);
@@ -257,15 +278,16 @@ scan_ckpt_fast_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int n
 // ---------------------------------------------------------------------------------------------------
 // pass 2: reverse walk
 // ---------------------------------------------------------------------------------------------------
-struct BwdMaps { CUtensorMap u, dl, z, go, bc, du, dd, dz; };
+struct BwdMaps { CUtensorMap u, dl, z, go, bc, du, dd, dz; };   // bc: 16-column boxes, or the 40-column box of kWide
 
 // 168 registers: the register file is split per scheduler (16 K each), so 3 one-warp CTAs per scheduler = 12
 // per SM need <= 170 (1536 units at batch 32 are 10.4 per SM); 184 would leave 2 per scheduler
+template <bool kWide>
 __global__ void __launch_bounds__(32, 12)
 scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps maps, const float* __restrict__ ckpt,
                      int nck, float* __restrict__ bc_slabs, float* __restrict__ pA, float* __restrict__ pD,
                      float* __restrict__ pBias) {
-  __shared__ __align__(1024) uint8_t smem[kSmemBwd];
+  __shared__ __align__(1024) uint8_t smem[kWide ? oWide + 2 * kWideBytes : kSmemBwd];
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
   const int unit = blockIdx.x, cw = unit * 16, b = blockIdx.y;
@@ -310,7 +332,8 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
   // zero region (never written again)
   for (int i = lane; i < kZeroBytes / 16; i += 32) reinterpret_cast<uint4*>(smem + oZero)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
-  const uint32_t kTileBytes = (has_z ? 6 : 5) * kRaw;
+  const uint32_t kTileBytes = (has_z ? 4 : 3) * kRaw + (kWide ? kWideBytes : 2 * kRaw);
+  const int bc_col0 = a.b_off & ~7;                 // kWide: first column of the 40-column box
   auto issue_tile = [&](int tile, int stg) {        // lane 0
     const uint32_t d = sbase + stg * kStage, bar = bar0 + 8 * stg;
     const int t0 = tile * kTT;
@@ -319,8 +342,12 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
     tma_load_3d(d + oDl, &maps.dl, bar, cw, t0, b);
     if (has_z) tma_load_3d(d + oZ, &maps.z, bar, cw, t0, b);
     tma_load_3d(d + oGo, &maps.go, bar, cw, t0, b);
-    tma_load_3d(d + oB, &maps.bc, bar, a.b_off, t0, b);
-    tma_load_3d(d + oC, &maps.bc, bar, a.c_off, t0, b);
+    if constexpr (kWide) {
+      tma_load_3d(sbase + oWide + stg * kWideBytes, &maps.bc, bar, bc_col0, t0, b);
+    } else {
+      tma_load_3d(d + oB, &maps.bc, bar, a.b_off, t0, b);
+      tma_load_3d(d + oC, &maps.bc, bar, a.c_off, t0, b);
+    }
   };
   // checkpoint records: 1 KB bulk copies into a ring of three, two sub-chunks ahead
   const float* rec_g = ckpt + ((int64_t)(b * gridDim.x + unit) * nck) * 256;
@@ -390,8 +417,16 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
     }
     {                                               // B_t / C_t rows -> permuted rows
       const int row = lane >> 1, half = lane & 1;
-      const uint4 vb = *reinterpret_cast<const uint4*>(raw + oB + row * 32 + half * 16);
-      const uint4 vc = *reinterpret_cast<const uint4*>(raw + oC + row * 32 + half * 16);
+      uint4 vb, vc;
+      if constexpr (kWide) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(smem + oWide + stg * kWideBytes + row * (kWideCols * 2) +
+                                                              (a.b_off - bc_col0) * 2 + half * 16);
+        vb = make_uint4(w[0], w[1], w[2], w[3]);
+        vc = make_uint4(w[8], w[9], w[10], w[11]);    // C_t = B_t + 16 columns
+      } else {
+        vb = *reinterpret_cast<const uint4*>(raw + oB + row * 32 + half * 16);
+        vc = *reinterpret_cast<const uint4*>(raw + oC + row * 32 + half * 16);
+      }
       uint32_t* pb = reinterpret_cast<uint32_t*>(smem + oBp + row * 32 + half * 4);
       uint32_t* pc = reinterpret_cast<uint32_t*>(smem + oCp + row * 32 + half * 4);
       pb[0] = vb.x; pb[2] = vb.y; pb[4] = vb.z; pb[6] = vb.w;
@@ -559,8 +594,12 @@ bool scan_bwd_fast_supported(const vmb_scan_bwd_args& a) {
   if (a.dtype != VMB_BF16 || a.N != kN || a.Di % 16 != 0 || a.L < 1 || a.B < 1) return false;
   if (!al16(a.u) || !al16(a.delta) || !al16(a.dout) || !al16(a.bc) || (a.z && !al16(a.z))) return false;
   if (!s8(a.u_bstride) || !s8(a.u_tstride) || !s8(a.d_bstride) || !s8(a.d_tstride) || !s8(a.dout_bstride) ||
-      !s8(a.dout_tstride) || !s8(a.bc_bstride) || !s8(a.bc_tstride) || !s8(a.b_off) || !s8(a.c_off))
+      !s8(a.dout_tstride) || !s8(a.bc_bstride) || !s8(a.bc_tstride) || (a.b_off & 1) || (a.c_off & 1) || a.b_off < 0 ||
+      a.c_off < 0)
     return false;
+  // B / C columns: 16-byte aligned starts, or [B | C] adjacent behind any even offset (one 40-column TMA box;
+  // 4-byte copies in pass 1)
+  if (((a.b_off | a.c_off) & 7) && a.c_off != a.b_off + kN) return false;
   if (a.z && (!s8(a.z_bstride) || !s8(a.z_tstride))) return false;
   if (!al16(a.du) || !al16(a.ddelta) || (a.dz && (!al16(a.dz) || !s8(a.dz_bstride) || !s8(a.dz_tstride)))) return false;
   return true;
@@ -579,7 +618,8 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
     int dev = 0;
     VMB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !carved[dev]) {
-      cudaFuncSetAttribute(scan_bwd_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(scan_bwd_fast_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(scan_bwd_fast_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       cudaFuncSetAttribute(scan_ckpt_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (dev >= 0 && dev < 64) carved[dev] = true;
     }
@@ -587,15 +627,19 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
   // 3-D maps (channel x token x batch), 16 x 16 boxes; a batch of one still needs a valid outer stride
   BwdMaps m;
   const uint64_t L = (uint64_t)a.L, B = (uint64_t)a.B, Di = (uint64_t)a.Di;
-  auto map_of = [&](CUtensorMap* out, const void* p, uint64_t d0, int64_t ts, int64_t bs) {
-    return make_tensor_map_3d_bf16(out, p, d0, L, B, (uint64_t)ts * 2, (uint64_t)(a.B > 1 ? bs : ts * a.L) * 2, 16, kTT, false);
+  const bool wide = ((a.b_off | a.c_off) & 7) != 0;
+  auto map_of = [&](CUtensorMap* out, const void* p, uint64_t d0, int64_t ts, int64_t bs, uint32_t box0 = 16) {
+    return make_tensor_map_3d_bf16(out, p, d0, L, B, (uint64_t)ts * 2, (uint64_t)(a.B > 1 ? bs : ts * a.L) * 2, box0, kTT,
+                                   false);
   };
   int rc;
   if ((rc = map_of(&m.u, a.u, Di, a.u_tstride, a.u_bstride))) return rc;
   if ((rc = map_of(&m.dl, a.delta, Di, a.d_tstride, a.d_bstride))) return rc;
   if (a.z) { if ((rc = map_of(&m.z, a.z, Di, a.z_tstride, a.z_bstride))) return rc; } else m.z = m.u;
   if ((rc = map_of(&m.go, a.dout, Di, a.dout_tstride, a.dout_bstride))) return rc;
-  if ((rc = map_of(&m.bc, a.bc, (uint64_t)std::max(a.b_off, a.c_off) + 16, a.bc_tstride, a.bc_bstride))) return rc;
+  if ((rc = map_of(&m.bc, a.bc, (uint64_t)std::max(a.b_off, a.c_off) + 16, a.bc_tstride, a.bc_bstride,
+                   wide ? kWideCols : 16)))
+    return rc;
   if ((rc = map_of(&m.du, a.du, Di, a.Di, (int64_t)a.L * a.Di))) return rc;
   if ((rc = map_of(&m.dd, a.ddelta, Di, a.Di, (int64_t)a.L * a.Di))) return rc;
   if (a.dz) {
@@ -611,7 +655,8 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
     scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
     VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
   }
-  scan_bwd_fast_kernel<<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
+  if (wide) scan_bwd_fast_kernel<true><<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
+  else scan_bwd_fast_kernel<false><<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
   VMB_LAUNCH_CHECK("scan_bwd_fast_kernel");
   return VMB_OK;
 }
