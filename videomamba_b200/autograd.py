@@ -405,7 +405,10 @@ class FusedScanFn(torch.autograd.Function):
         ckpt = None
         if SAVE_SCAN_STATES:
             B, L, Di = u.shape
-            ckpt = torch.empty(ops.scan_bwd_ckpt_bytes(B, L, Di), dtype=torch.uint8, device=u.device)
+            try:
+                ckpt = torch.empty(ops.scan_bwd_ckpt_bytes(B, L, Di), dtype=torch.uint8, device=u.device)
+            except torch.cuda.OutOfMemoryError:          # no room for the records: the backward recomputes them
+                ckpt = None
         out = ops.selective_scan_fused_tokens_raw(u, z, xdbl, w_dt, A2, R, N, Df, bias, h0, want_last, bwd_ckpt=ckpt)
         ctx.save_for_backward(u, z, xdbl, w_dt, A2, Df, bias, h0, ckpt)
         ctx.meta = (R, N, A.dtype, None if D is None else D.dtype, None if dt_bias is None else dt_bias.dtype)
