@@ -169,6 +169,9 @@ def test_conv_backward(geom, dtype):
     (1, 3, 16, 16, True, True, True, True),
     (2, 65, 64, 16, False, True, True, False),
     (1, 131, 32, 16, True, True, True, True),
+    # few units, long sequence: the reverse walk is split into segments (carry pass + chained g)
+    (1, 700, 32, 16, True, True, True, True),
+    (2, 1030, 16, 16, False, True, False, False),
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_scan_backward(geom, dtype):

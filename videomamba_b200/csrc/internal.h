@@ -51,8 +51,11 @@ int reduce_partials(const float* partial, int P, int64_t n, void* out, int out_d
 // runs the final reductions.
 bool scan_bwd_fast_supported(const vmb_scan_bwd_args& a);
 int64_t scan_bwd_fast_ckpt_bytes(int B, int L, int Di);
+int scan_bwd_fast_segments(int B, int L, int Di, int* seg_tiles);   // sequence split for small batches (1 = none)
+int64_t scan_bwd_fast_seg_bytes(int B, int L, int Di);              // scratch of the split (seg_ws)
+// *nparts = rows of the pA / pD / pBias partials written (segments x batch)
 int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* pA, float* pD, float* pBias,
-                  cudaStream_t st);
+                  float* seg_ws, int* nparts, cudaStream_t st);
 
 // scan_generic.cu
 int scan_generic(const vmb_scan_args& a, cudaStream_t st);

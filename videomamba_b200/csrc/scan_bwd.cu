@@ -335,7 +335,7 @@ __global__ void scan_bwd_bc_kernel(const float* __restrict__ slabs, int nslabs, 
 
 struct Plan {
   int nchunks, nslabs;
-  int64_t ckpt, slabs, pA, pD, pBias, total;
+  int64_t ckpt, slabs, pA, pD, pBias, seg, total;
 };
 Plan plan(int B, int L, int Di, int N) {
   Plan p{};
@@ -346,9 +346,11 @@ Plan plan(int B, int L, int Di, int N) {
   // the larger of the two checkpoint layouts (every 8 tokens here, every 4 in scan_bwd_fast.cu)
   p.ckpt = off; off += up(std::max((int64_t)B * p.nchunks * N * Di * 4, scan_bwd_fast_ckpt_bytes(B, L, Di)));
   p.slabs = off; off += up((int64_t)p.nslabs * B * L * 32 * 4);
-  p.pA = off; off += up((int64_t)B * Di * N * 4);
-  p.pD = off; off += up((int64_t)B * Di * 4);
-  p.pBias = off; off += up((int64_t)B * Di * 4);
+  const int64_t parts = (int64_t)B * (N == 16 ? scan_bwd_fast_segments(B, L, Di, nullptr) : 1);   // (segment, batch) rows
+  p.pA = off; off += up(parts * Di * N * 4);
+  p.pD = off; off += up(parts * Di * 4);
+  p.pBias = off; off += up(parts * Di * 4);
+  p.seg = off; off += up(N == 16 ? scan_bwd_fast_seg_bytes(B, L, Di) : 0);
   p.total = off;
   return p;
 }
@@ -364,8 +366,10 @@ int run(const vmb_scan_bwd_args& a, cudaStream_t st) {
   float* pA = reinterpret_cast<float*>(base + p.pA);
   float* pD = reinterpret_cast<float*>(base + p.pD);
   float* pBias = reinterpret_cast<float*>(base + p.pBias);
+  int nparts = a.B;
   if (scan_bwd_fast_supported(a)) {
-    const int rc = scan_bwd_fast(a, ckpt, slabs, pA, pD, pBias, st);
+    float* seg_ws = scan_bwd_fast_seg_bytes(a.B, a.L, a.Di) > 0 ? reinterpret_cast<float*>(base + p.seg) : nullptr;
+    const int rc = scan_bwd_fast(a, ckpt, slabs, pA, pD, pBias, seg_ws, &nparts, st);
     if (rc != VMB_OK) return rc;
   } else {
     dim3 grid((a.Di + kChan - 1) / kChan, a.B);
@@ -379,9 +383,9 @@ int run(const vmb_scan_bwd_args& a, cudaStream_t st) {
       slabs, p.nslabs, rows, a.N, reinterpret_cast<T*>(a.dbc), a.dbc_tstride, a.b_off, a.c_off);
   VMB_LAUNCH_CHECK("scan_bwd_bc_kernel");
   int rc;
-  if (a.dA && (rc = reduce_partials(pA, a.B, (int64_t)a.Di * a.N, a.dA, VMB_F32, st))) return rc;
-  if (a.dD && (rc = reduce_partials(pD, a.B, a.Di, a.dD, VMB_F32, st))) return rc;
-  if (a.ddt_bias && (rc = reduce_partials(pBias, a.B, a.Di, a.ddt_bias, VMB_F32, st))) return rc;
+  if (a.dA && (rc = reduce_partials(pA, nparts, (int64_t)a.Di * a.N, a.dA, VMB_F32, st))) return rc;
+  if (a.dD && (rc = reduce_partials(pD, nparts, a.Di, a.dD, VMB_F32, st))) return rc;
+  if (a.ddt_bias && (rc = reduce_partials(pBias, nparts, a.Di, a.ddt_bias, VMB_F32, st))) return rc;
   return VMB_OK;
 }
 

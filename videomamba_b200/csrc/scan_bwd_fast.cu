@@ -191,6 +191,18 @@ __device__ __forceinline__ void rec_to(const Rec& r, float2 (&h)[4]) {
   h[2] = make_float2(r.hi.x, r.hi.y); h[3] = make_float2(r.hi.z, r.hi.w);
 }
 
+// Sequence split of the reverse walk (small batches: B * Di / 16 units do not fill the GPU).  g enters the
+// recurrence linearly: over a segment, g_out = P * g_in + G with P = prod a_t = exp2(A2 * sum delta) and G the
+// result for g_in = 0.  scan_bwd_carry_kernel computes (G, sum delta) of every segment but the first from a
+// zero start (recurrence only), scan_bwd_chain_kernel chains g_in from the last segment down, and pass 2 then
+// runs all segments concurrently from their true g_in (the forward states come from the records anyway).
+struct SegPlan {
+  int nseg, seg_tiles;      // segments of seg_tiles 16-token tiles (the last one may be shorter)
+  float* G;                 // [seg][b * nunits + unit][256] fp32, record layout (lane l: floats 4l.., 128 + 4l..)
+  float* S;                 // [seg][b * nunits + unit][16]  sum of delta per channel of the unit
+  float* gin;               // [seg][b * nunits + unit][256] g entering segment seg from the future side
+};
+
 // ---------------------------------------------------------------------------------------------------
 // pass 1: forward walk, state before every 4-token sub-chunk -> ckpt[((b * nunits + unit) * nck + k) * 256]
 // ---------------------------------------------------------------------------------------------------
@@ -276,7 +288,126 @@ scan_ckpt_fast_kernel(const vmb_scan_bwd_args a, float* __restrict__ ckpt, int n
 }
 
 // ---------------------------------------------------------------------------------------------------
-// pass 2: reverse walk
+// sequence split, pass A: g over a segment from a zero start, and the segment's sum of delta
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStageC = 4 * kRaw;         // delta_raw, z, dout, C
+constexpr int kSmemCarry = 2 * kStageC + kTT * 128;
+
+__global__ void __launch_bounds__(32, 16)
+scan_bwd_carry_kernel(const vmb_scan_bwd_args a, const SegPlan sp_) {
+  __shared__ __align__(128) uint8_t smem[kSmemCarry];
+  const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
+  const int unit = blockIdx.x, cw = unit * 16, b = blockIdx.y, seg = blockIdx.z + 1;
+  const int L = a.L;
+  const bool sp = a.softplus != 0, has_z = a.z != nullptr;
+  const int ns[4] = {2 * tig, 2 * tig + 1, 2 * tig + 8, 2 * tig + 9};
+  float2 A2[4], gg[4];
+  {
+    const float* pa = a.A2 + (int64_t)(cw + g) * kN;
+    const float* pb = pa + 8 * kN;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      A2[s] = make_float2(pa[ns[s]], pb[ns[s]]);
+      gg[s] = make_float2(0.f, 0.f);
+    }
+  }
+  const float bias_a = a.dt_bias ? a.dt_bias[cw + g] : 0.f, bias_b = a.dt_bias ? a.dt_bias[cw + g + 8] : 0.f;
+  float sum_a = 0.f, sum_b = 0.f;
+  const int ntiles = (L + kTT - 1) / kTT;
+  const int tile_lo = seg * sp_.seg_tiles, tile_hi = min(ntiles, tile_lo + sp_.seg_tiles);
+  auto stage = [&](int tile, int stg) {
+    const uint32_t d = sbase + stg * kStageC;
+    stage_rows(d, a.delta, a.d_bstride, a.d_tstride, b, cw, tile * kTT, L, lane);
+    if (has_z) stage_rows(d + kRaw, a.z, a.z_bstride, a.z_tstride, b, cw, tile * kTT, L, lane);
+    stage_rows(d + 2 * kRaw, a.dout, a.dout_bstride, a.dout_tstride, b, cw, tile * kTT, L, lane);
+    if (a.c_off & 7) stage_rows_w(d + 3 * kRaw, a.bc, a.bc_bstride, a.bc_tstride, b, a.c_off, tile * kTT, L, lane);
+    else stage_rows(d + 3 * kRaw, a.bc, a.bc_bstride, a.bc_tstride, b, a.c_off, tile * kTT, L, lane);
+    cp_commit();
+  };
+  if (tile_hi > tile_lo) stage(tile_hi - 1, (tile_hi - 1) & 1);
+  uint8_t* const sdy = smem + 2 * kStageC;
+  int posoff[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) posoff[i] = (g ^ (i << 1)) << 4;
+  const int pos_own = (g ^ (tig << 1)) << 4;
+  for (int tile = tile_hi - 1; tile >= tile_lo; --tile) {
+    const int stg = tile & 1;
+    if (tile > tile_lo) { stage(tile - 1, stg ^ 1); cp_wait<1>(); } else { cp_wait<0>(); }
+    __syncwarp();
+    const uint8_t* raw = smem + stg * kStageC;
+    const int nvalid = min(kTT, L - tile * kTT);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = tig + 4 * j;
+      const uint8_t* r = raw + t * 32 + g * 2;
+      float da, db, sa, sb;
+      softplus_sig(ldbf(r) + bias_a, sp, da, sa);
+      softplus_sig(ldbf(r + 16) + bias_b, sp, db, sb);
+      if (t >= nvalid) { da = 0.f; db = 0.f; }
+      sum_a += da;
+      sum_b += db;
+      float dya = ldbf(r + 2 * kRaw), dyb = ldbf(r + 2 * kRaw + 16);          // zero beyond the sequence
+      if (has_z) {
+        const float za = ldbf(r + kRaw), zb = ldbf(r + kRaw + 16);
+        dya *= za * fmaf(tanh_approx(0.5f * za), 0.5f, 0.5f);
+        dyb *= zb * fmaf(tanh_approx(0.5f * zb), 0.5f, 0.5f);
+      }
+      *reinterpret_cast<float4*>(sdy + t * 128 + pos_own) = make_float4(dya, dyb, da, db);
+    }
+    __syncwarp();
+    const uint8_t* sC = raw + 3 * kRaw + 4 * tig;
+#pragma unroll
+    for (int t = kTT - 1; t >= 0; --t) {
+      const float4 yd = *reinterpret_cast<const float4*>(sdy + t * 128 + posoff[t & 3]);
+      const uint32_t cr0 = *reinterpret_cast<const uint32_t*>(sC + t * 32);
+      const uint32_t cr1 = *reinterpret_cast<const uint32_t*>(sC + t * 32 + 16);
+      const float Cv[4] = {bf16lo(cr0), bf16hi(cr0), bf16lo(cr1), bf16hi(cr1)};
+      const float2 dy = make_float2(yd.x, yd.y), dlt = make_float2(yd.z, yd.w);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        gg[s] = __fmul2_rn(__ffma2_rn(dy, bc2(Cv[s]), gg[s]), ex2_pair(__fmul2_rn(dlt, A2[s])));
+    }
+    __syncwarp();
+  }
+  const int64_t slot = (int64_t)seg * gridDim.y * gridDim.x + (int64_t)b * gridDim.x + unit;
+  float4* rec = reinterpret_cast<float4*>(sp_.G + slot * 256) + lane;
+  rec[0] = make_float4(gg[0].x, gg[0].y, gg[1].x, gg[1].y);
+  rec[32] = make_float4(gg[2].x, gg[2].y, gg[3].x, gg[3].y);
+  // sum of delta: the four tig lanes of a channel pair hold partial sums over their tokens
+  sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 1);  sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 1);
+  sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 2);  sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 2);
+  if (tig == 0) {
+    sp_.S[slot * 16 + g] = sum_a;
+    sp_.S[slot * 16 + g + 8] = sum_b;
+  }
+}
+
+// g_in of the last segment = dh_last (or 0); g_in(j - 1) = exp2(A2 * S_j) * g_in(j) + G_j.  One thread per
+// record element: e -> lane (e & 127) >> 2, register q = (e & 3) + 4 (e >> 7): state pair q >> 1, channel q & 1.
+__global__ void scan_bwd_chain_kernel(const vmb_scan_bwd_args a, const SegPlan sp_, int nunits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_seg = (int64_t)a.B * nunits * 256;
+  if (i >= per_seg) return;
+  const int e = (int)(i & 255);
+  const int64_t bu = i >> 8;                        // b * nunits + unit
+  const int unit = (int)(bu % nunits), b = (int)(bu / nunits);
+  const int lane = (e & 127) >> 2, q = (e & 3) + 4 * (e >> 7);
+  const int g = lane >> 2, tig = lane & 3, s = q >> 1;
+  const int ch = unit * 16 + g + 8 * (q & 1);
+  const int n = 2 * tig + (s & 1) + 8 * (s >> 1);
+  const float A2 = a.A2[(int64_t)ch * kN + n];
+  float gv = a.dh_last ? a.dh_last[((int64_t)b * a.Di + ch) * kN + n] : 0.f;
+  for (int j = sp_.nseg - 1; j >= 1; --j) {
+    sp_.gin[(int64_t)j * per_seg + i] = gv;
+    gv = fmaf(exp2f(A2 * sp_.S[((int64_t)j * a.B * nunits + bu) * 16 + g + 8 * (q & 1)]), gv,
+              sp_.G[(int64_t)j * per_seg + i]);
+  }
+  sp_.gin[i] = gv;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 2: reverse walk (of one segment: blockIdx.z)
 // ---------------------------------------------------------------------------------------------------
 struct BwdMaps { CUtensorMap u, dl, z, go, bc, du, dd, dz; };   // bc: 16-column boxes, or the 40-column box of kWide
 
@@ -286,7 +417,7 @@ template <bool kWide>
 __global__ void __launch_bounds__(32, 12)
 scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps maps, const float* __restrict__ ckpt,
                      int nck, float* __restrict__ bc_slabs, float* __restrict__ pA, float* __restrict__ pD,
-                     float* __restrict__ pBias) {
+                     float* __restrict__ pBias, const SegPlan sp_) {
   __shared__ __align__(1024) uint8_t smem[kWide ? oWide + 2 * kWideBytes : kSmemBwd];
   const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
@@ -295,6 +426,7 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
   const bool sp = a.softplus != 0, has_z = a.z != nullptr;
   const int ns[4] = {2 * tig, 2 * tig + 1, 2 * tig + 8, 2 * tig + 9};
   const int64_t ha = ((int64_t)b * Di + cw + g) * kN, hb = ha + 8 * kN;
+  const int seg = blockIdx.z;
   float2 A2[4], gg[4], dA[4];
   {
     const float* pa = a.A2 + (int64_t)(cw + g) * kN;
@@ -304,6 +436,11 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
       A2[s] = make_float2(pa[ns[s]], pb[ns[s]]);
       gg[s] = a.dh_last ? make_float2(a.dh_last[ha + ns[s]], a.dh_last[hb + ns[s]]) : make_float2(0.f, 0.f);
       dA[s] = make_float2(0.f, 0.f);
+    }
+    if (seg < sp_.nseg - 1) {                       // g entering this segment from the later ones
+      const float4* r = reinterpret_cast<const float4*>(
+                            sp_.gin + (((int64_t)seg * gridDim.y + b) * gridDim.x + unit) * 256) + lane;
+      rec_to(Rec{r[0], r[32]}, gg);
     }
   }
   const float bias_a = a.dt_bias ? a.dt_bias[cw + g] : 0.f, bias_b = a.dt_bias ? a.dt_bias[cw + g + 8] : 0.f;
@@ -323,6 +460,8 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
   const int pos_own = (g ^ (tig << 1)) << 4;        // entry of the tokens this lane prepares / finalises (t & 3 == tig)
 
   const int ntiles = (L + kTT - 1) / kTT;
+  const int tile_lo = seg * sp_.seg_tiles, tile_hi = min(ntiles, tile_lo + sp_.seg_tiles);
+  const int k_lo = 4 * tile_lo, k_hi = min(nck, 4 * tile_hi);   // sub-chunks (records) [k_lo, k_hi) of the segment
   const uint32_t bar0 = sbase + oBar;               // +8 s: stage s; +16 + 8 r: ring slot r
   if (lane == 0) {
 #pragma unroll
@@ -356,17 +495,17 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
     bulk_load(sbase + oRing + slot * 1024, rec_g + (int64_t)k * 256, 1024, bar0 + 16 + 8 * slot);
   };
   if (lane == 0) {
-    issue_tile(ntiles - 1, (ntiles - 1) & 1);
-    issue_rec(nck - 1, 0);
-    if (nck > 1) issue_rec(nck - 2, 1);
+    issue_tile(tile_hi - 1, (tile_hi - 1) & 1);
+    issue_rec(k_hi - 1, 0);
+    if (k_hi - 2 >= k_lo) issue_rec(k_hi - 2, 1);
   }
-  int krec = nck - 3;                               // next record to fetch
+  int krec = k_hi - 3;                              // next record to fetch
   int slot_cur = 0, slot_nxt = 2;                   // slot of this sub-chunk's record / of the record fetched now
   uint32_t ring_par = 0;                            // bit r: parity to wait for on slot r
 
   // output rows of the token this lane finalises in the current sub-chunk (4 k + tig), stepped back 4 tokens
   // per sub-chunk: dB / dC slab row (states g, g + 8)
-  int tok = 4 * (nck - 1) + tig;
+  int tok = 4 * (k_hi - 1) + tig;
   float* slab_p = bc_slabs + (((int64_t)unit * a.B + b) * L + tok) * 32 + g;
 
   uint8_t* const sdd = smem + oDD;
@@ -374,7 +513,7 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
   uint4* const sfin = reinterpret_cast<uint4*>(smem + oFin) + lane;
   uint32_t par_stage = 0;                           // bit s: parity to wait for on stage s
 
-  for (int tile = ntiles - 1; tile >= 0; --tile) {
+  for (int tile = tile_hi - 1; tile >= tile_lo; --tile) {
     const int stg = tile & 1;
     mbar_wait(bar0 + 8 * stg, (par_stage >> stg) & 1u);
     par_stage ^= 1u << stg;
@@ -435,7 +574,7 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
     __syncwarp();
     // the stage's raw rows are consumed: its u / delta / z arrays now stage du / ddelta / dz.  The other
     // stage is free for the next tile once the stores of the previous tile have read their rows.
-    if (lane == 0 && tile > 0) {
+    if (lane == 0 && tile > tile_lo) {
       bulk_wait_read_all();
       fence_async_smem();
       issue_tile(tile - 1, stg ^ 1);
@@ -450,7 +589,7 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
 #pragma unroll 1
     for (int c = nsub - 1; c >= 0; --c, sP -= 4 * 32, sD -= 4 * 128, sY -= 4 * 128, so -= 4 * 16) {
       float2 h[4], q[4][4], an[4][4];
-      if (lane == 0 && krec >= 0) {                 // the record two sub-chunks before this one (its slot was read last sub-chunk)
+      if (lane == 0 && krec >= k_lo) {              // the record two sub-chunks before this one (its slot was read last sub-chunk)
         fence_async_smem();
         issue_rec(krec, slot_nxt);
       }
@@ -565,14 +704,15 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
   if (lane == 0) bulk_wait_read_all();
 
   // ---- per-unit results ----------------------------------------------------------------------------------
+  const int64_t part = (int64_t)seg * a.B * Di;     // partial rows: (segment, batch)
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    if (a.dh0) {
+    if (a.dh0 && seg == 0) {
       a.dh0[ha + ns[s]] = gg[s].x;
       a.dh0[hb + ns[s]] = gg[s].y;
     }
-    pA[ha + ns[s]] = dA[s].x;
-    pA[hb + ns[s]] = dA[s].y;
+    pA[part * kN + ha + ns[s]] = dA[s].x;
+    pA[part * kN + hb + ns[s]] = dA[s].y;
   }
   // dD / d(dt_bias): the four tig lanes of a channel pair hold partial sums over their tokens
   dD_a += __shfl_xor_sync(0xffffffffu, dD_a, 1);  dD_b += __shfl_xor_sync(0xffffffffu, dD_b, 1);
@@ -580,7 +720,7 @@ scan_bwd_fast_kernel(const vmb_scan_bwd_args a, const __grid_constant__ BwdMaps 
   dBias_a += __shfl_xor_sync(0xffffffffu, dBias_a, 1);  dBias_b += __shfl_xor_sync(0xffffffffu, dBias_b, 1);
   dBias_a += __shfl_xor_sync(0xffffffffu, dBias_a, 2);  dBias_b += __shfl_xor_sync(0xffffffffu, dBias_b, 2);
   if (tig == 0) {
-    const int64_t o = (int64_t)b * Di + cw + g;
+    const int64_t o = part + (int64_t)b * Di + cw + g;
     pD[o] = dD_a;  pD[o + 8] = dD_b;
     pBias[o] = dBias_a;  pBias[o + 8] = dBias_b;
   }
@@ -609,10 +749,44 @@ int64_t scan_bwd_fast_ckpt_bytes(int B, int L, int Di) {
   return (int64_t)B * ((Di + 15) / 16) * ((L + 3) / 4) * 256 * 4;
 }
 
+// Segments only when the batch alone leaves the GPU short of warps (one warp per 16 channels of a sequence);
+// at least 8 tiles (128 tokens) each: the carry pass costs about a third of the walk it parallelises.
+int scan_bwd_fast_segments(int B, int L, int Di, int* seg_tiles) {
+  const int ntiles = (L + kTT - 1) / kTT;
+  const int64_t units = (int64_t)B * ((Di + 15) / 16);
+  int nseg = 1;
+  if (units < 6ll * sm_count() && ntiles >= 24) {
+    nseg = (int)std::min<int64_t>((10ll * sm_count() + units - 1) / units, ntiles / 8);
+    if (nseg < 3) nseg = 1;
+  }
+  const int per = (ntiles + nseg - 1) / nseg;
+  if (seg_tiles) *seg_tiles = per;
+  return (ntiles + per - 1) / per;
+}
+
+// bytes behind the caller's slabs / partials that the split needs: G, S, gin
+int64_t scan_bwd_fast_seg_bytes(int B, int L, int Di) {
+  const int nseg = scan_bwd_fast_segments(B, L, Di, nullptr);
+  if (nseg <= 1) return 0;
+  const int64_t slots = (int64_t)nseg * B * ((Di + 15) / 16);
+  return slots * (256 + 16 + 256) * 4;
+}
+
 int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* pA, float* pD, float* pBias,
-                  cudaStream_t st) {
+                  float* seg_ws, int* nparts, cudaStream_t st) {
   const int nck = (a.L + 3) / 4;
-  dim3 grid(a.Di / 16, a.B);
+  SegPlan sp{};
+  sp.nseg = seg_ws ? scan_bwd_fast_segments(a.B, a.L, a.Di, &sp.seg_tiles) : 1;
+  if (sp.nseg <= 1) { sp.nseg = 1; sp.seg_tiles = (a.L + kTT - 1) / kTT; }
+  const int nunits = a.Di / 16;
+  {
+    const int64_t slots = (int64_t)sp.nseg * a.B * nunits;
+    sp.G = seg_ws;
+    sp.S = seg_ws ? seg_ws + slots * 256 : nullptr;
+    sp.gin = seg_ws ? seg_ws + slots * (256 + 16) : nullptr;
+  }
+  *nparts = sp.nseg * a.B;                          // rows of the dA / dD / d(dt_bias) partials
+  dim3 grid(nunits, a.B, sp.nseg);
   {                                                 // 11 CTAs x 20 KB per SM need the largest shared-memory split
     static bool carved[64] = {false};
     int dev = 0;
@@ -652,11 +826,18 @@ int scan_bwd_fast(const vmb_scan_bwd_args& a, float* ckpt, float* slabs, float* 
     VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a.fwd_ckpt) % 16 == 0, "selective_scan_bwd: fwd_ckpt not 16-byte aligned");
     ckpt = const_cast<float*>(a.fwd_ckpt);
   } else {
-    scan_ckpt_fast_kernel<<<grid, 32, 0, st>>>(a, ckpt, nck);
+    scan_ckpt_fast_kernel<<<dim3(nunits, a.B), 32, 0, st>>>(a, ckpt, nck);
     VMB_LAUNCH_CHECK("scan_ckpt_fast_kernel");
   }
-  if (wide) scan_bwd_fast_kernel<true><<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
-  else scan_bwd_fast_kernel<false><<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias);
+  if (sp.nseg > 1) {
+    scan_bwd_carry_kernel<<<dim3(nunits, a.B, sp.nseg - 1), 32, 0, st>>>(a, sp);
+    VMB_LAUNCH_CHECK("scan_bwd_carry_kernel");
+    const int64_t n = (int64_t)a.B * nunits * 256;
+    scan_bwd_chain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, sp, nunits);
+    VMB_LAUNCH_CHECK("scan_bwd_chain_kernel");
+  }
+  if (wide) scan_bwd_fast_kernel<true><<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias, sp);
+  else scan_bwd_fast_kernel<false><<<grid, 32, 0, st>>>(a, m, ckpt, nck, slabs, pA, pD, pBias, sp);
   VMB_LAUNCH_CHECK("scan_bwd_fast_kernel");
   return VMB_OK;
 }
