@@ -214,6 +214,42 @@ def test_scan_backward(geom, dtype):
             _check(got[name], want[name], tol, name)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_scan_backward_bf16_kernels_against_fp32_kernels_on_random_geometries(seed):
+    """The bf16 production kernels (csrc/scan_bwd_fast.cu) against the true-fp32 kernels (csrc/scan_bwd.cu) on the
+    same bf16-representable inputs: lengths around the 4-token sub-chunk / 16-token tile / segment boundaries,
+    B / C columns behind dt_rank 12 / 24 / 36 and in a plain (B | C) tensor, every option combination."""
+    import random
+    rng = random.Random(seed)
+    bf = torch.bfloat16
+    for case in range(12):
+        B = rng.choice([1, 2, 3])
+        L = rng.choice([1, 2, 3, 4, 5, 15, 16, 17, 33, 63, 64, 65, 100, 385, 400, 777])
+        Di = rng.choice([16, 32, 48, 80])
+        R = rng.choice([12, 24, 36, 0])
+        N = 16
+        cols = (R + 2 * N + 15) // 16 * 16 if R else 2 * N
+        with_z, with_h0, with_D, with_last = (rng.random() < 0.7 for _ in range(4))
+        g = torch.Generator(device=DEV).manual_seed(100 * seed + case)
+        rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+        u, z, dout = rn(B, L, Di).to(bf), rn(B, L, Di).to(bf), rn(B, L, Di).to(bf)
+        delta = (0.5 * rn(B, L, Di) - 2).to(bf)
+        bc = rn(B, L, cols).to(bf)
+        A2 = -(torch.rand(Di, N, device=DEV, generator=g) * 8 + 0.1) * 1.4427
+        D = rn(Di) if with_D else None
+        bias = 0.3 * rn(Di)
+        h0 = rn(B, Di, N) if with_h0 else None
+        dlast = rn(B, Di, N) if with_last else None
+        zz = z if with_z else None
+        f32 = lambda t: None if t is None else t.float()
+        fast = ag._scan_bwd(u, delta, A2, bc, R, R + N, N, D, zz, bias, True, h0, dout, dlast, with_h0)
+        ref = ag._scan_bwd(f32(u), f32(delta), A2, f32(bc), R, R + N, N, D, f32(zz), bias, True, h0, f32(dout), dlast,
+                           with_h0)
+        for name, a, b in zip(("du", "ddelta", "dz", "dbc", "dA", "dD", "dbias", "dh0"), fast, ref):
+            if a is not None:
+                assert rel_err(a, b) <= 2e-2, (case, B, L, Di, R, name, rel_err(a, b))
+
+
 def test_scan_backward_is_deterministic_and_chunk_invariant():
     """No atomics: two runs are bit-identical; splitting the sequence in two calls with the state (and its
     gradient) carried between them gives the gradients of the single call."""
