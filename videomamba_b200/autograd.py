@@ -52,7 +52,8 @@ def colsum(x2: Tensor, out_dtype: torch.dtype) -> Tensor:
     lib = _lib.load()
     M, N = x2.shape
     out = torch.empty(N, dtype=torch.float32, device=x2.device)
-    nbytes = lib.vmb_colsum_workspace_bytes(M, N)
+    with _on_device(x2):
+        nbytes = lib.vmb_colsum_workspace_bytes(M, N)
     ws = _ws(nbytes, x2)
     with _on_device(x2):
         rc = lib.vmb_colsum(_p(x2), x2.stride(0) if M > 1 else N, M, N, _dt(x2), _p(out), VMB_F32, _p(ws),
@@ -75,7 +76,8 @@ def linear_wgrad(dy2: Tensor, x2: Tensor, out_dtype: torch.dtype) -> Tensor:
               and out_dtype in (torch.bfloat16, torch.float32))
     if direct:
         dw = torch.empty((N, K), dtype=out_dtype, device=dy2.device)
-        nbytes = lib.vmb_linear_wgrad_workspace_bytes(M, N, K)
+        with _on_device(dy2):          # the split over the tokens follows the SM count of the tensors' device
+            nbytes = lib.vmb_linear_wgrad_workspace_bytes(M, N, K)
         ws = _ws(nbytes, dy2)
         with _on_device(dy2):
             rc = lib.vmb_linear_wgrad(_p(dy2), lds[0], _p(x2), lds[1], _p(dw), _dt(dw), M, N, K, _p(ws), nbytes,
@@ -157,7 +159,8 @@ class AddNormFn(torch.autograd.Function):
         dres = torch.empty((rows, dim), dtype=res2.dtype, device=x2.device) if res2 is not None else None
         dw = torch.empty(dim, dtype=torch.float32, device=x2.device)
         db = torch.empty(dim, dtype=torch.float32, device=x2.device) if bias_dtype is not None else None
-        nbytes = lib.vmb_add_norm_bwd_workspace_bytes(rows, dim)
+        with _on_device(x2):
+            nbytes = lib.vmb_add_norm_bwd_workspace_bytes(rows, dim)
         ws = _ws(nbytes, x2)
         w = weight.contiguous()
         with _on_device(x2):
@@ -275,7 +278,8 @@ class ConvFn(torch.autograd.Function):
         dcs_in = torch.empty_like(cs) if cs is not None and ctx.needs_input_grad[3] else None
         dw = torch.empty((Di, W), dtype=torch.float32, device=x.device)
         db = torch.empty(Di, dtype=torch.float32, device=x.device) if bias is not None else None
-        nbytes = lib.vmb_causal_conv1d_bwd_workspace_bytes(B, L, Di, W)
+        with _on_device(x):
+            nbytes = lib.vmb_causal_conv1d_bwd_workspace_bytes(B, L, Di, W)
         ws = _ws(nbytes, x)
         with _on_device(x):
             rc = lib.vmb_causal_conv1d_bwd(
@@ -348,7 +352,8 @@ def _scan_bwd(u, delta, A2, bc, b_off, c_off, N, Df, z, bias, softplus, h0, dout
     if dh_last is not None:
         dh_last = dh_last.float().contiguous()
     h0c = None if h0 is None else h0.contiguous()
-    nbytes = lib.vmb_selective_scan_bwd_workspace_bytes(B, L, Di, N)
+    with _on_device(u):                # the segment plan follows the SM count of the tensors' device
+        nbytes = lib.vmb_selective_scan_bwd_workspace_bytes(B, L, Di, N)
     ws = _ws(nbytes, u)
     a = ScanBwdArgs()
     a.u, a.u_bstride, a.u_tstride = u.data_ptr(), u.stride(0), u.stride(1)
