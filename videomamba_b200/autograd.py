@@ -426,16 +426,22 @@ class FusedScanFn(torch.autograd.Function):
         u, z, xdbl, w_dt, A2, Df, bias, h0, ckpt = ctx.saved_tensors
         R, N, A_dtype, D_dtype, bias_dtype = ctx.meta
         B, L, Di = u.shape
-        dt_low = xdbl[..., :R]
-        delta = ops.linear_raw(dt_low, w_dt)                                  # (B, L, Di), bf16
+        # dt_rank 12 / 36 (Tiny, Middle) is not a multiple of 8, which the tensor-core kernels need for their
+        # 16-byte rows: run the three dt projections on R8 = round_up(R, 8) columns -- the x_dbl columns
+        # [R, R8) belong to B_t, so the weight gets zero columns there (exact) and the weight gradient's extra
+        # columns are dropped
+        R8 = (R + 7) // 8 * 8
+        w8 = w_dt if R8 == R else torch.nn.functional.pad(w_dt, (0, R8 - R))    # (Di, R8)
+        dt_low8 = xdbl[..., :R8]
+        delta = ops.linear_raw(dt_low8, w8)                                    # (B, L, Di), bf16
         du, dd, dz, dbc, dA, dD, dbias, dh0 = _scan_bwd(u, delta, A2, xdbl, R, R + N, N, Df, z, bias, True, h0,
                                                          dout, dh_last, ctx.needs_input_grad[7], ctx.arena, ckpt)
         dd2 = dd.reshape(B * L, Di)
-        w_t = transpose2d(w_dt)[:, :Di]                                       # (R, Di)
-        dbc[..., :R] = ops.linear_raw(dd2, w_t).reshape(B, L, R)              # d dt_low
+        w_t = transpose2d(w8)[:, :Di]                                          # (R8, Di), rows >= R zero
+        dbc[..., :R] = ops.linear_raw(dd2, w_t).reshape(B, L, R8)[..., :R]     # d dt_low
         dw_dt = None
         if ctx.needs_input_grad[3]:
-            dw_dt = linear_wgrad(dd2, _rows(dt_low, R), w_dt.dtype)           # (Di, R)
+            dw_dt = linear_wgrad(dd2, _rows(dt_low8, R8), w_dt.dtype)[:, :R]   # (Di, R)
         return (du, dz, dbc, dw_dt, dA.to(A_dtype), None if dD is None else dD.to(D_dtype),
                 None if dbias is None else dbias.to(bias_dtype), dh0, None, None, None, None)
 
