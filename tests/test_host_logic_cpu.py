@@ -308,3 +308,40 @@ def test_mixer_weight_cache_invalidation_hooks():
     assert m.weights_key() == m._weights_key
     m.refresh_weights()
     assert m._weights is None
+
+
+def test_split_xz_gradient_arena():
+    """``autograd.XZGrad``: the backward nodes of the x / z halves write into one d(xz) buffer and ``SplitXZ.backward``
+    returns it without copies; anything else (a foreign gradient, a missing half) takes the copying path and
+    gives the same values (host logic only: no kernel runs here)."""
+    from videomamba_b200 import autograd as ag
+    B, L, Di = 2, 5, 4
+    leaf = torch.randn(B, L, 2 * Di, requires_grad=True)
+    xz = leaf * 1.0                       # a non-leaf, so a hook sees the tensor SplitXZ.backward returned
+    seen = []
+    xz.register_hook(lambda g: seen.append(g.data_ptr()))
+    # (1) both halves written into the arena -> the buffer itself comes back
+    arena = ag.XZGrad(Di)
+    x, z = ag.SplitXZ.apply(xz, Di, arena)
+    gx = arena.half(0, B, L, xz.dtype, xz.device)
+    gz = arena.half(1, B, L, xz.dtype, xz.device)
+    buf = arena.buf
+    gx.copy_(torch.full((B, L, Di), 2.0))
+    gz.copy_(torch.full((B, L, Di), 3.0))
+    assert arena.owns(0, gx) and arena.owns(1, gz) and not arena.owns(0, gz)
+    torch.autograd.backward([x, z], [gx, gz])
+    assert seen == [buf.data_ptr()] and arena.buf is None
+    assert torch.equal(leaf.grad[..., :Di], torch.full((B, L, Di), 2.0))
+    assert torch.equal(leaf.grad[..., Di:], torch.full((B, L, Di), 3.0))
+    # (2) a gradient that does not live in the arena, and a missing half: copied / zero-filled
+    xz2 = torch.randn(B, L, 2 * Di, requires_grad=True)
+    arena2 = ag.XZGrad(Di)
+    x2, z2 = ag.SplitXZ.apply(xz2, Di, arena2)
+    foreign = torch.full((B, L, Di), 5.0)
+    torch.autograd.backward([x2], [foreign])
+    assert torch.equal(xz2.grad[..., :Di], foreign) and torch.count_nonzero(xz2.grad[..., Di:]) == 0
+    # (3) without an arena the node behaves the same
+    xz3 = torch.randn(B, L, 2 * Di, requires_grad=True)
+    x3, z3 = ag.SplitXZ.apply(xz3, Di)
+    torch.autograd.backward([x3, z3], [foreign, 2 * foreign])
+    assert torch.equal(xz3.grad, torch.cat([foreign, 2 * foreign], dim=-1))
