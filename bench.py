@@ -62,7 +62,10 @@ STREAM_TOTAL_FRAMES = 256      # stream64: a stream is reset after 4 chunks (tem
 # Instruction model of the one-warp scan kernel (general A), from its SASS (profiles/r02_scan_sass_*.txt):
 # the loop body of one 16-token tile is 789 warp instructions, 152 of them MUFU (geometric A: 790 / 88); a
 # MUFU occupies the XU pipe for 8 clk and costs ~4.6 issue slots (profiles/r01_mufu_issue_microbench.txt).
-SCAN_TILE_INSTR = {"general": (789, 152), "geometric": (790, 88)}
+# With SiLU(z) applied by the in_proj epilogue (the default; z_gate kernels) the tile loses 26 / 33 instructions, 8 of
+# them MUFU (same SASS listing, tools/scan_tile_instr.py).
+SCAN_TILE_INSTR = {"general": (789, 152), "geometric": (790, 88),
+                   "general+gate": (763, 144), "geometric+gate": (757, 80)}
 MUFU_ISSUE_SLOTS, MUFU_XU_CLK = 4.6, 8.0
 
 
@@ -81,6 +84,8 @@ def parse_args():
                     help="perturbed: general A (trained-checkpoint-like); init: reference random init")
     ap.add_argument("--in-flight", type=int, default=None,
                     help="steps kept in flight on separate CUDA streams (1 = strictly serial steps)")
+    ap.add_argument("--gate-in-scan", action="store_true",
+                    help="A/B: SiLU(z) inside the scan instead of the in_proj epilogue (Mamba.gate_in_proj = False)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=4, help="clips in the CPU baseline sample")
@@ -473,7 +478,8 @@ def scan_op_alone(args, B, L, Di, R, N, dev, iters=10):
                            + 0.1 * torch.randn(Di, N, generator=g, device=dev))
         A2 = (A * ops.LOG2E).contiguous()
         fn = lambda: ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias,
-                                                     a_geometric=name == "geometric")
+                                                     a_geometric=name == "geometric",
+                                                     z_gate=not args.gate_in_scan)    # as the step runs it
         out[name] = {}
         for label, nstreams in (("alone", 1), ("three_in_flight", 3)):
             streams = [torch.cuda.Stream(dev) for _ in range(nstreams)]
@@ -522,6 +528,9 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
 
     dtype = torch.bfloat16
+    if args.gate_in_scan:
+        from videomamba_b200.mixer import Mamba
+        Mamba.gate_in_proj = False
     model = build_model(args, dtype, dev)
     B = per_gpu_batch(args, world)
     nlanes = max(1, args.in_flight)
@@ -721,7 +730,7 @@ def run_ours(args):
 
     def issue_bound(ms_per_launch, which):
         """Instruction-issue and XU-pipe floors of one launch: warp-tokens x slots / (4 schedulers x SMs) / clock."""
-        instr, mufu = SCAN_TILE_INSTR[which]
+        instr, mufu = SCAN_TILE_INSTR[which if args.gate_in_scan else which + "+gate"]
         slots = (instr - mufu) / 16.0 + mufu / 16.0 * MUFU_ISSUE_SLOTS
         xu = mufu / 16.0 * MUFU_XU_CLK
         warp_tokens = tokens * (Di // 16)
@@ -807,6 +816,7 @@ def run_ours(args):
                    "weights": ("random init, A_log/dt_bias/temporal embedding perturbed (general-A "
                                "kernels)" if args.weights == "perturbed" else "reference random init"),
                    "parallelism": f"batch-sharded replicas x{world}, no collective",
+                   "gate": "SiLU(z) inside the scan" if args.gate_in_scan else "SiLU(z) in the in_proj epilogue",
                    "steps_in_flight": len(lanes),
                    "serial_ms_per_step": serial_ms,
                    "serial_value": world * wl.units / (serial_ms * 1e-3),

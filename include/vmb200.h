@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VMB_ABI_VERSION 4
+#define VMB_ABI_VERSION 5
 
 /* element types */
 #define VMB_F32 0
@@ -88,6 +88,15 @@ VMB_API int vmb_gate_blend_fwd(const void* g1, const void* g2 /* nullable */, co
 VMB_API int vmb_linear_fwd(const void* A, int64_t lda, const void* W, int64_t ldw,
                    const void* bias,                              /* nullable, same dtype */
                    void* C, int64_t ldc, int64_t M, int N, int K, int dtype,
+                   vmb_stream_t stream);
+/* The same projection with SiLU applied to the output columns [act_from, N) in the epilogue (on the fp32
+ * accumulator, before the one rounding to bf16).  in_proj with act_from = d_inner stores x | SiLU(z): the gate
+ * of mamba_simple.py:423-435 computed where the accumulator already sits in registers, so the fused scan
+ * (vmb_fused_scan_args.z_gate) only multiplies.  Tensor-core kernel only: VMB_BF16, TMA-compatible operands,
+ * act_from a multiple of 64 (or == N: no activation); VMB_ERR_UNSUPPORTED otherwise. */
+VMB_API int vmb_linear_fwd_act(const void* A, int64_t lda, const void* W, int64_t ldw,
+                   const void* bias,                              /* nullable, same dtype */
+                   void* C, int64_t ldc, int64_t M, int N, int K, int dtype, int act_from,
                    vmb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -207,6 +216,9 @@ typedef struct vmb_fused_scan_args {
    * aligned) that receive the state before every 4-token group -- handed to vmb_selective_scan_bwd as
    * vmb_scan_bwd_args.fwd_ckpt, the backward then skips its own forward pass over the sequence. */
   float* bwd_ckpt;
+  /* z_gate != 0: `z` already holds SiLU(z) (vmb_linear_fwd_act applied it in the in_proj epilogue): the
+   * scan multiplies by it as it is.  0 = `z` is the raw in_proj output (mamba_simple.py:369). */
+  int32_t z_gate;
 } vmb_fused_scan_args;
 VMB_API int64_t vmb_fused_scan_workspace_bytes(int B, int L, int Di, int N);
 VMB_API int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* args, vmb_stream_t stream);
@@ -291,6 +303,10 @@ typedef struct vmb_mixer_args {
   int32_t fuse_conv_xproj; /* != 0: stateless forward walks run conv + x_proj as ONE kernel (vmb_conv_xproj_fwd):
                             * less HBM traffic and faster for a single forward in flight, slower when several
                             * forwards share the GPU (it fills the SMs' shared memory); bit-identical results */
+  int32_t gate_in_proj;    /* != 0: on the fast path in_proj stores SiLU(z) (vmb_linear_fwd_act) and the scan multiplies
+                            * by it as it is: one activation less in the scan's instruction stream; the gate is
+                            * rounded to bf16 after the activation instead of before it (same bf16 tolerance,
+                            * not bit-identical to gate_in_proj == 0) */
 } vmb_mixer_args;
 VMB_API int64_t vmb_mixer_workspace_bytes(int B, int L, int D, int Di, int N, int R, int dtype);
 VMB_API int vmb_mixer_fwd(const vmb_mixer_args* args, vmb_stream_t stream);

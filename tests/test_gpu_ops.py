@@ -305,9 +305,9 @@ def test_selective_scan_fn_dropin(dtype, geom):
     assert rel_err(got, want) <= _tol(dtype)
 
 
-def _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, h0, reverse, R, N):
+def _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, h0, reverse, R, N, z_gate=False):
     """float64 evaluation of the fused op on the SAME bf16 inputs (mamba_simple.py:413-414 without
-    the intermediate rounding of delta, then :30-106)."""
+    the intermediate rounding of delta, then :30-106).  ``z_gate``: ``z`` is the gate itself."""
     if reverse:
         u, z, xdbl = u.flip(1), z.flip(1), xdbl.flip(1)
     u, z, xd = u.double(), z.double(), xdbl.double()
@@ -320,7 +320,7 @@ def _fused_scan_ref64(u, z, xdbl, w_dt, A, Dp, bias, h0, reverse, R, N):
     for t in range(L):
         h = torch.exp(dt[:, t, :, None] * Ad) * h + (dt[:, t] * u[:, t])[:, :, None] * Bm[:, t, None, :]
         ys[:, t] = (h * Cm[:, t, None, :]).sum(-1)
-    y = (ys + u * Dp.double()) * (z * torch.sigmoid(z))
+    y = (ys + u * Dp.double()) * (z if z_gate else z * torch.sigmoid(z))
     return (y.flip(1) if reverse else y), h
 
 
@@ -384,6 +384,93 @@ def test_fused_scan_against_float64(geom, reverse, geometric):
     got = ops.selective_scan_fused_tokens(xz[..., :Di], xz[..., Di:], xdbl, w_dt, A2, R, N, Dp, bias,
                                           reverse=reverse, a_geometric=geometric)
     assert rel_err(got, want) <= 6e-3
+
+
+@pytest.mark.parametrize("geom", [(2, 777, 768, 24, 64), (3, 33, 1152, 36, 80), (8, 100, 768, 24, 64),
+                                  (16, 50, 384, 12, 48), (32, 64, 768, 24, 64), (20, 100, 1152, 36, 80)])
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("geometric", [False, True])
+def test_fused_scan_with_stored_gate(geom, reverse, geometric):
+    """``z_gate``: z holds SiLU(z) already (the in_proj epilogue of ``vmb_linear_fwd_act`` wrote it) and the
+    kernels -- one warp and two warps per unit, both evaluators, both directions, the sequence split -- multiply
+    by it as it is: against float64 on identical inputs, and bit-identical to the raw-z kernels wherever the
+    gate is not involved (the last state)."""
+    Bsz, L, Di, R, Xp = geom
+    N = 16
+    u, z, xdbl, w_dt, A, Dp, bias, h0, gen = _fused_scan_case(geom, geometric)
+    A2 = (A * ops.LOG2E).contiguous()
+    gate = torch.nn.functional.silu(z.float()).to(torch.bfloat16)
+    for init in (None, h0):
+        want, want_h = _fused_scan_ref64(u, gate, xdbl, w_dt, A, Dp, bias, init, reverse, R, N, z_gate=True)
+        got, got_h = ops.selective_scan_fused_tokens(u, gate, xdbl, w_dt, A2, R, N, Dp, bias, init, want_last=True,
+                                                     reverse=reverse, a_geometric=geometric, z_gate=True)
+        assert rel_err(got, want) <= 6e-3, rel_err(got, want)
+        raw, raw_h = ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, init, want_last=True,
+                                                     reverse=reverse, a_geometric=geometric)
+        assert torch.equal(got_h, raw_h)
+        assert rel_err(got, raw) <= 8e-3, rel_err(got, raw)      # the gate's own rounding to bf16
+    ones = torch.ones_like(z)                                     # gate 1: the ungated sum, whatever z would do
+    a = ops.selective_scan_fused_tokens(u, ones, xdbl, w_dt, A2, R, N, Dp, bias, reverse=reverse,
+                                        a_geometric=geometric, z_gate=True)
+    b = ops.selective_scan_fused_tokens(u, 2 * ones, xdbl, w_dt, A2, R, N, Dp, bias, reverse=reverse,
+                                        a_geometric=geometric, z_gate=True)
+    assert torch.equal((2 * a.float()).to(torch.bfloat16), b)    # exact: a power of two commutes with the rounding
+
+
+@pytest.mark.parametrize("shape", [(1000, 1536, 384, 768), (515, 768, 192, 384), (300, 1536, 384, 768),
+                                   (4100, 2304, 576, 1152), (777, 1536, 384, 0), (2000, 512, 256, 448)])
+def test_projection_activation_epilogue(shape):
+    """``vmb_linear_fwd_act``: SiLU on the output columns [silu_from, N) inside the tensor-core projection (CTA
+    pairs from 512 rows on, the one-CTA kernel below): the columns before ``silu_from`` keep the bits of the plain
+    projection, the others are SiLU of the fp32 accumulator rounded once."""
+    M, N, K, frm = shape
+    gen = torch.Generator().manual_seed(M + N)
+    bf = torch.bfloat16
+    x = _rand(gen, M, K, dtype=bf).to(DEV)
+    w = _rand(gen, N, K, dtype=bf, scale=K ** -0.5).to(DEV)
+    b = _rand(gen, N, dtype=bf).to(DEV)
+    for bias in (None, b):
+        plain = ops.linear(x, w, bias)
+        got = ops.linear_act(x, w, bias, silu_from=frm)
+        assert torch.equal(got[:, :frm], plain[:, :frm])
+        acc = x.double() @ w.double().t() + (0 if bias is None else bias.double())
+        want = torch.nn.functional.silu(acc[:, frm:])
+        assert rel_err(got[:, frm:], want) <= 6e-3, rel_err(got[:, frm:], want)
+        # rounding after the activation: closer to the exact gate than SiLU of the rounded projection
+        late = (torch.nn.functional.silu(plain[:, frm:].double()) - want).abs().mean()
+        assert (got[:, frm:].double() - want).abs().mean() <= 1.05 * late
+    assert torch.equal(ops.linear_act(x, w, b, silu_from=N), ops.linear(x, w, b))
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        ops.linear_act(x, w, b, silu_from=frm + 8)
+    with pytest.raises(RuntimeError, match="tensor-core"):
+        ops.linear_act(x.float(), w.float(), b.float(), silu_from=frm)
+
+
+def test_mixer_gate_in_proj_matches_gate_in_scan():
+    """``vmb_mixer_args.gate_in_proj`` (default of the modules): the z half of in_proj leaves the GEMM as SiLU(z) and
+    the scan multiplies by it; against the path that applies SiLU inside the scan the outputs differ only by the
+    position of one bf16 rounding, the states not at all; shapes the tensor-core projection does not take keep
+    the raw z silently."""
+    from video_mamba.mamba_simple import Mamba
+    torch.manual_seed(5)
+    for d_model, Bsz, L in ((384, 4, 300), (192, 2, 77), (576, 2, 130)):
+        mx = Mamba(d_model=d_model, use_fast_path=False).to(DEV).to(torch.bfloat16)
+        x = torch.randn(Bsz, L, d_model, device=DEV).to(torch.bfloat16)
+        w = mx._kernel_weights()
+        with torch.no_grad():
+            a, ca, sa = ops.mixer_fwd(w, x, None, None, True, True, gate_in_proj=True)
+            b, cb, sb = ops.mixer_fwd(w, x, None, None, True, True, gate_in_proj=False)
+            ra, _, _ = ops.mixer_fwd(w, x, reverse=True, gate_in_proj=True)
+            rb, _, _ = ops.mixer_fwd(w, x, reverse=True, gate_in_proj=False)
+        assert torch.equal(ca, cb) and torch.equal(sa, sb)
+        assert not torch.equal(a, b)
+        assert rel_err(a, b) <= 8e-3 and rel_err(ra, rb) <= 8e-3, (rel_err(a, b), rel_err(ra, rb))
+    mx = Mamba(d_model=40, use_fast_path=False).to(DEV).to(torch.bfloat16)      # Di 80: generic kernels
+    x = torch.randn(2, 9, 40, device=DEV).to(torch.bfloat16)
+    with torch.no_grad():
+        a, _, _ = ops.mixer_fwd(mx._kernel_weights(), x, gate_in_proj=True)
+        b, _, _ = ops.mixer_fwd(mx._kernel_weights(), x, gate_in_proj=False)
+    assert torch.equal(a, b)
 
 
 def test_fused_scan_layouts_agree_bitwise():

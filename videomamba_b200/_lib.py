@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvmb200.so")
 
 VMB_F32, VMB_BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_int32, c_int64, c_float = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float
 
@@ -49,7 +49,7 @@ class FusedScanArgs(C.Structure):
         ("Rp", c_int32), ("Xp", c_int32), ("reverse", c_int32),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("a_geometric", c_int32), ("tune", c_int32), ("frame_len", c_int32),
-        ("bwd_ckpt", c_void_p),
+        ("bwd_ckpt", c_void_p), ("z_gate", c_int32),
     ]
 
 
@@ -71,7 +71,7 @@ class MixerArgs(C.Structure):
         ("R", c_int32), ("W", c_int32),
         ("dtype", c_int32), ("reverse", c_int32), ("path", c_int32),
         ("a_geometric", c_int32), ("scan_tune", c_int32), ("frame_len", c_int32),
-        ("fuse_conv_xproj", c_int32),
+        ("fuse_conv_xproj", c_int32), ("gate_in_proj", c_int32),
     ]
 
 
@@ -126,6 +126,8 @@ SIGNATURES = {
                                    c_void_p]),
     "vmb_linear_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                c_int64, c_int, c_int, c_int, c_void_p]),
+    "vmb_linear_fwd_act": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                   c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "vmb_causal_conv1d_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

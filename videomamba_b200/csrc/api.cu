@@ -166,6 +166,22 @@ extern "C" int vmb_linear_fwd(const void* A, int64_t lda, const void* W, int64_t
   return linear_simt(A, lda, W, ldw, bias, C, ldc, M, N, K, dtype, st);
 }
 
+extern "C" int vmb_linear_fwd_act(const void* A, int64_t lda, const void* W, int64_t ldw,
+                                  const void* bias, void* C, int64_t ldc, int64_t M, int N, int K,
+                                  int dtype, int act_from, vmb_stream_t stream) {
+  VMB_CHECK_ARG(dtype_ok(dtype), "linear_act: bad dtype %d", dtype);
+  VMB_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_act: bad sizes M=%lld N=%d K=%d", (long long)M, N, K);
+  VMB_CHECK_ARG(M == 0 || (A && W && C), "linear_act: null A / W / C");
+  VMB_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "linear_act: row stride smaller than row");
+  VMB_CHECK_ARG(act_from >= 0 && act_from <= N, "linear_act: act_from=%d outside [0, %d]", act_from, N);
+  if (act_from == N) return vmb_linear_fwd(A, lda, W, ldw, bias, C, ldc, M, N, K, dtype, stream);
+  if (dtype != VMB_BF16 || act_from % 64 != 0 || !gemm_tc_supported(A, lda, W, ldw, C, ldc, M, N, K))
+    VMB_UNSUPPORTED("linear_act: the activation epilogue exists on the tensor-core kernel only (bf16, TMA-aligned "
+                    "operands, act_from a multiple of 64)");
+  if (M == 0) return VMB_OK;
+  return gemm_tc(A, lda, W, ldw, bias, C, ldc, M, N, K, as_stream(stream), act_from);
+}
+
 extern "C" int vmb_selective_scan_fwd(const vmb_scan_args* a, vmb_stream_t stream) {
   VMB_CHECK_ARG(a != nullptr, "selective_scan: null args");
   VMB_CHECK_ARG(a->u && a->delta && a->bc && a->A2 && a->y, "selective_scan: null tensor");
@@ -208,6 +224,8 @@ extern "C" int vmb_selective_scan_fused_fwd(const vmb_fused_scan_args* a, vmb_st
   VMB_CHECK_ARG(a->bwd_ckpt == nullptr || (!a->reverse && reinterpret_cast<uintptr_t>(a->bwd_ckpt) % 16 == 0),
                 "fused_scan: bwd_ckpt needs the forward walk and 16-byte alignment");
   f.ckpt = a->bwd_ckpt;
+  f.z_gate = a->z_gate != 0;
+  VMB_CHECK_ARG(!(f.z_gate && f.ckpt), "fused_scan: the training forward (bwd_ckpt) needs the raw z, not the gate");
   f.seg_ws = reinterpret_cast<float*>(a->workspace);
   f.seg_ws_bytes = a->workspace ? a->workspace_bytes : 0;
   VMB_CHECK_ARG(reinterpret_cast<uintptr_t>(a->workspace) % 16 == 0, "fused_scan: workspace not 16-byte aligned");
@@ -257,13 +275,6 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   int rc;
 
-  // in_proj (mamba_simple.py:333-339): xz (M, 2Di), x = [:, :Di], z = [:, Di:]
-  {
-    ProfScope ps(VMB_PROF_IN_PROJ, st);
-    rc = vmb_linear_fwd(p->hidden, p->h_tstride, p->w_in, D, p->b_in, xz, 2 * Di, M, 2 * Di, D,
-                        p->dtype, stream);
-  }
-  if (rc) return rc;
   FastScanArgs f;
   f.u = xc; f.u_bs = (int64_t)L * Di; f.u_ts = Di;
   f.z = (char*)xz + (int64_t)Di * es; f.z_bs = (int64_t)L * 2 * Di; f.z_ts = 2 * Di;
@@ -282,6 +293,22 @@ extern "C" int vmb_mixer_fwd(const vmb_mixer_args* p, vmb_stream_t stream) {
                        scan_fast_supported(f);
   if (p->path == 2 && !fast_ok) VMB_UNSUPPORTED("mixer: fast path requested but not available");
   const bool fast = fast_ok && p->path != 1;
+
+  // in_proj (mamba_simple.py:333-339): xz (M, 2Di), x = [:, :Di], z = [:, Di:].  On request (gate_in_proj) and
+  // on the fast path the epilogue of the tensor-core projection applies SiLU to the z half before its one
+  // rounding to bf16, and the scan multiplies by the stored gate as it is (mamba_simple.py:423-435 applies
+  // SiLU to the rounded z inside the scan: same number of roundings, at the other side of the activation).
+  const bool gate = p->gate_in_proj != 0 && fast && Di % 64 == 0 &&
+                    gemm_tc_supported(p->hidden, p->h_tstride, p->w_in, D, xz, 2 * Di, M, 2 * Di, D);
+  {
+    ProfScope ps(VMB_PROF_IN_PROJ, st);
+    rc = gate ? vmb_linear_fwd_act(p->hidden, p->h_tstride, p->w_in, D, p->b_in, xz, 2 * Di, M, 2 * Di, D,
+                                   p->dtype, Di, stream)
+              : vmb_linear_fwd(p->hidden, p->h_tstride, p->w_in, D, p->b_in, xz, 2 * Di, M, 2 * Di, D,
+                               p->dtype, stream);
+  }
+  if (rc) return rc;
+  f.z_gate = gate ? 1 : 0;
 
   // Stateless forward walk on the fast path, on request (fuse_conv_xproj): the conv runs inside the x_proj
   // projection (its output tile goes from the conv warps to the tensor cores through shared memory and to

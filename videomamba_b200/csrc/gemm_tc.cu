@@ -22,6 +22,7 @@
 // Both operands are K-contiguous, exactly how nn.Linear stores its weight, so no transposes.
 #include <cuda.h>
 
+#include <climits>
 #include <cstdlib>
 #include <type_traits>
 #include <mutex>
@@ -146,6 +147,23 @@ __device__ __forceinline__ void tc_wait_ld() {
 __device__ __forceinline__ void epi_bar_sync() {  // named barrier 1: the 128 epilogue threads
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
+// SiLU on a thread's 64 accumulator values before the rounding to bf16 (in_proj's z half: the scan then
+// multiplies by the gate as it is).  x * (0.5 * tanh(x / 2) + 0.5): silu_fast's arithmetic, packed.
+__device__ __forceinline__ void epi_silu(uint32_t (&v0)[32], uint32_t (&v1)[32]) {
+  const float2 half2 = make_float2(0.5f, 0.5f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float2 a = make_float2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1]));
+    float2 b = make_float2(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1]));
+    const float2 ha = __fmul2_rn(a, half2), hb = __fmul2_rn(b, half2);
+    const float2 ta = make_float2(tanh_approx(ha.x), tanh_approx(ha.y));
+    const float2 tb = make_float2(tanh_approx(hb.x), tanh_approx(hb.y));
+    a = __fmul2_rn(a, __ffma2_rn(ta, half2, half2));
+    b = __fmul2_rn(b, __ffma2_rn(tb, half2, half2));
+    v0[j] = __float_as_uint(a.x); v0[j + 1] = __float_as_uint(a.y);
+    v1[j] = __float_as_uint(b.x); v1[j + 1] = __float_as_uint(b.y);
+  }
+}
 
 // UMMA shared-memory descriptor of a K-major, 128B-swizzled operand tile whose rows are 128 bytes
 // (64 bf16) and whose 8-row groups are 1024 bytes apart (dense):
@@ -173,7 +191,7 @@ template <int BN, int kStages>
 __global__ void __launch_bounds__(kThreads, kStages == 2 ? 3 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ bias,
-               int M, int N, int K) {
+               int M, int N, int K, int act_from) {
   constexpr int kTmemCols = tmem_cols_for(BN);
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kWBytes = BN * BK * 2;
@@ -312,6 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             v1[j] = __float_as_uint(__uint_as_float(v1[j]) + b1);
           }
         }
+        if (n0 + sub * kSubN >= act_from) epi_silu(v0, v1);   // gate columns (uniform per sub-tile)
         // the store that last read this staging buffer (two sub-tiles ago) must be done reading
         if (issuer) tma_store_wait_read<1>();
         epi_bar_sync();
@@ -416,7 +435,7 @@ template <int BN, int kStages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, kStages <= 3 ? 3 : 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c, const __nv_bfloat16* __restrict__ bias,
-                    int M, int N, int K) {
+                    int M, int N, int K, int act_from, int interleave) {
   constexpr int kTmemCols = tmem_cols_for(BN);
   constexpr uint32_t kABytes = BM * BK * 2;
   constexpr uint32_t kWBytes = (BN / 2) * BK * 2;          // this CTA's half of the W tile
@@ -483,7 +502,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m0 = (tile / n_tiles) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+        // W rows of this CTA's half of the tile; interleaved (in_proj with the gate): the leader holds 128 x
+        // columns, the peer the 128 z columns of the same channels, so every tile carries the same epilogue work
+        const int n0 = interleave ? (tile % n_tiles) * (BN / 2) + (int)rank * act_from
+                                  : (tile % n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (leader) mbar_expect_tx(full_bar(stage), 2 * (kABytes + kWBytes));
@@ -537,7 +559,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
       for (int sub = 0; sub < BN / kSubN; ++sub) {
-        const bool beyond = n0 + sub * kSubN >= N;   // whole sub-tile beyond N (uniform)
+        // first output column of the sub-tile (interleaved: accumulator columns [0, BN/2) are x, the rest z)
+        const int nb = interleave ? (n0 >> 1) + (sub & 1) * kSubN + (sub >= BN / kSubN / 2 ? act_from : 0)
+                                  : n0 + sub * kSubN;
+        const bool beyond = nb >= N;                 // whole sub-tile beyond N (uniform)
         uint32_t v0[32], v1[32];
         if (!beyond) {
           tc_ld_32x32(t_row + sub * kSubN, v0);
@@ -551,7 +576,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         if (beyond) continue;
         if (bias != nullptr) {
-          const int nb = n0 + sub * kSubN;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float b0 = nb + j < N ? __bfloat162float(bias[nb + j]) : 0.f;
@@ -560,6 +584,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             v1[j] = __float_as_uint(__uint_as_float(v1[j]) + b1);
           }
         }
+        if (nb >= act_from) epi_silu(v0, v1);        // gate columns (uniform per sub-tile)
         if (issuer) tma_store_wait_read<1>();
         epi_bar_sync();
         uint8_t* dst = smem_gen + (smem_c - smem_base) + buf * kSubBytes + row * 128;
@@ -579,7 +604,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         fence_proxy_async_smem();
         epi_bar_sync();
         if (issuer) {
-          tma_store_2d(&map_c, smem_c + buf * kSubBytes, n0 + sub * kSubN, m0);
+          tma_store_2d(&map_c, smem_c + buf * kSubBytes, nb, m0);
           tma_store_commit();
         }
         buf ^= 1;
@@ -1027,7 +1052,7 @@ namespace {
 
 template <int BN, int kStages>
 int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
-           int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+           int64_t ldc, int64_t M, int N, int K, int act_from, cudaStream_t st) {
   CUtensorMap ma, mw, mc;
   int rc;
   if ((rc = make_map(&ma, A, M, K, lda, BM))) return rc;
@@ -1045,14 +1070,14 @@ int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const void* b
   const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = (int)std::min<int64_t>(tiles, sm_count());
   gemm_tc_kernel<BN, kStages><<<grid, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias,
-                                                            (int)M, N, K);
+                                                            (int)M, N, K, act_from);
   VMB_LAUNCH_CHECK("gemm_tc_kernel");
   return VMB_OK;
 }
 
 template <int BN, int kStages>
 int launch_pair(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
-                int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+                int64_t ldc, int64_t M, int N, int K, int act_from, cudaStream_t st) {
   CUtensorMap ma, mw, mc;
   int rc;
   if ((rc = make_map(&ma, A, M, K, lda, BM))) return rc;
@@ -1070,8 +1095,10 @@ int launch_pair(const void* A, int64_t lda, const void* W, int64_t ldw, const vo
   }
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int pairs = (int)std::min<int64_t>(tiles, sm_count() / 2);
+  // x | gate projections (act_from == N / 2, whole 128-column halves): interleaved tiles
+  const int interleave = BN == 256 && act_from * 2 == N && act_from % (BN / 2) == 0;
   gemm_tc_pair_kernel<BN, kStages><<<2 * pairs, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias,
-                                                                      (int)M, N, K);
+                                                                      (int)M, N, K, act_from, interleave);
   VMB_LAUNCH_CHECK("gemm_tc_pair_kernel");
   return VMB_OK;
 }
@@ -1139,17 +1166,20 @@ bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, c
 }
 
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
-            int64_t ldc, int64_t M, int N, int K, cudaStream_t st) {
+            int64_t ldc, int64_t M, int N, int K, cudaStream_t st, int act_from) {
+  // act_from: SiLU on the output columns [act_from, N) before the rounding; whole 64-column sub-tiles only
+  if (act_from < 0 || act_from >= N) act_from = INT_MAX;
+  else if (act_from % kSubN != 0) return VMB_ERR_UNSUPPORTED;
   if (M >= 4 * BM) {   // CTA pairs: 256-row tiles, half a W tile per SM
-    if (N % 256 == 0) return launch_pair<256, stages_pair(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-    if (N % 192 == 0) return launch_pair<192, stages_pair(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    if (N % 256 == 0) return launch_pair<256, stages_pair(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
+    if (N % 192 == 0) return launch_pair<192, stages_pair(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
   }
-  if (N <= 64) return launch<64, stages_for(64)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  if (N <= 128) return launch<128, stages_for(128)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  if (N % 256 == 0) return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+  if (N <= 64) return launch<64, stages_for(64)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
+  if (N <= 128) return launch<128, stages_for(128)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
+  if (N % 256 == 0) return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
   if (N % 192 == 0 || N < 256)
-    return launch<192, stages_for(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
-  return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+    return launch<192, stages_for(192)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
+  return launch<256, stages_for(256)>(A, lda, W, ldw, bias, C, ldc, M, N, K, act_from, st);
 }
 
 bool conv_xproj_supported(const void* x, int64_t x_ld, const void* cw, const void* cb, const void* W,

@@ -14,8 +14,10 @@ int linear_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const vo
 // setting an error the caller must report) when the shape does not fit the tensor-core kernel.
 bool gemm_tc_supported(const void* A, int64_t lda, const void* W, int64_t ldw, const void* C,
                        int64_t ldc, int64_t M, int N, int K);
+// act_from in [0, N), a multiple of 64: SiLU on the output columns [act_from, N) in the epilogue (fp32, before the
+// one rounding to bf16); anything else = no activation.
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
-            int64_t ldc, int64_t M, int N, int K, cudaStream_t st);
+            int64_t ldc, int64_t M, int N, int K, cudaStream_t st, int act_from = -1);
 
 // gemm_tc.cu -- cached 3-D bf16 tensor map (dims d0 (contiguous) x d1 x d2, byte strides of d1 / d2,
 // box0 x box1 x 1 boxes, optional 128-byte swizzle) for TMA staging outside the GEMM.
@@ -74,6 +76,7 @@ struct FastScanArgs {
   int reverse;
   int frame_len = 0;     // with reverse: frame-axis reversal, frames of frame_len tokens (0 = whole-sequence reversal)
   int a_geometric = 0;   // caller's promise: A2[d][n] == (n+1) * A2[d][0] (checked when the weights are loaded)
+  int z_gate = 0;        // z already holds SiLU(z) (applied by the in_proj epilogue): the scan only multiplies
   int tune = 0;          // measurement aid: 10 * layout + evaluator, 0 = automatic (see scan_fast())
   float* ckpt = nullptr; // forward walk only: records of the state before every 4-token group (scan_bwd_fast.cu layout)
   // sequence split for small batches (filled by scan_fast itself): nseg segments of seg_len tokens,

@@ -344,7 +344,7 @@ __host__ __device__ constexpr Plan plan(int Xp) {
   return p;
 }
 
-template <int R, bool kStateOnly, bool kRev, int kExp, bool kCkpt = false>
+template <int R, bool kStateOnly, bool kRev, int kExp, bool kCkpt = false, bool kGate = false>
 __global__ void __launch_bounds__(32, 18)
 scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
@@ -503,8 +503,11 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
         const float ub = __bfloat162float(*reinterpret_cast<const bf16*>(su + so + 16));
         const float za = __bfloat162float(*reinterpret_cast<const bf16*>(sz + so));
         const float zb = __bfloat162float(*reinterpret_cast<const bf16*>(sz + so + 16));
-        sy[tf * (kRowBytes / 2) + g] = __float2bfloat16_rn(fmaf(Da, ua, ya) * silu_fast(za));
-        sy[tf * (kRowBytes / 2) + g + 8] = __float2bfloat16_rn(fmaf(Db, ub, yb) * silu_fast(zb));
+        // z_gate: the in_proj epilogue already applied SiLU (the staged tile holds the gate itself)
+        const float ga = kGate ? za : silu_fast(za);
+        const float gb = kGate ? zb : silu_fast(zb);
+        sy[tf * (kRowBytes / 2) + g] = __float2bfloat16_rn(fmaf(Da, ua, ya) * ga);
+        sy[tf * (kRowBytes / 2) + g + 8] = __float2bfloat16_rn(fmaf(Db, ub, yb) * gb);
       }
     }
     if constexpr (!kStateOnly) {
@@ -570,7 +573,7 @@ __host__ __device__ constexpr Plan plan(int Xp) {
   return p;
 }
 
-template <int R, bool kStateOnly, bool kRev, int kExp, bool kCkpt = false>
+template <int R, bool kStateOnly, bool kRev, int kExp, bool kCkpt = false, bool kGate = false>
 __global__ void __launch_bounds__(64, 11)
 scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
               const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_x) {
@@ -683,8 +686,9 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
       uint32_t o[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float lo = fmaf(Dv[2 * q], bf16lo(uw[q]), yv[2 * q]) * silu_fast(bf16lo(zw[q]));
-        const float hi = fmaf(Dv[2 * q + 1], bf16hi(uw[q]), yv[2 * q + 1]) * silu_fast(bf16hi(zw[q]));
+        const float zl = bf16lo(zw[q]), zh = bf16hi(zw[q]);
+        const float lo = fmaf(Dv[2 * q], bf16lo(uw[q]), yv[2 * q]) * (kGate ? zl : silu_fast(zl));
+        const float hi = fmaf(Dv[2 * q + 1], bf16hi(uw[q]), yv[2 * q + 1]) * (kGate ? zh : silu_fast(zh));
         o[q] = pack_bf16x2(lo, hi);
       }
       if (frow < valid)
@@ -855,12 +859,19 @@ int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
   constexpr int threads = kTwoWarp ? 64 : 32;
   auto run = [&](dim3 grid, auto state_only) {
     constexpr bool kSO = decltype(state_only)::value;
+    const bool rev = a.reverse && a.frame_len == 0;
     if constexpr (kTwoWarp) {
-      if (a.reverse && a.frame_len == 0) two_warp::scan2w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      if (!kSO && a.z_gate) {                       // z holds the gate itself (inference mixer; never with ckpt)
+        if (rev) two_warp::scan2w_kernel<R, false, true, kExp, false, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+        else two_warp::scan2w_kernel<R, false, false, kExp, false, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      } else if (rev) two_warp::scan2w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else if (!kSO && a.ckpt) two_warp::scan2w_kernel<R, false, false, kExp, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else two_warp::scan2w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
     } else {
-      if (a.reverse && a.frame_len == 0) one_warp::scan1w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      if (!kSO && a.z_gate) {
+        if (rev) one_warp::scan1w_kernel<R, false, true, kExp, false, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+        else one_warp::scan1w_kernel<R, false, false, kExp, false, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
+      } else if (rev) one_warp::scan1w_kernel<R, kSO, true, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else if (!kSO && a.ckpt) one_warp::scan1w_kernel<R, false, false, kExp, true><<<grid, threads, smem, st>>>(a, mu, mz, mx);
       else one_warp::scan1w_kernel<R, kSO, false, kExp><<<grid, threads, smem, st>>>(a, mu, mz, mx);
     }

@@ -114,6 +114,10 @@ class Mamba(nn.Module):
     #: HBM traffic, faster when ONE forward is in flight, slower when several share the GPU
     fuse_conv_xproj: bool = False
 
+    #: the in_proj epilogue stores SiLU(z) and the fused scan multiplies by it as it is (bf16 fast path; the gate is
+    #: rounded after the activation instead of before it).  False = the scan applies SiLU to the stored z.
+    gate_in_proj: bool = True
+
     def refresh_weights(self) -> None:
         """Drop the kernel-ready copies derived from the parameters (``A2 = -exp(A_log)*log2(e)``,
         fp32 ``D`` / ``dt_proj.bias``, zero-padded ``x_proj`` / ``dt_proj`` weights, the geometric-A
@@ -215,7 +219,8 @@ class Mamba(nn.Module):
         else:
             out, new_conv, last = ops.mixer_fwd(w, hidden_states, conv_state, ssm_state,
                                                 want_conv_state=return_state, want_ssm_state=want,
-                                                fuse_conv_xproj=self.fuse_conv_xproj)
+                                                fuse_conv_xproj=self.fuse_conv_xproj,
+                                                gate_in_proj=self.gate_in_proj)
         if inplace_ssm:
             with torch.no_grad():
                 ssm_state.copy_(last)

@@ -185,7 +185,9 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     return linear_raw(x, weight, bias)
 
 
-def linear_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+def linear_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, silu_from: Optional[int] = None) -> Tensor:
+    """``silu_from``: SiLU on the output columns ``[silu_from, N)`` in the projection's epilogue
+    (``vmb_linear_fwd_act``: tensor-core kernel only, a multiple of 64)."""
     _require_cuda(x)
     lib = _lib.load()
     K = x.shape[-1]
@@ -203,10 +205,20 @@ def linear_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tens
     if bias is not None:
         bias = bias.to(x.dtype).contiguous()
     with _on_device(x):
-        rc = lib.vmb_linear_fwd(_p(x2), x2.stride(0) if M > 1 else K, _p(weight), weight.stride(0),
-                                _p(bias), _p(out), N, M, N, K, _dt(x2), _stream(x))
-    _lib.check(rc, "vmb_linear_fwd")
+        if silu_from is None:
+            rc = lib.vmb_linear_fwd(_p(x2), x2.stride(0) if M > 1 else K, _p(weight), weight.stride(0),
+                                    _p(bias), _p(out), N, M, N, K, _dt(x2), _stream(x))
+        else:
+            rc = lib.vmb_linear_fwd_act(_p(x2), x2.stride(0) if M > 1 else K, _p(weight), weight.stride(0),
+                                        _p(bias), _p(out), N, M, N, K, _dt(x2), int(silu_from), _stream(x))
+    _lib.check(rc, "vmb_linear_fwd" if silu_from is None else "vmb_linear_fwd_act")
     return out.reshape(*x.shape[:-1], N)
+
+
+def linear_act(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, silu_from: int = 0) -> Tensor:
+    """``x @ weight.T (+ bias)`` with SiLU on the output columns ``[silu_from, N)`` applied in the epilogue of the
+    tensor-core projection (forward only).  ``in_proj`` with ``silu_from = d_inner`` gives ``x | SiLU(z)``."""
+    return forward_only(linear_raw(x, weight, bias, silu_from=silu_from), x, weight, bias)
 
 
 def conv_xproj_tokens(x: Tensor, conv_weight: Tensor, conv_bias: Optional[Tensor], w_x_pad: Tensor):
@@ -469,15 +481,16 @@ def selective_scan_fused_tokens(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Tensor
                                 dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
                                 want_last: bool = False, reverse: bool = False,
                                 allow_split: bool = True, a_geometric: bool = False, tune: int = 0,
-                                frame_len: int = 0):
+                                frame_len: int = 0, z_gate: bool = False):
     """Fused dt_proj + softplus + scan + D skip + SiLU(z) gate (bf16, d_state 16).
     ``u, z: (B, L, Di)``; ``xdbl: (B, L, Xp)`` rows ``[dt_low (R) | B (N) | C (N) | pad]`` with
     ``Xp = xdbl_pitch(R, N)``; ``w_dt: (Di, R)`` bf16, or already zero-padded to ``(Di, Rp)`` with
     ``Rp = round_up(R, 16)``; ``A2 = A*log2(e)`` fp32.  ``a_geometric``: the caller's promise that
-    ``A2[d, n] == (n+1) * A2[d, 0]`` (see ``is_geometric``).  Raises when the shape is not covered.
+    ``A2[d, n] == (n+1) * A2[d, 0]`` (see ``is_geometric``).  ``z_gate``: ``z`` already holds ``SiLU(z)``
+    (``linear(..., silu_from=Di)``).  Raises when the shape is not covered.
     Forward-only in this form; ``autograd.FusedScanFn`` is the differentiable operator over it."""
     out = selective_scan_fused_tokens_raw(u, z, xdbl, w_dt, A2, dt_rank, d_state, D, dt_bias, h0, want_last,
-                                          reverse, allow_split, a_geometric, tune, frame_len)
+                                          reverse, allow_split, a_geometric, tune, frame_len, z_gate=z_gate)
     return forward_only(out, u, z, xdbl, w_dt, A2, D, dt_bias, h0)
 
 
@@ -486,7 +499,8 @@ def selective_scan_fused_tokens_raw(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Te
                                     dt_bias: Optional[Tensor] = None, h0: Optional[Tensor] = None,
                                     want_last: bool = False, reverse: bool = False,
                                     allow_split: bool = True, a_geometric: bool = False, tune: int = 0,
-                                    frame_len: int = 0, bwd_ckpt: Optional[Tensor] = None):
+                                    frame_len: int = 0, bwd_ckpt: Optional[Tensor] = None,
+                                    z_gate: bool = False):
     """``bwd_ckpt``: a ``scan_bwd_ckpt_bytes(B, L, Di)`` byte buffer that receives the state records the
     backward kernel needs (training forward; forward walk only)."""
     _require_cuda(u)
@@ -519,6 +533,7 @@ def selective_scan_fused_tokens_raw(u: Tensor, z: Tensor, xdbl: Tensor, w_dt: Te
     a.frame_len = int(frame_len) if reverse else 0
     if bwd_ckpt is not None:
         a.bwd_ckpt = bwd_ckpt.data_ptr()
+    a.z_gate = 1 if z_gate else 0
     if u.dtype != torch.bfloat16 or z.dtype != u.dtype or xdbl.dtype != u.dtype \
             or w_dt.dtype != u.dtype:
         raise TypeError("the fused scan is a bf16 kernel")
@@ -592,7 +607,8 @@ class MixerWeights:
 def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = None,
               ssm_state: Optional[Tensor] = None, want_conv_state: bool = False,
               want_ssm_state: bool = False, reverse: bool = False, path: int = 0,
-              scan_tune: int = 0, fuse_conv_xproj: bool = False, frame_len: int = 0):
+              scan_tune: int = 0, fuse_conv_xproj: bool = False, frame_len: int = 0,
+              gate_in_proj: bool = True):
     """Whole Mamba mixer on token-major ``hidden (B, L, D)``.
     Returns ``(out, new_conv_state | None, last_ssm_state | None)``."""
     _require_cuda(hidden)
@@ -662,6 +678,7 @@ def mixer_fwd(w: MixerWeights, hidden: Tensor, conv_state: Optional[Tensor] = No
     a.dtype, a.reverse, a.path = dt, 1 if reverse else 0, path
     a.a_geometric, a.scan_tune = 1 if w.a_geometric else 0, int(scan_tune)
     a.fuse_conv_xproj = 1 if fuse_conv_xproj else 0
+    a.gate_in_proj = 1 if gate_in_proj else 0
     a.frame_len = int(frame_len) if reverse else 0
     with _on_device(hidden):
         rc = lib.vmb_mixer_fwd(C.byref(a), _stream(hidden))
