@@ -326,7 +326,9 @@ def test_mixer_backward_streaming_state(dtype, d_model, d_state):
 @pytest.mark.parametrize("dtype,d_model", [(torch.float32, 128), (torch.bfloat16, 384), (torch.bfloat16, 576)])
 def test_mixer_training_forward_matches_inference_path(dtype, d_model):
     """The training-mode mixer (op by op, differentiable; bf16 production widths run the fused scan in the
-    forward) and the fused inference entry point agree -- bit for bit where both run the fused scan."""
+    forward) and the fused inference entry point agree -- bit for bit where both run the fused scan with SiLU(z)
+    inside it; the inference default (SiLU(z) in the in_proj epilogue, the training forward keeps the raw z for its
+    backward) moves one bf16 rounding of the gate: same states, outputs within that rounding."""
     torch.manual_seed(1)
     mx = Mamba(d_model=d_model, use_fast_path=False).to(dtype).to(DEV)
     x = torch.randn(2, 70, d_model, device=DEV).to(dtype)
@@ -335,7 +337,12 @@ def test_mixer_training_forward_matches_inference_path(dtype, d_model):
         b, (cb, sb) = mx(x, return_state=True)
     assert a.requires_grad and not b.requires_grad
     if dtype == torch.bfloat16:
-        assert torch.equal(a, b) and torch.equal(ca, cb) and torch.equal(sa, sb)
+        assert torch.equal(ca, cb) and torch.equal(sa, sb)
+        assert rel_err(a, b) <= 8e-3, rel_err(a, b)
+        mx.gate_in_proj = False
+        with torch.no_grad():
+            c, (cc, sc) = mx(x, return_state=True)
+        assert torch.equal(a, c) and torch.equal(ca, cc) and torch.equal(sa, sc)
     else:
         assert rel_err(a, b) <= 1e-5 and rel_err(sa, sb) <= 1e-5
 
