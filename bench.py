@@ -1081,6 +1081,10 @@ def depth_of(model):
 
 def main():
     args = parse_args()
+    # a run that has not finished after 20 minutes is stuck (the default run takes well under 2): every thread's
+    # Python stack goes to stderr and the process exits non-zero instead of holding the GPU until someone kills it
+    import faulthandler
+    faulthandler.dump_traceback_later(1200, exit=True)
     if args.impl == "reference":
         return run_reference(args)
     if args.config == "train16f":

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Runs single operators of the hot path at the bench shapes (VideoMamba-S 16f, batch 32) so that
 one kernel can be captured with ncu or timed alone:   python tools/prof_ops.py scan|conv|norm|gemm [iters]
+(PGATE=1: the scan multiplies by a stored gate, as the inference mixer runs it; PACT=<column>: the projection applies
+SiLU from that output column on, PN=1536 PACT=768 = in_proj of the inference mixer.)
 Prints CUDA-event time per launch and achieved algorithmic GB/s."""
 import os
 import sys
@@ -45,7 +47,9 @@ if which == "scan":
     Dp = torch.ones(Di, device=dev)
     bias = torch.full((Di,), -3.0, device=dev)
     split = os.environ.get("PSPLIT", "1") != "0"      # tool-only switch: time the unsplit walk
-    timeit(lambda: ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, allow_split=split),
+    gate = os.environ.get("PGATE", "0") != "0"
+    timeit(lambda: ops.selective_scan_fused_tokens(u, z, xdbl, w_dt, A2, R, N, Dp, bias, allow_split=split,
+                                                   z_gate=gate),
            B * L * (3 * Di + Xp) * 2)
 elif which == "conv":
     xz = rn(B, L, 2 * Di)
@@ -59,4 +63,6 @@ elif which == "norm":
 elif which == "gemm":
     n, k = int(os.environ.get("PN", 4 * D)), int(os.environ.get("PK", D))
     a, w = rn(B * L, k), rn(n, k, scale=k ** -0.5)
-    timeit(lambda: ops.linear(a, w), (B * L * (k + n) + n * k) * 2)
+    act = os.environ.get("PACT")
+    timeit(lambda: ops.linear_raw(a, w, None, silu_from=None if act is None else int(act)),
+           (B * L * (k + n) + n * k) * 2)
