@@ -20,6 +20,11 @@
 //            stores (coalesced, rows beyond M / columns beyond N are clipped by the hardware).
 // Tiles are walked n-fastest so the CTAs running at the same time share the A rows in L2.
 // Both operands are K-contiguous, exactly how nn.Linear stores its weight, so no transposes.
+// Activation epilogue (act_from, vmb_linear_fwd_act): SiLU on the output columns [act_from, N) before the
+// rounding -- in_proj stores x | SiLU(z), the gate of mamba_simple.py:423-435, and the fused scan only
+// multiplies.  With act_from == N / 2 the CTA-pair kernel interleaves the halves: a 256-column tile is 128 x
+// columns (leader's W rows) + the 128 gate columns of the same channels (peer's W rows), so every tile has the
+// same epilogue work (with whole x tiles and z tiles the pairs holding more z tiles set the time).
 #include <cuda.h>
 
 #include <climits>

@@ -44,6 +44,10 @@
 //   * small batches split the sequence into segments: a first pass computes every segment's end
 //     state from a zero start (recurrence only) and sum(delta); a tiny kernel chains the carries;
 //     the second pass runs all segments concurrently from their true initial states.  Exact.
+//   * z_gate (template kGate): the staged z tile already holds SiLU(z) -- the in_proj epilogue applied it
+//     (gemm_tc.cu, vmb_linear_fwd_act) -- and the finalisation is one multiply: -0.5 MUFU and -1.1 other
+//     instructions per warp-token (392 -> 376 us per launch shared, profiles/r02_gate_ab.jsonl).  The
+//     training forward (kCkpt) and the first pass of the split never take it.
 //   * reverse = 1 walks the sequence back to front (the flipped branch of BiMambaRefinerBlock,
 //     models/refiner_backbone.py:61-68, :92-135, without flip copies); with frame_len > 0 only the
 //     frame axis is reversed (4-D input): every frame is cut into its own tiles (tile_geom).
