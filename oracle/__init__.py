@@ -12,8 +12,14 @@ path and its arithmetic lives in two un-vendored wheels that are absent here
 container: against the reference's own host code + its in-tree ``_selective_scan_ref``
 (``models/videomamba/mamba_simple.py:30-106``) imported live from ``/root/reference``
 (``oracle/ref_loader.py``), and against fixtures generated from that run
-(``tests/golden/``, generator ``tools/make_golden.py``).  The three leaf ops whose source is
-not in the tree (causal conv, fused add+norm, single-step state update) are restated from
-the published reference implementations of those wheels; for those leaves parity is
-"pinned to the reference's call sites, unpinned at the third-party boundary".
+(``tests/golden/``, generator ``tools/make_golden.py``).  The leaf ops whose source is
+not in the tree (causal conv + its single-token update, selective scan, single-step state
+update, fused add+norm) are restated from the published reference implementations of those
+wheels.  They cannot be pinned against the wheels themselves; they ARE cross-checked on the GPU
+box (``tests/test_gpu_leaf_crosscheck.py``, fp32, 2e-5) against an independent copy of the same
+upstream kernels: vllm (in the image) carries its own adaptations of ``selective_scan_fwd``
+(CUDA), ``selective_state_update``, ``causal_conv1d_fn`` / ``causal_conv1d_update`` and the
+Triton norm kernel ("Adapted from state-spaces/mamba v2.2.4").  Status for those leaves:
+"pinned to the reference's call sites and to vllm's copies of the upstream kernels, not to the
+pinned wheel versions themselves".
 """

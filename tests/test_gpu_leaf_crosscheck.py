@@ -1,0 +1,161 @@
+"""GPU: the third-party LEAVES of the path -- causal_conv1d_fn / causal_conv1d_update (causal-conv1d wheel) and
+selective_scan_fn / selective_state_update (mamba_ssm wheel), reference models/videomamba/mamba_simple.py:17-27 --
+against an independent copy of the upstream kernels.
+
+Neither wheel exists in this image, which is why oracle/ calls its restatements of these four "unpinned"
+(oracle/__init__.py).  vllm, which IS in the image (here and on the GPU box), carries its own adaptations of exactly
+those kernels (vllm/model_executor/layers/mamba/ops: "Adapted from state-spaces/mamba v2.2.4" and the
+selective_scan_fwd CUDA kernel).  tests/vllm_leaves_worker.py evaluates them in a separate process; here both the
+oracle's restatement (CPU) and libvmb200's kernels (through the drop-in operator signatures) are compared with the
+results on the same seeded fp32 inputs.  vllm is a checker only: nothing under videomamba_b200/ imports it.
+Skipped (not failed) when vllm's ops cannot be imported or a kernel of theirs does not run on this box."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import videomamba_oracle as orc
+from oracle.videomamba_oracle import rel_err
+from videomamba_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 2e-5          # fp32 kernels on both sides; the upstream kernels use exp2 of a pre-scaled A like ours
+
+
+def _cases():
+    g = torch.Generator().manual_seed(2024)
+    r = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale
+    cases = {}
+    for tag, (Bsz, Dm, L, N) in {"a": (2, 64, 37, 16), "b": (3, 192, 130, 16), "c": (1, 96, 300, 8)}.items():
+        A = -torch.exp(r(Dm, N, scale=0.3) + torch.log(torch.arange(1, N + 1).float()))
+        base = dict(u=r(Bsz, Dm, L), delta=r(Bsz, Dm, L, scale=0.5), z=r(Bsz, Dm, L), A=A, Bm=r(Bsz, N, L),
+                    Cm=r(Bsz, N, L), D=r(Dm), delta_bias=r(Dm) - 2.0)
+        cases[f"scan_{tag}"] = dict(base, h0=None)
+        cases[f"scan_{tag}_h0"] = dict(base, h0=r(Bsz, Dm, N))
+        cases[f"update_{tag}"] = dict(state=r(Bsz, Dm, N), x=r(Bsz, Dm), dt=r(Bsz, Dm, scale=0.5), A=A, Bm=r(Bsz, N),
+                                      Cm=r(Bsz, N), D=r(Dm), z=r(Bsz, Dm), dt_bias=r(Dm) - 2.0)
+        W = 4
+        conv = dict(x=r(Bsz, Dm, L), weight=r(Dm, W, scale=0.5), bias=r(Dm))
+        cases[f"conv_{tag}"] = dict(conv, init=None)
+        cases[f"conv_{tag}_init"] = dict(conv, init=r(Bsz, Dm, W - 1))
+        cases[f"convstep_{tag}"] = dict(x=r(Bsz, Dm), conv_state=r(Bsz, Dm, W - 1), weight=conv["weight"],
+                                        bias=conv["bias"])
+        cases[f"addnorm_{tag}"] = dict(x=r(Bsz * L, 2 * Dm), residual=r(Bsz * L, 2 * Dm, scale=3.0),
+                                       weight=1.0 + r(2 * Dm, scale=0.2), bias=r(2 * Dm, scale=0.2), eps=1e-5)
+    return cases
+
+
+@pytest.fixture(scope="module")
+def upstream(tmp_path_factory):
+    d = tmp_path_factory.mktemp("vllm_leaves")
+    src, dst = str(d / "in.pt"), str(d / "out.pt")
+    cases = _cases()
+    torch.save(cases, src)
+    env = dict(os.environ, VLLM_LOGGING_LEVEL="ERROR", TOKENIZERS_PARALLELISM="false")
+    try:
+        p = subprocess.run([sys.executable, os.path.join(HERE, "vllm_leaves_worker.py"), src, dst],
+                           capture_output=True, text=True, timeout=600, env=env)
+    except subprocess.TimeoutExpired:
+        pytest.skip("the vllm worker did not finish in 600 s")
+    if p.returncode != 0 or not os.path.isfile(dst):
+        pytest.skip(f"the vllm worker failed: {p.stderr[-400:]}")
+    got = torch.load(dst, weights_only=True)
+    if "unavailable" in got:
+        pytest.skip(f"vllm's mamba ops are not importable here: {got['unavailable']}")
+    return cases, got
+
+
+def _upstream_case(upstream, name):
+    cases, got = upstream
+    if "error" in got[name]:
+        pytest.skip(f"vllm kernel did not run for {name}: {got[name]['error'][-300:]}")
+    return cases[name], got[name]
+
+
+def _dev(c):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
+
+
+@pytest.mark.parametrize("name", ["scan_a", "scan_a_h0", "scan_b", "scan_b_h0", "scan_c", "scan_c_h0"])
+def test_selective_scan_leaf(upstream, name):
+    """mamba_simple.py:125-152 (selective_scan_fn with softplus, delta bias, D, z, initial / last state)."""
+    c, up = _upstream_case(upstream, name)
+    want, want_h = orc.selective_scan_ref(c["u"], c["delta"], c["A"], c["Bm"], c["Cm"], c["D"], c["z"], c["delta_bias"],
+                                          True, c["h0"], True)
+    assert rel_err(want, up["y"]) <= TOL and rel_err(want_h, up["last_state"]) <= TOL, "oracle vs upstream kernel"
+    d = _dev(c)
+    got, got_h = ops.selective_scan_fn(d["u"], d["delta"], d["A"], d["Bm"], d["Cm"], d["D"], d["z"], d["delta_bias"],
+                                       delta_softplus=True, return_last_state=True, initial_state=d["h0"])
+    assert rel_err(got, up["y"]) <= TOL and rel_err(got_h, up["last_state"]) <= TOL, "libvmb200 vs upstream kernel"
+
+
+@pytest.mark.parametrize("name", ["update_a", "update_b", "update_c"])
+def test_selective_state_update_leaf(upstream, name):
+    """mamba_simple.py:483-494 (selective_state_update: one recurrent step, state in place)."""
+    c, up = _upstream_case(upstream, name)
+    st = c["state"].clone()
+    want = orc.selective_state_update_ref(st, c["x"], c["dt"], c["A"], c["Bm"], c["Cm"], c["D"], c["z"], c["dt_bias"], True)
+    assert rel_err(want, up["y"]) <= TOL and rel_err(st, up["state"]) <= TOL, "oracle vs upstream kernel"
+    d = _dev(c)
+    st = d["state"].clone()
+    got = ops.selective_state_update(st, d["x"], d["dt"], d["A"], d["Bm"], d["Cm"], d["D"], d["z"], d["dt_bias"], True)
+    assert rel_err(got, up["y"]) <= TOL and rel_err(st, up["state"]) <= TOL, "libvmb200 vs upstream kernel"
+
+
+@pytest.mark.parametrize("name", ["conv_a", "conv_a_init", "conv_b", "conv_b_init", "conv_c", "conv_c_init"])
+def test_causal_conv1d_leaf(upstream, name):
+    """mamba_simple.py:383-404 (causal_conv1d_fn + SiLU; with history the reference concatenates the cached
+    inputs in front, :385-392 -- the upstream kernel takes them as its initial state)."""
+    c, up = _upstream_case(upstream, name)
+    W = c["weight"].shape[1]
+    x = c["x"] if c["init"] is None else torch.cat([c["init"], c["x"]], dim=-1)
+    want = orc.causal_conv1d_ref(x, c["weight"], c["bias"], "silu")[..., -c["x"].shape[-1]:]
+    assert rel_err(want, up["y"]) <= TOL, "oracle vs upstream kernel"
+    assert torch.equal(x[..., -(W - 1):], up["final"]), "final state = the last W - 1 inputs"
+    d = _dev(c)
+    state = None
+    if d["init"] is not None:        # our state keeps W columns (the reference's conv_state layout): pad in front
+        state = torch.cat([torch.zeros_like(d["init"][..., :1]), d["init"]], dim=-1).contiguous()
+    got, new_state = ops.causal_conv1d_tokens(d["x"].transpose(1, 2), d["weight"], d["bias"], state, True, silu=True)
+    assert rel_err(got.transpose(1, 2), up["y"]) <= TOL, "libvmb200 vs upstream kernel"
+    assert torch.equal(new_state[..., 1:].cpu(), up["final"])
+
+
+@pytest.mark.parametrize("name", ["convstep_a", "convstep_b", "convstep_c"])
+def test_causal_conv1d_update_leaf(upstream, name):
+    """mamba_simple.py:468-474 (causal_conv1d_update: roll the cached inputs, one output token)."""
+    c, up = _upstream_case(upstream, name)
+    W = c["weight"].shape[1]
+    pad = lambda s: torch.cat([torch.zeros_like(s[..., :1]), s], dim=-1).contiguous()     # W columns, oldest first
+    st = pad(c["conv_state"])
+    want = orc.causal_conv1d_update_ref(c["x"], st, c["weight"], c["bias"], "silu")
+    assert rel_err(want, up["y"]) <= TOL and torch.equal(st[..., 1:], up["conv_state"][..., -(W - 1):]), \
+        "oracle vs upstream kernel"
+    d = _dev(c)
+    st = pad(d["conv_state"])
+    got = ops.causal_conv1d_update(d["x"], st, d["weight"], d["bias"], "silu")
+    assert rel_err(got, up["y"]) <= TOL and torch.equal(st[..., 1:].cpu(), up["conv_state"][..., -(W - 1):]), \
+        "libvmb200 vs upstream kernel"
+
+
+@pytest.mark.parametrize("name", ["addnorm_a", "addnorm_b", "addnorm_c"])
+def test_add_norm_leaf(upstream, name):
+    """videomamba.py:151-166, :902-918 (rms_norm_fn / layer_norm_fn with residual, prenorm, residual_in_fp32): the
+    norm of the fp32 sum by the upstream Triton norm kernel family, and the whole add + RMSNorm by vllm's own fused
+    CUDA kernel (an independent implementation of the same formula, not an upstream port)."""
+    c, up = _upstream_case(upstream, name)
+    d = _dev(c)
+    for is_rms, key in ((True, "rms"), (False, "ln")):
+        bias = None if is_rms else c["bias"]
+        want, want_res = orc.add_norm_ref(c["x"], c["weight"], bias, c["residual"], c["eps"], True, True, is_rms)
+        assert rel_err(want, up[key]) <= TOL and torch.equal(want_res, up["sum"]), "oracle vs upstream kernel"
+        got, got_res = ops.add_norm(d["x"], d["weight"], None if is_rms else d["bias"], d["residual"], c["eps"],
+                                    is_rms, True, True)
+        assert rel_err(got, up[key]) <= TOL and torch.equal(got_res.cpu(), up["sum"]), "libvmb200 vs upstream kernel"
+        if is_rms and "fused_rms" in up:
+            assert rel_err(want, up["fused_rms"]) <= TOL and rel_err(got, up["fused_rms"]) <= TOL
+            assert torch.equal(want_res, up["fused_sum"])
