@@ -10,7 +10,7 @@ result is rounded to ``T`` once -- that is what the upstream CUDA/Triton leaves 
 is fp32 throughout and returns its last state in fp32.
 
 Parity pinning: see oracle/__init__.py ("pinned to the live reference host code and to
-tests/golden; unpinned at the third-party leaf boundary").
+tests/golden; the third-party leaves cross-checked against vllm's copies of the upstream kernels").
 """
 from __future__ import annotations
 

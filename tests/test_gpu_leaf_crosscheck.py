@@ -2,8 +2,8 @@
 selective_scan_fn / selective_state_update (mamba_ssm wheel), reference models/videomamba/mamba_simple.py:17-27 --
 against an independent copy of the upstream kernels.
 
-Neither wheel exists in this image, which is why oracle/ calls its restatements of these four "unpinned"
-(oracle/__init__.py).  vllm, which IS in the image (here and on the GPU box), carries its own adaptations of exactly
+Neither wheel exists in this image, so oracle/ restates these leaves from the wheels' published reference functions
+and cannot be pinned against the wheels themselves (oracle/__init__.py).  vllm, which IS in the image (here and on the GPU box), carries its own adaptations of exactly
 those kernels (vllm/model_executor/layers/mamba/ops: "Adapted from state-spaces/mamba v2.2.4" and the
 selective_scan_fwd CUDA kernel).  tests/vllm_leaves_worker.py evaluates them in a separate process; here both the
 oracle's restatement (CPU) and libvmb200's kernels (through the drop-in operator signatures) are compared with the
