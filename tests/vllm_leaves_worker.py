@@ -34,11 +34,23 @@ def main(src, dst):
                 # u, delta, z (B, D, L); Bm, Cm (B, N, L); the kernel writes the output over z and the last
                 # state over ssm_states (read as the initial state where has_initial_state is set)
                 u, delta, z = c["u"].contiguous(), c["delta"].contiguous(), c["z"].contiguous().clone()
-                state = (c["h0"].clone() if c.get("h0") is not None
-                         else torch.zeros(u.shape[0], u.shape[1], c["A"].shape[1], device=dev, dtype=u.dtype))
                 has = torch.full((u.shape[0],), c.get("h0") is not None, dtype=torch.bool, device=dev)
-                y = selective_scan_fn(u, state, delta, c["A"].contiguous(), c["Bm"].contiguous(), c["Cm"].contiguous(),
-                                      c["D"], z, c["delta_bias"], delta_softplus=True, has_initial_state=has)
+                err = None
+                for sdt in (torch.float32, u.dtype):        # the state cache: fp32 if the kernel takes it
+                    state = (c["h0"].to(sdt).clone() if c.get("h0") is not None
+                             else torch.zeros(u.shape[0], u.shape[1], c["A"].shape[1], device=dev, dtype=sdt))
+                    zz = z.clone()
+                    try:
+                        y = selective_scan_fn(u, state, delta, c["A"].contiguous(), c["Bm"].contiguous(),
+                                              c["Cm"].contiguous(), c["D"], zz, c["delta_bias"], delta_softplus=True,
+                                              has_initial_state=has)
+                        torch.cuda.synchronize()
+                        err = None
+                        break
+                    except Exception as e:      # noqa: BLE001
+                        err = e
+                if err is not None:
+                    raise err
                 out[name] = {"y": y.cpu(), "last_state": state.cpu()}
             elif name.startswith("update"):
                 state = c["state"].clone()
