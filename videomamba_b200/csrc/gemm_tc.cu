@@ -1101,7 +1101,7 @@ int launch_pair(const void* A, int64_t lda, const void* W, int64_t ldw, const vo
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int pairs = (int)std::min<int64_t>(tiles, sm_count() / 2);
   // x | gate projections (act_from == N / 2, whole 128-column halves): interleaved tiles
-  const int interleave = BN == 256 && act_from * 2 == N && act_from % (BN / 2) == 0;
+  const int interleave = BN == 256 && N % 2 == 0 && act_from == N / 2 && act_from % (BN / 2) == 0;
   gemm_tc_pair_kernel<BN, kStages><<<2 * pairs, kThreads, smem, st>>>(ma, mw, mc, (const __nv_bfloat16*)bias,
                                                                       (int)M, N, K, act_from, interleave);
   VMB_LAUNCH_CHECK("gemm_tc_pair_kernel");
