@@ -206,7 +206,8 @@ typedef struct vmb_fused_scan_args {
    * check it when the weights are loaded): the decay factors of a channel then come from two
    * exponentials and packed multiplies instead of sixteen exponentials.  0 = general A. */
   int32_t a_geometric;
-  /* measurement aid, 0 = automatic: 10 * layout (1 one warp per unit, 2 two warps, 3 two warps + sequence
+  /* measurement aid, 0 = automatic: 100 * minimum segment of the sequence split (1 .. 4 = 32 .. 128 tokens)
+   * + 10 * layout (1 one warp per unit, 2 two warps, 3 two warps + sequence
    * split) + evaluator (1 = MUFU only, 2..5 = 1..4 of a lane's four state pairs on the FMA-pipe
    * polynomial, 9 = geometric).  Evaluators other than the built default and 9 exist only in
    * measurement builds (-DVMB_SCAN_LAB) and return VMB_ERR_UNSUPPORTED otherwise. */

@@ -80,7 +80,7 @@ struct FastScanArgs {
   int tune = 0;          // measurement aid: 10 * layout + evaluator, 0 = automatic (see scan_fast())
   float* ckpt = nullptr; // forward walk only: records of the state before every 4-token group (scan_bwd_fast.cu layout)
   // sequence split for small batches (filled by scan_fast itself): nseg segments of seg_len tokens,
-  // carried through seg_ws = [H (nseg,B,Di,N) | S (nseg,B,Di) | Hin (nseg,B,Di,N)] fp32
+  // carried through seg_ws = [H (nseg,B,Di,N) | S (nseg,B,Di)] fp32 (pass 2 chains them itself)
   float* seg_ws = nullptr;
   int64_t seg_ws_bytes = 0;
   int nseg = 1, seg_len = 0;

@@ -166,8 +166,11 @@ struct Lane {
   float2 h[4];
   float sum_a, sum_b;
 
-  __device__ __forceinline__ void init(const FastScanArgs& a, int ch_a, int tig, int64_t hoff_a,
-                                       const float* h_in /* fp32 carry or nullptr */) {
+  // seg > 0 (second pass of the sequence split): the state at the start of segment `seg` is chained here from the
+  // records of the first pass, h <- exp2(A2 * S[s]) * h + H[s] for s < seg (H[s] = end state of segment s from a zero
+  // start, S[s] = its sum of delta): a few dozen instructions per preceding segment instead of a kernel between
+  // the passes.
+  __device__ __forceinline__ void init(const FastScanArgs& a, int ch_a, int tig, int64_t hoff_a, int seg, int b) {
     const float* pa = a.A2 + (int64_t)ch_a * kN;
     const float* pb = pa + 8 * kN;
     if constexpr (kExp == kExpGeo) {
@@ -182,7 +185,6 @@ struct Lane {
     const int64_t hoff_b = hoff_a + 8 * kN;
     auto ld = [&](int64_t off) -> float {
       if (kStateOnly) return 0.f;
-      if (h_in) return h_in[off];
       return a.h0 ? load_as_f32(a.h0, off, a.h0_dtype) : 0.f;
     };
     h[0] = make_float2(ld(hoff_a), ld(hoff_b));
@@ -190,6 +192,29 @@ struct Lane {
     h[2] = make_float2(ld(hoff_a + 8), ld(hoff_b + 8));
     h[3] = make_float2(ld(hoff_a + 9), ld(hoff_b + 9));
     sum_a = sum_b = 0.f;
+    if constexpr (!kStateOnly) {
+      if (seg > 0) {
+        const int n[4] = {2 * tig, 2 * tig + 1, 2 * tig + 8, 2 * tig + 9};
+        float2 An[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) An[i] = make_float2(pa[n[i]], pb[n[i]]);
+        const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
+        const float* H = a.seg_ws;
+        const float* S = a.seg_ws + (int64_t)a.nseg * seg_stride + (int64_t)b * a.Di + ch_a;
+        const int64_t s_stride = (int64_t)a.B * a.Di;
+        const int off[4] = {0, 1, 8, 9};
+#pragma unroll 4
+        for (int sg = 0; sg < seg; ++sg) {
+          const float sa = S[sg * s_stride], sb = S[sg * s_stride + 8];
+          const float* Hs = H + sg * seg_stride;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h[i].x = fmaf(exp2f(An[i].x * sa), h[i].x, Hs[hoff_a + off[i]]);
+            h[i].y = fmaf(exp2f(An[i].y * sb), h[i].y, Hs[hoff_b + off[i]]);
+          }
+        }
+      }
+    }
   }
 
   __device__ __forceinline__ void store(float* dst, int64_t hoff_a) const {
@@ -371,11 +396,10 @@ scan1w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
   float* const wsH = a.seg_ws;
   float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
-  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
 
   Lane<kExp, kStateOnly> st;
   const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
-  st.init(a, cw + g, tig, hoff_a, seg > 0 ? wsHin + seg * seg_stride : nullptr);
+  st.init(a, cw + g, tig, hoff_a, seg, b);
   const float Da = a.D ? a.D[cw + g] : 0.f, Db = a.D ? a.D[cw + g + 8] : 0.f;
   uint32_t bfrag[2][KST][2];
   float bias[2][2];
@@ -605,7 +629,6 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
   const int64_t seg_stride = (int64_t)a.B * a.Di * kN;
   float* const wsH = a.seg_ws;
   float* const wsS = a.seg_ws + (int64_t)a.nseg * seg_stride;
-  const float* const wsHin = wsS + (int64_t)a.nseg * a.B * a.Di;
 
   const uint32_t bar0 = sbase + sp.bar;
   auto tma_bar = [&](int s) { return bar0 + 8u * s; };          // tile % 3
@@ -740,7 +763,7 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
     // ================================ consumer ================================
     Lane<kExp, kStateOnly> st;
     const int64_t hoff_a = ((int64_t)b * a.Di + cw + g) * kN + 2 * tig;
-    st.init(a, cw + g, tig, hoff_a, seg > 0 ? wsHin + seg * seg_stride : nullptr);
+    st.init(a, cw + g, tig, hoff_a, seg, b);
     float4* const ckrec = kCkpt ? reinterpret_cast<float4*>(a.ckpt) +
                                       ((int64_t)(b * gridDim.x + blockIdx.x) * ((a.L + 3) / 4)) * 64 + lane
                                 : nullptr;
@@ -798,39 +821,28 @@ scan2w_kernel(const FastScanArgs a, const __grid_constant__ CUtensorMap map_u,
 
 }  // namespace two_warp
 
-// Chains the segment carries: Hin[0] = h0, Hin[s+1] = exp2(A2 * S[s]) * Hin[s] + H[s].
-__global__ void scan_carry_kernel(const FastScanArgs a) {
-  const int64_t per_seg = (int64_t)a.B * a.Di * kN;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b, c, n)
-  if (i >= per_seg) return;
-  const int64_t bc = i / kN;
-  const int c = (int)(bc % a.Di);
-  const float A2 = a.A2[(int64_t)c * kN + (i % kN)];
-  const float* H = a.seg_ws;
-  const float* S = a.seg_ws + (int64_t)a.nseg * per_seg;
-  float* Hin = a.seg_ws + (int64_t)a.nseg * per_seg + (int64_t)a.nseg * a.B * a.Di;
-  float h = a.h0 ? load_as_f32(a.h0, i, a.h0_dtype) : 0.f;
-  for (int s = 0; s + 1 < a.nseg; ++s) {
-    h = fmaf(exp2f(A2 * S[(int64_t)s * a.B * a.Di + bc]), h, H[s * per_seg + i]);
-    Hin[(s + 1) * per_seg + i] = h;
-  }
-}
-
 // Segments only when the batch alone cannot fill the GPU (one warp per 16 channels of a sequence).
-void plan_segments(const FastScanArgs& a, int* nseg, int* seg_len) {
+constexpr int kMinSegFloor = 32;      // smallest segment (sizes the workspace)
+// min_seg = 0: automatic.  A lone warp needs ~230 clk per token, three per scheduler ~120 each; the split costs one
+// more dependent launch (the state pass; the carries are chained by the second pass itself) and ~1.5x the work.
+// Measured as 24 dependent launches in a CUDA graph (profiles/r02_scan_split_latency.jsonl, us per launch, B = 1:
+// L 196 unsplit 17.5 / 32-token segments 14.6, L 392 28.3 / 16.7 (128-token segments 24.1), L 784 49.9 / 21.3;
+// B = 4: L 196 17.8 / 18.6, L 392 28.6 / 24.5, 96-token segments 26.3): 32 tokens up to one unit per SM, 96 above.
+void plan_segments(const FastScanArgs& a, int min_seg, int* nseg, int* seg_len) {
   const int64_t warps = (int64_t)a.B * (a.Di / kCh);
   const int64_t want = 12ll * sm_count();       // 3 warps per scheduler
+  if (min_seg <= 0) min_seg = warps <= sm_count() ? 32 : 96;
   *nseg = 1;
   *seg_len = (a.L + kTT - 1) / kTT * kTT;
-  // Segments of >= 128 tokens: a lone warp needs ~230 clk per token, three per scheduler ~120 each; below
-  // ~128 tokens the two extra dependent launches cost what the split saves (B = 1, graph replay, us per
-  // layer: L 392 unsplit 33 / split 34, L 1568 50 -> 35 at 128-token segments, 45 at 256, 37 at 64).
-  if (warps >= want || a.L < 3 * 128) return;
-  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / 128);
+  if (warps >= want || a.L < 3 * min_seg) return;
+  int n = (int)std::min<int64_t>((want + warps - 1) / warps, a.L / min_seg);
   if (n < 3) return;                           // two segments cost 1.26x the work for less than that in occupancy
   const int len = ((a.L + n - 1) / n + kTT - 1) / kTT * kTT;
   *nseg = (a.L + len - 1) / len;
   *seg_len = len;
+}
+int64_t seg_ws_bytes_for(int nseg, int B, int Di) {    // H (nseg,B,Di,N) | S (nseg,B,Di), fp32
+  return ((int64_t)nseg * B * Di * kN + (int64_t)nseg * B * Di) * 4;
 }
 
 int tensor_maps(const FastScanArgs& a, CUtensorMap* mu, CUtensorMap* mz, CUtensorMap* mx) {
@@ -851,9 +863,11 @@ template <int R, int kExp, bool kTwoWarp>
 int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
   FastScanArgs a = a0;
   if (!a.reverse) a.frame_len = 0;
-  plan_segments(a, &a.nseg, &a.seg_len);
+  // measurement aid (tune / 100: 1 .. 4 = segments of at least 32 / 64 / 96 / 128 tokens instead of the automatic choice)
+  const int ms_sel = a.tune / 100;
+  plan_segments(a, ms_sel >= 1 && ms_sel <= 4 ? 32 * ms_sel : 0, &a.nseg, &a.seg_len);
   if (!split || a.frame_len > 0 || (a.nseg > 1 && (a.seg_ws == nullptr ||
-                                a.seg_ws_bytes < scan_fast_workspace_bytes(a.B, a.L, a.Di, a.N)))) {
+                                a.seg_ws_bytes < seg_ws_bytes_for(a.nseg, a.B, a.Di)))) {
     a.nseg = 1;                                // no workspace given: run unsplit (still correct)
     a.seg_len = (a.L + kTT - 1) / kTT * kTT;
   }
@@ -883,9 +897,6 @@ int launch(const FastScanArgs& a0, cudaStream_t st, bool split) {
   if (a.nseg > 1) {
     run(dim3(a.Di / kCh, a.B, a.nseg - 1), std::true_type{});
     VMB_LAUNCH_CHECK("scan kernel <state pass>");
-    const int64_t n = (int64_t)a.B * a.Di * kN;
-    scan_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
-    VMB_LAUNCH_CHECK("scan_carry_kernel");
   }
   run(dim3(a.Di / kCh, a.B, a.nseg), std::false_type{});
   VMB_LAUNCH_CHECK("scan kernel");
@@ -939,9 +950,9 @@ int64_t scan_fast_workspace_bytes(int B, int L, int Di, int N) {
   FastScanArgs a;
   a.B = B; a.L = L; a.Di = Di; a.N = N;
   int nseg, seg_len;
-  plan_segments(a, &nseg, &seg_len);
+  plan_segments(a, kMinSegFloor, &nseg, &seg_len);      // upper bound over every minimum the tune field can select
   if (nseg <= 1) return 0;
-  return ((int64_t)nseg * B * Di * N * 2 + (int64_t)nseg * B * Di) * 4;
+  return seg_ws_bytes_for(nseg, B, Di);
 }
 
 int scan_fast(const FastScanArgs& a, cudaStream_t st) {
@@ -950,7 +961,7 @@ int scan_fast(const FastScanArgs& a, cudaStream_t st) {
   // sequence (B200, L = 3137 / 6273: -12 % at 7.8 units per SM, -26 % at 2.6, -30 % at 3.9 for the
   // Middle width); fewer units need the sequence split, more fill the schedulers anyway and the
   // one-warp kernel's smaller footprint lets two launches share the SMs (profiles/).
-  const int layout = a.tune / 10, exp_tune = a.tune % 10;
+  const int layout = (a.tune / 10) % 10, exp_tune = a.tune % 10;
   const int64_t units = (int64_t)a.B * (a.Di / kCh);
   const bool two_warp = layout == 2 || layout == 3 || (layout == 0 && 2 * units < 19ll * sm_count());
   const bool split = layout == 0 ? (!two_warp || units < 2ll * sm_count()) : layout != 2;
