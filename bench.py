@@ -72,8 +72,8 @@ MUFU_ISSUE_SLOTS, MUFU_XU_CLK = 4.6, 8.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="small16f", choices=sorted(CONFIGS))
     ap.add_argument("--model", default=None, choices=sorted(MODELS), help="override the configuration's model")
