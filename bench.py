@@ -290,9 +290,12 @@ def run_reference(args):
     else:
         for _ in range(min(args.warmup, 1)):
             cpu_baseline(args, 1, with_configs0=False)
+        # a bounded sample per step: about 48 clips over the whole run (4 per step up to 12 steps, 2 at 20), so that
+        # --steps 20 still ends within a few minutes on a 16-core host
+        clips = max(1, min(args.cpu_clips, 48 // max(1, args.steps)))
         times = []
         for _ in range(args.steps):
-            times.append(cpu_baseline(args, args.cpu_clips, with_configs0=False))
+            times.append(cpu_baseline(args, clips, with_configs0=False))
     total = sum(t["seconds"] for t in times)
     value = sum(t["value"] * t["seconds"] for t in times) / total
     last = times[-1]
@@ -305,7 +308,7 @@ def run_reference(args):
         "config": {"workload": workload_name(args, batch), "weights": args.weights,
                    "note": "reference rejects CPU tensors and its kernels live in absent wheels; "
                            "this is the CPU restatement (oracle/) of its use_fast_path=False path, "
-                           f"each step a sample of {args.cpu_clips} clips"},
+                           f"each step a sample of {last['clips'] if 'clips' in last else args.cpu_clips} clip(s)"},
         "cpu_baseline": {"value": value, "unit": cfg["unit"], "cores": last["cores"], "kind": "port",
                          "sample": last["sample"]},
         "e2e": {"value": value, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
