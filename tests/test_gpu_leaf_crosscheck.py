@@ -46,6 +46,14 @@ def _cases():
                                         bias=conv["bias"])
         cases[f"addnorm_{tag}"] = dict(x=r(Bsz * L, 2 * Dm), residual=r(Bsz * L, 2 * Dm, scale=3.0),
                                        weight=1.0 + r(2 * Dm, scale=0.2), bias=r(2 * Dm, scale=0.2), eps=1e-5)
+    # the whole mixer (reference slow path) with the upstream kernels in the places of the two wheels
+    for tag, (d_model, Bsz, L) in {"a": (64, 2, 50), "b": (192, 3, 131)}.items():
+        sd = orc.synthetic_state_dict(dict(img_size=32, patch_size=16, depth=1, embed_dim=d_model, kernel_size=1,
+                                           num_frames=4), seed=7, perturbed=True)
+        p = {k[len("layers.0.mixer."):]: v.float() for k, v in sd.items() if k.startswith("layers.0.mixer.")}
+        Di, N = p["A_log"].shape
+        cases[f"mixer_{tag}"] = dict(p, hidden=r(Bsz, L, d_model), conv_state=None, ssm_state=None)
+        cases[f"mixer_{tag}_state"] = dict(p, hidden=r(Bsz, L, d_model), conv_state=r(Bsz, Di, 4), ssm_state=r(Bsz, Di, N))
     # bf16 operands (weights of the scan stay fp32, as the module keeps them): pins the ROUNDING POINTS -- fp32 inside
     # an op, one rounding of its result -- not just the formulas
     bf = torch.bfloat16
@@ -210,3 +218,25 @@ def test_bf16_rounding_points_of_the_leaves(upstream):
     # the upstream norm kernel ran on the fp32 sum and returned fp32: its one rounding is applied here
     _same_rounding(want, up["rms"].to(torch.bfloat16), "oracle add + norm")
     _same_rounding(got, up["rms"].to(torch.bfloat16), "libvmb200 add + norm")
+
+
+@pytest.mark.parametrize("name", ["mixer_a", "mixer_a_state", "mixer_b", "mixer_b_state"])
+def test_whole_mixer_with_upstream_kernels(upstream, name):
+    """The reference's slow-path mixer forward (mamba_simple.py:333-446) composed in the worker from torch
+    projections and the UPSTREAM conv / scan kernels, against the oracle's mixer_ref and libvmb200's vmb_mixer_fwd
+    (true-fp32 kernels) on the same weights and inputs, with and without the streaming state."""
+    c, up = _upstream_case(upstream, name)
+    p = {k: v for k, v in c.items() if k not in ("hidden", "conv_state", "ssm_state")}
+    want, (want_cs, want_ss) = orc.mixer_ref(p, c["hidden"], c["conv_state"], c["ssm_state"], want_state=True)
+    assert rel_err(want, up["out"]) <= TOL and rel_err(want_ss, up["ssm_state"]) <= TOL, "oracle vs upstream kernels"
+    assert rel_err(want_cs[..., 1:], up["conv_tail"]) <= TOL       # in_proj outputs: three fp32 GEMMs, three summation orders
+    from video_mamba.mamba_simple import Mamba
+    mx = Mamba(d_model=c["hidden"].shape[-1], use_fast_path=False)
+    mx.load_state_dict(p, strict=True)
+    mx = mx.to(DEV)
+    d = _dev(c)
+    with torch.no_grad():
+        state = None if c["conv_state"] is None else (d["conv_state"].clone(), d["ssm_state"].clone())
+        got, (got_cs, got_ss) = mx(d["hidden"], state=state, return_state=True)
+    assert rel_err(got, up["out"]) <= TOL and rel_err(got_ss, up["ssm_state"]) <= TOL, "libvmb200 vs upstream kernels"
+    assert rel_err(got_cs[..., 1:], up["conv_tail"]) <= TOL

@@ -58,6 +58,41 @@ def main(src, dst):
                 selective_state_update(state, c["x"], c["dt"], c["A"], c["Bm"], c["Cm"], c["D"], c["dt_bias"],
                                        z=c["z"], dt_softplus=True, out=y)
                 out[name] = {"y": y.cpu(), "state": state.cpu()}
+            elif name.startswith("mixer"):
+                # the reference's use_fast_path=False forward (models/videomamba/mamba_simple.py:333-339, :369,
+                # :381-416, :423-446) with the upstream kernels in the places of its two wheels: projections by
+                # torch, conv and scan by vllm's copies; optional streaming state in, next state out
+                import torch.nn.functional as F
+                h = c["hidden"]
+                Bsz, L, _ = h.shape
+                Di, _, W = c["conv1d.weight"].shape
+                N, R = c["A_log"].shape[1], c["dt_proj.weight"].shape[1]
+                xz = F.linear(h, c["in_proj.weight"])                                   # (B, L, 2 Di)
+                x_tok, z = xz[..., :Di], xz[..., Di:]
+                cstate = torch.zeros(Bsz + 1, Di, W - 1, device=dev, dtype=h.dtype)
+                has_c = c.get("conv_state") is not None
+                if has_c:
+                    cstate[1:] = c["conv_state"][..., 1:]                                # the last W - 1 cached inputs
+                cstate = cstate.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+                qsl = torch.arange(0, Bsz + 1, device=dev, dtype=torch.int32) * L
+                idx = torch.arange(1, Bsz + 1, device=dev, dtype=torch.int32)
+                xc = causal_conv1d_fn(x_tok.reshape(Bsz * L, Di).contiguous().t(), c["conv1d.weight"].reshape(Di, W),
+                                      c["conv1d.bias"], cstate, qsl, cache_indices=idx,
+                                      has_initial_state=torch.full((Bsz,), has_c, dtype=torch.bool, device=dev),
+                                      activation="silu").t().reshape(Bsz, L, Di)
+                x_dbl = F.linear(xc, c["x_proj.weight"])
+                dt_low, Bm, Cm = torch.split(x_dbl, [R, N, N], dim=-1)
+                delta = F.linear(dt_low, c["dt_proj.weight"])
+                has_s = c.get("ssm_state") is not None
+                state = c["ssm_state"].clone() if has_s else torch.zeros(Bsz, Di, N, device=dev, dtype=h.dtype)
+                gate = z.transpose(1, 2).contiguous().clone()
+                y = selective_scan_fn(xc.transpose(1, 2).contiguous(), state, delta.transpose(1, 2).contiguous(),
+                                      -torch.exp(c["A_log"].float()), Bm.transpose(1, 2).contiguous(),
+                                      Cm.transpose(1, 2).contiguous(), c["D"].float(), gate, c["dt_proj.bias"].float(),
+                                      delta_softplus=True,
+                                      has_initial_state=torch.full((Bsz,), has_s, dtype=torch.bool, device=dev))
+                out[name] = {"out": F.linear(y.transpose(1, 2), c["out_proj.weight"]).cpu(), "ssm_state": state.cpu(),
+                             "conv_tail": cstate[1:].contiguous().cpu()}
             elif name.startswith("addnorm"):
                 # (a) the upstream Triton norm kernel family (vllm's copy of mamba_ssm/ops/triton/layernorm_gated.py,
                 # ungated) on the fp32 sum x + residual; (b) vllm's own fused add + RMSNorm CUDA kernel
