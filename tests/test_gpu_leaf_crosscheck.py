@@ -54,6 +54,7 @@ def _cases():
         Di, N = p["A_log"].shape
         cases[f"mixer_{tag}"] = dict(p, hidden=r(Bsz, L, d_model), conv_state=None, ssm_state=None)
         cases[f"mixer_{tag}_state"] = dict(p, hidden=r(Bsz, L, d_model), conv_state=r(Bsz, Di, 4), ssm_state=r(Bsz, Di, N))
+        cases[f"stepmixer_{tag}"] = dict(p, hidden=r(Bsz, 3, d_model), conv_state=r(Bsz, Di, 4), ssm_state=r(Bsz, Di, N))
     # bf16 operands (weights of the scan stay fp32, as the module keeps them): pins the ROUNDING POINTS -- fp32 inside
     # an op, one rounding of its result -- not just the formulas
     bf = torch.bfloat16
@@ -240,3 +241,26 @@ def test_whole_mixer_with_upstream_kernels(upstream, name):
         got, (got_cs, got_ss) = mx(d["hidden"], state=state, return_state=True)
     assert rel_err(got, up["out"]) <= TOL and rel_err(got_ss, up["ssm_state"]) <= TOL, "libvmb200 vs upstream kernels"
     assert rel_err(got_cs[..., 1:], up["conv_tail"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["stepmixer_a", "stepmixer_b"])
+def test_decode_step_with_upstream_kernels(upstream, name):
+    """Mamba.step (mamba_simple.py:453-497), three tokens in a row, composed in the worker from torch projections and
+    the upstream causal_conv1d_update / selective_state_update kernels, against the oracle's mixer_step_ref and
+    libvmb200's fused step kernel (fp32)."""
+    c, up = _upstream_case(upstream, name)
+    p = {k: v for k, v in c.items() if k not in ("hidden", "conv_state", "ssm_state")}
+    cs, ss = c["conv_state"].clone(), c["ssm_state"].clone()
+    want = torch.cat([orc.mixer_step_ref(p, c["hidden"][:, t:t + 1], cs, ss) for t in range(3)], dim=1)
+    assert rel_err(want, up["out"]) <= TOL and rel_err(ss, up["ssm_state"]) <= TOL, "oracle vs upstream kernels"
+    assert rel_err(cs[..., 1:], up["conv_tail"]) <= TOL
+    from video_mamba.mamba_simple import Mamba
+    mx = Mamba(d_model=c["hidden"].shape[-1], use_fast_path=False)
+    mx.load_state_dict(p, strict=True)
+    mx = mx.to(DEV)
+    d = _dev(c)
+    cs, ss = d["conv_state"].clone(), d["ssm_state"].clone()
+    with torch.no_grad():
+        got = torch.cat([mx.step(d["hidden"][:, t:t + 1], cs, ss)[0] for t in range(3)], dim=1)
+    assert rel_err(got, up["out"]) <= TOL and rel_err(ss, up["ssm_state"]) <= TOL, "libvmb200 vs upstream kernels"
+    assert rel_err(cs[..., 1:], up["conv_tail"]) <= TOL

@@ -58,6 +58,30 @@ def main(src, dst):
                 selective_state_update(state, c["x"], c["dt"], c["A"], c["Bm"], c["Cm"], c["D"], c["dt_bias"],
                                        z=c["z"], dt_softplus=True, out=y)
                 out[name] = {"y": y.cpu(), "state": state.cpu()}
+            elif name.startswith("stepmixer"):
+                # single-token decode (mamba_simple.py:453-497): in_proj, causal_conv1d_update, x_proj, dt_proj,
+                # selective_state_update, out_proj -- three tokens in a row so the rolled states are used again
+                import torch.nn.functional as F
+                Di, _, W = c["conv1d.weight"].shape
+                N, R = c["A_log"].shape[1], c["dt_proj.weight"].shape[1]
+                Bsz = c["hidden"].shape[0]
+                cstate = torch.cat([torch.zeros_like(c["conv_state"][:1, :, 1:]), c["conv_state"][..., 1:]], 0).contiguous()
+                idx = torch.arange(1, Bsz + 1, device=dev, dtype=torch.int32)
+                state = c["ssm_state"].clone()
+                A = -torch.exp(c["A_log"].float())
+                outs = []
+                for t in range(c["hidden"].shape[1]):
+                    xz = F.linear(c["hidden"][:, t], c["in_proj.weight"])
+                    x, z = xz[:, :Di].contiguous(), xz[:, Di:].contiguous()
+                    x = causal_conv1d_update(x, cstate, c["conv1d.weight"].reshape(Di, W), c["conv1d.bias"],
+                                             activation="silu", conv_state_indices=idx)
+                    dt_low, Bm, Cm = torch.split(F.linear(x, c["x_proj.weight"]), [R, N, N], dim=-1)
+                    dt = F.linear(dt_low, c["dt_proj.weight"])
+                    y = torch.empty_like(x)
+                    selective_state_update(state, x, dt, A, Bm.contiguous(), Cm.contiguous(), c["D"].float(),
+                                           c["dt_proj.bias"].float(), z=z, dt_softplus=True, out=y)
+                    outs.append(F.linear(y, c["out_proj.weight"]))
+                out[name] = {"out": torch.stack(outs, 1).cpu(), "ssm_state": state.cpu(), "conv_tail": cstate[1:].cpu()}
             elif name.startswith("mixer"):
                 # the reference's use_fast_path=False forward (models/videomamba/mamba_simple.py:333-339, :369,
                 # :381-416, :423-446) with the upstream kernels in the places of its two wheels: projections by
