@@ -71,7 +71,8 @@ def _same_rounding(a, b, what):
     the last bits straddles a rounding boundary (a different rounding point would move a large share of them)."""
     a, b = a.float().cpu(), b.float().cpu()
     differ = (a != b).float().mean().item()
-    assert differ <= 0.02 and rel_err(a, b) <= 8e-3, (what, differ, rel_err(a, b))
+    # (an extra rounding of an intermediate moves ~25-50 % of the elements: vllm's Triton conv, below, moves 27 %)
+    assert differ <= 0.05 and rel_err(a, b) <= 8e-3, (what, differ, rel_err(a, b))
 
 
 @pytest.fixture(scope="module")
